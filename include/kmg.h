@@ -1,0 +1,169 @@
+/*
+ * kmg.h -- C ABI of the B200-native k-mer engine (libkmg.so).
+ *
+ * This is the drop-in boundary for kmermaid's one data-parallel hot path:
+ *   extract  (kmermaid/seq.py:284-328, rc :245-282)
+ *   sort     (kmermaid/batch.py:156-168)
+ *   join     (kmermaid/join.py:63-130 merge+group, :243-263 uniq, :265-285 count)
+ * The reference is pure Python and has no FFI layer; these entry points are what a
+ * ctypes binding in kmermaid/batcher.py + kmermaid/join.py would call.
+ *
+ * Conventions
+ *   - plain C types only; every `d_*` pointer is a CUDA device pointer owned by the
+ *     caller, every `h_*` pointer is host memory owned by the caller;
+ *   - the library keeps no reference to caller memory after a call returns, except that
+ *     device work enqueued on `stream` may still be running (stage calls are asynchronous
+ *     with respect to the host unless stated otherwise);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - scratch memory is provided by the caller, sized by the matching *_workspace_bytes();
+ *   - return value: 0 = OK, <0 = error; kmg_last_error() gives the thread-local message;
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails.
+ *
+ * Key format ("narrow" stream, windows made only of the four plain bases):
+ *   k <= 32 : uint64, k <= 64 : 128-bit {lo, hi} little-endian limbs (16-byte aligned);
+ *   value = sum(code[j] << 2*(k-1-j)), A<C<G<T(U) = 0,1,2,3 -- integer order == the
+ *   reference's string order (batch.py:156-168) for equal-length upper-case strings.
+ * Key format ("wide" stream, windows that pass the alphabet test but hold >= 1 other
+ *   symbol, e.g. N): 4-bit ASCII-rank codes over "ABCDGHKMNRSTUVWY", MSB first,
+ *   k <= 16 : uint64, k <= 32 : 128-bit.
+ * Payload ("val") format: (global window start in the flat base buffer << 1) | strand
+ *   (0 '+', 1 '-'), as uint32 (val_bytes 4) or uint64 (val_bytes 8).
+ */
+#ifndef KMG_H_
+#define KMG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KMG_VERSION 100 /* 0.1.0 */
+
+#define KMG_OK 0
+#define KMG_ERR_ARG (-1)    /* invalid argument (the reference raises AssertionError) */
+#define KMG_ERR_CUDA (-2)   /* CUDA runtime error */
+#define KMG_ERR_WS (-3)     /* workspace too small */
+#define KMG_ERR_RANGE (-4)  /* size beyond what this build supports */
+#define KMG_ERR_STATE (-5)  /* device-side consistency check failed */
+
+/* LUT byte layout (one entry per input byte value, see kmg_build_lut):
+ *   bit 7    : symbol not in the alphabet -> every window touching it is skipped
+ *              (seq.py:318-327)
+ *   bit 6    : symbol in the alphabet but not one of the four plain bases
+ *   bits 5:2 : 4-bit ASCII rank code (wide stream)
+ *   bits 1:0 : 2-bit code (narrow stream)                                         */
+#define KMG_LUT_INVALID 0x80u
+#define KMG_LUT_NONPLAIN 0x40u
+
+int kmg_version(void);
+const char* kmg_last_error(void);
+/* number of CUDA devices visible, or <0 */
+int kmg_device_count(void);
+
+/* Host helper: fill lut[256] and comp4[16] from an alphabet given as the reference gives
+ * it: `symbols` and `complement` are the two rows of oligo_melting.AB_NA[t]
+ * (used at seq.py:318 and seq.py:279); case-folding per seq.py:313. */
+int kmg_build_lut(const char* symbols, const char* complement, uint8_t* h_lut256, uint8_t* h_comp16);
+
+/* Read back (and thereby wait for) the status word of a stage workspace after the stage's
+ * kernels were enqueued on `stream`: KMG_OK, KMG_ERR_STATE (device-side look-back gave up)
+ * or KMG_ERR_RANGE (a run length overflowed uint32).  Synchronises the stream. */
+int kmg_ws_status(void* d_ws, void* stream);
+
+/* ---- K1+K2: encode + rolling-window extraction (seq.py:284-328, rc :245-282) ----------
+ * Emits, in position order ('+' then '-' per position when rc), the keys of all windows
+ * whose start lies in [win_begin, win_end) of the flat buffer d_bases[0..n_bases) and that
+ *   wide == 0 : consist only of plain bases (narrow stream, 2-bit codes)
+ *   wide == 1 : pass the alphabet test and contain >= 1 non-plain symbol (4-bit codes)
+ * Record separators are any byte the LUT marks invalid (the loader uses '\n').
+ * d_vals_out may be NULL (val_bytes 0).  `pos_offset` is added to the window start before
+ * it is stored in the payload (multi-GPU chunks).
+ * d_counts[0] = number of keys emitted, d_counts[1] (narrow only) = number of windows
+ * that belong to the wide stream.  Output capacity must be (win_end-win_begin)*(1+rc). */
+size_t kmg_extract_workspace_bytes(uint64_t n_windows);
+int kmg_extract(const uint8_t* d_bases, uint64_t n_bases, uint64_t win_begin, uint64_t win_end, int k, int rc,
+                int wide, const uint8_t* d_lut256, const uint8_t* d_comp16, void* d_keys_out, int key_bytes,
+                void* d_vals_out, int val_bytes, uint64_t pos_offset, uint64_t* d_counts, void* d_ws,
+                size_t ws_bytes, void* stream);
+
+/* ---- K3: HBM-resident LSD radix sort (batch.py:156-168 + the merge of join.py:63-93) --
+ * Stable, sorts on key bits [begin_bit, end_bit).  Ping-pongs between (keys, keys_alt)
+ * [and (vals, vals_alt)]; *h_selector_out (host, written before return) is 0 if the
+ * result is in keys/vals, 1 if in keys_alt/vals_alt. */
+size_t kmg_radix_sort_workspace_bytes(uint64_t n, int key_bytes, int val_bytes, int begin_bit, int end_bit);
+int kmg_radix_sort(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_alt, uint64_t n, int key_bytes,
+                   int val_bytes, int begin_bit, int end_bit, int* h_selector_out, void* d_ws, size_t ws_bytes,
+                   void* stream);
+
+/* ---- K4: run-length / unique on sorted keys (join.py:95-130, :265-285, :243-263) ------
+ * rle_count: distinct keys ascending + run lengths; *d_n_out = number of runs.
+ * select_singletons: keys (and payload) of runs of length exactly 1. */
+size_t kmg_rle_workspace_bytes(uint64_t n);
+int kmg_rle_count(const void* d_sorted_keys, uint64_t n, int key_bytes, void* d_uniq_keys_out,
+                  uint32_t* d_counts_out, uint64_t* d_n_out, void* d_ws, size_t ws_bytes, void* stream);
+int kmg_select_singletons(const void* d_sorted_keys, const void* d_vals, uint64_t n, int key_bytes, int val_bytes,
+                          void* d_keys_out, void* d_vals_out, uint64_t* d_n_out, void* d_ws, size_t ws_bytes,
+                          void* stream);
+
+/* ---- K5: range partition for the multi-GPU exchange (no reference counterpart) --------
+ * Stable split of keys into n_parts contiguous regions of the output by
+ *   part = ((key >> (key_bits-16)) * n_parts) >> 16      (key_bits >= 16)
+ * so that concatenating the parts' sorted contents in part order is globally sorted.
+ * d_part_counts[n_parts] receives the region sizes. */
+size_t kmg_partition_workspace_bytes(uint64_t n, int key_bytes, int val_bytes);
+int kmg_range_partition(const void* d_keys, const void* d_vals, uint64_t n, int key_bytes, int val_bytes,
+                        int key_bits, int n_parts, void* d_keys_out, void* d_vals_out, uint64_t* d_part_counts,
+                        void* d_ws, size_t ws_bytes, void* stream);
+
+/* ---- K6: text emission (join.py:262,284; seq.py:103-104,489-495) ----------------------
+ * count lines "SEQ\tCOUNT\n"; *d_bytes_out = total bytes; d_text_out capacity must be
+ * n*(k+12).  Symbols: narrow keys decode through "ACGT"/"ACGU" (rna != 0), wide keys
+ * through the 16-letter table. */
+size_t kmg_format_workspace_bytes(uint64_t n);
+int kmg_format_counts(const void* d_keys, const uint32_t* d_counts, uint64_t n, int key_bytes, int k, int wide,
+                      int rna, uint8_t* d_text_out, uint64_t* d_bytes_out, void* d_ws, size_t ws_bytes,
+                      void* stream);
+/* uniq records ">NAME:START-END:STRAND\nSEQ\n".  Record r spans
+ * [d_rec_starts[r], d_rec_starts[r+1]-1) of the flat buffer (one separator byte after
+ * each record); its name is d_names[d_name_offs[r] .. d_name_offs[r+1]).
+ * d_text_out capacity must be n*(k+48+max_name_len). */
+int kmg_format_uniq(const void* d_keys, const void* d_vals, uint64_t n, int key_bytes, int val_bytes, int k,
+                    int wide, int rna, const uint64_t* d_rec_starts, uint32_t n_rec, const uint8_t* d_names,
+                    const uint64_t* d_name_offs, uint8_t* d_text_out, uint64_t* d_bytes_out, void* d_ws,
+                    size_t ws_bytes, void* stream);
+
+/* ---- merge ranks between the narrow and the wide stream -------------------------------
+ * For two sorted, disjoint key lists, rank_of_wide[i] = number of narrow keys that sort
+ * before wide key i in the reference's ASCII order (and vice versa), so that the merged
+ * position of an element is its own index + its rank in the other list. */
+int kmg_merge_ranks(const void* d_narrow_keys, uint64_t n_narrow, int narrow_key_bytes, const void* d_wide_keys,
+                    uint64_t n_wide, int wide_key_bytes, int k, int rna, uint64_t* d_rank_of_narrow,
+                    uint64_t* d_rank_of_wide, void* stream);
+
+/* ---- whole-path calls with HOST buffers (what FastaBatcher.do + KJoiner.join do) ------
+ * A context owns device scratch on one GPU and a private stream; calls are synchronous.
+ * h_bases is the flat buffer (records joined by '\n'), narrow stream only: the call
+ * fails with KMG_ERR_STATE if the input holds wide windows (use the stage API then).
+ * count: h_keys_out/h_counts_out capacity `cap` entries; *h_n_out = number of distinct
+ * k-mers.  uniq: singletons with payload. */
+typedef struct kmg_ctx kmg_ctx;
+int kmg_ctx_create(int device, kmg_ctx** out);
+void kmg_ctx_destroy(kmg_ctx* ctx);
+int kmg_count_host(kmg_ctx* ctx, const uint8_t* h_bases, uint64_t n_bases, int k, int rc, const uint8_t* h_lut256,
+                   void* h_keys_out, uint32_t* h_counts_out, uint64_t cap, uint64_t* h_n_out);
+int kmg_uniq_host(kmg_ctx* ctx, const uint8_t* h_bases, uint64_t n_bases, int k, int rc, const uint8_t* h_lut256,
+                  void* h_keys_out, uint64_t* h_vals_out, uint64_t cap, uint64_t* h_n_out);
+
+/* ---- tuning / introspection -----------------------------------------------------------
+ * kmg_set_option("sort_config", i) selects a tile configuration of the sort kernel;
+ * kmg_get_stat(name) returns counters of the last call made on this thread
+ * ("sort_passes", "sort_launches", "launches"). */
+int kmg_set_option(const char* name, int64_t value);
+int64_t kmg_get_stat(const char* name);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KMG_H_ */

@@ -1,0 +1,203 @@
+// Shared device/host helpers for libkmg (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/kmg.h"
+
+namespace kmg {
+
+// ---- error plumbing ---------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+void bump_launches(int n = 1);
+
+#define KMG_CUDA(call)                                                                          \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess) {                                                               \
+            kmg::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return KMG_ERR_CUDA;                                                                \
+        }                                                                                       \
+    } while (0)
+
+#define KMG_REQUIRE(cond, code, ...)    \
+    do {                                \
+        if (!(cond)) {                  \
+            kmg::set_error(__VA_ARGS__); \
+            return (code);              \
+        }                               \
+    } while (0)
+
+#define KMG_LAUNCH_CHECK()                                                                \
+    do {                                                                                  \
+        cudaError_t e__ = cudaGetLastError();                                             \
+        if (e__ != cudaSuccess) {                                                         \
+            kmg::set_error("%s:%d: launch failed: %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+            return KMG_ERR_CUDA;                                                          \
+        }                                                                                 \
+        kmg::bump_launches();                                                             \
+    } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- 128-bit key ------------------------------------------------------------------------
+struct __align__(16) u128 {
+    uint64_t lo, hi;
+};
+
+__host__ __device__ __forceinline__ bool operator==(const u128& a, const u128& b) { return a.lo == b.lo && a.hi == b.hi; }
+__host__ __device__ __forceinline__ bool operator!=(const u128& a, const u128& b) { return !(a == b); }
+__host__ __device__ __forceinline__ bool operator<(const u128& a, const u128& b) {
+    return a.hi < b.hi || (a.hi == b.hi && a.lo < b.lo);
+}
+
+// digit = (key >> shift) & mask ; shift < 8*sizeof(key), digit width <= 16
+__device__ __forceinline__ uint32_t key_digit(uint64_t k, int shift, uint32_t mask) {
+    return (uint32_t)(k >> shift) & mask;
+}
+__device__ __forceinline__ uint32_t key_digit(const u128& k, int shift, uint32_t mask) {
+    uint64_t v;
+    if (shift >= 64) {
+        v = k.hi >> (shift - 64);
+    } else if (shift == 0) {
+        v = k.lo;
+    } else {
+        v = (k.lo >> shift) | (k.hi << (64 - shift));
+    }
+    return (uint32_t)v & mask;
+}
+__device__ __forceinline__ uint64_t key_all_ones(uint64_t) { return ~0ull; }
+__device__ __forceinline__ u128 key_all_ones(u128) { return u128{~0ull, ~0ull}; }
+
+// ---- memory-ordering primitives for decoupled look-back -----------------------------------
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_acquire_u64(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u64(uint64_t* p, uint64_t v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(uint64_t* p, uint64_t v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// A spin that can never hang the GPU: after SPIN_LIMIT polls the kernel raises a device
+// error flag and returns garbage; the host turns the flag into KMG_ERR_STATE.
+constexpr uint32_t SPIN_LIMIT = 1u << 24;
+
+// ---- 64-bit single-word tile prefix (flag in the top 2 bits, 62-bit value) ----------------
+// Used by extract (compaction), select_singletons and format (byte offsets).
+constexpr uint64_t TP_FLAG_AGG = 1ull << 62;
+constexpr uint64_t TP_FLAG_INCL = 2ull << 62;
+constexpr uint64_t TP_VALUE_MASK = (1ull << 62) - 1;
+
+// Called by ONE thread of the tile.  `state` must be zero-initialised; tile ids must be
+// handed out in launch order (atomic ticket).  Returns the exclusive prefix.
+__device__ __forceinline__ uint64_t tile_prefix_exclusive(uint64_t* state, uint32_t tile, uint64_t aggregate,
+                                                          uint32_t* err_flag) {
+    if (tile == 0) {
+        st_release_u64(&state[0], TP_FLAG_INCL | aggregate);
+        return 0;
+    }
+    st_release_u64(&state[tile], TP_FLAG_AGG | aggregate);
+    uint64_t excl = 0;
+    int64_t p = (int64_t)tile - 1;
+    uint32_t spins = 0;
+    while (true) {
+        uint64_t w = ld_acquire_u64(&state[p]);
+        uint64_t f = w & ~TP_VALUE_MASK;
+        if (f == 0) {
+            if (++spins > SPIN_LIMIT) {
+                atomicExch(err_flag, 1u);
+                break;
+            }
+            __nanosleep(20);
+            continue;
+        }
+        excl += w & TP_VALUE_MASK;
+        if (f == TP_FLAG_INCL) break;
+        --p;
+    }
+    st_release_u64(&state[tile], TP_FLAG_INCL | (excl + aggregate));
+    return excl;
+}
+
+// ---- workspace header ---------------------------------------------------------------------
+// Every stage workspace starts with this 256-byte header, zeroed by the host entry point
+// before the launch; kmg_ws_status() reads `err` back.
+struct WsHeader {
+    uint32_t ticket;  // dynamic tile id dispenser
+    uint32_t err;     // != 0: a look-back spin hit SPIN_LIMIT (cannot happen on a healthy device)
+    uint32_t pad[62];
+};
+static_assert(sizeof(WsHeader) == 256, "WsHeader must be 256 bytes");
+
+// shared-memory staging index with one padding slot every 16 (8-byte items) / 8 (16-byte)
+template <int ITEM_BYTES>
+__host__ __device__ __forceinline__ uint32_t pad_idx(uint32_t i) {
+    return ITEM_BYTES >= 16 ? i + (i >> 3) : i + (i >> 4);
+}
+
+// ---- warp helpers ---------------------------------------------------------------------
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ uint32_t lanemask_lt() {
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_incl_scan(T v) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        T t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane_id() >= (uint32_t)o) v += t;
+    }
+    return v;
+}
+
+// Block-wide exclusive scan of one value per thread; returns exclusive prefix and total.
+// `smem` needs (BLOCK/32 + 1) entries of T.  Contains two __syncthreads().
+template <int BLOCK, typename T>
+__device__ __forceinline__ T block_excl_scan(T v, T* smem, T& total) {
+    constexpr int WARPS = BLOCK / 32;
+    T incl = warp_incl_scan(v);
+    const uint32_t w = threadIdx.x >> 5;
+    if (lane_id() == 31) smem[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        T x = (lane_id() < WARPS) ? smem[lane_id()] : T(0);
+        T xi = warp_incl_scan(x);
+        if (lane_id() < WARPS) smem[lane_id()] = xi - x;
+        if (lane_id() == WARPS - 1) smem[WARPS] = xi;
+    }
+    __syncthreads();
+    total = smem[WARPS];
+    return smem[w] + incl - v;
+}
+
+}  // namespace kmg

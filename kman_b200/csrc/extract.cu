@@ -1,0 +1,400 @@
+// K1+K2: LUT encode + rolling-window key extraction.
+//
+// Replaces Sequence.yield_kmers (kmermaid/seq.py:284-328), its reverse-complement variant
+// (seq.py:245-282) and the second alphabet filter (seq.py:500-509 via batcher.py:559-561).
+//
+// Narrow stream: a tile of 16-base words is staged in shared memory as 2-bit codes plus two
+// bitmasks (bad-for-narrow, invalid-for-any-stream); every thread then produces the keys of
+// its consecutive window starts with funnel shifts out of 64-bit big-endian code words, so a
+// base is looked up in the LUT exactly once.  Valid keys are compacted in position order
+// (block scan + decoupled look-back across tiles), staged in shared memory and written with
+// fully coalesced stores.
+#include "common.cuh"
+
+namespace kmg {
+
+constexpr int EX_BLOCK = 256;
+constexpr int EX_HALO_WORDS = 8;  // 16-base words past the tile that masks/codes may touch
+
+struct ExtractParams {
+    const uint8_t* bases;
+    uint64_t n_bases;
+    uint64_t win_begin, win_end;
+    uint64_t first_tile;  // absolute tile index (tile = EX_BLOCK*PPT window starts, buffer-aligned)
+    int k;
+    const uint8_t* lut;
+    const uint8_t* comp16;
+    void* keys_out;
+    void* vals_out;
+    uint64_t pos_offset;
+    unsigned long long* counts;  // [0] emitted, [1] wide windows seen
+    uint64_t* tile_state;
+    uint32_t* ticket;
+    uint32_t* err;
+};
+
+__device__ __forceinline__ uint64_t rev2_64(uint64_t x) {
+    x = __brevll(x);
+    return ((x >> 1) & 0x5555555555555555ull) | ((x & 0x5555555555555555ull) << 1);
+}
+__device__ __forceinline__ uint64_t rc_key(uint64_t key, int k) { return rev2_64(~key) >> (64 - 2 * k); }
+__device__ __forceinline__ u128 rc_key(const u128& key, int k) {
+    uint64_t hi = rev2_64(~key.lo), lo = rev2_64(~key.hi);
+    int s = 128 - 2 * k;  // 0 <= s <= 62 because k >= 33
+    u128 r;
+    if (s == 0) {
+        r.lo = lo;
+        r.hi = hi;
+    } else {
+        r.lo = (lo >> s) | (hi << (64 - s));
+        r.hi = hi >> s;
+    }
+    return r;
+}
+
+template <typename ValT>
+__device__ __forceinline__ ValT make_val(uint64_t pos, uint32_t strand) {
+    return (ValT)((pos << 1) | strand);
+}
+
+// KeyT: uint64_t (k<=32) or u128 (33<=k<=64).  PPT: window starts per thread (8 or 16).
+template <typename KeyT, int PPT, bool RC, int VAL_BYTES>
+__global__ void __launch_bounds__(EX_BLOCK) extract_narrow_kernel(const ExtractParams p) {
+    constexpr int TILE = EX_BLOCK * PPT;
+    constexpr int WORDS = TILE / 16 + EX_HALO_WORDS;
+    constexpr int OUT_PER_WIN = RC ? 2 : 1;
+    using ValT = typename std::conditional<VAL_BYTES == 4, uint32_t, uint64_t>::type;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr uint32_t STAGE = TILE * OUT_PER_WIN;
+    constexpr uint32_t STAGE_PAD = STAGE + STAGE / 8 + 8;  // room for pad_idx() of either width
+    KeyT* s_keys = reinterpret_cast<KeyT*>(smem_raw);
+    ValT* s_vals = reinterpret_cast<ValT*>(smem_raw + sizeof(KeyT) * STAGE_PAD);
+    constexpr int KB = sizeof(KeyT);
+    constexpr int VB = VAL_BYTES == 0 ? 8 : VAL_BYTES;
+    __shared__ uint32_t s_codes[WORDS];
+    __shared__ uint16_t s_bad[WORDS];
+    __shared__ uint16_t s_inv[WORDS];
+    __shared__ uint8_t s_lut[256];
+    __shared__ uint32_t s_scan[EX_BLOCK / 32 + 1];
+    __shared__ uint32_t s_tile;
+    __shared__ uint64_t s_base;
+    __shared__ uint32_t s_wide;
+
+    const int t = threadIdx.x;
+    if (t == 0) {
+        s_tile = atomicAdd(p.ticket, 1u);
+        s_wide = 0;
+    }
+    s_lut[t] = p.lut[t];
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint64_t tile_pos = (p.first_tile + tile) * (uint64_t)TILE;
+
+    // ---- K1: encode 16 bases per word ----------------------------------------------------
+    for (int w = t; w < WORDS; w += EX_BLOCK) {
+        const uint64_t pos = tile_pos + (uint64_t)w * 16;
+        uint32_t b[4];
+        if (pos + 16 <= p.n_bases) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.bases + pos));
+            b[0] = v.x; b[1] = v.y; b[2] = v.z; b[3] = v.w;
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint32_t x = 0;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const uint64_t pp = pos + q * 4 + r;
+                    // 0xFF is never in an alphabet built by kmg_build_lut; the explicit
+                    // range test below does not rely on that.
+                    const uint32_t byte = (pp < p.n_bases) ? p.bases[pp] : 0xFFu;
+                    x |= byte << (8 * r);
+                }
+                b[q] = x;
+            }
+        }
+        uint32_t codes = 0, bad = 0, inv = 0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const uint32_t byte = (b[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+            uint32_t e = s_lut[byte];
+            if (pos + j >= p.n_bases) e = KMG_LUT_INVALID;
+            codes |= (e & 3u) << (30 - 2 * j);
+            bad |= ((e & 0xC0u) ? 1u : 0u) << (15 - j);
+            inv |= ((e & 0x80u) ? 1u : 0u) << (15 - j);
+        }
+        s_codes[w] = codes;
+        s_bad[w] = (uint16_t)bad;
+        s_inv[w] = (uint16_t)inv;
+    }
+    __syncthreads();
+
+    // ---- K2: rolling windows ---------------------------------------------------------------
+    const int k = p.k;
+    const int wbase = (t * PPT) >> 4;
+    const int joff = (t * PPT) & 15;
+    const uint64_t X0 = ((uint64_t)s_codes[wbase] << 32) | s_codes[wbase + 1];
+    const uint64_t X1 = ((uint64_t)s_codes[wbase + 2] << 32) | s_codes[wbase + 3];
+    const uint64_t X2 = ((uint64_t)s_codes[wbase + 4] << 32) | s_codes[wbase + 5];
+    const uint64_t B0 = ((uint64_t)s_bad[wbase] << 48) | ((uint64_t)s_bad[wbase + 1] << 32) |
+                        ((uint64_t)s_bad[wbase + 2] << 16) | s_bad[wbase + 3];
+    const uint64_t B1 = ((uint64_t)s_bad[wbase + 4] << 48) | ((uint64_t)s_bad[wbase + 5] << 32) |
+                        ((uint64_t)s_bad[wbase + 6] << 16) | s_bad[wbase + 7];
+    const uint64_t I0 = ((uint64_t)s_inv[wbase] << 48) | ((uint64_t)s_inv[wbase + 1] << 32) |
+                        ((uint64_t)s_inv[wbase + 2] << 16) | s_inv[wbase + 3];
+    const uint64_t I1 = ((uint64_t)s_inv[wbase + 4] << 48) | ((uint64_t)s_inv[wbase + 5] << 32) |
+                        ((uint64_t)s_inv[wbase + 6] << 16) | s_inv[wbase + 7];
+
+    KeyT keys[PPT];
+    uint32_t vf = 0, nwide = 0;
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+        const int je = joff + j;  // 0..15
+        const uint64_t pos = tile_pos + (uint64_t)t * PPT + j;
+        const uint64_t bm = (je == 0 ? B0 : ((B0 << je) | (B1 >> (64 - je)))) >> (64 - k);
+        const uint64_t im = (je == 0 ? I0 : ((I0 << je) | (I1 >> (64 - je)))) >> (64 - k);
+        const bool in_range = pos >= p.win_begin && pos < p.win_end;
+        if (in_range && bm == 0) vf |= 1u << j;
+        if (in_range && im == 0 && bm != 0) ++nwide;
+        const int s2 = 2 * je;
+        const uint64_t hi = je == 0 ? X0 : ((X0 << s2) | (X1 >> (64 - s2)));
+        if constexpr (sizeof(KeyT) == 8) {
+            keys[j] = hi >> (64 - 2 * k);
+        } else {
+            const uint64_t lo = je == 0 ? X1 : ((X1 << s2) | (X2 >> (64 - s2)));
+            const int s = 128 - 2 * k;
+            u128 kk;
+            if (s == 0) {
+                kk.lo = lo;
+                kk.hi = hi;
+            } else {
+                kk.lo = (lo >> s) | (hi << (64 - s));
+                kk.hi = hi >> s;
+            }
+            keys[j] = kk;
+        }
+    }
+
+    // ---- compaction in position order ---------------------------------------------------
+    const uint32_t cnt = __popc(vf);
+    uint32_t total;
+    const uint32_t excl = block_excl_scan<EX_BLOCK, uint32_t>(cnt, s_scan, total);
+    if (nwide) atomicAdd(&s_wide, nwide);
+    if (t == 0) {
+        s_base = tile_prefix_exclusive(p.tile_state, tile, (uint64_t)total * OUT_PER_WIN, p.err);
+    }
+    uint32_t r = excl;
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+        if (vf & (1u << j)) {
+            const uint64_t pos = tile_pos + (uint64_t)t * PPT + j + p.pos_offset;
+            s_keys[pad_idx<KB>(r * OUT_PER_WIN)] = keys[j];
+            if constexpr (VAL_BYTES != 0) s_vals[pad_idx<VB>(r * OUT_PER_WIN)] = make_val<ValT>(pos, 0);
+            if constexpr (RC) {
+                s_keys[pad_idx<KB>(r * 2 + 1)] = rc_key(keys[j], k);
+                if constexpr (VAL_BYTES != 0) s_vals[pad_idx<VB>(r * 2 + 1)] = make_val<ValT>(pos, 1);
+            }
+            ++r;
+        }
+    }
+    __syncthreads();
+    const uint64_t base = s_base;
+    const uint32_t n_out = total * OUT_PER_WIN;
+    KeyT* keys_out = reinterpret_cast<KeyT*>(p.keys_out) + base;
+    for (uint32_t i = t; i < n_out; i += EX_BLOCK) keys_out[i] = s_keys[pad_idx<KB>(i)];
+    if constexpr (VAL_BYTES != 0) {
+        ValT* vals_out = reinterpret_cast<ValT*>(p.vals_out) + base;
+        for (uint32_t i = t; i < n_out; i += EX_BLOCK) vals_out[i] = s_vals[pad_idx<VB>(i)];
+    }
+    if (t == 0) {
+        if (s_wide) atomicAdd(&p.counts[1], (unsigned long long)s_wide);
+        if (tile == gridDim.x - 1) p.counts[0] = base + n_out;
+    }
+}
+
+// ---- wide stream: windows that pass the alphabet test but contain a non-plain symbol -----
+// Rare by construction (N runs, IUPAC codes), so the kernel is simple: 4 consecutive window
+// starts per thread, bytes staged in shared memory, 4-bit ASCII-rank codes, 128-bit keys.
+constexpr int EXW_BLOCK = 256;
+constexpr int EXW_PPT = 4;
+constexpr int EXW_TILE = EXW_BLOCK * EXW_PPT;
+
+template <bool RC, int VAL_BYTES>
+__global__ void __launch_bounds__(EXW_BLOCK) extract_wide_kernel(const ExtractParams p) {
+    using ValT = typename std::conditional<VAL_BYTES == 4, uint32_t, uint64_t>::type;
+    constexpr int OUT_PER_WIN = RC ? 2 : 1;
+    __shared__ uint8_t s_e[EXW_TILE + 64];  // LUT entries of the tile bytes (+ halo)
+    __shared__ uint8_t s_lut[256];
+    __shared__ uint8_t s_comp[16];
+    __shared__ uint32_t s_scan[EXW_BLOCK / 32 + 1];
+    __shared__ uint32_t s_tile;
+    __shared__ uint64_t s_base;
+
+    const int t = threadIdx.x;
+    if (t == 0) s_tile = atomicAdd(p.ticket, 1u);
+    s_lut[t] = p.lut[t];
+    if (t < 16) s_comp[t] = p.comp16[t];
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint64_t tile_pos = (p.first_tile + tile) * (uint64_t)EXW_TILE;
+    for (int i = t; i < EXW_TILE + 64; i += EXW_BLOCK) {
+        const uint64_t pos = tile_pos + i;
+        s_e[i] = pos < p.n_bases ? s_lut[p.bases[pos]] : (uint8_t)KMG_LUT_INVALID;
+    }
+    __syncthreads();
+
+    const int k = p.k;
+    u128 keys[EXW_PPT];
+    uint32_t vf = 0;
+#pragma unroll
+    for (int j = 0; j < EXW_PPT; ++j) {
+        const int o = t * EXW_PPT + j;
+        const uint64_t pos = tile_pos + o;
+        uint32_t any_inv = 0, any_nonplain = 0;
+        uint64_t lo = 0, hi = 0;
+        for (int q = 0; q < k; ++q) {
+            const uint32_t e = s_e[o + q];
+            any_inv |= e & 0x80u;
+            any_nonplain |= e & 0x40u;
+            hi = (hi << 4) | (lo >> 60);
+            lo = (lo << 4) | ((e >> 2) & 0xFu);
+        }
+        keys[j] = u128{lo, hi};
+        if (pos >= p.win_begin && pos < p.win_end && !any_inv && any_nonplain) vf |= 1u << j;
+    }
+    const uint32_t cnt = __popc(vf);
+    uint32_t total;
+    const uint32_t excl = block_excl_scan<EXW_BLOCK, uint32_t>(cnt, s_scan, total);
+    if (t == 0) s_base = tile_prefix_exclusive(p.tile_state, tile, (uint64_t)total * OUT_PER_WIN, p.err);
+    __syncthreads();
+    const uint64_t base = s_base;
+    u128* keys_out = reinterpret_cast<u128*>(p.keys_out);
+    ValT* vals_out = reinterpret_cast<ValT*>(p.vals_out);
+    uint64_t r = base + (uint64_t)excl * OUT_PER_WIN;
+#pragma unroll
+    for (int j = 0; j < EXW_PPT; ++j) {
+        if (!(vf & (1u << j))) continue;
+        const uint64_t pos = tile_pos + t * EXW_PPT + j + p.pos_offset;
+        keys_out[r] = keys[j];
+        if constexpr (VAL_BYTES != 0) vals_out[r] = make_val<ValT>(pos, 0);
+        ++r;
+        if constexpr (RC) {
+            // reverse complement: symbol q of the window becomes nibble q (from the LSB)
+            uint64_t lo = 0, hi = 0;
+            u128 f = keys[j];
+            for (int q = k - 1; q >= 0; --q) {  // q-th symbol sits at nibble k-1-q of f
+                const uint32_t c = s_comp[f.lo & 0xFu];
+                f.lo = (f.lo >> 4) | (f.hi << 60);
+                f.hi >>= 4;
+                // symbol index q (just popped, from the end) -> nibble index q
+                if (q < 16) lo |= (uint64_t)c << (4 * q);
+                else hi |= (uint64_t)c << (4 * (q - 16));
+            }
+            keys_out[r] = u128{lo, hi};
+            if constexpr (VAL_BYTES != 0) vals_out[r] = make_val<ValT>(pos, 1);
+            ++r;
+        }
+    }
+    if (t == 0 && tile == gridDim.x - 1) p.counts[0] = base + (uint64_t)total * OUT_PER_WIN;
+}
+
+template <typename KeyT, int PPT, bool RC, int VB>
+static int launch_narrow(const ExtractParams& p, uint32_t n_tiles, cudaStream_t st) {
+    constexpr int TILE = EX_BLOCK * PPT;
+    constexpr uint32_t STAGE = TILE * (RC ? 2 : 1);
+    constexpr uint32_t STAGE_PAD = STAGE + STAGE / 8 + 8;
+    const size_t smem = (sizeof(KeyT) + (VB == 4 ? 4 : (VB == 8 ? 8 : 0))) * (size_t)STAGE_PAD;
+    auto kern = extract_narrow_kernel<KeyT, PPT, RC, VB>;
+    KMG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<n_tiles, EX_BLOCK, smem, st>>>(p);
+    KMG_LAUNCH_CHECK();
+    return KMG_OK;
+}
+
+template <typename KeyT, int PPT>
+static int dispatch_narrow(const ExtractParams& p, uint32_t n_tiles, int rc, int vb, cudaStream_t st) {
+    if (rc) {
+        if (vb == 0) return launch_narrow<KeyT, PPT, true, 0>(p, n_tiles, st);
+        if (vb == 4) return launch_narrow<KeyT, PPT, true, 4>(p, n_tiles, st);
+        return launch_narrow<KeyT, PPT, true, 8>(p, n_tiles, st);
+    }
+    if (vb == 0) return launch_narrow<KeyT, PPT, false, 0>(p, n_tiles, st);
+    if (vb == 4) return launch_narrow<KeyT, PPT, false, 4>(p, n_tiles, st);
+    return launch_narrow<KeyT, PPT, false, 8>(p, n_tiles, st);
+}
+
+template <bool RC>
+static int dispatch_wide(const ExtractParams& p, uint32_t n_tiles, int vb, cudaStream_t st) {
+    if (vb == 0) extract_wide_kernel<RC, 0><<<n_tiles, EXW_BLOCK, 0, st>>>(p);
+    else if (vb == 4) extract_wide_kernel<RC, 4><<<n_tiles, EXW_BLOCK, 0, st>>>(p);
+    else extract_wide_kernel<RC, 8><<<n_tiles, EXW_BLOCK, 0, st>>>(p);
+    KMG_LAUNCH_CHECK();
+    return KMG_OK;
+}
+
+}  // namespace kmg
+
+using namespace kmg;
+
+// smallest tile any extract kernel uses -> upper bound on the number of tiles
+static constexpr uint64_t EX_MIN_TILE = 1024;
+
+extern "C" size_t kmg_extract_workspace_bytes(uint64_t n_windows) {
+    // header + tile states (+2 tiles for the unaligned head/tail)
+    return sizeof(WsHeader) + align_up((n_windows / EX_MIN_TILE + 3) * sizeof(uint64_t), 256);
+}
+
+extern "C" int kmg_extract(const uint8_t* d_bases, uint64_t n_bases, uint64_t win_begin, uint64_t win_end, int k,
+                           int rc, int wide, const uint8_t* d_lut256, const uint8_t* d_comp16, void* d_keys_out,
+                           int key_bytes, void* d_vals_out, int val_bytes, uint64_t pos_offset,
+                           uint64_t* d_counts, void* d_ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    KMG_REQUIRE(k >= 2, KMG_ERR_ARG, "k must be >= 2, got %d", k);  // batcher.py:477-478
+    KMG_REQUIRE(k <= 64, KMG_ERR_RANGE, "k=%d: this build supports k <= 64 (no CPU fallback)", k);
+    KMG_REQUIRE(!wide || k <= 32, KMG_ERR_RANGE, "wide (non-ACGT) stream supports k <= 32, got %d", k);
+    KMG_REQUIRE(win_begin <= win_end, KMG_ERR_ARG, "win_begin > win_end");
+    KMG_REQUIRE(val_bytes == 0 || val_bytes == 4 || val_bytes == 8, KMG_ERR_ARG, "val_bytes must be 0, 4 or 8");
+    KMG_REQUIRE((val_bytes == 0) == (d_vals_out == nullptr), KMG_ERR_ARG, "d_vals_out / val_bytes mismatch");
+    const int want_kb = wide ? 16 : (k <= 32 ? 8 : 16);
+    KMG_REQUIRE(key_bytes == want_kb, KMG_ERR_ARG, "key_bytes must be %d for k=%d wide=%d", want_kb, k, wide);
+    KMG_REQUIRE(((uintptr_t)d_bases & 15) == 0, KMG_ERR_ARG, "d_bases must be 16-byte aligned");
+    KMG_REQUIRE(((uintptr_t)d_keys_out & (key_bytes - 1)) == 0, KMG_ERR_ARG, "d_keys_out misaligned");
+    KMG_REQUIRE(d_lut256 && d_counts && d_ws, KMG_ERR_ARG, "null pointer argument");
+    KMG_REQUIRE(!(wide && rc) || d_comp16, KMG_ERR_ARG, "d_comp16 required for wide rc");
+    if (val_bytes == 4)
+        KMG_REQUIRE(((pos_offset + n_bases) << 1) < (1ull << 32), KMG_ERR_RANGE, "val_bytes=4 needs < 2^31 positions");
+    KMG_REQUIRE(ws_bytes >= kmg_extract_workspace_bytes(win_end - win_begin), KMG_ERR_WS, "extract workspace too small");
+
+    KMG_CUDA(cudaMemsetAsync(d_counts, 0, 2 * sizeof(uint64_t), st));
+    if (win_end == win_begin) return KMG_OK;
+
+    const uint64_t tile = wide ? (uint64_t)EXW_TILE : (uint64_t)(EX_BLOCK * (key_bytes == 8 ? 16 : 8));
+    const uint64_t first_tile = win_begin / tile;
+    const uint64_t n_tiles = (win_end + tile - 1) / tile - first_tile;
+    KMG_REQUIRE(n_tiles < (1ull << 31), KMG_ERR_RANGE, "too many tiles");
+    const size_t state_bytes = align_up(n_tiles * sizeof(uint64_t), 256);
+    KMG_CUDA(cudaMemsetAsync(d_ws, 0, sizeof(WsHeader) + state_bytes, st));
+    WsHeader* hdr = reinterpret_cast<WsHeader*>(d_ws);
+
+    ExtractParams p;
+    p.bases = d_bases;
+    p.n_bases = n_bases;
+    p.win_begin = win_begin;
+    p.win_end = win_end;
+    p.first_tile = first_tile;
+    p.k = k;
+    p.lut = d_lut256;
+    p.comp16 = d_comp16;
+    p.keys_out = d_keys_out;
+    p.vals_out = d_vals_out;
+    p.pos_offset = pos_offset;
+    p.counts = reinterpret_cast<unsigned long long*>(d_counts);
+    p.tile_state = reinterpret_cast<uint64_t*>(hdr + 1);
+    p.ticket = &hdr->ticket;
+    p.err = &hdr->err;
+
+    if (wide) return rc ? dispatch_wide<true>(p, (uint32_t)n_tiles, val_bytes, st)
+                        : dispatch_wide<false>(p, (uint32_t)n_tiles, val_bytes, st);
+    if (key_bytes == 8) return dispatch_narrow<uint64_t, 16>(p, (uint32_t)n_tiles, rc, val_bytes, st);
+    return dispatch_narrow<u128, 8>(p, (uint32_t)n_tiles, rc, val_bytes, st);
+}

@@ -1,0 +1,572 @@
+// K3: HBM-resident stable LSD radix sort ("onesweep": one read + one write of the keys per
+// digit pass, chained-scan look-back between tiles instead of a separate scan pass), and
+// K5: the range partition used before the multi-GPU exchange (the same kernel with a
+// different digit function).
+//
+// Replaces Batch.sorted (kmermaid/batch.py:156-168: stable sort by sequence string) and the
+// ordering work of the n-way heap merge (kmermaid/join.py:63-93).  For equal-length
+// upper-case strings the packed integer order equals the string order, and stability keeps
+// equal k-mers in emission (position) order exactly like Timsort + heapq.merge do.
+//
+// Per pass and tile:
+//   1. coalesced warp-striped load of ITEMS keys per thread
+//   2. per-warp digit ranking with ballot matching into per-warp shared-memory histograms
+//   3. block prefix over warps and digits -> tile-local sorted position of every key
+//   4. one thread per digit publishes the tile's digit count and looks back over earlier
+//      tiles (32-bit word: 2 flag bits + 30-bit count) -> global base of the digit run
+//   5. keys (then payload) are reordered through shared memory so that every digit run is
+//      written with consecutive threads -> coalesced stores of run-length ~TILE/RADIX keys
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace kmg {
+
+constexpr int MAX_PASSES = 16;
+
+struct PassPlan {
+    int num_passes;
+    int shift[MAX_PASSES];
+    int bits[MAX_PASSES];
+};
+
+// ---- digit functions --------------------------------------------------------------------
+struct ShiftDigit {
+    int shift;
+    uint32_t mask;
+    template <typename KeyT>
+    __device__ __forceinline__ uint32_t operator()(const KeyT& k) const {
+        return key_digit(k, shift, mask);
+    }
+};
+// part = ((key >> (key_bits-16)) * n_parts) >> 16
+struct RangeDigit {
+    int shift;  // key_bits - 16
+    uint32_t n_parts;
+    template <typename KeyT>
+    __device__ __forceinline__ uint32_t operator()(const KeyT& k) const {
+        return (key_digit(k, shift, 0xFFFFu) * n_parts) >> 16;
+    }
+};
+
+// ---- histogram of every pass in one read sweep ---------------------------------------------
+template <typename KeyT, int RADIX_BITS>
+__global__ void __launch_bounds__(512) radix_hist_kernel(const KeyT* __restrict__ keys, uint64_t n, PassPlan plan,
+                                                         unsigned long long* __restrict__ hist) {
+    constexpr int RADIX = 1 << RADIX_BITS;
+    extern __shared__ uint32_t s_hist[];  // [num_passes][RADIX]
+    const int np = plan.num_passes;
+    for (int i = threadIdx.x; i < np * RADIX; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const KeyT key = keys[i];
+        for (int p = 0; p < np; ++p) {
+            const uint32_t d = key_digit(key, plan.shift[p], (1u << plan.bits[p]) - 1u);
+            atomicAdd(&s_hist[p * RADIX + d], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < np * RADIX; i += blockDim.x) {
+        const uint32_t c = s_hist[i];
+        if (c) atomicAdd(&hist[i], (unsigned long long)c);
+    }
+}
+
+template <typename KeyT, typename DigitOp>
+__global__ void __launch_bounds__(512) digit_hist_kernel(const KeyT* __restrict__ keys, uint64_t n, DigitOp op,
+                                                         int radix, unsigned long long* __restrict__ hist) {
+    extern __shared__ uint32_t s_hist[];
+    for (int i = threadIdx.x; i < radix; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        atomicAdd(&s_hist[op(keys[i])], 1u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < radix; i += blockDim.x) {
+        const uint32_t c = s_hist[i];
+        if (c) atomicAdd(&hist[i], (unsigned long long)c);
+    }
+}
+
+// exclusive scan of each pass' histogram: one warp per pass.  bins[p][d] = sum(hist[p][<d]).
+// `counts_out` (optional) receives a copy of the raw histogram of pass 0 (partition sizes).
+__global__ void radix_scan_kernel(const unsigned long long* __restrict__ hist, uint64_t* __restrict__ bins,
+                                  int radix, int bins_stride, uint64_t* counts_out) {
+    const int p = blockIdx.x;
+    const unsigned long long* h = hist + (size_t)p * radix;
+    uint64_t* b = bins + (size_t)p * bins_stride;
+    uint64_t run = 0;
+    for (int base = 0; base < radix; base += 32) {
+        const int d = base + threadIdx.x;
+        const uint64_t c = d < radix ? h[d] : 0;
+        if (counts_out && p == 0 && d < radix) counts_out[d] = c;
+        const uint64_t incl = warp_incl_scan(c);
+        if (d < radix) b[d] = run + incl - c;
+        run += __shfl_sync(0xffffffffu, incl, 31);
+    }
+}
+
+// ---- the onesweep pass ----------------------------------------------------------------------
+constexpr uint32_t LB_VALUE_MASK = (1u << 30) - 1;
+
+struct OnesweepParams {
+    const void* keys_in;
+    void* keys_out;
+    const void* vals_in;
+    void* vals_out;
+    uint32_t n;  // keys in this part (< 2^30)
+    const uint64_t* bins_in;  // [RADIX] global base of each digit run for this part
+    uint64_t* bins_out;       // [RADIX] base for the next part (may be null)
+    uint32_t* lookback;       // [tiles][RADIX]
+    uint32_t* ticket;
+    uint32_t* err;
+    uint32_t parity;  // flips per launch so the look-back words need no re-zeroing
+};
+
+template <int VAL_BYTES>
+struct ValType {
+    using type = uint64_t;
+};
+template <>
+struct ValType<4> {
+    using type = uint32_t;
+};
+
+template <typename KeyT, int VAL_BYTES, int RADIX_BITS, int BLOCK, int IPT, typename DigitOp>
+__global__ void __launch_bounds__(BLOCK) onesweep_kernel(const OnesweepParams p, const DigitOp digit_of) {
+    constexpr int RADIX = 1 << RADIX_BITS;
+    constexpr int WARPS = BLOCK / 32;
+    constexpr int TILE = BLOCK * IPT;
+    constexpr int DPT = (RADIX + BLOCK - 1) / BLOCK;  // digits handled per thread in the prefix phase
+    using ValT = typename ValType<VAL_BYTES>::type;
+    constexpr int ITEM_BYTES = sizeof(KeyT) > sizeof(ValT) ? sizeof(KeyT) : sizeof(ValT);
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    KeyT* s_keys = reinterpret_cast<KeyT*>(smem_raw);
+    ValT* s_vals = reinterpret_cast<ValT*>(smem_raw);
+    uint32_t* s_whist = reinterpret_cast<uint32_t*>(smem_raw + (size_t)ITEM_BYTES * TILE);  // [WARPS][RADIX]
+    uint64_t* s_goff = reinterpret_cast<uint64_t*>(s_whist + WARPS * RADIX);               // [RADIX]
+    __shared__ uint32_t s_scan[WARPS + 1];
+    __shared__ uint32_t s_tile;
+
+    const int t = threadIdx.x;
+    const uint32_t lane = t & 31, warp = t >> 5;
+    if (t == 0) s_tile = atomicAdd(p.ticket, 1u);
+    uint32_t* my_hist = s_whist + warp * RADIX;
+    for (int i = lane; i < RADIX; i += 32) my_hist[i] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t n_tiles = gridDim.x;
+    if (t == 0 && tile == n_tiles - 1) *p.ticket = 0;  // every ticket of this launch is taken
+    const uint32_t tile_base = tile * (uint32_t)TILE;
+    const uint32_t n_valid = min((uint32_t)TILE, p.n - tile_base);
+
+    // ---- 1. load ----------------------------------------------------------------------------
+    const KeyT* keys_in = reinterpret_cast<const KeyT*>(p.keys_in) + tile_base;
+    KeyT keys[IPT];
+    const uint32_t wbase = warp * 32 * IPT + lane;
+    if (n_valid == TILE) {
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) keys[i] = keys_in[wbase + i * 32];
+    } else {
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) {
+            const uint32_t idx = wbase + i * 32;
+            keys[i] = idx < n_valid ? keys_in[idx] : key_all_ones(KeyT{});
+        }
+    }
+
+    // ---- 2. rank inside the warp ------------------------------------------------------------
+    uint32_t ranks[IPT];
+    const uint32_t lt = lanemask_lt();
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+        const uint32_t idx = wbase + i * 32;
+        const uint32_t d = idx < n_valid ? digit_of(keys[i]) : (uint32_t)(RADIX - 1);
+        uint32_t m = 0xffffffffu;
+#pragma unroll
+        for (int b = 0; b < RADIX_BITS; ++b) {
+            const bool bit = (d >> b) & 1u;
+            const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+            m &= bit ? bal : ~bal;
+        }
+        const uint32_t lower = __popc(m & lt);
+        uint32_t old = 0;
+        if (lower == 0) {
+            old = my_hist[d];
+            my_hist[d] = old + __popc(m);
+        }
+        __syncwarp();
+        old = __shfl_sync(0xffffffffu, old, __ffs(m) - 1);
+        ranks[i] = old + lower;
+    }
+    __syncthreads();
+
+    // ---- 3. prefix over warps and digits ------------------------------------------------------
+    uint32_t cnt[DPT];
+    uint32_t tsum = 0;
+#pragma unroll
+    for (int q = 0; q < DPT; ++q) {
+        const int d = t * DPT + q;
+        uint32_t run = 0;
+        if (d < RADIX) {
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) {
+                const uint32_t c = s_whist[w * RADIX + d];
+                s_whist[w * RADIX + d] = run;
+                run += c;
+            }
+        }
+        cnt[q] = run;
+        tsum += run;
+    }
+    uint32_t total;
+    uint32_t bin_excl = block_excl_scan<BLOCK, uint32_t>(tsum, s_scan, total);
+
+    // ---- 4. publish + look back, one digit chain per thread ------------------------------------
+    const uint32_t padding = (uint32_t)TILE - n_valid;
+    const uint32_t fl_agg = ((1u + 2u * p.parity) & 3u) << 30;
+    const uint32_t fl_incl = ((2u + 2u * p.parity) & 3u) << 30;
+    const uint32_t fl_empty = ((0u + 2u * p.parity) & 3u) << 30;
+#pragma unroll
+    for (int q = 0; q < DPT; ++q) {
+        const int d = t * DPT + q;
+        if (d < RADIX) {
+            uint32_t c = cnt[q];
+            if (d == RADIX - 1) c -= padding;  // padded slots were ranked into the last digit
+            uint32_t* lb = p.lookback + d;
+            uint32_t excl = 0;
+            if (tile == 0) {
+                st_relaxed_u32(lb, fl_incl | c);
+            } else {
+                st_relaxed_u32(lb + (size_t)tile * RADIX, fl_agg | c);
+                int64_t pt = (int64_t)tile - 1;
+                uint32_t spins = 0;
+                while (true) {
+                    const uint32_t w = ld_relaxed_u32(lb + (size_t)pt * RADIX);
+                    const uint32_t f = w & ~LB_VALUE_MASK;
+                    if (f == fl_empty || (f != fl_agg && f != fl_incl)) {
+                        if (++spins > SPIN_LIMIT) {
+                            atomicExch(p.err, 1u);
+                            break;
+                        }
+                        continue;
+                    }
+                    excl += w & LB_VALUE_MASK;
+                    if (f == fl_incl) break;
+                    --pt;
+                }
+                st_relaxed_u32(lb + (size_t)tile * RADIX, fl_incl | (excl + c));
+            }
+            const uint64_t gbase = p.bins_in[d];
+            // destination of local sorted slot s holding digit d:  s_goff[d] + s
+            s_goff[d] = gbase + excl - bin_excl;
+            if (p.bins_out && tile == n_tiles - 1) p.bins_out[d] = gbase + excl + c;
+            // fold the digit's tile-local base into every warp's offset
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) s_whist[w * RADIX + d] += bin_excl;
+            bin_excl += cnt[q];
+        }
+    }
+    __syncthreads();
+
+    // ---- 5. reorder through shared memory, coalesced run writes ---------------------------------
+    uint32_t dig[IPT];
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+        const uint32_t idx = wbase + i * 32;
+        const uint32_t d = idx < n_valid ? digit_of(keys[i]) : (uint32_t)(RADIX - 1);
+        ranks[i] += my_hist[d];  // tile-local sorted slot
+        s_keys[ranks[i]] = keys[i];
+    }
+    __syncthreads();
+    KeyT* keys_out = reinterpret_cast<KeyT*>(p.keys_out);
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+        const uint32_t s = t + i * BLOCK;
+        if (s < n_valid) {
+            const KeyT key = s_keys[s];
+            const uint32_t d = digit_of(key);
+            dig[i] = d;
+            keys_out[s_goff[d] + s] = key;
+        }
+    }
+    if constexpr (VAL_BYTES != 0) {
+        const ValT* vals_in = reinterpret_cast<const ValT*>(p.vals_in) + tile_base;
+        ValT vals[IPT];
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) {
+            const uint32_t idx = wbase + i * 32;
+            vals[i] = idx < n_valid ? vals_in[idx] : ValT(0);
+        }
+        __syncthreads();  // all key reads from the staging buffer are done
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) s_vals[ranks[i]] = vals[i];
+        __syncthreads();
+        ValT* vals_out = reinterpret_cast<ValT*>(p.vals_out);
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) {
+            const uint32_t s = t + i * BLOCK;
+            if (s < n_valid) vals_out[s_goff[dig[i]] + s] = s_vals[s];
+        }
+    }
+}
+
+// ---- tile configurations ----------------------------------------------------------------------
+struct SortTile {
+    int radix_bits, block, ipt;
+};
+// index = kmg_set_option("sort_config", i); entry 0 is the default.
+static const SortTile kSortTiles[] = {
+    {8, 256, 16}, {8, 384, 12}, {8, 512, 8}, {8, 256, 24}, {8, 512, 12},
+};
+constexpr int kNumSortTiles = sizeof(kSortTiles) / sizeof(kSortTiles[0]);
+
+template <typename KeyT, int VB, int RB, int BLOCK, int IPT, typename DigitOp>
+static size_t onesweep_smem() {
+    using ValT = typename ValType<VB>::type;
+    const size_t item = sizeof(KeyT) > (VB ? sizeof(ValT) : 0) ? sizeof(KeyT) : sizeof(ValT);
+    return item * BLOCK * IPT + (size_t)(BLOCK / 32) * (1 << RB) * 4 + (size_t)(1 << RB) * 8;
+}
+
+template <typename KeyT, int VB, int RB, int BLOCK, int IPT, typename DigitOp>
+static int launch_onesweep(const OnesweepParams& p, const DigitOp& op, cudaStream_t st) {
+    auto kern = onesweep_kernel<KeyT, VB, RB, BLOCK, IPT, DigitOp>;
+    const size_t smem = onesweep_smem<KeyT, VB, RB, BLOCK, IPT, DigitOp>();
+    KMG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint32_t tiles = (p.n + BLOCK * IPT - 1) / (BLOCK * IPT);
+    kern<<<tiles, BLOCK, smem, st>>>(p, op);
+    KMG_LAUNCH_CHECK();
+    return KMG_OK;
+}
+
+template <typename KeyT, int VB, typename DigitOp>
+static int dispatch_tile(int cfg, const OnesweepParams& p, const DigitOp& op, cudaStream_t st) {
+    switch (cfg) {
+        case 1: return launch_onesweep<KeyT, VB, 8, 384, 12>(p, op, st);
+        case 2: return launch_onesweep<KeyT, VB, 8, 512, 8>(p, op, st);
+        case 3: return launch_onesweep<KeyT, VB, 8, 256, 24>(p, op, st);
+        case 4: return launch_onesweep<KeyT, VB, 8, 512, 12>(p, op, st);
+        default: return launch_onesweep<KeyT, VB, 8, 256, 16>(p, op, st);
+    }
+}
+
+template <typename DigitOp>
+static int dispatch_onesweep(int cfg, int key_bytes, int val_bytes, const OnesweepParams& p, const DigitOp& op,
+                             cudaStream_t st) {
+    if (key_bytes == 8) {
+        if (val_bytes == 0) return dispatch_tile<uint64_t, 0>(cfg, p, op, st);
+        if (val_bytes == 4) return dispatch_tile<uint64_t, 4>(cfg, p, op, st);
+        return dispatch_tile<uint64_t, 8>(cfg, p, op, st);
+    }
+    // 16-byte keys: halve the items per thread by using the narrower configurations only
+    if (val_bytes == 0) return launch_onesweep<u128, 0, 8, 256, 8>(p, op, st);
+    if (val_bytes == 4) return launch_onesweep<u128, 4, 8, 256, 8>(p, op, st);
+    return launch_onesweep<u128, 8, 8, 256, 8>(p, op, st);
+}
+
+int g_sort_config = 0;
+thread_local int64_t g_stat_sort_passes = 0;
+
+static int tile_items(int cfg, int key_bytes) {
+    if (key_bytes == 16) return 256 * 8;
+    if (cfg < 0 || cfg >= kNumSortTiles) cfg = 0;
+    return kSortTiles[cfg].block * kSortTiles[cfg].ipt;
+}
+
+static PassPlan make_plan(int begin_bit, int end_bit, int radix_bits) {
+    PassPlan plan;
+    memset(&plan, 0, sizeof(plan));
+    const int bits = end_bit - begin_bit;
+    const int np = (bits + radix_bits - 1) / radix_bits;
+    plan.num_passes = np;
+    int at = begin_bit;
+    for (int i = 0; i < np; ++i) {
+        // spread the bits evenly: the first (bits % np) passes get one more bit
+        const int b = bits / np + (i < bits % np ? 1 : 0);
+        plan.shift[i] = at;
+        plan.bits[i] = b;
+        at += b;
+    }
+    return plan;
+}
+
+constexpr int SORT_RADIX_BITS = 8;
+constexpr int SORT_RADIX = 1 << SORT_RADIX_BITS;
+// keys per look-back part: 30-bit counts, multiple of every tile size (lcm of tiles | 2^k*3)
+constexpr uint64_t PART_MAX = ((1ull << 30) - 1) / (4096ull * 3 * 3) * (4096ull * 3 * 3);
+
+struct SortWs {
+    WsHeader* hdr;
+    unsigned long long* hist;  // [MAX_PASSES][RADIX]
+    uint64_t* bins;            // [MAX_PASSES][2][RADIX]
+    uint32_t* lookback;        // [tiles_per_part][RADIX]
+    size_t total;
+};
+
+static SortWs carve_sort_ws(void* ws, uint64_t n, int key_bytes) {
+    SortWs w;
+    char* p = (char*)ws;
+    w.hdr = (WsHeader*)p;
+    p += sizeof(WsHeader);
+    w.hist = (unsigned long long*)p;
+    p += sizeof(uint64_t) * MAX_PASSES * SORT_RADIX;
+    w.bins = (uint64_t*)p;
+    p += sizeof(uint64_t) * MAX_PASSES * 2 * SORT_RADIX;
+    w.lookback = (uint32_t*)p;
+    const uint64_t part = n < PART_MAX ? n : PART_MAX;
+    const uint64_t min_tile = key_bytes == 16 ? 2048 : 4096;  // smallest tile of any configuration
+    const uint64_t tiles = (part + min_tile - 1) / min_tile + 1;
+    p += align_up(tiles * SORT_RADIX * sizeof(uint32_t), 256);
+    w.total = p - (char*)ws;
+    return w;
+}
+
+}  // namespace kmg
+
+using namespace kmg;
+
+extern "C" size_t kmg_radix_sort_workspace_bytes(uint64_t n, int key_bytes, int val_bytes, int begin_bit,
+                                                 int end_bit) {
+    (void)val_bytes; (void)begin_bit; (void)end_bit;
+    return carve_sort_ws(nullptr, n, key_bytes).total;
+}
+
+extern "C" int kmg_radix_sort(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_alt, uint64_t n,
+                              int key_bytes, int val_bytes, int begin_bit, int end_bit, int* h_selector_out,
+                              void* d_ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    KMG_REQUIRE(key_bytes == 8 || key_bytes == 16, KMG_ERR_ARG, "key_bytes must be 8 or 16");
+    KMG_REQUIRE(val_bytes == 0 || val_bytes == 4 || val_bytes == 8, KMG_ERR_ARG, "val_bytes must be 0, 4 or 8");
+    KMG_REQUIRE(begin_bit >= 0 && end_bit <= key_bytes * 8 && begin_bit <= end_bit, KMG_ERR_ARG,
+                "bad bit range [%d,%d)", begin_bit, end_bit);
+    KMG_REQUIRE(h_selector_out, KMG_ERR_ARG, "h_selector_out is null");
+    KMG_REQUIRE((val_bytes == 0) == (d_vals == nullptr), KMG_ERR_ARG, "d_vals / val_bytes mismatch");
+    *h_selector_out = 0;
+    g_stat_sort_passes = 0;
+    if (n <= 1 || end_bit == begin_bit) return KMG_OK;
+    KMG_REQUIRE(d_keys && d_keys_alt && d_ws, KMG_ERR_ARG, "null pointer argument");
+    KMG_REQUIRE(val_bytes == 0 || d_vals_alt, KMG_ERR_ARG, "d_vals_alt is null");
+    KMG_REQUIRE(((uintptr_t)d_keys % key_bytes) == 0 && ((uintptr_t)d_keys_alt % key_bytes) == 0, KMG_ERR_ARG,
+                "key buffers misaligned");
+    SortWs w = carve_sort_ws(d_ws, n, key_bytes);
+    KMG_REQUIRE(ws_bytes >= w.total, KMG_ERR_WS, "sort workspace too small: %zu < %zu", ws_bytes, w.total);
+
+    const PassPlan plan = make_plan(begin_bit, end_bit, SORT_RADIX_BITS);
+    const int np = plan.num_passes;
+    const int cfg = g_sort_config;
+    const uint64_t n_parts = (n + PART_MAX - 1) / PART_MAX;
+
+    // header + hist zero; look-back words zero once (parity trick) -- see OnesweepParams::parity
+    KMG_CUDA(cudaMemsetAsync(d_ws, 0, w.total, st));
+
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    {
+        const int grid = (int)std::min<uint64_t>((n + 511) / 512, (uint64_t)sms * 4);
+        const size_t smem = (size_t)np * SORT_RADIX * sizeof(uint32_t);
+        if (key_bytes == 8)
+            radix_hist_kernel<uint64_t, SORT_RADIX_BITS><<<grid, 512, smem, st>>>((const uint64_t*)d_keys, n, plan, w.hist);
+        else
+            radix_hist_kernel<u128, SORT_RADIX_BITS><<<grid, 512, smem, st>>>((const u128*)d_keys, n, plan, w.hist);
+        KMG_LAUNCH_CHECK();
+        radix_scan_kernel<<<np, 32, 0, st>>>(w.hist, w.bins, SORT_RADIX, 2 * SORT_RADIX, nullptr);
+        KMG_LAUNCH_CHECK();
+    }
+
+    char* kin = (char*)d_keys;
+    char* kout = (char*)d_keys_alt;
+    char* vin = (char*)d_vals;
+    char* vout = (char*)d_vals_alt;
+    uint32_t launch = 0;
+    for (int pass = 0; pass < np; ++pass) {
+        const ShiftDigit op{plan.shift[pass], (1u << plan.bits[pass]) - 1u};
+        for (uint64_t part = 0; part < n_parts; ++part) {
+            const uint64_t off = part * PART_MAX;
+            OnesweepParams p;
+            p.keys_in = kin + off * key_bytes;
+            p.keys_out = kout;
+            p.vals_in = vin ? vin + off * val_bytes : nullptr;
+            p.vals_out = vout;
+            p.n = (uint32_t)std::min<uint64_t>(PART_MAX, n - off);
+            uint64_t* bins = w.bins + (size_t)pass * 2 * SORT_RADIX;
+            p.bins_in = bins + (part & 1) * SORT_RADIX;
+            p.bins_out = (part + 1 < n_parts) ? bins + ((part + 1) & 1) * SORT_RADIX : nullptr;
+            p.lookback = w.lookback;
+            p.ticket = &w.hdr->ticket;
+            p.err = &w.hdr->err;
+            if (n_parts > 1) {
+                // tile counts differ between parts, so stale words could alias: re-zero
+                if (launch > 0)
+                    KMG_CUDA(cudaMemsetAsync(w.lookback, 0, (char*)d_ws + w.total - (char*)w.lookback, st));
+                p.parity = 0;
+            } else {
+                p.parity = launch & 1u;
+            }
+            int rcode = dispatch_onesweep(cfg, key_bytes, val_bytes, p, op, st);
+            if (rcode != KMG_OK) return rcode;
+            ++launch;
+        }
+        std::swap(kin, kout);
+        std::swap(vin, vout);
+        ++g_stat_sort_passes;
+    }
+    *h_selector_out = np & 1;
+    return KMG_OK;
+}
+
+extern "C" size_t kmg_partition_workspace_bytes(uint64_t n, int key_bytes, int val_bytes) {
+    return kmg_radix_sort_workspace_bytes(n, key_bytes, val_bytes, 0, 8);
+}
+
+extern "C" int kmg_range_partition(const void* d_keys, const void* d_vals, uint64_t n, int key_bytes, int val_bytes,
+                                   int key_bits, int n_parts, void* d_keys_out, void* d_vals_out,
+                                   uint64_t* d_part_counts, void* d_ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    KMG_REQUIRE(key_bytes == 8 || key_bytes == 16, KMG_ERR_ARG, "key_bytes must be 8 or 16");
+    KMG_REQUIRE(val_bytes == 0 || val_bytes == 4 || val_bytes == 8, KMG_ERR_ARG, "val_bytes must be 0, 4 or 8");
+    KMG_REQUIRE(n_parts >= 1 && n_parts <= SORT_RADIX, KMG_ERR_ARG, "n_parts must be in [1,%d]", SORT_RADIX);
+    KMG_REQUIRE(key_bits >= 16 && key_bits <= key_bytes * 8, KMG_ERR_ARG, "key_bits must be in [16,%d]", key_bytes * 8);
+    KMG_REQUIRE(d_part_counts && d_ws, KMG_ERR_ARG, "null pointer argument");
+    KMG_REQUIRE((val_bytes == 0) == (d_vals == nullptr), KMG_ERR_ARG, "d_vals / val_bytes mismatch");
+    KMG_CUDA(cudaMemsetAsync(d_part_counts, 0, sizeof(uint64_t) * n_parts, st));
+    if (n == 0) return KMG_OK;
+    SortWs w = carve_sort_ws(d_ws, n, key_bytes);
+    KMG_REQUIRE(ws_bytes >= w.total, KMG_ERR_WS, "partition workspace too small");
+    KMG_CUDA(cudaMemsetAsync(d_ws, 0, w.total, st));
+    const RangeDigit op{key_bits - 16, (uint32_t)n_parts};
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = (int)std::min<uint64_t>((n + 511) / 512, (uint64_t)sms * 4);
+    if (key_bytes == 8)
+        digit_hist_kernel<uint64_t, RangeDigit><<<grid, 512, SORT_RADIX * 4, st>>>((const uint64_t*)d_keys, n, op, SORT_RADIX, w.hist);
+    else
+        digit_hist_kernel<u128, RangeDigit><<<grid, 512, SORT_RADIX * 4, st>>>((const u128*)d_keys, n, op, SORT_RADIX, w.hist);
+    KMG_LAUNCH_CHECK();
+    radix_scan_kernel<<<1, 32, 0, st>>>(w.hist, w.bins, SORT_RADIX, 2 * SORT_RADIX, nullptr);
+    KMG_LAUNCH_CHECK();
+    KMG_CUDA(cudaMemcpyAsync(d_part_counts, w.hist, sizeof(uint64_t) * n_parts, cudaMemcpyDeviceToDevice, st));
+    const uint64_t n_lb_parts = (n + PART_MAX - 1) / PART_MAX;
+    for (uint64_t part = 0; part < n_lb_parts; ++part) {
+        const uint64_t off = part * PART_MAX;
+        OnesweepParams p;
+        p.keys_in = (const char*)d_keys + off * key_bytes;
+        p.keys_out = d_keys_out;
+        p.vals_in = d_vals ? (const char*)d_vals + off * val_bytes : nullptr;
+        p.vals_out = d_vals_out;
+        p.n = (uint32_t)std::min<uint64_t>(PART_MAX, n - off);
+        p.bins_in = w.bins + (part & 1) * SORT_RADIX;
+        p.bins_out = (part + 1 < n_lb_parts) ? w.bins + ((part + 1) & 1) * SORT_RADIX : nullptr;
+        p.lookback = w.lookback;
+        p.ticket = &w.hdr->ticket;
+        p.err = &w.hdr->err;
+        p.parity = 0;
+        if (part > 0) KMG_CUDA(cudaMemsetAsync(w.lookback, 0, (char*)d_ws + w.total - (char*)w.lookback, st));
+        int rcode = dispatch_onesweep(g_sort_config, key_bytes, val_bytes, p, op, st);
+        if (rcode != KMG_OK) return rcode;
+    }
+    return KMG_OK;
+}

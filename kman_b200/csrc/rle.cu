@@ -1,0 +1,353 @@
+// K4: run-length / singleton selection on sorted keys.
+//
+// Replaces the grouping loop of Crawler.do_batch (kmermaid/join.py:95-130) and the two emit
+// rules: KJoiner.join_sequence_count (join.py:265-285: every group, with its size) and
+// KJoiner.join_unique (join.py:243-263: only groups of size exactly one).
+//
+// A warp walks its contiguous chunk 32 keys at a time; "is the key different from its
+// predecessor" becomes one ballot per step, so ranks are popcounts and no shared-memory
+// transposition of the keys is needed.  Tiles are chained with a decoupled look-back that
+// carries (number of run heads, position of the last run head); a run's length is written
+// by the tile that sees the run END, which is what makes the pass single-sweep.
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace kmg {
+
+constexpr int RLE_BLOCK = 256;
+constexpr int RLE_WARPS = RLE_BLOCK / 32;
+
+template <typename KeyT>
+__device__ __forceinline__ KeyT shfl_key(const KeyT& k, int src);
+template <>
+__device__ __forceinline__ uint64_t shfl_key<uint64_t>(const uint64_t& k, int src) {
+    return __shfl_sync(0xffffffffu, k, src);
+}
+template <>
+__device__ __forceinline__ u128 shfl_key<u128>(const u128& k, int src) {
+    return u128{__shfl_sync(0xffffffffu, k.lo, src), __shfl_sync(0xffffffffu, k.hi, src)};
+}
+
+// Loads the warp's chunk (IPT steps of 32 consecutive keys starting at `first`) and returns
+// the extended head ballots: bit l of hb[j] is set iff element idx = first + 32*j + l starts
+// a run, where idx == n counts as a head (end sentinel) and idx > n does not.
+// hnext = head flag of the element right after the chunk.
+template <typename KeyT, int IPT>
+__device__ __forceinline__ void load_heads(const KeyT* __restrict__ keys_in, uint64_t n, uint64_t first,
+                                           KeyT (&keys)[IPT], uint32_t (&hb)[IPT], uint32_t& hnext) {
+    const uint32_t lane = lane_id();
+#pragma unroll
+    for (int j = 0; j < IPT; ++j) {
+        const uint64_t idx = first + 32 * j + lane;
+        keys[j] = idx < n ? keys_in[idx] : KeyT{};
+    }
+    KeyT before = KeyT{};
+    if (lane == 0 && first > 0 && first <= n) before = keys_in[first - 1];
+#pragma unroll
+    for (int j = 0; j < IPT; ++j) {
+        const uint64_t idx = first + 32 * j + lane;
+        KeyT prev = shfl_key(keys[j], (int)lane - 1);
+        if (lane == 0) prev = before;
+        const bool head = (idx < n && (idx == 0 || keys[j] != prev)) || idx == n;
+        hb[j] = __ballot_sync(0xffffffffu, head);
+        before = shfl_key(keys[j], 31);  // only lane 0 uses it
+    }
+    const uint64_t nidx = first + 32 * IPT;
+    uint32_t h = 0;
+    if (lane == 0) {
+        if (nidx == n) h = 1;
+        else if (nidx < n) h = keys_in[nidx] != before ? 1u : 0u;
+    }
+    hnext = __shfl_sync(0xffffffffu, h, 0);
+}
+
+struct RleParams {
+    const void* keys_in;
+    const void* vals_in;
+    uint64_t n;
+    void* keys_out;
+    void* vals_out;
+    uint32_t* counts_out;
+    unsigned long long* n_out;
+    uint64_t* state_a;  // flag | heads
+    uint64_t* state_b;  // last head position + 1 (0 = none)
+    uint32_t* ticket;
+    uint32_t* err;
+};
+
+template <typename KeyT, int IPT>
+__global__ void __launch_bounds__(RLE_BLOCK) rle_count_kernel(const RleParams p) {
+    constexpr int TILE = RLE_BLOCK * IPT;
+    __shared__ uint32_t s_hpos[TILE];  // local position of the i-th head of the tile
+    __shared__ uint32_t s_wheads[RLE_WARPS];
+    __shared__ uint32_t s_tile;
+    __shared__ uint64_t s_excl_heads, s_carry;
+
+    const int t = threadIdx.x;
+    const uint32_t lane = t & 31, warp = t >> 5;
+    if (t == 0) s_tile = atomicAdd(p.ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint64_t tile_base = (uint64_t)tile * TILE;
+    const uint64_t first = tile_base + (uint64_t)warp * 32 * IPT;
+    const KeyT* keys_in = reinterpret_cast<const KeyT*>(p.keys_in);
+
+    KeyT keys[IPT];
+    uint32_t hb[IPT];
+    uint32_t hnext;
+    load_heads<KeyT, IPT>(keys_in, p.n, first, keys, hb, hnext);
+
+    // heads that are real elements (idx < n)
+    uint32_t wheads = 0;
+#pragma unroll
+    for (int j = 0; j < IPT; ++j) {
+        const uint64_t step_first = first + 32 * j;
+        uint32_t vm = 0;  // lanes with idx < n
+        if (step_first < p.n) vm = (p.n - step_first >= 32) ? 0xffffffffu : ((1u << (uint32_t)(p.n - step_first)) - 1u);
+        wheads += __popc(hb[j] & vm);
+    }
+    if (lane == 0) s_wheads[warp] = wheads;
+    __syncthreads();
+    uint32_t wexcl = 0, theads = 0;
+#pragma unroll
+    for (int w = 0; w < RLE_WARPS; ++w) {
+        const uint32_t c = s_wheads[w];
+        if (w < (int)warp) wexcl += c;
+        theads += c;
+    }
+    // local positions of heads -> s_hpos
+    {
+        uint32_t run = wexcl;
+#pragma unroll
+        for (int j = 0; j < IPT; ++j) {
+            const uint64_t idx = first + 32 * j + lane;
+            const uint32_t b = hb[j];
+            if (((b >> lane) & 1u) && idx < p.n) s_hpos[run + __popc(b & lanemask_lt())] = (uint32_t)(idx - tile_base);
+            const uint64_t step_first = first + 32 * j;
+            uint32_t vm = 0;
+            if (step_first < p.n) vm = (p.n - step_first >= 32) ? 0xffffffffu : ((1u << (uint32_t)(p.n - step_first)) - 1u);
+            run += __popc(b & vm);
+        }
+    }
+    __syncthreads();
+    if (t == 0) {
+        const uint64_t last_plus1 = theads ? tile_base + s_hpos[theads - 1] + 1 : 0;
+        uint64_t excl = 0, carry = 0;
+        if (tile == 0) {
+            st_relaxed_u64(&p.state_b[0], last_plus1);
+            st_release_u64(&p.state_a[0], TP_FLAG_INCL | theads);
+        } else {
+            st_relaxed_u64(&p.state_b[tile], last_plus1);
+            st_release_u64(&p.state_a[tile], TP_FLAG_AGG | theads);
+            int64_t q = (int64_t)tile - 1;
+            uint32_t spins = 0;
+            while (true) {
+                const uint64_t a = ld_acquire_u64(&p.state_a[q]);
+                const uint64_t f = a & ~TP_VALUE_MASK;
+                if (f == 0) {
+                    if (++spins > SPIN_LIMIT) {
+                        atomicExch(p.err, 1u);
+                        break;
+                    }
+                    __nanosleep(20);
+                    continue;
+                }
+                const uint64_t b = ld_relaxed_u64(&p.state_b[q]);
+                excl += a & TP_VALUE_MASK;
+                if (carry == 0) carry = b;
+                if (f == TP_FLAG_INCL) break;
+                --q;
+            }
+            st_relaxed_u64(&p.state_b[tile], last_plus1 ? last_plus1 : carry);
+            st_release_u64(&p.state_a[tile], TP_FLAG_INCL | (excl + theads));
+        }
+        s_excl_heads = excl;
+        s_carry = carry;  // position+1 of the head of the run that is open when the tile starts
+        if (tile == gridDim.x - 1) *p.n_out = excl + theads;
+    }
+    __syncthreads();
+    const uint64_t excl_heads = s_excl_heads;
+    const uint64_t carry = s_carry;
+    KeyT* keys_out = reinterpret_cast<KeyT*>(p.keys_out);
+
+    uint32_t run = wexcl;  // heads of the tile before the current step
+#pragma unroll
+    for (int j = 0; j < IPT; ++j) {
+        const uint64_t step_first = first + 32 * j;
+        const uint64_t idx = step_first + lane;
+        const uint32_t b = hb[j];
+        const uint32_t nb = (j + 1 < IPT) ? hb[j + 1 < IPT ? j + 1 : j] : hnext;
+        const uint32_t tb = (b >> 1) | ((nb & 1u) << 31);  // tail: the next element is a head
+        const uint32_t h_before = run + __popc(b & lanemask_lt());
+        const bool is_head = (b >> lane) & 1u;
+        if (idx < p.n) {
+            if (is_head) keys_out[excl_heads + h_before] = keys[j];
+            if ((tb >> lane) & 1u) {
+                const uint32_t h_incl = h_before + (is_head ? 1u : 0u);
+                const uint64_t hpos = h_incl ? tile_base + s_hpos[h_incl - 1] : carry - 1;
+                const uint64_t len = idx - hpos + 1;
+                if (len > 0xffffffffull) atomicExch(p.err, 2u);
+                p.counts_out[excl_heads + h_incl - 1] = (uint32_t)len;
+            }
+        }
+        uint32_t vm = 0;
+        if (step_first < p.n) vm = (p.n - step_first >= 32) ? 0xffffffffu : ((1u << (uint32_t)(p.n - step_first)) - 1u);
+        run += __popc(b & vm);
+    }
+}
+
+// singletons: head && tail, compacted in order, with payload
+template <typename KeyT, int VAL_BYTES, int IPT>
+__global__ void __launch_bounds__(RLE_BLOCK) select_singletons_kernel(const RleParams p) {
+    constexpr int TILE = RLE_BLOCK * IPT;
+    using ValT = typename std::conditional<VAL_BYTES == 4, uint32_t, uint64_t>::type;
+    __shared__ uint32_t s_wcnt[RLE_WARPS];
+    __shared__ uint32_t s_tile;
+    __shared__ uint64_t s_excl;
+
+    const int t = threadIdx.x;
+    const uint32_t lane = t & 31, warp = t >> 5;
+    if (t == 0) s_tile = atomicAdd(p.ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint64_t tile_base = (uint64_t)tile * TILE;
+    const uint64_t first = tile_base + (uint64_t)warp * 32 * IPT;
+    const KeyT* keys_in = reinterpret_cast<const KeyT*>(p.keys_in);
+
+    KeyT keys[IPT];
+    uint32_t hb[IPT];
+    uint32_t hnext;
+    load_heads<KeyT, IPT>(keys_in, p.n, first, keys, hb, hnext);
+
+    uint32_t sb[IPT];  // singleton ballots
+    uint32_t wcnt = 0;
+#pragma unroll
+    for (int j = 0; j < IPT; ++j) {
+        const uint64_t step_first = first + 32 * j;
+        const uint32_t nb = (j + 1 < IPT) ? hb[j + 1 < IPT ? j + 1 : j] : hnext;
+        const uint32_t tb = (hb[j] >> 1) | ((nb & 1u) << 31);
+        uint32_t vm = 0;
+        if (step_first < p.n) vm = (p.n - step_first >= 32) ? 0xffffffffu : ((1u << (uint32_t)(p.n - step_first)) - 1u);
+        sb[j] = hb[j] & tb & vm;
+        wcnt += __popc(sb[j]);
+    }
+    if (lane == 0) s_wcnt[warp] = wcnt;
+    __syncthreads();
+    uint32_t wexcl = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < RLE_WARPS; ++w) {
+        const uint32_t c = s_wcnt[w];
+        if (w < (int)warp) wexcl += c;
+        total += c;
+    }
+    if (t == 0) {
+        const uint64_t excl = tile_prefix_exclusive(p.state_a, tile, total, p.err);
+        s_excl = excl;
+        if (tile == gridDim.x - 1) *p.n_out = excl + total;
+    }
+    __syncthreads();
+    const uint64_t base = s_excl + wexcl;
+    KeyT* keys_out = reinterpret_cast<KeyT*>(p.keys_out);
+    const ValT* vals_in = reinterpret_cast<const ValT*>(p.vals_in);
+    ValT* vals_out = reinterpret_cast<ValT*>(p.vals_out);
+    uint32_t run = 0;
+#pragma unroll
+    for (int j = 0; j < IPT; ++j) {
+        const uint64_t idx = first + 32 * j + lane;
+        if ((sb[j] >> lane) & 1u) {
+            const uint64_t o = base + run + __popc(sb[j] & lanemask_lt());
+            keys_out[o] = keys[j];
+            if constexpr (VAL_BYTES != 0) vals_out[o] = vals_in[idx];
+        }
+        run += __popc(sb[j]);
+    }
+}
+
+constexpr int RLE_IPT8 = 16;   // 8-byte keys: 4096-key tiles
+constexpr int RLE_IPT16 = 8;   // 16-byte keys: 2048-key tiles
+
+}  // namespace kmg
+
+using namespace kmg;
+
+extern "C" size_t kmg_rle_workspace_bytes(uint64_t n) {
+    const uint64_t tiles = n / 2048 + 2;
+    return sizeof(WsHeader) + 2 * align_up(tiles * sizeof(uint64_t), 256);
+}
+
+static int rle_setup(RleParams& p, uint64_t n, int key_bytes, void* d_ws, size_t ws_bytes, uint32_t& tiles,
+                     cudaStream_t st) {
+    KMG_REQUIRE(key_bytes == 8 || key_bytes == 16, KMG_ERR_ARG, "key_bytes must be 8 or 16");
+    KMG_REQUIRE(d_ws, KMG_ERR_ARG, "null workspace");
+    KMG_REQUIRE(ws_bytes >= kmg_rle_workspace_bytes(n), KMG_ERR_WS, "rle workspace too small");
+    const uint64_t tile = key_bytes == 8 ? RLE_BLOCK * RLE_IPT8 : RLE_BLOCK * RLE_IPT16;
+    const uint64_t nt = (n + tile - 1) / tile;
+    KMG_REQUIRE(nt < (1ull << 31), KMG_ERR_RANGE, "too many tiles");
+    tiles = (uint32_t)nt;
+    const size_t arr = align_up((n / 2048 + 2) * sizeof(uint64_t), 256);
+    KMG_CUDA(cudaMemsetAsync(d_ws, 0, sizeof(WsHeader) + 2 * arr, st));
+    WsHeader* hdr = reinterpret_cast<WsHeader*>(d_ws);
+    p.n = n;
+    p.state_a = reinterpret_cast<uint64_t*>(hdr + 1);
+    p.state_b = reinterpret_cast<uint64_t*>((char*)(hdr + 1) + arr);
+    p.ticket = &hdr->ticket;
+    p.err = &hdr->err;
+    return KMG_OK;
+}
+
+extern "C" int kmg_rle_count(const void* d_sorted_keys, uint64_t n, int key_bytes, void* d_uniq_keys_out,
+                             uint32_t* d_counts_out, uint64_t* d_n_out, void* d_ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    KMG_REQUIRE(d_n_out, KMG_ERR_ARG, "d_n_out is null");
+    KMG_CUDA(cudaMemsetAsync(d_n_out, 0, sizeof(uint64_t), st));
+    if (n == 0) return KMG_OK;  // join.py:107-111: nothing to crawl -> empty output
+    KMG_REQUIRE(d_sorted_keys && d_uniq_keys_out && d_counts_out, KMG_ERR_ARG, "null pointer argument");
+    RleParams p;
+    memset(&p, 0, sizeof(p));
+    uint32_t tiles = 0;
+    int rcode = rle_setup(p, n, key_bytes, d_ws, ws_bytes, tiles, st);
+    if (rcode != KMG_OK) return rcode;
+    p.keys_in = d_sorted_keys;
+    p.keys_out = d_uniq_keys_out;
+    p.counts_out = d_counts_out;
+    p.n_out = reinterpret_cast<unsigned long long*>(d_n_out);
+    if (key_bytes == 8) rle_count_kernel<uint64_t, RLE_IPT8><<<tiles, RLE_BLOCK, 0, st>>>(p);
+    else rle_count_kernel<u128, RLE_IPT16><<<tiles, RLE_BLOCK, 0, st>>>(p);
+    KMG_LAUNCH_CHECK();
+    return KMG_OK;
+}
+
+extern "C" int kmg_select_singletons(const void* d_sorted_keys, const void* d_vals, uint64_t n, int key_bytes,
+                                     int val_bytes, void* d_keys_out, void* d_vals_out, uint64_t* d_n_out,
+                                     void* d_ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    KMG_REQUIRE(d_n_out, KMG_ERR_ARG, "d_n_out is null");
+    KMG_REQUIRE(val_bytes == 0 || val_bytes == 4 || val_bytes == 8, KMG_ERR_ARG, "val_bytes must be 0, 4 or 8");
+    KMG_REQUIRE((val_bytes == 0) == (d_vals == nullptr), KMG_ERR_ARG, "d_vals / val_bytes mismatch");
+    KMG_REQUIRE(val_bytes == 0 || d_vals_out, KMG_ERR_ARG, "d_vals_out is null");
+    KMG_CUDA(cudaMemsetAsync(d_n_out, 0, sizeof(uint64_t), st));
+    if (n == 0) return KMG_OK;
+    KMG_REQUIRE(d_sorted_keys && d_keys_out, KMG_ERR_ARG, "null pointer argument");
+    RleParams p;
+    memset(&p, 0, sizeof(p));
+    uint32_t tiles = 0;
+    int rcode = rle_setup(p, n, key_bytes, d_ws, ws_bytes, tiles, st);
+    if (rcode != KMG_OK) return rcode;
+    p.keys_in = d_sorted_keys;
+    p.vals_in = d_vals;
+    p.keys_out = d_keys_out;
+    p.vals_out = d_vals_out;
+    p.n_out = reinterpret_cast<unsigned long long*>(d_n_out);
+    if (key_bytes == 8) {
+        if (val_bytes == 0) select_singletons_kernel<uint64_t, 0, RLE_IPT8><<<tiles, RLE_BLOCK, 0, st>>>(p);
+        else if (val_bytes == 4) select_singletons_kernel<uint64_t, 4, RLE_IPT8><<<tiles, RLE_BLOCK, 0, st>>>(p);
+        else select_singletons_kernel<uint64_t, 8, RLE_IPT8><<<tiles, RLE_BLOCK, 0, st>>>(p);
+    } else {
+        if (val_bytes == 0) select_singletons_kernel<u128, 0, RLE_IPT16><<<tiles, RLE_BLOCK, 0, st>>>(p);
+        else if (val_bytes == 4) select_singletons_kernel<u128, 4, RLE_IPT16><<<tiles, RLE_BLOCK, 0, st>>>(p);
+        else select_singletons_kernel<u128, 8, RLE_IPT16><<<tiles, RLE_BLOCK, 0, st>>>(p);
+    }
+    KMG_LAUNCH_CHECK();
+    return KMG_OK;
+}

@@ -1,0 +1,132 @@
+"""Pins the CPU oracle (oracle/kmer_oracle.py) against
+
+  * every golden vector under tests/golden/ -- produced by running the UNMODIFIED
+    reference (oracle/gen_golden.py), both alphabets, with and without -r;
+  * the reference's own known-answer tests (tests/test_seq.py:125-181,
+    tests/test_batch.py:80-87 in /root/reference), restated here as data.
+"""
+import hashlib
+
+import numpy as np
+import pytest
+
+import kmer_oracle as ko
+
+
+def _sha(b):
+    return hashlib.sha256(b).hexdigest()
+
+
+def test_golden_edge_cases_both_tiers(golden):
+    assert len(golden["cases"]) >= 100
+    for c in golden["cases"]:
+        recs = ko.parse_fasta_text(c["fasta_text"])
+        for cmd, f_py, f_np in (("count", ko.count_text_py, ko.count_text_np), ("uniq", ko.uniq_text_py, ko.uniq_text_np)):
+            want = c[cmd].encode("latin-1")
+            tag = (c["name"], c["k"], c["alphabet"], c["rc"], cmd)
+            assert f_py(recs, c["k"], c["rc"], alphabet=c["alphabet"]) == want, tag
+            assert f_np(recs, c["k"], c["rc"], alphabet=c["alphabet"]) == want, tag
+
+
+def test_golden_batch_files(golden):
+    n = 0
+    for c in golden["cases"]:
+        if "batch_b10" not in c:
+            continue
+        recs = ko.parse_fasta_text(c["fasta_text"])
+        got = sorted(ko.batch_text_py(recs, c["k"], c["rc"], batch_size=10, alphabet=c["alphabet"]))
+        assert got == sorted(x.encode("latin-1") for x in c["batch_b10"])
+        n += 1
+    assert n >= 4
+
+
+def test_batch_size_independence(golden):
+    c = [c for c in golden["cases"] if c["name"] == "tiny" and c["k"] == 4 and c["alphabet"] == "IUPAC" and not c["rc"]][0]
+    recs = ko.parse_fasta_text(c["fasta_text"])
+    for b in (1, 3, 7, 1000):
+        assert ko.count_text_py(recs, 4, batch_size=b).decode("latin-1") == c["count"]
+        assert ko.uniq_text_py(recs, 4, batch_size=b).decode("latin-1") == c["uniq"]
+
+
+@pytest.mark.parametrize("name", ["syn_100k", "syn_1m"])
+def test_golden_synthetic_hashes(golden, name):
+    ent = [e for e in golden["synthetic"] if e["name"] == name][0]
+    data = ko.synth_fasta_bytes([("chr1 synthetic seed=%d" % ent["seed"], ko.synth_bases(ent["n"], ent["seed"]))])
+    assert _sha(data) == ent["fasta_sha256"]
+    recs = ko.parse_fasta_text(data.decode())
+    out = ko.count_text_np(recs, ent["k"])
+    assert (out.count(b"\n"), _sha(out)) == (ent["count_lines"], ent["count_sha256"])
+    out = ko.uniq_text_np(recs, ent["k"])
+    assert (out.count(b"\n"), _sha(out)) == (ent["uniq_lines"], ent["uniq_sha256"])
+    if name == "syn_100k":
+        assert _sha(ko.count_text_py(recs, ent["k"])) == ent["count_sha256"]
+        assert _sha(ko.uniq_text_py(recs, ent["k"])) == ent["uniq_sha256"]
+
+
+def test_golden_syn_dup(golden):
+    ents = [e for e in golden["synthetic"] if e["name"] == "syn_dup"]
+    assert len(ents) == 8
+    for ent in ents:
+        recs = ko.parse_fasta_text(ent["fasta_text"])
+        for cmd, f_py, f_np in (("count", ko.count_text_py, ko.count_text_np), ("uniq", ko.uniq_text_py, ko.uniq_text_np)):
+            for f in (f_py, f_np):
+                out = f(recs, ent["k"], ent["rc"])
+                assert (out.count(b"\n"), _sha(out)) == (ent[cmd + "_lines"], ent[cmd + "_sha256"]), (ent["k"], ent["rc"], cmd)
+
+
+# ---- the reference's own known-answer tests, restated as data ---------------------------------
+def test_ref_kat_kmers_of_ACGAT():  # /root/reference/tests/test_seq.py:125-130
+    got = list(ko.kmers_py("ACGAT", 4, "stest"))
+    assert got == [("stest", 0, 4, "+", "ACGA"), ("stest", 1, 5, "+", "CGAT")]
+
+
+def test_ref_kat_batcher_overlap():  # tests/test_seq.py:136-138
+    assert list(ko.batcher_py("ACGATCGATCG", 3, 5)) == [("ACGAT", 0), ("ATCGA", 3), ("GATCG", 6)]
+
+
+def test_ref_kat_batched_coords_and_rc():  # tests/test_seq.py:140-181
+    seq = "ACGATCGATCG"
+    chunks = list(ko.batcher_py(seq, 4, 5))
+    got = [[(s, e, st, km) for _, s, e, st, km in ko.kmers_py(c, 4, "ref", off, rc=True)] for c, off in chunks]
+    want = [
+        [(0, 4, "+", "ACGA"), (0, 4, "-", "TCGT"), (1, 5, "+", "CGAT"), (1, 5, "-", "ATCG")],
+        [(2, 6, "+", "GATC"), (2, 6, "-", "GATC"), (3, 7, "+", "ATCG"), (3, 7, "-", "CGAT")],
+        [(4, 8, "+", "TCGA"), (4, 8, "-", "TCGA"), (5, 9, "+", "CGAT"), (5, 9, "-", "ATCG")],
+        [(6, 10, "+", "GATC"), (6, 10, "-", "GATC"), (7, 11, "+", "ATCG"), (7, 11, "-", "CGAT")],
+    ]
+    assert got == want
+
+
+def test_ref_kat_header_format():  # tests/test_seq.py:11-54,110-112 ; seq.py:103-104
+    assert ko.header_py("chr1", 0, 1000, "+") == "chr1:0-1000:+"
+    assert ko.header_py("chr1", 5, 9, "-") == "chr1:5-9:-"
+
+
+def test_ref_kat_sorted_batch():  # tests/test_batch.py:80-87: Python's sorted() on the records
+    recs = [("h%d" % i, s) for i, s in enumerate(["TTTT", "ACGT", "ACGA", "GGGG", "ACGT"])]
+    assert [r[1] for r in sorted(recs, key=lambda r: r[1])] == ["ACGA", "ACGT", "ACGT", "GGGG", "TTTT"]
+    # stability: equal sequences keep emission order
+    assert [r[0] for r in sorted(recs, key=lambda r: r[1]) if r[1] == "ACGT"] == ["h1", "h4"]
+
+
+def test_np_extract_matches_py_random():
+    rng = np.random.default_rng(5)
+    for trial in range(20):
+        n_rec = int(rng.integers(1, 4))
+        recs = []
+        for r in range(n_rec):
+            n = int(rng.integers(0, 200))
+            s = "".join(rng.choice(list("ACGTacgtNRYXn-"), p=[.2, .2, .2, .2, .03, .03, .03, .03, .02, .01, .01, .02, .01, .01], size=n))
+            recs.append(("r%d x" % r, s))
+        for k in (2, 5, 16, 17, 31, 32, 33, 40, 64):
+            for rc in (False, True):
+                for ab in ("IUPAC", "ACGT"):
+                    assert ko.count_text_np(recs, k, rc, ab) == ko.count_text_py(recs, k, rc, alphabet=ab), (trial, k, rc, ab)
+                    assert ko.uniq_text_np(recs, k, rc, ab) == ko.uniq_text_py(recs, k, rc, alphabet=ab), (trial, k, rc, ab)
+
+
+def test_k_must_exceed_one():  # batcher.py:477-478
+    with pytest.raises(AssertionError):
+        ko.count_text_py([("a", "ACGT")], 1)
+    with pytest.raises(AssertionError):
+        ko.count_text_np([("a", "ACGT")], 1)
