@@ -366,6 +366,7 @@ extern "C" int kmg_extract(const uint8_t* d_bases, uint64_t n_bases, uint64_t wi
     KMG_REQUIRE(ws_bytes >= kmg_extract_workspace_bytes(win_end - win_begin), KMG_ERR_WS, "extract workspace too small");
 
     KMG_CUDA(cudaMemsetAsync(d_counts, 0, 2 * sizeof(uint64_t), st));
+    KMG_CUDA(cudaMemsetAsync(d_ws, 0, sizeof(WsHeader), st));
     if (win_end == win_begin) return KMG_OK;
 
     const uint64_t tile = wide ? (uint64_t)EXW_TILE : (uint64_t)(EX_BLOCK * (key_bytes == 8 ? 16 : 8));

@@ -1,0 +1,367 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the golden
+vectors produced by the unmodified reference.  Bit-exact everywhere (integer/byte work)."""
+import ctypes as C
+import hashlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import kmer_oracle as ko  # noqa: E402
+from gpu_util import first_diff, limbs_to_rows, widen  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from kman_b200.engine import get_engine
+
+    return get_engine()
+
+
+def _flat(recs):
+    from kman_b200 import fasta
+
+    return fasta.from_records(recs)
+
+
+def _rand_records(rng, n_rec, max_len, alphabet="ACGT", p_other=0.0):
+    recs = []
+    for r in range(n_rec):
+        n = int(rng.integers(0, max_len))
+        s = rng.choice(list("ACGT"), size=n)
+        if p_other:
+            m = rng.random(n) < p_other
+            s[m] = rng.choice(list("NRYacgtnX-"), size=int(m.sum()))
+        recs.append(("rec%d desc" % r, "".join(s)))
+    return recs
+
+
+# ---- K1+K2 ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("k", [2, 3, 15, 16, 17, 21, 31, 32, 33, 47, 63, 64])
+@pytest.mark.parametrize("rc", [False, True])
+def test_extract_narrow_matches_oracle(eng, k, rc):
+    rng = np.random.default_rng(100 + k)
+    recs = _rand_records(rng, 4, 9000, p_other=0.01)
+    ex = ko.extract_np(recs, k, rc)
+    d = eng.upload(_flat(recs))
+    for vb in (0, 4, 8):
+        a = eng.extract(d, k, rc, wide=False, val_bytes=vb)
+        want = limbs_to_rows(ex["narrow"]["keys"])
+        assert a.n == want.shape[0], (a.n, want.shape[0])
+        assert first_diff(a.keys_host(), want) == "equal"
+        assert a.n_other == ex["wide"]["pos"].shape[0] // (2 if rc else 1)
+        if vb:
+            wv = (ex["narrow"]["pos"].astype(np.uint64) << np.uint64(1)) | ex["narrow"]["strand"].astype(np.uint64)
+            assert first_diff(a.vals_host().astype(np.uint64), wv) == "equal"
+
+
+@pytest.mark.parametrize("k", [2, 5, 16, 17, 25, 32])
+@pytest.mark.parametrize("rc", [False, True])
+def test_extract_wide_matches_oracle(eng, k, rc):
+    rng = np.random.default_rng(200 + k)
+    recs = _rand_records(rng, 3, 6000, p_other=0.03)
+    ex = ko.extract_np(recs, k, rc)
+    d = eng.upload(_flat(recs))
+    a = eng.extract(d, k, rc, wide=True, val_bytes=8)
+    want = limbs_to_rows(widen(ex["wide"]["keys"]))
+    assert a.n == want.shape[0]
+    assert first_diff(a.keys_host(), want) == "equal"
+    wv = (ex["wide"]["pos"].astype(np.uint64) << np.uint64(1)) | ex["wide"]["strand"].astype(np.uint64)
+    assert first_diff(a.vals_host(), wv) == "equal"
+
+
+def test_extract_window_ranges_partition_the_input(eng):
+    """k-1 overlap chunking (seq.py:361-383): windows of disjoint start ranges concatenate."""
+    rng = np.random.default_rng(7)
+    recs = _rand_records(rng, 3, 20000, p_other=0.005)
+    k = 31
+    d = eng.upload(_flat(recs))
+    full = eng.extract(d, k, False, val_bytes=8)
+    n_win = d.n_bases - k + 1
+    cuts = [0, 1, 4095, 4096, 4097, 12345, n_win // 2, n_win - 1, n_win]
+    keys, vals = [], []
+    for b, e in zip(cuts[:-1], cuts[1:]):
+        a = eng.extract(d, k, False, val_bytes=8, win_begin=b, win_end=e)
+        keys.append(a.keys_host().copy())
+        vals.append(a.vals_host().copy())
+    assert first_diff(np.concatenate(keys), full.keys_host()) == "equal"
+    assert first_diff(np.concatenate(vals), full.vals_host()) == "equal"
+
+
+# ---- K3 ---------------------------------------------------------------------------------------
+def _sort_case(eng, n, kb, vb, bits, seed, cfg=0, dup=False):
+    import torch
+
+    from kman_b200.engine import KeyArray
+
+    rng = np.random.default_rng(seed)
+    limbs = kb // 8
+    raw = rng.integers(0, 2**63, size=(n, limbs), dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=(n, limbs), dtype=np.uint64)
+    if dup:
+        raw = raw[rng.integers(0, max(1, n // 50), size=n)]
+    # keep only `bits` low bits
+    if limbs == 1:
+        raw[:, 0] &= np.uint64((1 << bits) - 1) if bits < 64 else np.uint64(2**64 - 1)
+    else:
+        hb = bits - 64
+        raw[:, 1] &= np.uint64((1 << hb) - 1) if hb < 64 else np.uint64(2**64 - 1)
+    vals = np.arange(n, dtype=np.uint32 if vb == 4 else np.uint64)
+    dev = eng.device
+    t = lambda x: torch.from_numpy(x.view(np.uint8).reshape(-1).copy()).to(dev)  # noqa: E731
+    a = KeyArray(t(raw), t(np.zeros_like(raw)), t(vals) if vb else None, t(np.zeros_like(vals)) if vb else None,
+                 n, kb, vb, bits // 2, False)
+    eng.lib.kmg_set_option(b"sort_config", cfg)
+    try:
+        a = eng.sort(a, 0, bits)
+        eng._status(eng._last_sort_ws) if n > 1 else None
+    finally:
+        eng.lib.kmg_set_option(b"sort_config", 0)
+    if limbs == 1:
+        order = np.argsort(raw[:, 0], kind="stable")
+        want = raw[order, 0]
+    else:
+        order = np.lexsort((raw[:, 0], raw[:, 1]))
+        want = raw[order]
+    assert first_diff(a.keys_host(), want) == "equal", (n, kb, vb, bits, cfg)
+    if vb:
+        assert first_diff(a.vals_host().astype(np.uint64), vals[order].astype(np.uint64)) == "equal", "payload/stability"
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 31, 4095, 4096, 4097, 70001, 1_000_003])
+def test_radix_sort_u64_sizes(eng, n):
+    _sort_case(eng, n, 8, 0, 62, seed=n)
+    _sort_case(eng, n, 8, 8, 62, seed=n + 1, dup=True)
+
+
+@pytest.mark.parametrize("bits", [4, 8, 9, 16, 42, 50, 62, 64])
+def test_radix_sort_u64_bit_ranges(eng, bits):
+    _sort_case(eng, 300_000, 8, 4, bits, seed=bits, dup=True)
+
+
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("vb", [0, 4, 8])
+def test_radix_sort_u64_tile_configs(eng, cfg, vb):
+    _sort_case(eng, 500_009, 8, vb, 62, seed=cfg * 10 + vb, cfg=cfg, dup=True)
+
+
+@pytest.mark.parametrize("bits", [66, 100, 126, 128])
+@pytest.mark.parametrize("vb", [0, 8])
+def test_radix_sort_u128(eng, bits, vb):
+    _sort_case(eng, 200_003, 16, vb, bits, seed=bits + vb, dup=True)
+
+
+# ---- K4 ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kb", [8, 16])
+@pytest.mark.parametrize("n", [1, 2, 33, 4096, 4097, 300_001])
+def test_rle_and_singletons(eng, kb, n):
+    import torch
+
+    from kman_b200.engine import KeyArray
+
+    rng = np.random.default_rng(n + kb)
+    limbs = kb // 8
+    # long runs, short runs and singletons mixed; a run longer than a tile when n allows
+    base = np.sort(rng.integers(0, max(2, n // 3), size=n).astype(np.uint64))
+    if n > 10000:
+        base[1000:9000] = base[1000]
+        base = np.sort(base)
+    raw = np.zeros((n, limbs), np.uint64)
+    raw[:, 0] = base
+    if limbs == 2:
+        raw[:, 1] = base // np.uint64(7)
+        raw = raw[np.lexsort((raw[:, 0], raw[:, 1]))]
+    vals = rng.permutation(n).astype(np.uint64)
+    dev = eng.device
+    t = lambda x: torch.from_numpy(x.view(np.uint8).reshape(-1).copy()).to(dev)  # noqa: E731
+    a = KeyArray(t(raw), t(np.zeros_like(raw)), t(vals), t(np.zeros_like(vals)), n, kb, 8, 31, False, is_sorted=True)
+    rows = raw[:, 0] if limbs == 1 else raw
+    diff = (raw[1:] != raw[:-1]).any(axis=1)
+    heads = np.concatenate(([0], np.flatnonzero(diff) + 1))
+    lens = np.diff(np.concatenate((heads, [n])))
+    tab = eng.rle_count(a)
+    assert tab.n == heads.size
+    assert first_diff(tab.keys_host(), rows[heads]) == "equal"
+    assert first_diff(tab.counts_host().astype(np.int64), lens) == "equal"
+    a = KeyArray(t(raw), t(np.zeros_like(raw)), t(vals), t(np.zeros_like(vals)), n, kb, 8, 31, False, is_sorted=True)
+    s = eng.singletons(a)
+    sel = heads[lens == 1]
+    assert s.n == sel.size
+    assert first_diff(s.keys_host(), rows[sel]) == "equal"
+    assert first_diff(s.vals_host(), vals[sel]) == "equal"
+
+
+# ---- K5 ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_parts", [1, 2, 3, 4, 8])
+def test_range_partition(eng, n_parts):
+    import torch
+
+    from kman_b200.engine import KeyArray
+
+    rng = np.random.default_rng(n_parts)
+    n, k = 400_007, 31
+    raw = rng.integers(0, 1 << 62, size=n, dtype=np.uint64)
+    vals = np.arange(n, dtype=np.uint64)
+    dev = eng.device
+    t = lambda x: torch.from_numpy(x.view(np.uint8).reshape(-1).copy()).to(dev)  # noqa: E731
+    a = KeyArray(t(raw), t(np.zeros_like(raw)), t(vals), t(np.zeros_like(vals)), n, 8, 8, k, False)
+    a, pc = eng.range_partition(a, n_parts)
+    part = ((raw >> np.uint64(62 - 16)) * np.uint64(n_parts)) >> np.uint64(16)
+    order = np.argsort(part, kind="stable")
+    assert list(pc) == list(np.bincount(part.astype(np.int64), minlength=n_parts))
+    assert first_diff(a.keys_host(), raw[order]) == "equal"
+    assert first_diff(a.vals_host(), vals[order]) == "equal"
+    # parts are ordered ranges of the key space
+    bounds = np.concatenate(([0], np.cumsum(pc)))
+    ks = a.keys_host()
+    for p in range(1, n_parts):
+        if pc[p - 1] and pc[p]:
+            assert ks[bounds[p - 1] : bounds[p]].max() < ks[bounds[p] : bounds[p + 1]].min()
+
+
+# ---- whole path vs goldens -----------------------------------------------------------------------
+def test_golden_edge_cases(eng, golden):
+    from kman_b200 import fasta
+
+    bad = []
+    for c in golden["cases"]:
+        d = eng.upload(fasta.parse_bytes(c["fasta_text"].encode("latin-1")), alphabet=c["alphabet"])
+        for cmd, fn in (("count", eng.count_text), ("uniq", eng.uniq_text)):
+            got = fn(d, c["k"], c["rc"])
+            if got != c[cmd].encode("latin-1"):
+                bad.append((c["name"], c["k"], c["alphabet"], c["rc"], cmd, got[:80], c[cmd][:80]))
+    assert not bad, (len(bad), bad[:5])
+
+
+@pytest.mark.parametrize("name", ["syn_100k", "syn_1m"])
+def test_golden_synthetic_hashes(eng, golden, name):
+    from kman_b200 import fasta
+
+    ent = [e for e in golden["synthetic"] if e["name"] == name][0]
+    data = ko.synth_fasta_bytes([("chr1 synthetic seed=%d" % ent["seed"], ko.synth_bases(ent["n"], ent["seed"]))])
+    assert hashlib.sha256(data).hexdigest() == ent["fasta_sha256"]
+    d = eng.upload(fasta.parse_bytes(data))
+    out = eng.count_text(d, ent["k"])
+    assert (out.count(b"\n"), hashlib.sha256(out).hexdigest()) == (ent["count_lines"], ent["count_sha256"])
+    out = eng.uniq_text(d, ent["k"])
+    assert (out.count(b"\n"), hashlib.sha256(out).hexdigest()) == (ent["uniq_lines"], ent["uniq_sha256"])
+
+
+def test_golden_syn_dup(eng, golden):
+    from kman_b200 import fasta
+
+    for ent in [e for e in golden["synthetic"] if e["name"] == "syn_dup"]:
+        d = eng.upload(fasta.parse_bytes(ent["fasta_text"].encode()))
+        for cmd, fn in (("count", eng.count_text), ("uniq", eng.uniq_text)):
+            out = fn(d, ent["k"], ent["rc"])
+            assert (out.count(b"\n"), hashlib.sha256(out).hexdigest()) == (ent[cmd + "_lines"], ent[cmd + "_sha256"]), (ent["k"], ent["rc"], cmd)
+
+
+@pytest.mark.parametrize("k,rc", [(25, False), (25, True), (31, False), (12, True)])
+def test_cfg4_like_n_runs_and_softmask_vs_oracle(eng, k, rc):
+    """config 4: N-runs, soft-masked lower case, isolated IUPAC symbols, runs touching record ends."""
+    from kman_b200 import fasta
+
+    rng = np.random.default_rng(4321)
+    recs = []
+    for r, n in enumerate((300_000, 150_000, 50_000)):
+        s = np.frombuffer(ko.synth_bases(n, 4321 + r), np.uint8).copy()
+        for _ in range(12):
+            L = int(np.exp(rng.uniform(0, np.log(20000))))
+            p = int(rng.integers(0, n))
+            s[p : p + L] = ord("N")
+        for _ in range(30):
+            L = int(rng.integers(100, 5000))
+            p = int(rng.integers(0, n))
+            s[p : p + L] |= 0x20  # lower-case
+        for c in b"RYKMSW":
+            s[int(rng.integers(0, n))] = c
+        if r == 0:
+            s[:37] = ord("N")
+        if r == 1:
+            s[-41:] = ord("n")
+        recs.append(("chr%d cfg4" % (r + 1), s.tobytes().decode()))
+    # second half of record 3 repeats its first half -> counts > 1
+    a = recs[2][1]
+    recs[2] = (recs[2][0], a[: len(a) // 2] + a[: len(a) // 2])
+    d = eng.upload(fasta.from_records(recs))
+    for ab in ("IUPAC", "ACGT"):
+        d = eng.upload(fasta.from_records(recs), alphabet=ab)
+        assert eng.count_text(d, k, rc) == ko.count_text_np(recs, k, rc, ab), ("count", ab)
+        assert eng.uniq_text(d, k, rc) == ko.uniq_text_np(recs, k, rc, ab), ("uniq", ab)
+
+
+# ---- host-buffer C-ABI calls ----------------------------------------------------------------------
+@pytest.mark.parametrize("k,rc", [(21, False), (31, True), (40, False)])
+def test_host_api_count_and_uniq(eng, k, rc):
+    from kman_b200 import _lib, alphabet as ab, fasta
+
+    lib = _lib.load()
+    seq = ko.synth_bases(200_000, 99).decode()
+    recs = [("a", seq[:120_000] + seq[:30_000]), ("b", seq[100_000:])]
+    flat = fasta.from_records(recs)
+    lut, _ = ab.lut_tables("ACGT", ab.NATYPES.DNA)
+    ctx = C.c_void_p()
+    _lib.check(lib.kmg_ctx_create(0, C.byref(ctx)))
+    try:
+        kb = 8 if k <= 32 else 16
+        cap = flat.bases.size * (2 if rc else 1)
+        keys = np.zeros(cap * kb // 8, np.uint64)
+        counts = np.zeros(cap, np.uint32)
+        n_out = C.c_uint64(0)
+        _lib.check(lib.kmg_count_host(ctx, flat.bases.ctypes.data, flat.bases.size, k, int(rc), lut.ctypes.data,
+                                      keys.ctypes.data, counts.ctypes.data, cap, C.byref(n_out)))
+        _, cw, det = ko.count_np(recs, k, rc, "ACGT")
+        want = limbs_to_rows(det["narrow"]["keys"])
+        got = keys[: n_out.value] if kb == 8 else keys[: 2 * n_out.value].reshape(-1, 2)
+        assert first_diff(got, want) == "equal"
+        assert first_diff(counts[: n_out.value].astype(np.int64), det["narrow"]["counts"]) == "equal"
+        vals = np.zeros(cap, np.uint64)
+        _lib.check(lib.kmg_uniq_host(ctx, flat.bases.ctypes.data, flat.bases.size, k, int(rc), lut.ctypes.data,
+                                     keys.ctypes.data, vals.ctypes.data, cap, C.byref(n_out)))
+        *_, det = ko.uniq_np(recs, k, rc, "ACGT")
+        want = limbs_to_rows(det["narrow"]["keys"])
+        got = keys[: n_out.value] if kb == 8 else keys[: 2 * n_out.value].reshape(-1, 2)
+        assert first_diff(got, want) == "equal"
+        wv = (det["narrow"]["pos"].astype(np.uint64) << np.uint64(1)) | det["narrow"]["strand"].astype(np.uint64)
+        assert first_diff(vals[: n_out.value], wv) == "equal"
+    finally:
+        lib.kmg_ctx_destroy(ctx)
+
+
+def test_errors_follow_reference_conventions(eng):
+    from kman_b200 import fasta
+
+    d = eng.upload(fasta.from_records([("a", "ACGTACGT")]))
+    with pytest.raises(AssertionError):  # batcher.py:477-478
+        eng.count_text(d, 1)
+    with pytest.raises(ValueError):
+        eng.count_text(d, 65)
+    assert eng.count_text(d, 9) == b""  # k > len -> empty output (join.py:107-111)
+
+
+# ---- full-size properties (config 2: 100 Mbp, k=31) ------------------------------------------------
+def test_cfg2_properties_100mbp(eng):
+    """Size-independent invariants at BASELINE.json's config-2 size: counts sum to the number
+    of windows, distinct keys strictly ascending, and the duplicated-half variant doubles counts."""
+    import torch
+
+    from kman_b200 import fasta
+
+    n, k = 100_000_000, 31
+    half = np.frombuffer(ko.synth_bases(n // 2, 1234), np.uint8)
+    bases = np.concatenate([half, half, np.array([10], np.uint8)])
+    flat = fasta.FlatInput(bases, np.array([0, n + 1], np.uint64), ["chr1"], ["chr1"])
+    d = eng.upload(flat, alphabet="ACGT", with_names=False)
+    (tab,) = eng.count(d, k)
+    keys = tab.keys[: tab.n * 8].view(torch.int64)
+    counts = tab.counts[: tab.n * 4].view(torch.int32)
+    assert int(counts.sum(dtype=torch.int64)) == n - k + 1
+    assert bool((keys[1:] > keys[:-1]).all())  # 62-bit keys: signed compare is fine
+    # windows fully inside either half occur twice; the k-1 windows spanning the seam are extra
+    assert int((counts == 2).sum()) >= n // 2 - k + 1 - 64
+    assert int(counts.max()) <= 4
+    # checksum of checksums: sum(key*count) equals the sum over all extracted keys
+    a = eng.extract(d, k)
+    all_keys = a.keys[: a.n * 8].view(torch.int64)
+    assert int((keys * counts.to(torch.int64)).sum()) == int(all_keys.sum())
