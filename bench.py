@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""Benchmark of the k-mer hot path (extract + sort + count, k=31) -- BASELINE.json's metric.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg2|cfg3]
+  (N>1: launched by torchrun, one rank per GPU; rank 0 prints ONE JSON line)
+
+A "step" is one pass of the hot path over one synthetic input:
+  N=1 : config 2 of BASELINE.json -- 100 Mbp random-ACGT single record, k=31, count
+  N>1 : weak scaling -- the genome is N x 100 Mbp, every rank holds a 100 Mbp chunk (k-1 base
+        overlap), keys are range-partitioned and exchanged with one all-to-all
+        (--workload cfg3 runs the 3.1 Gbp strong-scaling configuration instead)
+`value`  : whole-job k-mers/s with the bases already resident in HBM (device-timed, max over ranks)
+`e2e`    : the same metric through the host-buffer C-ABI call kmg_count_host (N=1) or the
+           distributed Python API (N>1), pinned host memory, H2D of the bases and D2H of the
+           (k-mer, count) table inside the timed region
+`roofline`: onesweep pass kernel, algorithmic bytes 2*W per key per launch, live CUDA-event
+           timing of every launch inside the timed region; `sort_model_frac` is SURVEY.md §8d's
+           fixed 8-bit-digit model N*W*(2*P8+1) over the whole sort
+`cpu_baseline` / --impl reference: the oracle's numpy port of the reference algorithm on the
+           host cores (bounded sample) -- a reported baseline, not the target.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K = 31
+CFG2_BASES = 100_000_000
+CFG3_BASES = 3_100_000_000
+METRIC = "k-mers/sec (extract+sort+count, k=31)"
+
+
+def synth_bases(n: int, seed: int) -> np.ndarray:
+    """SURVEY.md §8d generator: uniform random ACGT."""
+    rng = np.random.default_rng(seed)
+    out = np.empty(n, np.uint8)
+    step = 1 << 26
+    lut = np.frombuffer(b"ACGT", np.uint8)
+    for s in range(0, n, step):
+        m = min(step, n - s)
+        out[s : s + m] = lut[rng.integers(0, 4, size=m, dtype=np.uint8)]
+    return out
+
+
+def peak_hbm_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        # the busiest samples are the ones under load
+        sm_sorted = sorted(sm)
+        med = sm_sorted[len(sm_sorted) // 2] if sm_sorted else None
+        return {"sm_mhz": med, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---- reference arm / cpu baseline -------------------------------------------------------------------
+def cpu_port_rate(sample_bases: int, steps: int, warmup: int):
+    """k-mers/s of the oracle's numpy port (extract -> stable sort -> run-length), 1 host core."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import kmer_oracle as ko
+
+    seq = synth_bases(sample_bases, 1234).tobytes().decode()
+    recs = [("chr1 synthetic seed=1234", seq)]
+    ts = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        txt, counts, det = ko.count_np(recs, K, False, "ACGT")
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            ts.append(dt)
+    n_win = sample_bases - K + 1
+    assert int(counts.sum()) == n_win
+    return n_win / (sum(ts) / len(ts)), sum(ts) / len(ts)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 10_000_000
+    steps = max(1, min(args.steps, 5))
+    warm = max(0, min(args.warmup, 1))
+    rate, sec = cpu_port_rate(sample, steps, warm)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": "k-mers/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": workload_config(args, sample_note=f"bounded sample: {sample} bases of the same generator"),
+        "cpu_baseline": {"value": rate, "unit": "k-mers/s", "cores": 1, "kind": "port",
+                         "sample": f"{sample} bp random ACGT, k={K}, count; oracle numpy port (np.sort is single-threaded)",
+                         "host_cores_available": os.cpu_count()},
+        "e2e": {"value": rate, "unit": "k-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, sample_note=None):
+    n = args.gpus
+    if args.workload == "cfg3":
+        wl = f"config 3: {CFG3_BASES} bp synthetic random-ACGT genome, k={K}, count, strong scaling over {n} GPU(s)"
+    elif n == 1:
+        wl = f"config 2: {CFG2_BASES} bp synthetic random-ACGT single record (seed 1234), k={K}, count"
+    else:
+        wl = (f"config 2 x {n} (weak): {n}x{CFG2_BASES} bp synthetic random-ACGT genome, one {CFG2_BASES} bp chunk per GPU "
+              f"with k-1 overlap, range partition + one all-to-all, k={K}, count")
+    cfg = {"workload": wl, "k": K, "mode": "count", "alphabet": "ACGT",
+           "l2": "working set per step (keys 2x0.8 GB + table 1.2 GB per GPU) >> 126 MB L2; no explicit flush"}
+    if sample_note:
+        cfg["reference_sample"] = sample_note
+    return cfg
+
+
+# ---- GPU arm --------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="kmg", choices=["kmg", "reference"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "cfg2", "cfg3"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.workload == "auto":
+        args.workload = "cfg2"
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+
+    from kman_b200 import _lib, alphabet as ab, fasta
+    from kman_b200.engine import get_engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torchrun for N>1)"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    eng = get_engine(local_rank)
+    lib = eng.lib
+
+    # ---- synthetic input (this rank's chunk only) ---------------------------------------------
+    if args.workload == "cfg3":
+        from kman_b200.dist import chunk_bases
+
+        total = CFG3_BASES
+        b, e = chunk_bases(total, K, world)[rank]
+        # every rank generates only its slice: seed per 100 Mbp block keeps it reproducible
+        blk = 100_000_000
+        parts = []
+        for i in range(b // blk, (e + blk - 1) // blk):
+            x = synth_bases(blk, 1234 + i)
+            parts.append(x[max(b - i * blk, 0) : min(e - i * blk, blk)])
+        chunk = np.concatenate(parts)
+    else:
+        total = CFG2_BASES * world
+        # weak scaling: rank r owns block r (+ k-1 bases of block r+1)
+        chunk = synth_bases(CFG2_BASES, 1234 + rank)
+        if rank + 1 < world:
+            chunk = np.concatenate([chunk, synth_bases(CFG2_BASES, 1234 + rank + 1)[: K - 1]])
+        b = rank * CFG2_BASES
+    n_win_global = total - K + 1
+    flat = fasta.FlatInput(chunk, np.array([0, chunk.size + 1], np.uint64), ["chr1"], ["chr1"])
+    d = eng.upload(flat, alphabet="ACGT", with_names=False)
+    d.pos_offset = b
+    n_local = d.n_bases - K + 1
+
+    if world > 1:
+        from kman_b200.dist import DistributedCounter
+
+        dc = DistributedCounter(eng)
+
+        def step():
+            return dc.count(d, K, False)
+    else:
+        def step():
+            a = eng.sort(eng.extract(d, K, False, val_bytes=0, reuse="bench_"))
+            return eng.rle_count(a, reuse="bench_")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        tab = step()
+    # sanity: the job counted every window exactly once
+    tot = torch.tensor([int(tab.counts[: tab.n * 4].view(torch.int32).sum(dtype=torch.int64))], dtype=torch.int64, device=eng.device)
+    if world > 1:
+        dist.all_reduce(tot)
+    assert int(tot.item()) == n_win_global, (int(tot.item()), n_win_global)
+
+    lib.kmg_set_option(b"time_passes", 1)
+    lib.kmg_get_stat(b"reset_launches")
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        ev[i][0].record()
+        tab = step()
+        ev[i][1].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if sampler else None
+    launches = int(lib.kmg_get_stat(b"launches"))
+    pass_ns = int(lib.kmg_get_stat(b"sort_pass_ns"))
+    pass_cnt = int(lib.kmg_get_stat(b"sort_pass_count"))
+    lib.kmg_set_option(b"time_passes", 0)
+    dev_ms = sum(a.elapsed_time(b_) for a, b_ in ev)
+    tmax = torch.tensor([dev_ms], dtype=torch.float64, device=eng.device)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dev_ms = float(tmax.item())
+    ms_per_step = dev_ms / args.steps
+    value = n_win_global / (ms_per_step / 1e3)
+
+    # ---- roofline of the dominant kernel (rank 0's launches) ------------------------------------
+    peak, peak_src = peak_hbm_gbs()
+    W = 8
+    P8 = (2 * K + 7) // 8
+    roofline = None
+    if pass_cnt:
+        avg_pass_ms = pass_ns / 1e6 / pass_cnt
+        n_keys = n_local if world == 1 else n_win_global / world
+        alg_bytes = 2 * W * n_keys
+        achieved = alg_bytes / (avg_pass_ms / 1e3) / 1e9
+        passes_per_sort = pass_cnt / args.steps
+        sort_ms = avg_pass_ms * passes_per_sort
+        roofline = {
+            "bound": "hbm", "kernel": "kmg::onesweep_kernel (one radix pass: read + write of every key)",
+            "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": None, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_pass_ms,
+            "launches_per_step": passes_per_sort,
+            "sort_model_bytes_per_kmer": W * (2 * P8 + 1),
+            "sort_model_frac": (W * (2 * P8 + 1) * n_keys) / (sort_ms / 1e3) / 1e9 / peak,
+            "sort_passes_ms_per_step": sort_ms,
+        }
+        prof = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(prof):
+            try:
+                roofline["traffic"] = json.load(open(prof)).get("onesweep_dram_bytes_per_launch")
+            except Exception:
+                pass
+
+    # ---- e2e: host buffers in, host table out ------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        e2e_steps = max(1, min(args.steps, 5))
+        h_bases = torch.from_numpy(chunk).pin_memory()
+        if world == 1:
+            lut, _ = ab.lut_tables("ACGT", ab.NATYPES.DNA)
+            cap = n_local
+            h_keys = torch.empty(cap, dtype=torch.int64).pin_memory()
+            h_counts = torch.empty(cap, dtype=torch.int32).pin_memory()
+            n_out = C.c_uint64(0)
+            ctx = C.c_void_p()
+            _lib.check(lib.kmg_ctx_create(local_rank, C.byref(ctx)))
+
+            def e2e_step():
+                _lib.check(lib.kmg_count_host(ctx, h_bases.data_ptr(), chunk.size, K, 0, lut.ctypes.data,
+                                              h_keys.data_ptr(), h_counts.data_ptr(), cap, C.byref(n_out)))
+                return chunk.size, n_out.value * 12
+
+            e2e_step()
+        else:
+            h_keys = h_counts = None
+
+            def e2e_step():
+                nonlocal h_keys, h_counts
+                d.bases[: chunk.size].copy_(h_bases, non_blocking=True)
+                t = dc.count(d, K, False)
+                if h_keys is None or h_keys.numel() < t.n * 8:
+                    h_keys = torch.empty(int(t.n * 8 * 1.05), dtype=torch.uint8).pin_memory()
+                    h_counts = torch.empty(int(t.n * 4 * 1.05), dtype=torch.uint8).pin_memory()
+                h_keys[: t.n * 8].copy_(t.keys[: t.n * 8], non_blocking=True)
+                h_counts[: t.n * 4].copy_(t.counts[: t.n * 4], non_blocking=True)
+                torch.cuda.synchronize()
+                return chunk.size, t.n * 12
+
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            h2d, d2h = e2e_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=eng.device)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": n_win_global / (float(tt.item()) / e2e_steps), "unit": "k-mers/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+               "api": "kmg_count_host (C ABI, pinned host buffers)" if world == 1 else "kman_b200.dist.DistributedCounter.count + pinned copies (per rank bytes)"}
+        if world == 1:
+            lib.kmg_ctx_destroy(ctx)
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, sec = cpu_port_rate(10_000_000, 2, 0)
+        cpu_baseline = {"value": rate, "unit": "k-mers/s", "cores": 1, "kind": "port",
+                        "sample": f"10000000 bp of the same generator, k={K}, count; oracle numpy port, {sec:.1f} s per pass",
+                        "host_cores_available": os.cpu_count()}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "k-mers/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong" if args.workload == "cfg3" else "weak", "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic", "config": workload_config(args), "clocks": clocks, "e2e": e2e,
+            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "wall_ms_per_step": t_wall / args.steps * 1e3, "kmers_per_step": n_win_global,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

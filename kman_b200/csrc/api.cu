@@ -13,7 +13,12 @@ namespace kmg {
 static thread_local char g_err[512] = "";
 static thread_local int64_t g_launches = 0;
 extern int g_sort_config;
+extern int g_time_passes;
 extern thread_local int64_t g_stat_sort_passes;
+void timing_collect();
+double timing_total_ms();
+int64_t timing_count();
+void timing_reset();
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -47,6 +52,11 @@ extern "C" int kmg_set_option(const char* name, int64_t value) {
         g_sort_config = (int)value;
         return KMG_OK;
     }
+    if (!strcmp(name, "time_passes")) {
+        g_time_passes = (int)value;
+        timing_reset();
+        return KMG_OK;
+    }
     set_error("unknown option '%s'", name);
     return KMG_ERR_ARG;
 }
@@ -55,6 +65,14 @@ extern "C" int64_t kmg_get_stat(const char* name) {
     if (!name) return -1;
     if (!strcmp(name, "launches")) return g_launches;
     if (!strcmp(name, "sort_passes")) return g_stat_sort_passes;
+    if (!strcmp(name, "sort_pass_ns")) {  // total device time of the timed onesweep launches
+        timing_collect();
+        return (int64_t)(timing_total_ms() * 1e6);
+    }
+    if (!strcmp(name, "sort_pass_count")) {
+        timing_collect();
+        return timing_count();
+    }
     if (!strcmp(name, "reset_launches")) {
         g_launches = 0;
         return 0;

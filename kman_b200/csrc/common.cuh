@@ -5,6 +5,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <type_traits>
+
 #include "../../include/kmg.h"
 
 namespace kmg {
@@ -115,34 +117,47 @@ constexpr uint64_t TP_FLAG_AGG = 1ull << 62;
 constexpr uint64_t TP_FLAG_INCL = 2ull << 62;
 constexpr uint64_t TP_VALUE_MASK = (1ull << 62) - 1;
 
-// Called by ONE thread of the tile.  `state` must be zero-initialised; tile ids must be
-// handed out in launch order (atomic ticket).  Returns the exclusive prefix.
-__device__ __forceinline__ uint64_t tile_prefix_exclusive(uint64_t* state, uint32_t tile, uint64_t aggregate,
-                                                          uint32_t* err_flag) {
+// Called by ALL 32 lanes of ONE warp of the tile; every lane receives the exclusive prefix.
+// `state` must be zero-initialised and tile ids handed out in launch order (atomic ticket).
+// One round inspects the 32 preceding tiles with a single load per lane, so the walk back to
+// the newest tile that already knows its inclusive prefix costs ~1 L2 round trip instead of
+// one per tile.  The flag travels in the same word as the value: relaxed accesses suffice.
+__device__ __forceinline__ uint64_t tile_prefix_exclusive_warp(uint64_t* state, uint32_t tile, uint64_t aggregate,
+                                                               uint32_t* err_flag) {
+    const uint32_t lane = threadIdx.x & 31;
     if (tile == 0) {
-        st_release_u64(&state[0], TP_FLAG_INCL | aggregate);
+        if (lane == 0) st_relaxed_u64(&state[0], TP_FLAG_INCL | aggregate);
         return 0;
     }
-    st_release_u64(&state[tile], TP_FLAG_AGG | aggregate);
+    if (lane == 0) st_relaxed_u64(&state[tile], TP_FLAG_AGG | aggregate);
     uint64_t excl = 0;
-    int64_t p = (int64_t)tile - 1;
+    int64_t base = (int64_t)tile - 1;
     uint32_t spins = 0;
     while (true) {
-        uint64_t w = ld_acquire_u64(&state[p]);
-        uint64_t f = w & ~TP_VALUE_MASK;
-        if (f == 0) {
+        const int64_t idx = base - (int64_t)lane;
+        // tiles before the first one behave like a finished tile with prefix 0
+        const uint64_t w = idx >= 0 ? ld_relaxed_u64(&state[idx]) : TP_FLAG_INCL;
+        const uint64_t f = w & ~TP_VALUE_MASK;
+        const uint32_t empty_mask = __ballot_sync(0xffffffffu, f == 0);
+        const uint32_t incl_mask = __ballot_sync(0xffffffffu, f == TP_FLAG_INCL);
+        const uint32_t first_incl = incl_mask ? (uint32_t)__ffs(incl_mask) - 1u : 32u;
+        const uint32_t first_empty = empty_mask ? (uint32_t)__ffs(empty_mask) - 1u : 32u;
+        const uint32_t usable = min(first_incl + 1u, first_empty);  // leading lanes that count
+        uint64_t v = lane < usable ? (w & TP_VALUE_MASK) : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        excl += v;
+        if (first_incl < first_empty) break;  // reached a tile with a known inclusive prefix
+        base -= usable;
+        if (usable == 0) {
             if (++spins > SPIN_LIMIT) {
-                atomicExch(err_flag, 1u);
+                if (lane == 0) atomicExch(err_flag, 1u);
                 break;
             }
-            __nanosleep(20);
-            continue;
+            __nanosleep(32);
         }
-        excl += w & TP_VALUE_MASK;
-        if (f == TP_FLAG_INCL) break;
-        --p;
     }
-    st_release_u64(&state[tile], TP_FLAG_INCL | (excl + aggregate));
+    if (lane == 0) st_relaxed_u64(&state[tile], TP_FLAG_INCL | (excl + aggregate));
     return excl;
 }
 

@@ -81,9 +81,12 @@ __global__ void __launch_bounds__(FMT_BLOCK) format_counts_kernel(const FmtParam
     }
     uint32_t total;
     uint32_t off = block_excl_scan<FMT_BLOCK, uint32_t>(len, s_scan, total);
-    if (t == 0) {
-        s_base = tile_prefix_exclusive(p.state, tile, total, p.err);
-        if (tile == gridDim.x - 1) *p.bytes_out = s_base + total;
+    if (t < 32) {
+        const uint64_t e = tile_prefix_exclusive_warp(p.state, tile, total, p.err);
+        if (t == 0) {
+            s_base = e;
+            if (tile == gridDim.x - 1) *p.bytes_out = e + total;
+        }
     }
 #pragma unroll
     for (int r = 0; r < FMT_RPT; ++r) {
@@ -153,9 +156,12 @@ __global__ void __launch_bounds__(FMT_BLOCK) format_uniq_kernel(const FmtParams 
     }
     uint64_t total;
     const uint64_t off = block_excl_scan<FMT_BLOCK, uint64_t>(len, s_scan, total);
-    if (t == 0) {
-        s_base = tile_prefix_exclusive(p.state, tile, total, p.err);
-        if (tile == gridDim.x - 1) *p.bytes_out = s_base + total;
+    if (t < 32) {
+        const uint64_t e = tile_prefix_exclusive_warp(p.state, tile, total, p.err);
+        if (t == 0) {
+            s_base = e;
+            if (tile == gridDim.x - 1) *p.bytes_out = e + total;
+        }
     }
     __syncthreads();
     if (i < p.n) {

@@ -180,8 +180,9 @@ __global__ void __launch_bounds__(EX_BLOCK) extract_narrow_kernel(const ExtractP
     uint32_t total;
     const uint32_t excl = block_excl_scan<EX_BLOCK, uint32_t>(cnt, s_scan, total);
     if (nwide) atomicAdd(&s_wide, nwide);
-    if (t == 0) {
-        s_base = tile_prefix_exclusive(p.tile_state, tile, (uint64_t)total * OUT_PER_WIN, p.err);
+    if (t < 32) {
+        const uint64_t e = tile_prefix_exclusive_warp(p.tile_state, tile, (uint64_t)total * OUT_PER_WIN, p.err);
+        if (t == 0) s_base = e;
     }
     uint32_t r = excl;
 #pragma unroll
@@ -265,7 +266,10 @@ __global__ void __launch_bounds__(EXW_BLOCK) extract_wide_kernel(const ExtractPa
     const uint32_t cnt = __popc(vf);
     uint32_t total;
     const uint32_t excl = block_excl_scan<EXW_BLOCK, uint32_t>(cnt, s_scan, total);
-    if (t == 0) s_base = tile_prefix_exclusive(p.tile_state, tile, (uint64_t)total * OUT_PER_WIN, p.err);
+    if (t < 32) {
+        const uint64_t e = tile_prefix_exclusive_warp(p.tile_state, tile, (uint64_t)total * OUT_PER_WIN, p.err);
+        if (t == 0) s_base = e;
+    }
     __syncthreads();
     const uint64_t base = s_base;
     u128* keys_out = reinterpret_cast<u128*>(p.keys_out);

@@ -133,8 +133,12 @@ struct ValType<4> {
     using type = uint32_t;
 };
 
-template <typename KeyT, int VAL_BYTES, int RADIX_BITS, int BLOCK, int IPT, typename DigitOp>
-__global__ void __launch_bounds__(BLOCK) onesweep_kernel(const OnesweepParams p, const DigitOp digit_of) {
+// number of predecessor tiles a digit's look-back inspects per round (independent loads)
+constexpr int LB_BATCH = 8;
+
+template <typename KeyT, int VAL_BYTES, int RADIX_BITS, int BLOCK, int IPT, typename DigitOp, bool FULL>
+__device__ __forceinline__ void onesweep_tile(const OnesweepParams& p, const DigitOp& digit_of, unsigned char* smem_raw,
+                                              uint32_t* s_scan, const uint32_t tile, const uint32_t n_valid) {
     constexpr int RADIX = 1 << RADIX_BITS;
     constexpr int WARPS = BLOCK / 32;
     constexpr int TILE = BLOCK * IPT;
@@ -142,68 +146,41 @@ __global__ void __launch_bounds__(BLOCK) onesweep_kernel(const OnesweepParams p,
     using ValT = typename ValType<VAL_BYTES>::type;
     constexpr int ITEM_BYTES = sizeof(KeyT) > sizeof(ValT) ? sizeof(KeyT) : sizeof(ValT);
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
     KeyT* s_keys = reinterpret_cast<KeyT*>(smem_raw);
     ValT* s_vals = reinterpret_cast<ValT*>(smem_raw);
     uint32_t* s_whist = reinterpret_cast<uint32_t*>(smem_raw + (size_t)ITEM_BYTES * TILE);  // [WARPS][RADIX]
     uint64_t* s_goff = reinterpret_cast<uint64_t*>(s_whist + WARPS * RADIX);               // [RADIX]
-    __shared__ uint32_t s_scan[WARPS + 1];
-    __shared__ uint32_t s_tile;
 
     const int t = threadIdx.x;
     const uint32_t lane = t & 31, warp = t >> 5;
-    if (t == 0) s_tile = atomicAdd(p.ticket, 1u);
-    uint32_t* my_hist = s_whist + warp * RADIX;
-    for (int i = lane; i < RADIX; i += 32) my_hist[i] = 0;
-    __syncthreads();
-    const uint32_t tile = s_tile;
     const uint32_t n_tiles = gridDim.x;
-    if (t == 0 && tile == n_tiles - 1) *p.ticket = 0;  // every ticket of this launch is taken
     const uint32_t tile_base = tile * (uint32_t)TILE;
-    const uint32_t n_valid = min((uint32_t)TILE, p.n - tile_base);
+    uint32_t* my_hist = s_whist + warp * RADIX;
 
-    // ---- 1. load ----------------------------------------------------------------------------
+    // ---- 1. load (warp-striped, coalesced) + per-warp digit histogram ------------------------
     const KeyT* keys_in = reinterpret_cast<const KeyT*>(p.keys_in) + tile_base;
     KeyT keys[IPT];
     const uint32_t wbase = warp * 32 * IPT + lane;
-    if (n_valid == TILE) {
-#pragma unroll
-        for (int i = 0; i < IPT; ++i) keys[i] = keys_in[wbase + i * 32];
-    } else {
-#pragma unroll
-        for (int i = 0; i < IPT; ++i) {
-            const uint32_t idx = wbase + i * 32;
-            keys[i] = idx < n_valid ? keys_in[idx] : key_all_ones(KeyT{});
-        }
-    }
-
-    // ---- 2. rank inside the warp ------------------------------------------------------------
-    uint32_t ranks[IPT];
-    const uint32_t lt = lanemask_lt();
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
         const uint32_t idx = wbase + i * 32;
-        const uint32_t d = idx < n_valid ? digit_of(keys[i]) : (uint32_t)(RADIX - 1);
-        uint32_t m = 0xffffffffu;
+        if (FULL) keys[i] = keys_in[idx];
+        else keys[i] = idx < n_valid ? keys_in[idx] : key_all_ones(KeyT{});
+    }
+    uint32_t dg[IPT];
 #pragma unroll
-        for (int b = 0; b < RADIX_BITS; ++b) {
-            const bool bit = (d >> b) & 1u;
-            const uint32_t bal = __ballot_sync(0xffffffffu, bit);
-            m &= bit ? bal : ~bal;
-        }
-        const uint32_t lower = __popc(m & lt);
-        uint32_t old = 0;
-        if (lower == 0) {
-            old = my_hist[d];
-            my_hist[d] = old + __popc(m);
-        }
-        __syncwarp();
-        old = __shfl_sync(0xffffffffu, old, __ffs(m) - 1);
-        ranks[i] = old + lower;
+    for (int i = 0; i < IPT; ++i) {
+        const uint32_t idx = wbase + i * 32;
+        // slots past the end of a partial tile rank into the last digit, after every real key
+        dg[i] = (FULL || idx < n_valid) ? digit_of(keys[i]) : (uint32_t)(RADIX - 1);
+        atomicAdd(&my_hist[dg[i]], 1u);
     }
     __syncthreads();
 
-    // ---- 3. prefix over warps and digits ------------------------------------------------------
+    // ---- 2. prefix over warps and digits; publish the tile's digit counts EARLY ----------------
+    const uint32_t padding = (uint32_t)TILE - n_valid;
+    const uint32_t fl_agg = ((1u + 2u * p.parity) & 3u) << 30;
+    const uint32_t fl_incl = ((2u + 2u * p.parity) & 3u) << 30;
     uint32_t cnt[DPT];
     uint32_t tsum = 0;
 #pragma unroll
@@ -217,78 +194,115 @@ __global__ void __launch_bounds__(BLOCK) onesweep_kernel(const OnesweepParams p,
                 s_whist[w * RADIX + d] = run;
                 run += c;
             }
+            uint32_t c = run;
+            if (!FULL && d == RADIX - 1) c -= padding;
+            st_relaxed_u32(p.lookback + (size_t)tile * RADIX + d, (tile == 0 ? fl_incl : fl_agg) | c);
         }
         cnt[q] = run;
         tsum += run;
     }
     uint32_t total;
     uint32_t bin_excl = block_excl_scan<BLOCK, uint32_t>(tsum, s_scan, total);
+    uint32_t bexcl[DPT];
+#pragma unroll
+    for (int q = 0; q < DPT; ++q) {
+        const int d = t * DPT + q;
+        bexcl[q] = bin_excl;
+        if (d < RADIX) {
+            // fold the digit's tile-local base into every warp's running offset
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) s_whist[w * RADIX + d] += bin_excl;
+        }
+        bin_excl += cnt[q];
+    }
+    __syncthreads();
 
-    // ---- 4. publish + look back, one digit chain per thread ------------------------------------
-    const uint32_t padding = (uint32_t)TILE - n_valid;
-    const uint32_t fl_agg = ((1u + 2u * p.parity) & 3u) << 30;
-    const uint32_t fl_incl = ((2u + 2u * p.parity) & 3u) << 30;
-    const uint32_t fl_empty = ((0u + 2u * p.parity) & 3u) << 30;
+    // ---- 3. rank inside the warp: ballot matching, offsets already final ------------------------
+    uint32_t slot[IPT];
+    const uint32_t lt = lanemask_lt();
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+        const uint32_t d = dg[i];
+        uint32_t m = 0xffffffffu;
+#pragma unroll
+        for (int b = 0; b < RADIX_BITS; ++b) {
+            const uint32_t bal = __ballot_sync(0xffffffffu, (d >> b) & 1u);
+            m &= bal ^ (((d >> b) & 1u) - 1u);  // bal where my bit is 1, ~bal where it is 0
+        }
+        const uint32_t lower = __popc(m & lt);
+        uint32_t cur = 0;
+        if (lower == 0) {
+            cur = my_hist[d];
+            my_hist[d] = cur + __popc(m);
+        }
+        __syncwarp();
+        cur = __shfl_sync(0xffffffffu, cur, __ffs(m) - 1);
+        slot[i] = cur + lower;
+    }
+
+    // ---- 4. look back (one digit chain per thread, LB_BATCH tiles per round) while the keys
+    //         are being staged into shared memory ----------------------------------------------
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) s_keys[slot[i]] = keys[i];
 #pragma unroll
     for (int q = 0; q < DPT; ++q) {
         const int d = t * DPT + q;
         if (d < RADIX) {
             uint32_t c = cnt[q];
-            if (d == RADIX - 1) c -= padding;  // padded slots were ranked into the last digit
-            uint32_t* lb = p.lookback + d;
+            if (!FULL && d == RADIX - 1) c -= padding;
+            const uint32_t* lb = p.lookback + d;
             uint32_t excl = 0;
-            if (tile == 0) {
-                st_relaxed_u32(lb, fl_incl | c);
-            } else {
-                st_relaxed_u32(lb + (size_t)tile * RADIX, fl_agg | c);
+            if (tile != 0) {
                 int64_t pt = (int64_t)tile - 1;
                 uint32_t spins = 0;
-                while (true) {
-                    const uint32_t w = ld_relaxed_u32(lb + (size_t)pt * RADIX);
-                    const uint32_t f = w & ~LB_VALUE_MASK;
-                    if (f == fl_empty || (f != fl_agg && f != fl_incl)) {
-                        if (++spins > SPIN_LIMIT) {
-                            atomicExch(p.err, 1u);
-                            break;
-                        }
-                        continue;
+                bool done = false;
+                while (!done) {
+                    uint32_t w[LB_BATCH];
+#pragma unroll
+                    for (int j = 0; j < LB_BATCH; ++j) {
+                        const int64_t idx = pt - j;
+                        w[j] = idx >= 0 ? ld_relaxed_u32(lb + (size_t)idx * RADIX) : fl_incl;
                     }
-                    excl += w & LB_VALUE_MASK;
-                    if (f == fl_incl) break;
-                    --pt;
+                    int used = 0;
+                    bool stalled = false;
+#pragma unroll
+                    for (int j = 0; j < LB_BATCH; ++j) {
+                        const uint32_t f = w[j] & ~LB_VALUE_MASK;
+                        if (!done && !stalled) {
+                            if (f != fl_agg && f != fl_incl) {
+                                stalled = true;
+                            } else {
+                                excl += w[j] & LB_VALUE_MASK;
+                                ++used;
+                                if (f == fl_incl) done = true;
+                            }
+                        }
+                    }
+                    pt -= used;
+                    if (used == 0 && ++spins > SPIN_LIMIT) {
+                        atomicExch(p.err, 1u);
+                        break;
+                    }
                 }
-                st_relaxed_u32(lb + (size_t)tile * RADIX, fl_incl | (excl + c));
+                st_relaxed_u32(p.lookback + (size_t)tile * RADIX + d, fl_incl | (excl + c));
             }
             const uint64_t gbase = p.bins_in[d];
             // destination of local sorted slot s holding digit d:  s_goff[d] + s
-            s_goff[d] = gbase + excl - bin_excl;
+            s_goff[d] = gbase + excl - bexcl[q];
             if (p.bins_out && tile == n_tiles - 1) p.bins_out[d] = gbase + excl + c;
-            // fold the digit's tile-local base into every warp's offset
-#pragma unroll
-            for (int w = 0; w < WARPS; ++w) s_whist[w * RADIX + d] += bin_excl;
-            bin_excl += cnt[q];
         }
     }
     __syncthreads();
 
-    // ---- 5. reorder through shared memory, coalesced run writes ---------------------------------
-    uint32_t dig[IPT];
-#pragma unroll
-    for (int i = 0; i < IPT; ++i) {
-        const uint32_t idx = wbase + i * 32;
-        const uint32_t d = idx < n_valid ? digit_of(keys[i]) : (uint32_t)(RADIX - 1);
-        ranks[i] += my_hist[d];  // tile-local sorted slot
-        s_keys[ranks[i]] = keys[i];
-    }
-    __syncthreads();
+    // ---- 5. coalesced run writes -----------------------------------------------------------------
     KeyT* keys_out = reinterpret_cast<KeyT*>(p.keys_out);
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
         const uint32_t s = t + i * BLOCK;
-        if (s < n_valid) {
+        if (FULL || s < n_valid) {
             const KeyT key = s_keys[s];
             const uint32_t d = digit_of(key);
-            dig[i] = d;
+            dg[i] = d;
             keys_out[s_goff[d] + s] = key;
         }
     }
@@ -298,19 +312,44 @@ __global__ void __launch_bounds__(BLOCK) onesweep_kernel(const OnesweepParams p,
 #pragma unroll
         for (int i = 0; i < IPT; ++i) {
             const uint32_t idx = wbase + i * 32;
-            vals[i] = idx < n_valid ? vals_in[idx] : ValT(0);
+            vals[i] = (FULL || idx < n_valid) ? vals_in[idx] : ValT(0);
         }
         __syncthreads();  // all key reads from the staging buffer are done
 #pragma unroll
-        for (int i = 0; i < IPT; ++i) s_vals[ranks[i]] = vals[i];
+        for (int i = 0; i < IPT; ++i) s_vals[slot[i]] = vals[i];
         __syncthreads();
         ValT* vals_out = reinterpret_cast<ValT*>(p.vals_out);
 #pragma unroll
         for (int i = 0; i < IPT; ++i) {
             const uint32_t s = t + i * BLOCK;
-            if (s < n_valid) vals_out[s_goff[dig[i]] + s] = s_vals[s];
+            if (FULL || s < n_valid) vals_out[s_goff[dg[i]] + s] = s_vals[s];
         }
     }
+}
+
+template <typename KeyT, int VAL_BYTES, int RADIX_BITS, int BLOCK, int IPT, typename DigitOp>
+__global__ void __launch_bounds__(BLOCK) onesweep_kernel(const OnesweepParams p, const DigitOp digit_of) {
+    constexpr int RADIX = 1 << RADIX_BITS;
+    constexpr int WARPS = BLOCK / 32;
+    constexpr int TILE = BLOCK * IPT;
+    using ValT = typename ValType<VAL_BYTES>::type;
+    constexpr int ITEM_BYTES = sizeof(KeyT) > sizeof(ValT) ? sizeof(KeyT) : sizeof(ValT);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t* s_whist = reinterpret_cast<uint32_t*>(smem_raw + (size_t)ITEM_BYTES * TILE);
+    __shared__ uint32_t s_scan[WARPS + 1];
+    __shared__ uint32_t s_tile;
+
+    const int t = threadIdx.x;
+    if (t == 0) s_tile = atomicAdd(p.ticket, 1u);
+    for (int i = t; i < WARPS * RADIX; i += BLOCK) s_whist[i] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    if (t == 0 && tile == gridDim.x - 1) *p.ticket = 0;  // every ticket of this launch is taken
+    const uint32_t n_valid = min((uint32_t)TILE, p.n - tile * (uint32_t)TILE);
+    if (n_valid == (uint32_t)TILE)
+        onesweep_tile<KeyT, VAL_BYTES, RADIX_BITS, BLOCK, IPT, DigitOp, true>(p, digit_of, smem_raw, s_scan, tile, n_valid);
+    else
+        onesweep_tile<KeyT, VAL_BYTES, RADIX_BITS, BLOCK, IPT, DigitOp, false>(p, digit_of, smem_raw, s_scan, tile, n_valid);
 }
 
 // ---- tile configurations ----------------------------------------------------------------------
@@ -367,7 +406,46 @@ static int dispatch_onesweep(int cfg, int key_bytes, int val_bytes, const Oneswe
 }
 
 int g_sort_config = 0;
+int g_time_passes = 0;  // kmg_set_option("time_passes", 1): bracket every pass launch with events
 thread_local int64_t g_stat_sort_passes = 0;
+
+// live per-launch timing of the dominant kernel (bench.py's roofline): event pairs recorded
+// on the caller's stream around each onesweep launch, read back by kmg_get_stat().
+constexpr int MAX_TIMED = 64;
+thread_local cudaEvent_t g_ev[2 * MAX_TIMED];
+thread_local int g_ev_made = 0, g_ev_used = 0;
+thread_local double g_pass_ms_total = 0;
+thread_local int64_t g_pass_count_total = 0;
+
+static void timing_begin(cudaStream_t st) {
+    if (!g_time_passes || g_ev_used >= MAX_TIMED) return;
+    while (g_ev_made < 2 * MAX_TIMED) cudaEventCreate(&g_ev[g_ev_made++]);
+    cudaEventRecord(g_ev[2 * g_ev_used], st);
+}
+static void timing_end(cudaStream_t st) {
+    if (!g_time_passes || g_ev_used >= MAX_TIMED) return;
+    cudaEventRecord(g_ev[2 * g_ev_used + 1], st);
+    ++g_ev_used;
+}
+// folds the recorded pairs into the running totals (synchronises on the last event)
+void timing_collect() {
+    for (int i = 0; i < g_ev_used; ++i) {
+        float ms = 0;
+        if (cudaEventSynchronize(g_ev[2 * i + 1]) == cudaSuccess &&
+            cudaEventElapsedTime(&ms, g_ev[2 * i], g_ev[2 * i + 1]) == cudaSuccess) {
+            g_pass_ms_total += ms;
+            ++g_pass_count_total;
+        }
+    }
+    g_ev_used = 0;
+}
+double timing_total_ms() { return g_pass_ms_total; }
+int64_t timing_count() { return g_pass_count_total; }
+void timing_reset() {
+    g_ev_used = 0;
+    g_pass_ms_total = 0;
+    g_pass_count_total = 0;
+}
 
 static int tile_items(int cfg, int key_bytes) {
     if (key_bytes == 16) return 256 * 8;
@@ -505,7 +583,10 @@ extern "C" int kmg_radix_sort(void* d_keys, void* d_keys_alt, void* d_vals, void
             } else {
                 p.parity = launch & 1u;
             }
+            if (g_ev_used >= MAX_TIMED) timing_collect();
+            timing_begin(st);
             int rcode = dispatch_onesweep(cfg, key_bytes, val_bytes, p, op, st);
+            timing_end(st);
             if (rcode != KMG_OK) return rcode;
             ++launch;
         }

@@ -131,40 +131,66 @@ __global__ void __launch_bounds__(RLE_BLOCK) rle_count_kernel(const RleParams p)
         }
     }
     __syncthreads();
-    if (t == 0) {
+    if (t < 32) {
+        // Warp-cooperative look-back over (number of heads, position of the last head).
+        // Both words carry their own flag, so no fence is needed: a slot counts only when
+        // both flags are set, and a B word that is already the inclusive version while A is
+        // still the aggregate is harmless (it names the same "last head at or before here").
         const uint64_t last_plus1 = theads ? tile_base + s_hpos[theads - 1] + 1 : 0;
         uint64_t excl = 0, carry = 0;
         if (tile == 0) {
-            st_relaxed_u64(&p.state_b[0], last_plus1);
-            st_release_u64(&p.state_a[0], TP_FLAG_INCL | theads);
+            if (lane == 0) {
+                st_relaxed_u64(&p.state_b[0], TP_FLAG_INCL | last_plus1);
+                st_relaxed_u64(&p.state_a[0], TP_FLAG_INCL | theads);
+            }
         } else {
-            st_relaxed_u64(&p.state_b[tile], last_plus1);
-            st_release_u64(&p.state_a[tile], TP_FLAG_AGG | theads);
-            int64_t q = (int64_t)tile - 1;
+            if (lane == 0) {
+                st_relaxed_u64(&p.state_b[tile], TP_FLAG_AGG | last_plus1);
+                st_relaxed_u64(&p.state_a[tile], TP_FLAG_AGG | theads);
+            }
+            int64_t base = (int64_t)tile - 1;
             uint32_t spins = 0;
             while (true) {
-                const uint64_t a = ld_acquire_u64(&p.state_a[q]);
-                const uint64_t f = a & ~TP_VALUE_MASK;
-                if (f == 0) {
+                const int64_t idx = base - (int64_t)lane;
+                uint64_t a = TP_FLAG_INCL, b = TP_FLAG_INCL;  // before tile 0: finished, no head
+                if (idx >= 0) {
+                    a = ld_relaxed_u64(&p.state_a[idx]);
+                    b = ld_relaxed_u64(&p.state_b[idx]);
+                }
+                const uint64_t fa = a & ~TP_VALUE_MASK, fb = b & ~TP_VALUE_MASK;
+                const bool ready = fa != 0 && fb != 0 && !(fa == TP_FLAG_INCL && fb != TP_FLAG_INCL);
+                const uint32_t empty_mask = __ballot_sync(0xffffffffu, !ready);
+                const uint32_t incl_mask = __ballot_sync(0xffffffffu, ready && fa == TP_FLAG_INCL);
+                const uint32_t first_incl = incl_mask ? (uint32_t)__ffs(incl_mask) - 1u : 32u;
+                const uint32_t first_empty = empty_mask ? (uint32_t)__ffs(empty_mask) - 1u : 32u;
+                const uint32_t usable = min(first_incl + 1u, first_empty);
+                uint64_t v = lane < usable ? (a & TP_VALUE_MASK) : 0ull;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                excl += v;
+                // nearest preceding head: the lowest usable lane whose B value is non-zero
+                const uint32_t has_mask = __ballot_sync(0xffffffffu, lane < usable && (b & TP_VALUE_MASK) != 0);
+                if (carry == 0 && has_mask) carry = __shfl_sync(0xffffffffu, b & TP_VALUE_MASK, __ffs(has_mask) - 1);
+                if (first_incl < first_empty) break;
+                base -= usable;
+                if (usable == 0) {
                     if (++spins > SPIN_LIMIT) {
-                        atomicExch(p.err, 1u);
+                        if (lane == 0) atomicExch(p.err, 1u);
                         break;
                     }
-                    __nanosleep(20);
-                    continue;
+                    __nanosleep(32);
                 }
-                const uint64_t b = ld_relaxed_u64(&p.state_b[q]);
-                excl += a & TP_VALUE_MASK;
-                if (carry == 0) carry = b;
-                if (f == TP_FLAG_INCL) break;
-                --q;
             }
-            st_relaxed_u64(&p.state_b[tile], last_plus1 ? last_plus1 : carry);
-            st_release_u64(&p.state_a[tile], TP_FLAG_INCL | (excl + theads));
+            if (lane == 0) {
+                st_relaxed_u64(&p.state_b[tile], TP_FLAG_INCL | (last_plus1 ? last_plus1 : carry));
+                st_relaxed_u64(&p.state_a[tile], TP_FLAG_INCL | (excl + theads));
+            }
         }
-        s_excl_heads = excl;
-        s_carry = carry;  // position+1 of the head of the run that is open when the tile starts
-        if (tile == gridDim.x - 1) *p.n_out = excl + theads;
+        if (lane == 0) {
+            s_excl_heads = excl;
+            s_carry = carry;  // position+1 of the head of the run that is open when the tile starts
+            if (tile == gridDim.x - 1) *p.n_out = excl + theads;
+        }
     }
     __syncthreads();
     const uint64_t excl_heads = s_excl_heads;
@@ -241,10 +267,12 @@ __global__ void __launch_bounds__(RLE_BLOCK) select_singletons_kernel(const RleP
         if (w < (int)warp) wexcl += c;
         total += c;
     }
-    if (t == 0) {
-        const uint64_t excl = tile_prefix_exclusive(p.state_a, tile, total, p.err);
-        s_excl = excl;
-        if (tile == gridDim.x - 1) *p.n_out = excl + total;
+    if (t < 32) {
+        const uint64_t excl = tile_prefix_exclusive_warp(p.state_a, tile, total, p.err);
+        if (t == 0) {
+            s_excl = excl;
+            if (tile == gridDim.x - 1) *p.n_out = excl + total;
+        }
     }
     __syncthreads();
     const uint64_t base = s_excl + wexcl;
