@@ -118,10 +118,12 @@ struct OnesweepParams {
     uint32_t n;  // keys in this part (< 2^30)
     const uint64_t* bins_in;  // [RADIX] global base of each digit run for this part
     uint64_t* bins_out;       // [RADIX] base for the next part (may be null)
-    uint32_t* lookback;       // [tiles][RADIX]
+    uint32_t* lb_agg;         // [tiles][RADIX]  tag | digit count of the tile
+    uint32_t* lb_incl;        // [tiles][RADIX]  tag | digit count of all tiles up to and including this one
     uint32_t* ticket;
     uint32_t* err;
-    uint32_t parity;  // flips per launch so the look-back words need no re-zeroing
+    uint32_t tag;  // (epoch 1..3) << 30: words carrying another tag are "not written yet", so the
+                   // arrays need no re-zeroing between the passes of one sort
 };
 
 template <int VAL_BYTES>
@@ -133,7 +135,7 @@ struct ValType<4> {
     using type = uint32_t;
 };
 
-// number of predecessor tiles a digit's look-back inspects per round (independent loads)
+// predecessor words a look-back lane keeps in flight at once
 constexpr int LB_BATCH = 8;
 
 template <typename KeyT, int VAL_BYTES, int RADIX_BITS, int BLOCK, int IPT, typename DigitOp, bool FULL>
@@ -142,20 +144,22 @@ __device__ __forceinline__ void onesweep_tile(const OnesweepParams& p, const Dig
     constexpr int RADIX = 1 << RADIX_BITS;
     constexpr int WARPS = BLOCK / 32;
     constexpr int TILE = BLOCK * IPT;
-    constexpr int DPT = (RADIX + BLOCK - 1) / BLOCK;  // digits handled per thread in the prefix phase
+    static_assert(RADIX <= BLOCK, "one thread per digit in the prefix / look-back phases");
     using ValT = typename ValType<VAL_BYTES>::type;
     constexpr int ITEM_BYTES = sizeof(KeyT) > sizeof(ValT) ? sizeof(KeyT) : sizeof(ValT);
 
     KeyT* s_keys = reinterpret_cast<KeyT*>(smem_raw);
     ValT* s_vals = reinterpret_cast<ValT*>(smem_raw);
     uint32_t* s_whist = reinterpret_cast<uint32_t*>(smem_raw + (size_t)ITEM_BYTES * TILE);  // [WARPS][RADIX]
-    uint64_t* s_goff = reinterpret_cast<uint64_t*>(s_whist + WARPS * RADIX);               // [RADIX]
+    uint32_t* s_tbl = s_whist + WARPS * RADIX;                                               // [2][WARPS][RADIX]
+    uint64_t* s_goff = reinterpret_cast<uint64_t*>(s_tbl + 2 * WARPS * RADIX);               // [RADIX]
 
     const int t = threadIdx.x;
     const uint32_t lane = t & 31, warp = t >> 5;
     const uint32_t n_tiles = gridDim.x;
     const uint32_t tile_base = tile * (uint32_t)TILE;
     uint32_t* my_hist = s_whist + warp * RADIX;
+    const uint32_t tag = p.tag;
 
     // ---- 1. load (warp-striped, coalesced) + per-warp digit histogram ------------------------
     const KeyT* keys_in = reinterpret_cast<const KeyT*>(p.keys_in) + tile_base;
@@ -179,118 +183,123 @@ __device__ __forceinline__ void onesweep_tile(const OnesweepParams& p, const Dig
 
     // ---- 2. prefix over warps and digits; publish the tile's digit counts EARLY ----------------
     const uint32_t padding = (uint32_t)TILE - n_valid;
-    const uint32_t fl_agg = ((1u + 2u * p.parity) & 3u) << 30;
-    const uint32_t fl_incl = ((2u + 2u * p.parity) & 3u) << 30;
-    uint32_t cnt[DPT];
-    uint32_t tsum = 0;
-#pragma unroll
-    for (int q = 0; q < DPT; ++q) {
-        const int d = t * DPT + q;
+    const int d = t;  // digit owned by this thread in phases 2 and 4 (if < RADIX)
+    uint32_t cnt = 0;
+    if (d < RADIX) {
         uint32_t run = 0;
-        if (d < RADIX) {
 #pragma unroll
-            for (int w = 0; w < WARPS; ++w) {
-                const uint32_t c = s_whist[w * RADIX + d];
-                s_whist[w * RADIX + d] = run;
-                run += c;
-            }
-            uint32_t c = run;
-            if (!FULL && d == RADIX - 1) c -= padding;
-            st_relaxed_u32(p.lookback + (size_t)tile * RADIX + d, (tile == 0 ? fl_incl : fl_agg) | c);
+        for (int w = 0; w < WARPS; ++w) {
+            const uint32_t c = s_whist[w * RADIX + d];
+            s_whist[w * RADIX + d] = run;
+            run += c;
         }
-        cnt[q] = run;
-        tsum += run;
+        cnt = run;
+        uint32_t c = run;
+        if (!FULL && d == RADIX - 1) c -= padding;
+        st_relaxed_u32(p.lb_agg + (size_t)tile * RADIX + d, tag | c);
+        if (tile == 0) st_relaxed_u32(p.lb_incl + d, tag | c);
     }
     uint32_t total;
-    uint32_t bin_excl = block_excl_scan<BLOCK, uint32_t>(tsum, s_scan, total);
-    uint32_t bexcl[DPT];
+    const uint32_t bin_excl = block_excl_scan<BLOCK, uint32_t>(cnt, s_scan, total);
+    if (d < RADIX) {
+        // fold the digit's tile-local base into every warp's running offset
 #pragma unroll
-    for (int q = 0; q < DPT; ++q) {
-        const int d = t * DPT + q;
-        bexcl[q] = bin_excl;
-        if (d < RADIX) {
-            // fold the digit's tile-local base into every warp's running offset
-#pragma unroll
-            for (int w = 0; w < WARPS; ++w) s_whist[w * RADIX + d] += bin_excl;
-        }
-        bin_excl += cnt[q];
+        for (int w = 0; w < WARPS; ++w) s_whist[w * RADIX + d] += bin_excl;
     }
     __syncthreads();
 
-    // ---- 3. rank inside the warp: ballot matching, offsets already final ------------------------
+    // ---- 3. rank inside the warp.  Lanes holding the same digit find each other through a
+    //         per-warp shared-memory table of lane masks (one atomicOr + one load per key);
+    //         two tables alternate so that the leader's clear never races the next item.
+    //         my_hist[] already holds final tile-local offsets, so slot = offset + rank. ------------
     uint32_t slot[IPT];
     const uint32_t lt = lanemask_lt();
+    const uint32_t my_bit = 1u << lane;
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
-        const uint32_t d = dg[i];
-        uint32_t m = 0xffffffffu;
-#pragma unroll
-        for (int b = 0; b < RADIX_BITS; ++b) {
-            const uint32_t bal = __ballot_sync(0xffffffffu, (d >> b) & 1u);
-            m &= bal ^ (((d >> b) & 1u) - 1u);  // bal where my bit is 1, ~bal where it is 0
-        }
-        const uint32_t lower = __popc(m & lt);
-        uint32_t cur = 0;
-        if (lower == 0) {
-            cur = my_hist[d];
-            my_hist[d] = cur + __popc(m);
-        }
+        uint32_t* tbl = s_tbl + ((i & 1) * WARPS + warp) * RADIX;
+        const uint32_t dd = dg[i];
+        atomicOr(&tbl[dd], my_bit);
         __syncwarp();
-        cur = __shfl_sync(0xffffffffu, cur, __ffs(m) - 1);
-        slot[i] = cur + lower;
+        const uint32_t m = tbl[dd];
+        const uint32_t cur = my_hist[dd];
+        __syncwarp();
+        if ((m & lt) == 0) {  // lowest lane of the group
+            tbl[dd] = 0;
+            my_hist[dd] = cur + __popc(m);
+        }
+        slot[i] = cur + __popc(m & lt);
     }
 
-    // ---- 4. look back (one digit chain per thread, LB_BATCH tiles per round) while the keys
-    //         are being staged into shared memory ----------------------------------------------
+    // ---- 4. stage the keys in shared memory; meanwhile warp g resolves the global base of
+    //         digits 32g..32g+31 by looking back over the preceding tiles -----------------------
 #pragma unroll
     for (int i = 0; i < IPT; ++i) s_keys[slot[i]] = keys[i];
-#pragma unroll
-    for (int q = 0; q < DPT; ++q) {
-        const int d = t * DPT + q;
-        if (d < RADIX) {
-            uint32_t c = cnt[q];
-            if (!FULL && d == RADIX - 1) c -= padding;
-            const uint32_t* lb = p.lookback + d;
-            uint32_t excl = 0;
-            if (tile != 0) {
-                int64_t pt = (int64_t)tile - 1;
-                uint32_t spins = 0;
-                bool done = false;
-                while (!done) {
+    if (d < RADIX) {
+        uint32_t c = cnt;
+        if (!FULL && d == RADIX - 1) c -= padding;
+        uint32_t excl = 0;
+        if (tile != 0) {
+            const uint32_t* agg_rep = p.lb_agg + (warp * 32);   // hint: the warp's first digit
+            const uint32_t* incl_rep = p.lb_incl + (warp * 32);
+            const uint32_t* agg_d = p.lb_agg + d;
+            const uint32_t* incl_d = p.lb_incl + d;
+            int64_t hi = (int64_t)tile - 1;  // newest predecessor not yet accounted for
+            uint32_t spins = 0;
+            while (true) {
+                // lane j inspects predecessor hi-j; tiles before the first one count as
+                // finished with prefix 0
+                const int64_t idx = hi - (int64_t)lane;
+                uint32_t ri = tag, ra = tag;
+                if (idx >= 0) {
+                    ri = ld_relaxed_u32(incl_rep + (size_t)idx * RADIX);
+                    ra = ld_relaxed_u32(agg_rep + (size_t)idx * RADIX);
+                }
+                const bool incl_ok = (ri & ~LB_VALUE_MASK) == tag;
+                const bool agg_ok = (ra & ~LB_VALUE_MASK) == tag;
+                const uint32_t incl_mask = __ballot_sync(0xffffffffu, incl_ok);
+                const uint32_t bad_mask = __ballot_sync(0xffffffffu, !incl_ok && !agg_ok);
+                const uint32_t first_incl = incl_mask ? (uint32_t)__ffs(incl_mask) - 1u : 32u;
+                const uint32_t first_bad = bad_mask ? (uint32_t)__ffs(bad_mask) - 1u : 32u;
+                const uint32_t m_agg = min(first_incl, first_bad);  // tiles hi .. hi-m_agg+1: sum their counts
+                const bool has_incl = first_incl < first_bad;      // then tile hi-first_incl closes the walk
+                uint32_t sum = 0;
+                bool ok = true;
+                for (uint32_t j0 = 0; j0 < m_agg; j0 += LB_BATCH) {
                     uint32_t w[LB_BATCH];
 #pragma unroll
-                    for (int j = 0; j < LB_BATCH; ++j) {
-                        const int64_t idx = pt - j;
-                        w[j] = idx >= 0 ? ld_relaxed_u32(lb + (size_t)idx * RADIX) : fl_incl;
-                    }
-                    int used = 0;
-                    bool stalled = false;
+                    for (int q = 0; q < LB_BATCH; ++q)
+                        w[q] = (j0 + q < m_agg) ? ld_relaxed_u32(agg_d + (size_t)(hi - (int64_t)(j0 + q)) * RADIX) : tag;
 #pragma unroll
-                    for (int j = 0; j < LB_BATCH; ++j) {
-                        const uint32_t f = w[j] & ~LB_VALUE_MASK;
-                        if (!done && !stalled) {
-                            if (f != fl_agg && f != fl_incl) {
-                                stalled = true;
-                            } else {
-                                excl += w[j] & LB_VALUE_MASK;
-                                ++used;
-                                if (f == fl_incl) done = true;
-                            }
-                        }
+                    for (int q = 0; q < LB_BATCH; ++q) {
+                        ok = ok && ((w[q] & ~LB_VALUE_MASK) == tag);
+                        sum += w[q] & LB_VALUE_MASK;
                     }
-                    pt -= used;
-                    if (used == 0 && ++spins > SPIN_LIMIT) {
+                }
+                if (has_incl) {
+                    const int64_t pi = hi - (int64_t)first_incl;
+                    const uint32_t w = pi >= 0 ? ld_relaxed_u32(incl_d + (size_t)pi * RADIX) : tag;
+                    ok = ok && ((w & ~LB_VALUE_MASK) == tag);
+                    sum += w & LB_VALUE_MASK;
+                }
+                // a word of MY digit may not be visible yet although the hint digit's was
+                if (__any_sync(0xffffffffu, !ok) || (m_agg == 0 && !has_incl)) {
+                    if (++spins > SPIN_LIMIT) {
                         atomicExch(p.err, 1u);
                         break;
                     }
+                    continue;
                 }
-                st_relaxed_u32(p.lookback + (size_t)tile * RADIX + d, fl_incl | (excl + c));
+                excl += sum;
+                if (has_incl) break;
+                hi -= m_agg;
             }
-            const uint64_t gbase = p.bins_in[d];
-            // destination of local sorted slot s holding digit d:  s_goff[d] + s
-            s_goff[d] = gbase + excl - bexcl[q];
-            if (p.bins_out && tile == n_tiles - 1) p.bins_out[d] = gbase + excl + c;
+            st_relaxed_u32(p.lb_incl + (size_t)tile * RADIX + d, tag | (excl + c));
         }
+        const uint64_t gbase = p.bins_in[d];
+        // destination of local sorted slot s holding digit d:  s_goff[d] + s
+        s_goff[d] = gbase + excl - bin_excl;
+        if (p.bins_out && tile == n_tiles - 1) p.bins_out[d] = gbase + excl + c;
     }
     __syncthreads();
 
@@ -301,9 +310,9 @@ __device__ __forceinline__ void onesweep_tile(const OnesweepParams& p, const Dig
         const uint32_t s = t + i * BLOCK;
         if (FULL || s < n_valid) {
             const KeyT key = s_keys[s];
-            const uint32_t d = digit_of(key);
-            dg[i] = d;
-            keys_out[s_goff[d] + s] = key;
+            const uint32_t dd = digit_of(key);
+            dg[i] = dd;
+            keys_out[s_goff[dd] + s] = key;
         }
     }
     if constexpr (VAL_BYTES != 0) {
@@ -341,7 +350,7 @@ __global__ void __launch_bounds__(BLOCK) onesweep_kernel(const OnesweepParams p,
 
     const int t = threadIdx.x;
     if (t == 0) s_tile = atomicAdd(p.ticket, 1u);
-    for (int i = t; i < WARPS * RADIX; i += BLOCK) s_whist[i] = 0;
+    for (int i = t; i < 3 * WARPS * RADIX; i += BLOCK) s_whist[i] = 0;  // warp histograms + both match tables
     __syncthreads();
     const uint32_t tile = s_tile;
     if (t == 0 && tile == gridDim.x - 1) *p.ticket = 0;  // every ticket of this launch is taken
@@ -366,7 +375,7 @@ template <typename KeyT, int VB, int RB, int BLOCK, int IPT, typename DigitOp>
 static size_t onesweep_smem() {
     using ValT = typename ValType<VB>::type;
     const size_t item = sizeof(KeyT) > (VB ? sizeof(ValT) : 0) ? sizeof(KeyT) : sizeof(ValT);
-    return item * BLOCK * IPT + (size_t)(BLOCK / 32) * (1 << RB) * 4 + (size_t)(1 << RB) * 8;
+    return item * BLOCK * IPT + (size_t)3 * (BLOCK / 32) * (1 << RB) * 4 + (size_t)(1 << RB) * 8;
 }
 
 template <typename KeyT, int VB, int RB, int BLOCK, int IPT, typename DigitOp>
@@ -405,7 +414,7 @@ static int dispatch_onesweep(int cfg, int key_bytes, int val_bytes, const Oneswe
     return launch_onesweep<u128, 8, 8, 256, 8>(p, op, st);
 }
 
-int g_sort_config = 0;
+int g_sort_config = 3;  // 256 threads x 24 keys: best measured on B200 (profiles/)
 int g_time_passes = 0;  // kmg_set_option("time_passes", 1): bracket every pass launch with events
 thread_local int64_t g_stat_sort_passes = 0;
 
@@ -479,7 +488,8 @@ struct SortWs {
     WsHeader* hdr;
     unsigned long long* hist;  // [MAX_PASSES][RADIX]
     uint64_t* bins;            // [MAX_PASSES][2][RADIX]
-    uint32_t* lookback;        // [tiles_per_part][RADIX]
+    uint32_t* lookback;        // [2][tiles_per_part][RADIX]: counts, then inclusive prefixes
+    size_t lb_words;           // words per array
     size_t total;
 };
 
@@ -496,7 +506,8 @@ static SortWs carve_sort_ws(void* ws, uint64_t n, int key_bytes) {
     const uint64_t part = n < PART_MAX ? n : PART_MAX;
     const uint64_t min_tile = key_bytes == 16 ? 2048 : 4096;  // smallest tile of any configuration
     const uint64_t tiles = (part + min_tile - 1) / min_tile + 1;
-    p += align_up(tiles * SORT_RADIX * sizeof(uint32_t), 256);
+    w.lb_words = align_up(tiles * SORT_RADIX * sizeof(uint32_t), 256) / sizeof(uint32_t);
+    p += 2 * w.lb_words * sizeof(uint32_t);
     w.total = p - (char*)ws;
     return w;
 }
@@ -536,7 +547,7 @@ extern "C" int kmg_radix_sort(void* d_keys, void* d_keys_alt, void* d_vals, void
     const int cfg = g_sort_config;
     const uint64_t n_parts = (n + PART_MAX - 1) / PART_MAX;
 
-    // header + hist zero; look-back words zero once (parity trick) -- see OnesweepParams::parity
+    // header + hist zero; look-back words zero once per sort -- see OnesweepParams::tag
     KMG_CUDA(cudaMemsetAsync(d_ws, 0, w.total, st));
 
     int dev = 0, sms = 148;
@@ -572,16 +583,19 @@ extern "C" int kmg_radix_sort(void* d_keys, void* d_keys_alt, void* d_vals, void
             uint64_t* bins = w.bins + (size_t)pass * 2 * SORT_RADIX;
             p.bins_in = bins + (part & 1) * SORT_RADIX;
             p.bins_out = (part + 1 < n_parts) ? bins + ((part + 1) & 1) * SORT_RADIX : nullptr;
-            p.lookback = w.lookback;
+            p.lb_agg = w.lookback;
+            p.lb_incl = w.lookback + w.lb_words;
             p.ticket = &w.hdr->ticket;
             p.err = &w.hdr->err;
             if (n_parts > 1) {
                 // tile counts differ between parts, so stale words could alias: re-zero
                 if (launch > 0)
                     KMG_CUDA(cudaMemsetAsync(w.lookback, 0, (char*)d_ws + w.total - (char*)w.lookback, st));
-                p.parity = 0;
+                p.tag = 1u << 30;
             } else {
-                p.parity = launch & 1u;
+                // every word is rewritten by every launch, so a 3-cycle of tags tells the
+                // current launch's words from the two previous launches' (and from zero)
+                p.tag = (launch % 3u + 1u) << 30;
             }
             if (g_ev_used >= MAX_TIMED) timing_collect();
             timing_begin(st);
@@ -641,10 +655,11 @@ extern "C" int kmg_range_partition(const void* d_keys, const void* d_vals, uint6
         p.n = (uint32_t)std::min<uint64_t>(PART_MAX, n - off);
         p.bins_in = w.bins + (part & 1) * SORT_RADIX;
         p.bins_out = (part + 1 < n_lb_parts) ? w.bins + ((part + 1) & 1) * SORT_RADIX : nullptr;
-        p.lookback = w.lookback;
+        p.lb_agg = w.lookback;
+        p.lb_incl = w.lookback + w.lb_words;
         p.ticket = &w.hdr->ticket;
         p.err = &w.hdr->err;
-        p.parity = 0;
+        p.tag = 1u << 30;
         if (part > 0) KMG_CUDA(cudaMemsetAsync(w.lookback, 0, (char*)d_ws + w.total - (char*)w.lookback, st));
         int rcode = dispatch_onesweep(g_sort_config, key_bytes, val_bytes, p, op, st);
         if (rcode != KMG_OK) return rcode;
