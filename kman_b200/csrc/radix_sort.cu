@@ -118,8 +118,8 @@ struct OnesweepParams {
     uint32_t n;  // keys in this part (< 2^30)
     const uint64_t* bins_in;  // [RADIX] global base of each digit run for this part
     uint64_t* bins_out;       // [RADIX] base for the next part (may be null)
-    uint32_t* lb_agg;         // [tiles][RADIX]  tag | digit count of the tile
-    uint32_t* lb_incl;        // [tiles][RADIX]  tag | digit count of all tiles up to and including this one
+    uint32_t* lb_agg;         // [tiles][RADIX]   tag | digit count of the tile
+    uint32_t* lb_ginc;        // [groups][RADIX]  tag | digit count of all tiles up to the END of the group
     uint32_t* ticket;
     uint32_t* err;
     uint32_t tag;  // (epoch 1..3) << 30: words carrying another tag are "not written yet", so the
@@ -135,15 +135,60 @@ struct ValType<4> {
     using type = uint32_t;
 };
 
-// predecessor words a look-back lane keeps in flight at once
-constexpr int LB_BATCH = 8;
+// Two-level look-back.  Tiles form groups of LB_GROUP consecutive tiles.  A tile's exclusive
+// prefix = (inclusive prefix of the previous GROUP) + (counts of the earlier tiles of its own
+// group).  Tile counts are published early in every tile's life and depend on nothing, so the
+// only dependency chain runs over the groups' last tiles, which resolve their prefix EARLY
+// (right after publishing their counts): one link per LB_GROUP tiles instead of one per tile.
+// Every word carries the launch's 2-bit tag; a word with another tag has not been written yet.
+constexpr uint32_t LB_GROUP = 32;
+constexpr int LB_BATCH = 16;  // loads a thread keeps in flight
 
-template <typename KeyT, int VAL_BYTES, int RADIX_BITS, int BLOCK, int IPT, typename DigitOp, bool FULL>
+__device__ __forceinline__ uint32_t lookback_two_level(const uint32_t* __restrict__ lb_agg,
+                                                       const uint32_t* __restrict__ lb_ginc, uint32_t tile, int d,
+                                                       int radix, uint32_t tag, uint32_t* err) {
+    const uint32_t g = tile / LB_GROUP, r = tile % LB_GROUP;
+    uint32_t excl = 0, spins = 0;
+    const uint32_t* gsrc = lb_ginc + (size_t)(g ? g - 1 : 0) * radix + d;
+    uint32_t gw = g ? ld_relaxed_u32(gsrc) : tag;  // issued first: it is the one that may lag
+    const uint32_t* row = lb_agg + (size_t)tile * radix + d;
+    for (uint32_t j0 = 1; j0 <= r; j0 += LB_BATCH) {
+        uint32_t w[LB_BATCH];
+#pragma unroll
+        for (int q = 0; q < LB_BATCH; ++q) w[q] = (j0 + q <= r) ? ld_relaxed_u32(row - (size_t)(j0 + q) * radix) : tag;
+#pragma unroll
+        for (int q = 0; q < LB_BATCH; ++q) {
+            while ((w[q] & ~LB_VALUE_MASK) != tag) {
+                if (++spins > SPIN_LIMIT) {
+                    atomicExch(err, 1u);
+                    w[q] = tag;
+                    break;
+                }
+                w[q] = ld_relaxed_u32(row - (size_t)(j0 + q) * radix);
+            }
+            excl += w[q] & LB_VALUE_MASK;
+        }
+    }
+    while ((gw & ~LB_VALUE_MASK) != tag) {
+        if (++spins > SPIN_LIMIT) {
+            atomicExch(err, 1u);
+            gw = tag;
+            break;
+        }
+        gw = ld_relaxed_u32(gsrc);
+    }
+    return excl + (gw & LB_VALUE_MASK);
+}
+
+// MIX: how a warp finds the lanes that hold the same digit
+//   0 = 8 ballots per key (ALU), 1 = shared-memory lane-mask table (LSU), 2 = alternate per item
+template <typename KeyT, int VAL_BYTES, int RADIX_BITS, int BLOCK, int IPT, int MIX, typename DigitOp, bool FULL>
 __device__ __forceinline__ void onesweep_tile(const OnesweepParams& p, const DigitOp& digit_of, unsigned char* smem_raw,
                                               uint32_t* s_scan, const uint32_t tile, const uint32_t n_valid) {
     constexpr int RADIX = 1 << RADIX_BITS;
     constexpr int WARPS = BLOCK / 32;
     constexpr int TILE = BLOCK * IPT;
+    constexpr int NTBL = MIX == 0 ? 0 : (MIX == 1 ? 2 : 1);
     static_assert(RADIX <= BLOCK, "one thread per digit in the prefix / look-back phases");
     using ValT = typename ValType<VAL_BYTES>::type;
     constexpr int ITEM_BYTES = sizeof(KeyT) > sizeof(ValT) ? sizeof(KeyT) : sizeof(ValT);
@@ -151,8 +196,8 @@ __device__ __forceinline__ void onesweep_tile(const OnesweepParams& p, const Dig
     KeyT* s_keys = reinterpret_cast<KeyT*>(smem_raw);
     ValT* s_vals = reinterpret_cast<ValT*>(smem_raw);
     uint32_t* s_whist = reinterpret_cast<uint32_t*>(smem_raw + (size_t)ITEM_BYTES * TILE);  // [WARPS][RADIX]
-    uint32_t* s_tbl = s_whist + WARPS * RADIX;                                               // [2][WARPS][RADIX]
-    uint64_t* s_goff = reinterpret_cast<uint64_t*>(s_tbl + 2 * WARPS * RADIX);               // [RADIX]
+    uint32_t* s_tbl = s_whist + WARPS * RADIX;                                               // [NTBL][WARPS][RADIX]
+    uint64_t* s_goff = reinterpret_cast<uint64_t*>(s_tbl + NTBL * WARPS * RADIX);            // [RADIX]
 
     const int t = threadIdx.x;
     const uint32_t lane = t & 31, warp = t >> 5;
@@ -197,105 +242,70 @@ __device__ __forceinline__ void onesweep_tile(const OnesweepParams& p, const Dig
         uint32_t c = run;
         if (!FULL && d == RADIX - 1) c -= padding;
         st_relaxed_u32(p.lb_agg + (size_t)tile * RADIX + d, tag | c);
-        if (tile == 0) st_relaxed_u32(p.lb_incl + d, tag | c);
     }
     uint32_t total;
     const uint32_t bin_excl = block_excl_scan<BLOCK, uint32_t>(cnt, s_scan, total);
+    const bool group_end = tile % LB_GROUP == LB_GROUP - 1;
+    uint32_t excl = 0;
     if (d < RADIX) {
         // fold the digit's tile-local base into every warp's running offset
 #pragma unroll
         for (int w = 0; w < WARPS; ++w) s_whist[w * RADIX + d] += bin_excl;
+        if (group_end) {  // the chain link: resolve and publish the group's inclusive prefix now
+            uint32_t c = cnt;
+            if (!FULL && d == RADIX - 1) c -= padding;
+            excl = lookback_two_level(p.lb_agg, p.lb_ginc, tile, d, RADIX, tag, p.err);
+            st_relaxed_u32(p.lb_ginc + (size_t)(tile / LB_GROUP) * RADIX + d, tag | (excl + c));
+        }
     }
     __syncthreads();
 
-    // ---- 3. rank inside the warp.  Lanes holding the same digit find each other through a
-    //         per-warp shared-memory table of lane masks (one atomicOr + one load per key);
-    //         two tables alternate so that the leader's clear never races the next item.
-    //         my_hist[] already holds final tile-local offsets, so slot = offset + rank. ------------
+    // ---- 3. rank inside the warp; my_hist[] already holds final tile-local offsets, so
+    //         slot = offset + rank among the same-digit lanes.  The lanes holding the same digit
+    //         are found either with 8 ballots (ALU) or through a shared-memory table of lane
+    //         masks (one atomicOr + one load per key, LSU); mixing both keeps either pipe off
+    //         its limit (profiles/r01_ncu_summary.md). ------------------------------------------
     uint32_t slot[IPT];
     const uint32_t lt = lanemask_lt();
     const uint32_t my_bit = 1u << lane;
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
-        uint32_t* tbl = s_tbl + ((i & 1) * WARPS + warp) * RADIX;
         const uint32_t dd = dg[i];
-        atomicOr(&tbl[dd], my_bit);
-        __syncwarp();
-        const uint32_t m = tbl[dd];
-        const uint32_t cur = my_hist[dd];
-        __syncwarp();
-        if ((m & lt) == 0) {  // lowest lane of the group
-            tbl[dd] = 0;
-            my_hist[dd] = cur + __popc(m);
+        const bool use_table = MIX == 1 || (MIX == 2 && (i & 1));
+        uint32_t m, cur;
+        if (use_table) {
+            uint32_t* tbl = s_tbl + ((MIX == 1 ? (i & 1) : 0) * WARPS + warp) * RADIX;
+            atomicOr(&tbl[dd], my_bit);
+            __syncwarp();
+            m = tbl[dd];
+            cur = my_hist[dd];
+            __syncwarp();
+            if ((m & lt) == 0) {  // lowest lane of the group
+                tbl[dd] = 0;
+                my_hist[dd] = cur + __popc(m);
+            }
+        } else {
+            m = 0xffffffffu;
+#pragma unroll
+            for (int b = 0; b < RADIX_BITS; ++b) {
+                const uint32_t bal = __ballot_sync(0xffffffffu, (dd >> b) & 1u);
+                m &= bal ^ (((dd >> b) & 1u) - 1u);  // bal where my bit is 1, ~bal where it is 0
+            }
+            __syncwarp();  // the previous item's leader update is visible
+            cur = my_hist[dd];
+            __syncwarp();  // everyone has read before the leader overwrites
+            if ((m & lt) == 0) my_hist[dd] = cur + __popc(m);
         }
         slot[i] = cur + __popc(m & lt);
     }
 
-    // ---- 4. stage the keys in shared memory; meanwhile warp g resolves the global base of
-    //         digits 32g..32g+31 by looking back over the preceding tiles -----------------------
+    // ---- 4. stage the keys in shared memory; every digit's thread resolves its global base ---------
 #pragma unroll
     for (int i = 0; i < IPT; ++i) s_keys[slot[i]] = keys[i];
     if (d < RADIX) {
         uint32_t c = cnt;
         if (!FULL && d == RADIX - 1) c -= padding;
-        uint32_t excl = 0;
-        if (tile != 0) {
-            const uint32_t* agg_rep = p.lb_agg + (warp * 32);   // hint: the warp's first digit
-            const uint32_t* incl_rep = p.lb_incl + (warp * 32);
-            const uint32_t* agg_d = p.lb_agg + d;
-            const uint32_t* incl_d = p.lb_incl + d;
-            int64_t hi = (int64_t)tile - 1;  // newest predecessor not yet accounted for
-            uint32_t spins = 0;
-            while (true) {
-                // lane j inspects predecessor hi-j; tiles before the first one count as
-                // finished with prefix 0
-                const int64_t idx = hi - (int64_t)lane;
-                uint32_t ri = tag, ra = tag;
-                if (idx >= 0) {
-                    ri = ld_relaxed_u32(incl_rep + (size_t)idx * RADIX);
-                    ra = ld_relaxed_u32(agg_rep + (size_t)idx * RADIX);
-                }
-                const bool incl_ok = (ri & ~LB_VALUE_MASK) == tag;
-                const bool agg_ok = (ra & ~LB_VALUE_MASK) == tag;
-                const uint32_t incl_mask = __ballot_sync(0xffffffffu, incl_ok);
-                const uint32_t bad_mask = __ballot_sync(0xffffffffu, !incl_ok && !agg_ok);
-                const uint32_t first_incl = incl_mask ? (uint32_t)__ffs(incl_mask) - 1u : 32u;
-                const uint32_t first_bad = bad_mask ? (uint32_t)__ffs(bad_mask) - 1u : 32u;
-                const uint32_t m_agg = min(first_incl, first_bad);  // tiles hi .. hi-m_agg+1: sum their counts
-                const bool has_incl = first_incl < first_bad;      // then tile hi-first_incl closes the walk
-                uint32_t sum = 0;
-                bool ok = true;
-                for (uint32_t j0 = 0; j0 < m_agg; j0 += LB_BATCH) {
-                    uint32_t w[LB_BATCH];
-#pragma unroll
-                    for (int q = 0; q < LB_BATCH; ++q)
-                        w[q] = (j0 + q < m_agg) ? ld_relaxed_u32(agg_d + (size_t)(hi - (int64_t)(j0 + q)) * RADIX) : tag;
-#pragma unroll
-                    for (int q = 0; q < LB_BATCH; ++q) {
-                        ok = ok && ((w[q] & ~LB_VALUE_MASK) == tag);
-                        sum += w[q] & LB_VALUE_MASK;
-                    }
-                }
-                if (has_incl) {
-                    const int64_t pi = hi - (int64_t)first_incl;
-                    const uint32_t w = pi >= 0 ? ld_relaxed_u32(incl_d + (size_t)pi * RADIX) : tag;
-                    ok = ok && ((w & ~LB_VALUE_MASK) == tag);
-                    sum += w & LB_VALUE_MASK;
-                }
-                // a word of MY digit may not be visible yet although the hint digit's was
-                if (__any_sync(0xffffffffu, !ok) || (m_agg == 0 && !has_incl)) {
-                    if (++spins > SPIN_LIMIT) {
-                        atomicExch(p.err, 1u);
-                        break;
-                    }
-                    continue;
-                }
-                excl += sum;
-                if (has_incl) break;
-                hi -= m_agg;
-            }
-            st_relaxed_u32(p.lb_incl + (size_t)tile * RADIX + d, tag | (excl + c));
-        }
+        if (!group_end && tile != 0) excl = lookback_two_level(p.lb_agg, p.lb_ginc, tile, d, RADIX, tag, p.err);
         const uint64_t gbase = p.bins_in[d];
         // destination of local sorted slot s holding digit d:  s_goff[d] + s
         s_goff[d] = gbase + excl - bin_excl;
@@ -336,11 +346,15 @@ __device__ __forceinline__ void onesweep_tile(const OnesweepParams& p, const Dig
     }
 }
 
-template <typename KeyT, int VAL_BYTES, int RADIX_BITS, int BLOCK, int IPT, typename DigitOp>
-__global__ void __launch_bounds__(BLOCK) onesweep_kernel(const OnesweepParams p, const DigitOp digit_of) {
+// resident CTAs per SM the register allocation aims for
+constexpr int min_ctas(int block, int ipt) { return block == 256 ? (ipt <= 16 ? 3 : 2) : 2; }
+
+template <typename KeyT, int VAL_BYTES, int RADIX_BITS, int BLOCK, int IPT, int MIX, typename DigitOp>
+__global__ void __launch_bounds__(BLOCK, min_ctas(BLOCK, IPT)) onesweep_kernel(const OnesweepParams p, const DigitOp digit_of) {
     constexpr int RADIX = 1 << RADIX_BITS;
     constexpr int WARPS = BLOCK / 32;
     constexpr int TILE = BLOCK * IPT;
+    constexpr int NTBL = MIX == 0 ? 0 : (MIX == 1 ? 2 : 1);
     using ValT = typename ValType<VAL_BYTES>::type;
     constexpr int ITEM_BYTES = sizeof(KeyT) > sizeof(ValT) ? sizeof(KeyT) : sizeof(ValT);
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -350,38 +364,39 @@ __global__ void __launch_bounds__(BLOCK) onesweep_kernel(const OnesweepParams p,
 
     const int t = threadIdx.x;
     if (t == 0) s_tile = atomicAdd(p.ticket, 1u);
-    for (int i = t; i < 3 * WARPS * RADIX; i += BLOCK) s_whist[i] = 0;  // warp histograms + both match tables
+    for (int i = t; i < (1 + NTBL) * WARPS * RADIX; i += BLOCK) s_whist[i] = 0;  // warp histograms + match tables
     __syncthreads();
     const uint32_t tile = s_tile;
     if (t == 0 && tile == gridDim.x - 1) *p.ticket = 0;  // every ticket of this launch is taken
     const uint32_t n_valid = min((uint32_t)TILE, p.n - tile * (uint32_t)TILE);
     if (n_valid == (uint32_t)TILE)
-        onesweep_tile<KeyT, VAL_BYTES, RADIX_BITS, BLOCK, IPT, DigitOp, true>(p, digit_of, smem_raw, s_scan, tile, n_valid);
+        onesweep_tile<KeyT, VAL_BYTES, RADIX_BITS, BLOCK, IPT, MIX, DigitOp, true>(p, digit_of, smem_raw, s_scan, tile, n_valid);
     else
-        onesweep_tile<KeyT, VAL_BYTES, RADIX_BITS, BLOCK, IPT, DigitOp, false>(p, digit_of, smem_raw, s_scan, tile, n_valid);
+        onesweep_tile<KeyT, VAL_BYTES, RADIX_BITS, BLOCK, IPT, MIX, DigitOp, false>(p, digit_of, smem_raw, s_scan, tile, n_valid);
 }
 
 // ---- tile configurations ----------------------------------------------------------------------
 struct SortTile {
-    int radix_bits, block, ipt;
+    int block, ipt, mix;
 };
-// index = kmg_set_option("sort_config", i); entry 0 is the default.
+// index = kmg_set_option("sort_config", i)
 static const SortTile kSortTiles[] = {
-    {8, 256, 16}, {8, 384, 12}, {8, 512, 8}, {8, 256, 24}, {8, 512, 12},
+    {256, 16, 2}, {256, 16, 0}, {256, 16, 1}, {256, 24, 2}, {512, 16, 2}, {512, 16, 0}, {384, 16, 2}, {256, 24, 0},
 };
 constexpr int kNumSortTiles = sizeof(kSortTiles) / sizeof(kSortTiles[0]);
 
-template <typename KeyT, int VB, int RB, int BLOCK, int IPT, typename DigitOp>
+template <typename KeyT, int VB, int RB, int BLOCK, int IPT, int MIX>
 static size_t onesweep_smem() {
     using ValT = typename ValType<VB>::type;
     const size_t item = sizeof(KeyT) > (VB ? sizeof(ValT) : 0) ? sizeof(KeyT) : sizeof(ValT);
-    return item * BLOCK * IPT + (size_t)3 * (BLOCK / 32) * (1 << RB) * 4 + (size_t)(1 << RB) * 8;
+    const int ntbl = MIX == 0 ? 0 : (MIX == 1 ? 2 : 1);
+    return item * BLOCK * IPT + (size_t)(1 + ntbl) * (BLOCK / 32) * (1 << RB) * 4 + (size_t)(1 << RB) * 8;
 }
 
-template <typename KeyT, int VB, int RB, int BLOCK, int IPT, typename DigitOp>
+template <typename KeyT, int VB, int RB, int BLOCK, int IPT, int MIX, typename DigitOp>
 static int launch_onesweep(const OnesweepParams& p, const DigitOp& op, cudaStream_t st) {
-    auto kern = onesweep_kernel<KeyT, VB, RB, BLOCK, IPT, DigitOp>;
-    const size_t smem = onesweep_smem<KeyT, VB, RB, BLOCK, IPT, DigitOp>();
+    auto kern = onesweep_kernel<KeyT, VB, RB, BLOCK, IPT, MIX, DigitOp>;
+    const size_t smem = onesweep_smem<KeyT, VB, RB, BLOCK, IPT, MIX>();
     KMG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t tiles = (p.n + BLOCK * IPT - 1) / (BLOCK * IPT);
     kern<<<tiles, BLOCK, smem, st>>>(p, op);
@@ -389,15 +404,23 @@ static int launch_onesweep(const OnesweepParams& p, const DigitOp& op, cudaStrea
     return KMG_OK;
 }
 
-template <typename KeyT, int VB, typename DigitOp>
-static int dispatch_tile(int cfg, const OnesweepParams& p, const DigitOp& op, cudaStream_t st) {
+template <typename KeyT, int VB>
+static int dispatch_tile(int cfg, const OnesweepParams& p, const ShiftDigit& op, cudaStream_t st) {
     switch (cfg) {
-        case 1: return launch_onesweep<KeyT, VB, 8, 384, 12>(p, op, st);
-        case 2: return launch_onesweep<KeyT, VB, 8, 512, 8>(p, op, st);
-        case 3: return launch_onesweep<KeyT, VB, 8, 256, 24>(p, op, st);
-        case 4: return launch_onesweep<KeyT, VB, 8, 512, 12>(p, op, st);
-        default: return launch_onesweep<KeyT, VB, 8, 256, 16>(p, op, st);
+        case 1: return launch_onesweep<KeyT, VB, 8, 256, 16, 0>(p, op, st);
+        case 2: return launch_onesweep<KeyT, VB, 8, 256, 16, 1>(p, op, st);
+        case 3: return launch_onesweep<KeyT, VB, 8, 256, 24, 2>(p, op, st);
+        case 4: return launch_onesweep<KeyT, VB, 8, 512, 16, 2>(p, op, st);
+        case 5: return launch_onesweep<KeyT, VB, 8, 512, 16, 0>(p, op, st);
+        case 6: return launch_onesweep<KeyT, VB, 8, 384, 16, 2>(p, op, st);
+        case 7: return launch_onesweep<KeyT, VB, 8, 256, 24, 0>(p, op, st);
+        default: return launch_onesweep<KeyT, VB, 8, 256, 16, 2>(p, op, st);
     }
+}
+// the partition pass runs once per exchange: one configuration is enough
+template <typename KeyT, int VB>
+static int dispatch_tile(int, const OnesweepParams& p, const RangeDigit& op, cudaStream_t st) {
+    return launch_onesweep<KeyT, VB, 8, 256, 16, 2>(p, op, st);
 }
 
 template <typename DigitOp>
@@ -408,13 +431,13 @@ static int dispatch_onesweep(int cfg, int key_bytes, int val_bytes, const Oneswe
         if (val_bytes == 4) return dispatch_tile<uint64_t, 4>(cfg, p, op, st);
         return dispatch_tile<uint64_t, 8>(cfg, p, op, st);
     }
-    // 16-byte keys: halve the items per thread by using the narrower configurations only
-    if (val_bytes == 0) return launch_onesweep<u128, 0, 8, 256, 8>(p, op, st);
-    if (val_bytes == 4) return launch_onesweep<u128, 4, 8, 256, 8>(p, op, st);
-    return launch_onesweep<u128, 8, 8, 256, 8>(p, op, st);
+    // 16-byte keys: half the items per thread
+    if (val_bytes == 0) return launch_onesweep<u128, 0, 8, 256, 8, 2>(p, op, st);
+    if (val_bytes == 4) return launch_onesweep<u128, 4, 8, 256, 8, 2>(p, op, st);
+    return launch_onesweep<u128, 8, 8, 256, 8, 2>(p, op, st);
 }
 
-int g_sort_config = 3;  // 256 threads x 24 keys: best measured on B200 (profiles/)
+int g_sort_config = 0;
 int g_time_passes = 0;  // kmg_set_option("time_passes", 1): bracket every pass launch with events
 thread_local int64_t g_stat_sort_passes = 0;
 
@@ -488,8 +511,8 @@ struct SortWs {
     WsHeader* hdr;
     unsigned long long* hist;  // [MAX_PASSES][RADIX]
     uint64_t* bins;            // [MAX_PASSES][2][RADIX]
-    uint32_t* lookback;        // [2][tiles_per_part][RADIX]: counts, then inclusive prefixes
-    size_t lb_words;           // words per array
+    uint32_t* lookback;        // [tiles_per_part][RADIX] tile counts, then [groups][RADIX] group prefixes
+    size_t lb_words;           // words of the tile-count array
     size_t total;
 };
 
@@ -507,7 +530,7 @@ static SortWs carve_sort_ws(void* ws, uint64_t n, int key_bytes) {
     const uint64_t min_tile = key_bytes == 16 ? 2048 : 4096;  // smallest tile of any configuration
     const uint64_t tiles = (part + min_tile - 1) / min_tile + 1;
     w.lb_words = align_up(tiles * SORT_RADIX * sizeof(uint32_t), 256) / sizeof(uint32_t);
-    p += 2 * w.lb_words * sizeof(uint32_t);
+    p += w.lb_words * sizeof(uint32_t) + align_up((tiles / LB_GROUP + 2) * SORT_RADIX * sizeof(uint32_t), 256);
     w.total = p - (char*)ws;
     return w;
 }
@@ -584,7 +607,7 @@ extern "C" int kmg_radix_sort(void* d_keys, void* d_keys_alt, void* d_vals, void
             p.bins_in = bins + (part & 1) * SORT_RADIX;
             p.bins_out = (part + 1 < n_parts) ? bins + ((part + 1) & 1) * SORT_RADIX : nullptr;
             p.lb_agg = w.lookback;
-            p.lb_incl = w.lookback + w.lb_words;
+            p.lb_ginc = w.lookback + w.lb_words;
             p.ticket = &w.hdr->ticket;
             p.err = &w.hdr->err;
             if (n_parts > 1) {
@@ -656,7 +679,7 @@ extern "C" int kmg_range_partition(const void* d_keys, const void* d_vals, uint6
         p.bins_in = w.bins + (part & 1) * SORT_RADIX;
         p.bins_out = (part + 1 < n_lb_parts) ? w.bins + ((part + 1) & 1) * SORT_RADIX : nullptr;
         p.lb_agg = w.lookback;
-        p.lb_incl = w.lookback + w.lb_words;
+        p.lb_ginc = w.lookback + w.lb_words;
         p.ticket = &w.hdr->ticket;
         p.err = &w.hdr->err;
         p.tag = 1u << 30;

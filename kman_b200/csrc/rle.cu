@@ -29,39 +29,6 @@ __device__ __forceinline__ u128 shfl_key<u128>(const u128& k, int src) {
     return u128{__shfl_sync(0xffffffffu, k.lo, src), __shfl_sync(0xffffffffu, k.hi, src)};
 }
 
-// Loads the warp's chunk (IPT steps of 32 consecutive keys starting at `first`) and returns
-// the extended head ballots: bit l of hb[j] is set iff element idx = first + 32*j + l starts
-// a run, where idx == n counts as a head (end sentinel) and idx > n does not.
-// hnext = head flag of the element right after the chunk.
-template <typename KeyT, int IPT>
-__device__ __forceinline__ void load_heads(const KeyT* __restrict__ keys_in, uint64_t n, uint64_t first,
-                                           KeyT (&keys)[IPT], uint32_t (&hb)[IPT], uint32_t& hnext) {
-    const uint32_t lane = lane_id();
-#pragma unroll
-    for (int j = 0; j < IPT; ++j) {
-        const uint64_t idx = first + 32 * j + lane;
-        keys[j] = idx < n ? keys_in[idx] : KeyT{};
-    }
-    KeyT before = KeyT{};
-    if (lane == 0 && first > 0 && first <= n) before = keys_in[first - 1];
-#pragma unroll
-    for (int j = 0; j < IPT; ++j) {
-        const uint64_t idx = first + 32 * j + lane;
-        KeyT prev = shfl_key(keys[j], (int)lane - 1);
-        if (lane == 0) prev = before;
-        const bool head = (idx < n && (idx == 0 || keys[j] != prev)) || idx == n;
-        hb[j] = __ballot_sync(0xffffffffu, head);
-        before = shfl_key(keys[j], 31);  // only lane 0 uses it
-    }
-    const uint64_t nidx = first + 32 * IPT;
-    uint32_t h = 0;
-    if (lane == 0) {
-        if (nidx == n) h = 1;
-        else if (nidx < n) h = keys_in[nidx] != before ? 1u : 0u;
-    }
-    hnext = __shfl_sync(0xffffffffu, h, 0);
-}
-
 struct RleParams {
     const void* keys_in;
     const void* vals_in;
@@ -71,42 +38,76 @@ struct RleParams {
     uint32_t* counts_out;
     unsigned long long* n_out;
     uint64_t* state_a;  // flag | heads
-    uint64_t* state_b;  // last head position + 1 (0 = none)
+    uint64_t* state_b;  // flag | last head position + 1 (0 = none)
     uint32_t* ticket;
     uint32_t* err;
 };
 
-template <typename KeyT, int IPT>
-__global__ void __launch_bounds__(RLE_BLOCK) rle_count_kernel(const RleParams p) {
-    constexpr int TILE = RLE_BLOCK * IPT;
-    __shared__ uint32_t s_hpos[TILE];  // local position of the i-th head of the tile
-    __shared__ uint32_t s_wheads[RLE_WARPS];
-    __shared__ uint32_t s_tile;
-    __shared__ uint64_t s_excl_heads, s_carry;
+// lanes of step j whose element exists (tile-local index < n_local)
+__device__ __forceinline__ uint32_t valid_mask(uint32_t step_first, uint32_t n_local) {
+    if (step_first >= n_local) return 0u;
+    const uint32_t left = n_local - step_first;
+    return left >= 32 ? 0xffffffffu : ((1u << left) - 1u);
+}
 
+// Loads the warp's chunk (IPT steps of 32 consecutive keys starting at tile-local index
+// `wfirst`) and returns the extended head ballots: bit l of hb[j] is set iff element
+// wfirst + 32*j + l starts a run, where the element one past the end of the whole array counts
+// as a head (end sentinel) and anything beyond does not.  hnext = head flag of the element
+// right after the chunk.  FULL: every element of the tile exists.
+template <typename KeyT, int IPT, bool FULL>
+__device__ __forceinline__ void load_heads(const KeyT* __restrict__ kin, uint64_t tile_base, uint32_t n_local,
+                                           bool more_after_tile, uint32_t wfirst, KeyT (&keys)[IPT],
+                                           uint32_t (&hb)[IPT], uint32_t& hnext) {
+    const uint32_t lane = lane_id();
+#pragma unroll
+    for (int j = 0; j < IPT; ++j) {
+        const uint32_t li = wfirst + 32 * j + lane;
+        keys[j] = (FULL || li < n_local) ? kin[li] : KeyT{};
+    }
+    const bool first_of_all = tile_base == 0 && wfirst == 0;
+    KeyT before = KeyT{};
+    if (lane == 0 && !first_of_all && (FULL || wfirst <= n_local)) before = *(kin + wfirst - 1);
+#pragma unroll
+    for (int j = 0; j < IPT; ++j) {
+        const uint32_t li = wfirst + 32 * j + lane;
+        KeyT prev = shfl_key(keys[j], (int)lane - 1);
+        if (lane == 0) prev = before;
+        bool head = keys[j] != prev || (first_of_all && j == 0 && lane == 0);
+        if (!FULL) head = (li < n_local && head) || li == n_local;
+        hb[j] = __ballot_sync(0xffffffffu, head);
+        before = shfl_key(keys[j], 31);  // only lane 0 uses it
+    }
+    const uint32_t nli = wfirst + 32 * IPT;
+    uint32_t h = 0;
+    if (lane == 0) {
+        if (nli < n_local || (nli == n_local && more_after_tile)) h = kin[nli] != before ? 1u : 0u;
+        else if (nli == n_local) h = 1;  // end of the array
+    }
+    hnext = __shfl_sync(0xffffffffu, h, 0);
+}
+
+template <typename KeyT, int IPT, bool FULL>
+__device__ __forceinline__ void rle_count_tile(const RleParams& p, const uint32_t tile, uint32_t* s_hpos,
+                                               uint32_t* s_wheads, uint64_t* s_bcast) {
+    constexpr int TILE = RLE_BLOCK * IPT;
     const int t = threadIdx.x;
     const uint32_t lane = t & 31, warp = t >> 5;
-    if (t == 0) s_tile = atomicAdd(p.ticket, 1u);
-    __syncthreads();
-    const uint32_t tile = s_tile;
     const uint64_t tile_base = (uint64_t)tile * TILE;
-    const uint64_t first = tile_base + (uint64_t)warp * 32 * IPT;
-    const KeyT* keys_in = reinterpret_cast<const KeyT*>(p.keys_in);
+    const uint32_t n_local = FULL ? (uint32_t)TILE : (uint32_t)(p.n - tile_base);
+    const bool more_after = tile_base + TILE < p.n;
+    const uint32_t wfirst = warp * 32 * IPT;
+    const KeyT* kin = reinterpret_cast<const KeyT*>(p.keys_in) + tile_base;
 
     KeyT keys[IPT];
     uint32_t hb[IPT];
     uint32_t hnext;
-    load_heads<KeyT, IPT>(keys_in, p.n, first, keys, hb, hnext);
+    load_heads<KeyT, IPT, FULL>(kin, tile_base, n_local, more_after, wfirst, keys, hb, hnext);
 
-    // heads that are real elements (idx < n)
+    // real heads per warp -> tile-local ordinals
     uint32_t wheads = 0;
 #pragma unroll
-    for (int j = 0; j < IPT; ++j) {
-        const uint64_t step_first = first + 32 * j;
-        uint32_t vm = 0;  // lanes with idx < n
-        if (step_first < p.n) vm = (p.n - step_first >= 32) ? 0xffffffffu : ((1u << (uint32_t)(p.n - step_first)) - 1u);
-        wheads += __popc(hb[j] & vm);
-    }
+    for (int j = 0; j < IPT; ++j) wheads += __popc(FULL ? hb[j] : (hb[j] & valid_mask(wfirst + 32 * j, n_local)));
     if (lane == 0) s_wheads[warp] = wheads;
     __syncthreads();
     uint32_t wexcl = 0, theads = 0;
@@ -116,18 +117,14 @@ __global__ void __launch_bounds__(RLE_BLOCK) rle_count_kernel(const RleParams p)
         if (w < (int)warp) wexcl += c;
         theads += c;
     }
-    // local positions of heads -> s_hpos
+    const uint32_t lt = lanemask_lt();
     {
         uint32_t run = wexcl;
 #pragma unroll
         for (int j = 0; j < IPT; ++j) {
-            const uint64_t idx = first + 32 * j + lane;
-            const uint32_t b = hb[j];
-            if (((b >> lane) & 1u) && idx < p.n) s_hpos[run + __popc(b & lanemask_lt())] = (uint32_t)(idx - tile_base);
-            const uint64_t step_first = first + 32 * j;
-            uint32_t vm = 0;
-            if (step_first < p.n) vm = (p.n - step_first >= 32) ? 0xffffffffu : ((1u << (uint32_t)(p.n - step_first)) - 1u);
-            run += __popc(b & vm);
+            const uint32_t b = FULL ? hb[j] : (hb[j] & valid_mask(wfirst + 32 * j, n_local));
+            if ((b >> lane) & 1u) s_hpos[run + __popc(b & lt)] = wfirst + 32 * j + lane;
+            run += __popc(b);
         }
     }
     __syncthreads();
@@ -170,7 +167,8 @@ __global__ void __launch_bounds__(RLE_BLOCK) rle_count_kernel(const RleParams p)
                 excl += v;
                 // nearest preceding head: the lowest usable lane whose B value is non-zero
                 const uint32_t has_mask = __ballot_sync(0xffffffffu, lane < usable && (b & TP_VALUE_MASK) != 0);
-                if (carry == 0 && has_mask) carry = __shfl_sync(0xffffffffu, b & TP_VALUE_MASK, __ffs(has_mask) - 1);
+                const uint64_t cand = __shfl_sync(0xffffffffu, b & TP_VALUE_MASK, has_mask ? __ffs(has_mask) - 1 : 0);
+                if (carry == 0 && has_mask) carry = cand;
                 if (first_incl < first_empty) break;
                 base -= usable;
                 if (usable == 0) {
@@ -187,75 +185,81 @@ __global__ void __launch_bounds__(RLE_BLOCK) rle_count_kernel(const RleParams p)
             }
         }
         if (lane == 0) {
-            s_excl_heads = excl;
-            s_carry = carry;  // position+1 of the head of the run that is open when the tile starts
+            s_bcast[0] = excl;
+            s_bcast[1] = carry;  // position+1 of the head of the run that is open when the tile starts
             if (tile == gridDim.x - 1) *p.n_out = excl + theads;
         }
     }
     __syncthreads();
-    const uint64_t excl_heads = s_excl_heads;
-    const uint64_t carry = s_carry;
-    KeyT* keys_out = reinterpret_cast<KeyT*>(p.keys_out);
+    const uint64_t excl_heads = s_bcast[0];
+    const uint64_t carry = s_bcast[1];
+    KeyT* keys_out = reinterpret_cast<KeyT*>(p.keys_out) + excl_heads;
+    uint32_t* counts_out = p.counts_out + excl_heads;  // slot -1 (the run open at tile start) is valid when used
 
     uint32_t run = wexcl;  // heads of the tile before the current step
 #pragma unroll
     for (int j = 0; j < IPT; ++j) {
-        const uint64_t step_first = first + 32 * j;
-        const uint64_t idx = step_first + lane;
+        const uint32_t li = wfirst + 32 * j + lane;
+        const uint32_t vm = FULL ? 0xffffffffu : valid_mask(wfirst + 32 * j, n_local);
         const uint32_t b = hb[j];
         const uint32_t nb = (j + 1 < IPT) ? hb[j + 1 < IPT ? j + 1 : j] : hnext;
         const uint32_t tb = (b >> 1) | ((nb & 1u) << 31);  // tail: the next element is a head
-        const uint32_t h_before = run + __popc(b & lanemask_lt());
+        const uint32_t h_before = run + __popc(b & vm & lt);
         const bool is_head = (b >> lane) & 1u;
-        if (idx < p.n) {
-            if (is_head) keys_out[excl_heads + h_before] = keys[j];
+        if (FULL || li < n_local) {
+            if (is_head) keys_out[h_before] = keys[j];
             if ((tb >> lane) & 1u) {
                 const uint32_t h_incl = h_before + (is_head ? 1u : 0u);
-                const uint64_t hpos = h_incl ? tile_base + s_hpos[h_incl - 1] : carry - 1;
-                const uint64_t len = idx - hpos + 1;
+                uint64_t len;
+                if (h_incl) len = (uint64_t)(li - s_hpos[h_incl - 1]) + 1;
+                else len = tile_base + li - (carry - 1) + 1;
                 if (len > 0xffffffffull) atomicExch(p.err, 2u);
-                p.counts_out[excl_heads + h_incl - 1] = (uint32_t)len;
+                *(counts_out + (int64_t)h_incl - 1) = (uint32_t)len;
             }
         }
-        uint32_t vm = 0;
-        if (step_first < p.n) vm = (p.n - step_first >= 32) ? 0xffffffffu : ((1u << (uint32_t)(p.n - step_first)) - 1u);
         run += __popc(b & vm);
     }
 }
 
-// singletons: head && tail, compacted in order, with payload
-template <typename KeyT, int VAL_BYTES, int IPT>
-__global__ void __launch_bounds__(RLE_BLOCK) select_singletons_kernel(const RleParams p) {
+template <typename KeyT, int IPT>
+__global__ void __launch_bounds__(RLE_BLOCK) rle_count_kernel(const RleParams p) {
     constexpr int TILE = RLE_BLOCK * IPT;
-    using ValT = typename std::conditional<VAL_BYTES == 4, uint32_t, uint64_t>::type;
-    __shared__ uint32_t s_wcnt[RLE_WARPS];
+    __shared__ uint32_t s_hpos[TILE];  // local position of the i-th head of the tile
+    __shared__ uint32_t s_wheads[RLE_WARPS];
     __shared__ uint32_t s_tile;
-    __shared__ uint64_t s_excl;
-
-    const int t = threadIdx.x;
-    const uint32_t lane = t & 31, warp = t >> 5;
-    if (t == 0) s_tile = atomicAdd(p.ticket, 1u);
+    __shared__ uint64_t s_bcast[2];
+    if (threadIdx.x == 0) s_tile = atomicAdd(p.ticket, 1u);
     __syncthreads();
     const uint32_t tile = s_tile;
+    if ((uint64_t)(tile + 1) * TILE <= p.n) rle_count_tile<KeyT, IPT, true>(p, tile, s_hpos, s_wheads, s_bcast);
+    else rle_count_tile<KeyT, IPT, false>(p, tile, s_hpos, s_wheads, s_bcast);
+}
+
+// singletons: head && tail, compacted in order, with payload
+template <typename KeyT, int VAL_BYTES, int IPT, bool FULL>
+__device__ __forceinline__ void select_tile(const RleParams& p, const uint32_t tile, uint32_t* s_wcnt, uint64_t* s_bcast) {
+    constexpr int TILE = RLE_BLOCK * IPT;
+    using ValT = typename std::conditional<VAL_BYTES == 4, uint32_t, uint64_t>::type;
+    const int t = threadIdx.x;
+    const uint32_t lane = t & 31, warp = t >> 5;
     const uint64_t tile_base = (uint64_t)tile * TILE;
-    const uint64_t first = tile_base + (uint64_t)warp * 32 * IPT;
-    const KeyT* keys_in = reinterpret_cast<const KeyT*>(p.keys_in);
+    const uint32_t n_local = FULL ? (uint32_t)TILE : (uint32_t)(p.n - tile_base);
+    const bool more_after = tile_base + TILE < p.n;
+    const uint32_t wfirst = warp * 32 * IPT;
+    const KeyT* kin = reinterpret_cast<const KeyT*>(p.keys_in) + tile_base;
 
     KeyT keys[IPT];
     uint32_t hb[IPT];
     uint32_t hnext;
-    load_heads<KeyT, IPT>(keys_in, p.n, first, keys, hb, hnext);
+    load_heads<KeyT, IPT, FULL>(kin, tile_base, n_local, more_after, wfirst, keys, hb, hnext);
 
     uint32_t sb[IPT];  // singleton ballots
     uint32_t wcnt = 0;
 #pragma unroll
     for (int j = 0; j < IPT; ++j) {
-        const uint64_t step_first = first + 32 * j;
         const uint32_t nb = (j + 1 < IPT) ? hb[j + 1 < IPT ? j + 1 : j] : hnext;
         const uint32_t tb = (hb[j] >> 1) | ((nb & 1u) << 31);
-        uint32_t vm = 0;
-        if (step_first < p.n) vm = (p.n - step_first >= 32) ? 0xffffffffu : ((1u << (uint32_t)(p.n - step_first)) - 1u);
-        sb[j] = hb[j] & tb & vm;
+        sb[j] = hb[j] & tb & (FULL ? 0xffffffffu : valid_mask(wfirst + 32 * j, n_local));
         wcnt += __popc(sb[j]);
     }
     if (lane == 0) s_wcnt[warp] = wcnt;
@@ -270,37 +274,50 @@ __global__ void __launch_bounds__(RLE_BLOCK) select_singletons_kernel(const RleP
     if (t < 32) {
         const uint64_t excl = tile_prefix_exclusive_warp(p.state_a, tile, total, p.err);
         if (t == 0) {
-            s_excl = excl;
+            s_bcast[0] = excl;
             if (tile == gridDim.x - 1) *p.n_out = excl + total;
         }
     }
     __syncthreads();
-    const uint64_t base = s_excl + wexcl;
-    KeyT* keys_out = reinterpret_cast<KeyT*>(p.keys_out);
-    const ValT* vals_in = reinterpret_cast<const ValT*>(p.vals_in);
-    ValT* vals_out = reinterpret_cast<ValT*>(p.vals_out);
+    const uint64_t base = s_bcast[0] + wexcl;
+    KeyT* keys_out = reinterpret_cast<KeyT*>(p.keys_out) + base;
+    const ValT* vals_in = reinterpret_cast<const ValT*>(p.vals_in) + tile_base;
+    ValT* vals_out = reinterpret_cast<ValT*>(p.vals_out) + base;
+    const uint32_t lt = lanemask_lt();
     uint32_t run = 0;
 #pragma unroll
     for (int j = 0; j < IPT; ++j) {
-        const uint64_t idx = first + 32 * j + lane;
         if ((sb[j] >> lane) & 1u) {
-            const uint64_t o = base + run + __popc(sb[j] & lanemask_lt());
+            const uint32_t o = run + __popc(sb[j] & lt);
             keys_out[o] = keys[j];
-            if constexpr (VAL_BYTES != 0) vals_out[o] = vals_in[idx];
+            if constexpr (VAL_BYTES != 0) vals_out[o] = vals_in[wfirst + 32 * j + lane];
         }
         run += __popc(sb[j]);
     }
 }
 
-constexpr int RLE_IPT8 = 16;   // 8-byte keys: 4096-key tiles
-constexpr int RLE_IPT16 = 8;   // 16-byte keys: 2048-key tiles
+template <typename KeyT, int VAL_BYTES, int IPT>
+__global__ void __launch_bounds__(RLE_BLOCK) select_singletons_kernel(const RleParams p) {
+    constexpr int TILE = RLE_BLOCK * IPT;
+    __shared__ uint32_t s_wcnt[RLE_WARPS];
+    __shared__ uint32_t s_tile;
+    __shared__ uint64_t s_bcast[2];
+    if (threadIdx.x == 0) s_tile = atomicAdd(p.ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    if ((uint64_t)(tile + 1) * TILE <= p.n) select_tile<KeyT, VAL_BYTES, IPT, true>(p, tile, s_wcnt, s_bcast);
+    else select_tile<KeyT, VAL_BYTES, IPT, false>(p, tile, s_wcnt, s_bcast);
+}
+
+constexpr int RLE_IPT8 = 8;    // 8-byte keys: 2048-key tiles
+constexpr int RLE_IPT16 = 4;   // 16-byte keys: 1024-key tiles
 
 }  // namespace kmg
 
 using namespace kmg;
 
 extern "C" size_t kmg_rle_workspace_bytes(uint64_t n) {
-    const uint64_t tiles = n / 2048 + 2;
+    const uint64_t tiles = n / 1024 + 2;
     return sizeof(WsHeader) + 2 * align_up(tiles * sizeof(uint64_t), 256);
 }
 
@@ -313,7 +330,7 @@ static int rle_setup(RleParams& p, uint64_t n, int key_bytes, void* d_ws, size_t
     const uint64_t nt = (n + tile - 1) / tile;
     KMG_REQUIRE(nt < (1ull << 31), KMG_ERR_RANGE, "too many tiles");
     tiles = (uint32_t)nt;
-    const size_t arr = align_up((n / 2048 + 2) * sizeof(uint64_t), 256);
+    const size_t arr = align_up((n / 1024 + 2) * sizeof(uint64_t), 256);
     KMG_CUDA(cudaMemsetAsync(d_ws, 0, sizeof(WsHeader) + 2 * arr, st));
     WsHeader* hdr = reinterpret_cast<WsHeader*>(d_ws);
     p.n = n;

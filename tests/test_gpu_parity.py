@@ -139,7 +139,7 @@ def test_radix_sort_u64_bit_ranges(eng, bits):
     _sort_case(eng, 300_000, 8, 4, bits, seed=bits, dup=True)
 
 
-@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 5, 6, 7])
 @pytest.mark.parametrize("vb", [0, 4, 8])
 def test_radix_sort_u64_tile_configs(eng, cfg, vb):
     _sort_case(eng, 500_009, 8, vb, 62, seed=cfg * 10 + vb, cfg=cfg, dup=True)

@@ -36,7 +36,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=100_000_000)
     ap.add_argument("--k", type=int, default=31)
-    ap.add_argument("--configs", default="0,1,2,3,4")
+    ap.add_argument("--configs", default="0,1,2,3,4,5,6,7")
     ap.add_argument("--vb", type=int, default=0)
     ap.add_argument("--yardstick", action="store_true")
     args = ap.parse_args()
