@@ -117,48 +117,63 @@ constexpr uint64_t TP_FLAG_AGG = 1ull << 62;
 constexpr uint64_t TP_FLAG_INCL = 2ull << 62;
 constexpr uint64_t TP_VALUE_MASK = (1ull << 62) - 1;
 
-// Called by ALL 32 lanes of ONE warp of the tile; every lane receives the exclusive prefix.
-// `state` must be zero-initialised and tile ids handed out in launch order (atomic ticket).
-// One round inspects the 32 preceding tiles with a single load per lane, so the walk back to
-// the newest tile that already knows its inclusive prefix costs ~1 L2 round trip instead of
-// one per tile.  The flag travels in the same word as the value: relaxed accesses suffice.
-__device__ __forceinline__ uint64_t tile_prefix_exclusive_warp(uint64_t* state, uint32_t tile, uint64_t aggregate,
-                                                               uint32_t* err_flag) {
-    const uint32_t lane = threadIdx.x & 31;
-    if (tile == 0) {
-        if (lane == 0) st_relaxed_u64(&state[0], TP_FLAG_INCL | aggregate);
-        return 0;
-    }
-    if (lane == 0) st_relaxed_u64(&state[tile], TP_FLAG_AGG | aggregate);
-    uint64_t excl = 0;
-    int64_t base = (int64_t)tile - 1;
-    uint32_t spins = 0;
-    while (true) {
-        const int64_t idx = base - (int64_t)lane;
-        // tiles before the first one behave like a finished tile with prefix 0
-        const uint64_t w = idx >= 0 ? ld_relaxed_u64(&state[idx]) : TP_FLAG_INCL;
-        const uint64_t f = w & ~TP_VALUE_MASK;
-        const uint32_t empty_mask = __ballot_sync(0xffffffffu, f == 0);
-        const uint32_t incl_mask = __ballot_sync(0xffffffffu, f == TP_FLAG_INCL);
-        const uint32_t first_incl = incl_mask ? (uint32_t)__ffs(incl_mask) - 1u : 32u;
-        const uint32_t first_empty = empty_mask ? (uint32_t)__ffs(empty_mask) - 1u : 32u;
-        const uint32_t usable = min(first_incl + 1u, first_empty);  // leading lanes that count
-        uint64_t v = lane < usable ? (w & TP_VALUE_MASK) : 0ull;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        excl += v;
-        if (first_incl < first_empty) break;  // reached a tile with a known inclusive prefix
-        base -= usable;
-        if (usable == 0) {
-            if (++spins > SPIN_LIMIT) {
-                if (lane == 0) atomicExch(err_flag, 1u);
-                break;
-            }
-            __nanosleep(32);
+// ---- two-level tile prefix for single-value scans ------------------------------------------------
+// Tiles form groups of SC_GROUP consecutive tiles.  A tile's exclusive prefix is
+//   (inclusive prefix of the previous GROUP) + (aggregates of the earlier tiles of its own group).
+// Aggregates depend on nothing but the tile's own data, so the only dependency chain is
+// ginc[g-1] -> ginc[g], one link per SC_GROUP tiles and one L2 round trip long; a chained or
+// decoupled look-back over single tiles cannot keep up with B200's tile rate (the walk back to
+// the newest finished prefix grew to 60-90 tiles, see profiles/r01_ncu_summary.md).
+// Layout: state[0 .. n_tiles) = aggregates, state[n_tiles .. ) = group prefixes; zero-initialised;
+// tile ids handed out in launch order (atomic ticket).  The flag travels in the word (bit 63).
+constexpr uint32_t SC_GROUP = 128;
+constexpr uint64_t SC_FLAG = 1ull << 63;
+constexpr uint64_t SC_VALUE_MASK = SC_FLAG - 1;
+
+// words the state array needs for n_tiles tiles
+static inline size_t sc_state_words(uint64_t n_tiles) { return n_tiles + n_tiles / SC_GROUP + 2; }
+
+__device__ __forceinline__ uint64_t sc_wait(const uint64_t* p, uint64_t w, uint32_t& spins, uint32_t* err_flag) {
+    while (!(w & SC_FLAG)) {
+        if (++spins > SPIN_LIMIT) {
+            atomicExch(err_flag, 1u);
+            return SC_FLAG;
         }
+        w = ld_relaxed_u64(p);
     }
-    if (lane == 0) st_relaxed_u64(&state[tile], TP_FLAG_INCL | (excl + aggregate));
-    return excl;
+    return w;
+}
+
+// Called by ALL 32 lanes of ONE warp of the tile; every lane receives the exclusive prefix
+// (sum of the aggregates of all earlier tiles).
+__device__ __forceinline__ uint64_t tile_prefix_exclusive_warp(uint64_t* state, uint32_t n_tiles, uint32_t tile,
+                                                               uint64_t aggregate, uint32_t* err_flag) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t g = tile / SC_GROUP, r = tile % SC_GROUP;
+    uint64_t* ginc = state + n_tiles;
+    if (lane == 0) st_relaxed_u64(&state[tile], SC_FLAG | aggregate);
+    uint32_t spins = 0;
+    uint64_t gv = SC_FLAG;
+    if (lane == 0 && g > 0) gv = ld_relaxed_u64(&ginc[g - 1]);
+    uint64_t w[SC_GROUP / 32];
+#pragma unroll
+    for (int q = 0; q < (int)(SC_GROUP / 32); ++q) {
+        const uint32_t j = lane + 1 + 32 * q;
+        w[q] = j <= r ? ld_relaxed_u64(&state[tile - j]) : SC_FLAG;
+    }
+    uint64_t sum = 0;
+#pragma unroll
+    for (int q = 0; q < (int)(SC_GROUP / 32); ++q) {
+        const uint32_t j = lane + 1 + 32 * q;
+        if (j <= r) w[q] = sc_wait(&state[tile - j], w[q], spins, err_flag);
+        sum += w[q] & SC_VALUE_MASK;
+    }
+    if (lane == 0 && g > 0) gv = sc_wait(&ginc[g - 1], gv, spins, err_flag);
+    sum += gv & SC_VALUE_MASK;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (r == SC_GROUP - 1 && lane == 0) st_relaxed_u64(&ginc[g], SC_FLAG | (sum + aggregate));
+    return sum;
 }
 
 // ---- workspace header ---------------------------------------------------------------------

@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(FMT_BLOCK) format_counts_kernel(const FmtParam
     uint32_t total;
     uint32_t off = block_excl_scan<FMT_BLOCK, uint32_t>(len, s_scan, total);
     if (t < 32) {
-        const uint64_t e = tile_prefix_exclusive_warp(p.state, tile, total, p.err);
+        const uint64_t e = tile_prefix_exclusive_warp(p.state, gridDim.x, tile, total, p.err);
         if (t == 0) {
             s_base = e;
             if (tile == gridDim.x - 1) *p.bytes_out = e + total;
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(FMT_BLOCK) format_uniq_kernel(const FmtParams 
     uint64_t total;
     const uint64_t off = block_excl_scan<FMT_BLOCK, uint64_t>(len, s_scan, total);
     if (t < 32) {
-        const uint64_t e = tile_prefix_exclusive_warp(p.state, tile, total, p.err);
+        const uint64_t e = tile_prefix_exclusive_warp(p.state, gridDim.x, tile, total, p.err);
         if (t == 0) {
             s_base = e;
             if (tile == gridDim.x - 1) *p.bytes_out = e + total;
@@ -254,7 +254,7 @@ __global__ void rank_wide_kernel(const uint64_t* __restrict__ narrow, uint64_t n
 using namespace kmg;
 
 extern "C" size_t kmg_format_workspace_bytes(uint64_t n) {
-    return sizeof(WsHeader) + align_up((n / FMT_BLOCK + 2) * sizeof(uint64_t), 256);
+    return sizeof(WsHeader) + align_up(sc_state_words(n / FMT_BLOCK + 2) * sizeof(uint64_t), 256);
 }
 
 static int fmt_setup(FmtParams& p, uint64_t n, uint64_t tile, void* d_ws, size_t ws_bytes, uint32_t& tiles,

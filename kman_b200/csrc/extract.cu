@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(EX_BLOCK) extract_narrow_kernel(const ExtractP
     const uint32_t excl = block_excl_scan<EX_BLOCK, uint32_t>(cnt, s_scan, total);
     if (nwide) atomicAdd(&s_wide, nwide);
     if (t < 32) {
-        const uint64_t e = tile_prefix_exclusive_warp(p.tile_state, tile, (uint64_t)total * OUT_PER_WIN, p.err);
+        const uint64_t e = tile_prefix_exclusive_warp(p.tile_state, gridDim.x, tile, (uint64_t)total * OUT_PER_WIN, p.err);
         if (t == 0) s_base = e;
     }
     uint32_t r = excl;
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(EXW_BLOCK) extract_wide_kernel(const ExtractPa
     uint32_t total;
     const uint32_t excl = block_excl_scan<EXW_BLOCK, uint32_t>(cnt, s_scan, total);
     if (t < 32) {
-        const uint64_t e = tile_prefix_exclusive_warp(p.tile_state, tile, (uint64_t)total * OUT_PER_WIN, p.err);
+        const uint64_t e = tile_prefix_exclusive_warp(p.tile_state, gridDim.x, tile, (uint64_t)total * OUT_PER_WIN, p.err);
         if (t == 0) s_base = e;
     }
     __syncthreads();
@@ -345,7 +345,7 @@ static constexpr uint64_t EX_MIN_TILE = 1024;
 
 extern "C" size_t kmg_extract_workspace_bytes(uint64_t n_windows) {
     // header + tile states (+2 tiles for the unaligned head/tail)
-    return sizeof(WsHeader) + align_up((n_windows / EX_MIN_TILE + 3) * sizeof(uint64_t), 256);
+    return sizeof(WsHeader) + align_up(sc_state_words(n_windows / EX_MIN_TILE + 3) * sizeof(uint64_t), 256);
 }
 
 extern "C" int kmg_extract(const uint8_t* d_bases, uint64_t n_bases, uint64_t win_begin, uint64_t win_end, int k,
@@ -377,7 +377,7 @@ extern "C" int kmg_extract(const uint8_t* d_bases, uint64_t n_bases, uint64_t wi
     const uint64_t first_tile = win_begin / tile;
     const uint64_t n_tiles = (win_end + tile - 1) / tile - first_tile;
     KMG_REQUIRE(n_tiles < (1ull << 31), KMG_ERR_RANGE, "too many tiles");
-    const size_t state_bytes = align_up(n_tiles * sizeof(uint64_t), 256);
+    const size_t state_bytes = align_up(sc_state_words(n_tiles) * sizeof(uint64_t), 256);
     KMG_CUDA(cudaMemsetAsync(d_ws, 0, sizeof(WsHeader) + state_bytes, st));
     WsHeader* hdr = reinterpret_cast<WsHeader*>(d_ws);
 

@@ -129,62 +129,58 @@ __device__ __forceinline__ void rle_count_tile(const RleParams& p, const uint32_
     }
     __syncthreads();
     if (t < 32) {
-        // Warp-cooperative look-back over (number of heads, position of the last head).
-        // Both words carry their own flag, so no fence is needed: a slot counts only when
-        // both flags are set, and a B word that is already the inclusive version while A is
-        // still the aggregate is harmless (it names the same "last head at or before here").
+        // Two-level prefix (common.cuh) over the pair (number of heads: SUM, position+1 of the
+        // last head: MAX -- positions grow with the tile index, so the nearest preceding head is
+        // the maximum).  Both words carry their own flag; a slot counts when both are set.
+        const uint32_t n_tiles = gridDim.x;
+        const uint32_t g = tile / SC_GROUP, r = tile % SC_GROUP;
+        uint64_t* ginc_a = p.state_a + n_tiles;
+        uint64_t* ginc_b = p.state_b + n_tiles;
         const uint64_t last_plus1 = theads ? tile_base + s_hpos[theads - 1] + 1 : 0;
-        uint64_t excl = 0, carry = 0;
-        if (tile == 0) {
-            if (lane == 0) {
-                st_relaxed_u64(&p.state_b[0], TP_FLAG_INCL | last_plus1);
-                st_relaxed_u64(&p.state_a[0], TP_FLAG_INCL | theads);
-            }
-        } else {
-            if (lane == 0) {
-                st_relaxed_u64(&p.state_b[tile], TP_FLAG_AGG | last_plus1);
-                st_relaxed_u64(&p.state_a[tile], TP_FLAG_AGG | theads);
-            }
-            int64_t base = (int64_t)tile - 1;
-            uint32_t spins = 0;
-            while (true) {
-                const int64_t idx = base - (int64_t)lane;
-                uint64_t a = TP_FLAG_INCL, b = TP_FLAG_INCL;  // before tile 0: finished, no head
-                if (idx >= 0) {
-                    a = ld_relaxed_u64(&p.state_a[idx]);
-                    b = ld_relaxed_u64(&p.state_b[idx]);
-                }
-                const uint64_t fa = a & ~TP_VALUE_MASK, fb = b & ~TP_VALUE_MASK;
-                const bool ready = fa != 0 && fb != 0 && !(fa == TP_FLAG_INCL && fb != TP_FLAG_INCL);
-                const uint32_t empty_mask = __ballot_sync(0xffffffffu, !ready);
-                const uint32_t incl_mask = __ballot_sync(0xffffffffu, ready && fa == TP_FLAG_INCL);
-                const uint32_t first_incl = incl_mask ? (uint32_t)__ffs(incl_mask) - 1u : 32u;
-                const uint32_t first_empty = empty_mask ? (uint32_t)__ffs(empty_mask) - 1u : 32u;
-                const uint32_t usable = min(first_incl + 1u, first_empty);
-                uint64_t v = lane < usable ? (a & TP_VALUE_MASK) : 0ull;
+        if (lane == 0) {
+            st_relaxed_u64(&p.state_b[tile], SC_FLAG | last_plus1);
+            st_relaxed_u64(&p.state_a[tile], SC_FLAG | theads);
+        }
+        uint32_t spins = 0;
+        uint64_t ga = SC_FLAG, gb = SC_FLAG;
+        if (lane == 0 && g > 0) {
+            ga = ld_relaxed_u64(&ginc_a[g - 1]);
+            gb = ld_relaxed_u64(&ginc_b[g - 1]);
+        }
+        uint64_t wa[SC_GROUP / 32], wb[SC_GROUP / 32];
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                excl += v;
-                // nearest preceding head: the lowest usable lane whose B value is non-zero
-                const uint32_t has_mask = __ballot_sync(0xffffffffu, lane < usable && (b & TP_VALUE_MASK) != 0);
-                const uint64_t cand = __shfl_sync(0xffffffffu, b & TP_VALUE_MASK, has_mask ? __ffs(has_mask) - 1 : 0);
-                if (carry == 0 && has_mask) carry = cand;
-                if (first_incl < first_empty) break;
-                base -= usable;
-                if (usable == 0) {
-                    if (++spins > SPIN_LIMIT) {
-                        if (lane == 0) atomicExch(p.err, 1u);
-                        break;
-                    }
-                    __nanosleep(32);
-                }
+        for (int q = 0; q < (int)(SC_GROUP / 32); ++q) {
+            const uint32_t j = lane + 1 + 32 * q;
+            wa[q] = j <= r ? ld_relaxed_u64(&p.state_a[tile - j]) : SC_FLAG;
+            wb[q] = j <= r ? ld_relaxed_u64(&p.state_b[tile - j]) : SC_FLAG;
+        }
+        uint64_t excl = 0, carry = 0;
+#pragma unroll
+        for (int q = 0; q < (int)(SC_GROUP / 32); ++q) {
+            const uint32_t j = lane + 1 + 32 * q;
+            if (j <= r) {
+                wa[q] = sc_wait(&p.state_a[tile - j], wa[q], spins, p.err);
+                wb[q] = sc_wait(&p.state_b[tile - j], wb[q], spins, p.err);
             }
-            if (lane == 0) {
-                st_relaxed_u64(&p.state_b[tile], TP_FLAG_INCL | (last_plus1 ? last_plus1 : carry));
-                st_relaxed_u64(&p.state_a[tile], TP_FLAG_INCL | (excl + theads));
-            }
+            excl += wa[q] & SC_VALUE_MASK;
+            carry = max(carry, wb[q] & SC_VALUE_MASK);
+        }
+        if (lane == 0 && g > 0) {
+            ga = sc_wait(&ginc_a[g - 1], ga, spins, p.err);
+            gb = sc_wait(&ginc_b[g - 1], gb, spins, p.err);
+        }
+        excl += ga & SC_VALUE_MASK;
+        carry = max(carry, gb & SC_VALUE_MASK);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            excl += __shfl_xor_sync(0xffffffffu, excl, o);
+            carry = max(carry, __shfl_xor_sync(0xffffffffu, carry, o));
         }
         if (lane == 0) {
+            if (r == SC_GROUP - 1) {
+                st_relaxed_u64(&ginc_b[g], SC_FLAG | max(carry, last_plus1));
+                st_relaxed_u64(&ginc_a[g], SC_FLAG | (excl + theads));
+            }
             s_bcast[0] = excl;
             s_bcast[1] = carry;  // position+1 of the head of the run that is open when the tile starts
             if (tile == gridDim.x - 1) *p.n_out = excl + theads;
@@ -222,7 +218,7 @@ __device__ __forceinline__ void rle_count_tile(const RleParams& p, const uint32_
 }
 
 template <typename KeyT, int IPT>
-__global__ void __launch_bounds__(RLE_BLOCK) rle_count_kernel(const RleParams p) {
+__global__ void __launch_bounds__(RLE_BLOCK, 3) rle_count_kernel(const RleParams p) {
     constexpr int TILE = RLE_BLOCK * IPT;
     __shared__ uint32_t s_hpos[TILE];  // local position of the i-th head of the tile
     __shared__ uint32_t s_wheads[RLE_WARPS];
@@ -272,7 +268,7 @@ __device__ __forceinline__ void select_tile(const RleParams& p, const uint32_t t
         total += c;
     }
     if (t < 32) {
-        const uint64_t excl = tile_prefix_exclusive_warp(p.state_a, tile, total, p.err);
+        const uint64_t excl = tile_prefix_exclusive_warp(p.state_a, gridDim.x, tile, total, p.err);
         if (t == 0) {
             s_bcast[0] = excl;
             if (tile == gridDim.x - 1) *p.n_out = excl + total;
@@ -297,7 +293,7 @@ __device__ __forceinline__ void select_tile(const RleParams& p, const uint32_t t
 }
 
 template <typename KeyT, int VAL_BYTES, int IPT>
-__global__ void __launch_bounds__(RLE_BLOCK) select_singletons_kernel(const RleParams p) {
+__global__ void __launch_bounds__(RLE_BLOCK, 3) select_singletons_kernel(const RleParams p) {
     constexpr int TILE = RLE_BLOCK * IPT;
     __shared__ uint32_t s_wcnt[RLE_WARPS];
     __shared__ uint32_t s_tile;
@@ -309,8 +305,8 @@ __global__ void __launch_bounds__(RLE_BLOCK) select_singletons_kernel(const RleP
     else select_tile<KeyT, VAL_BYTES, IPT, false>(p, tile, s_wcnt, s_bcast);
 }
 
-constexpr int RLE_IPT8 = 8;    // 8-byte keys: 2048-key tiles
-constexpr int RLE_IPT16 = 4;   // 16-byte keys: 1024-key tiles
+constexpr int RLE_IPT8 = 16;   // 8-byte keys: 4096-key tiles
+constexpr int RLE_IPT16 = 8;   // 16-byte keys: 2048-key tiles
 
 }  // namespace kmg
 
@@ -318,7 +314,7 @@ using namespace kmg;
 
 extern "C" size_t kmg_rle_workspace_bytes(uint64_t n) {
     const uint64_t tiles = n / 1024 + 2;
-    return sizeof(WsHeader) + 2 * align_up(tiles * sizeof(uint64_t), 256);
+    return sizeof(WsHeader) + 2 * align_up(sc_state_words(tiles) * sizeof(uint64_t), 256);
 }
 
 static int rle_setup(RleParams& p, uint64_t n, int key_bytes, void* d_ws, size_t ws_bytes, uint32_t& tiles,
@@ -330,7 +326,7 @@ static int rle_setup(RleParams& p, uint64_t n, int key_bytes, void* d_ws, size_t
     const uint64_t nt = (n + tile - 1) / tile;
     KMG_REQUIRE(nt < (1ull << 31), KMG_ERR_RANGE, "too many tiles");
     tiles = (uint32_t)nt;
-    const size_t arr = align_up((n / 1024 + 2) * sizeof(uint64_t), 256);
+    const size_t arr = align_up(sc_state_words(n / 1024 + 2) * sizeof(uint64_t), 256);
     KMG_CUDA(cudaMemsetAsync(d_ws, 0, sizeof(WsHeader) + 2 * arr, st));
     WsHeader* hdr = reinterpret_cast<WsHeader*>(d_ws);
     p.n = n;
