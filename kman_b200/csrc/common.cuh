@@ -144,14 +144,19 @@ __device__ __forceinline__ uint64_t sc_wait(const uint64_t* p, uint64_t w, uint3
     return w;
 }
 
-// Called by ALL 32 lanes of ONE warp of the tile; every lane receives the exclusive prefix
-// (sum of the aggregates of all earlier tiles).
-__device__ __forceinline__ uint64_t tile_prefix_exclusive_warp(uint64_t* state, uint32_t n_tiles, uint32_t tile,
-                                                               uint64_t aggregate, uint32_t* err_flag) {
+// Publish the tile's aggregate (one thread).  Do this as EARLY as the aggregate is known and
+// resolve as LATE as possible: the slack is what keeps tiles from waiting for each other.
+__device__ __forceinline__ void tile_prefix_publish(uint64_t* state, uint32_t tile, uint64_t aggregate) {
+    st_relaxed_u64(&state[tile], SC_FLAG | aggregate);
+}
+
+// Called by ALL 32 lanes of ONE warp of the tile, after tile_prefix_publish(); every lane receives
+// the exclusive prefix (sum of the aggregates of all earlier tiles).
+__device__ __forceinline__ uint64_t tile_prefix_resolve_warp(uint64_t* state, uint32_t n_tiles, uint32_t tile,
+                                                             uint64_t aggregate, uint32_t* err_flag) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t g = tile / SC_GROUP, r = tile % SC_GROUP;
     uint64_t* ginc = state + n_tiles;
-    if (lane == 0) st_relaxed_u64(&state[tile], SC_FLAG | aggregate);
     uint32_t spins = 0;
     uint64_t gv = SC_FLAG;
     if (lane == 0 && g > 0) gv = ld_relaxed_u64(&ginc[g - 1]);
@@ -174,6 +179,13 @@ __device__ __forceinline__ uint64_t tile_prefix_exclusive_warp(uint64_t* state, 
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     if (r == SC_GROUP - 1 && lane == 0) st_relaxed_u64(&ginc[g], SC_FLAG | (sum + aggregate));
     return sum;
+}
+
+// publish + resolve back to back (kernels without useful work to put in between)
+__device__ __forceinline__ uint64_t tile_prefix_exclusive_warp(uint64_t* state, uint32_t n_tiles, uint32_t tile,
+                                                               uint64_t aggregate, uint32_t* err_flag) {
+    if ((threadIdx.x & 31) == 0) tile_prefix_publish(state, tile, aggregate);
+    return tile_prefix_resolve_warp(state, n_tiles, tile, aggregate, err_flag);
 }
 
 // ---- workspace header ---------------------------------------------------------------------

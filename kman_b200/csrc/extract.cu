@@ -145,7 +145,8 @@ __global__ void __launch_bounds__(EX_BLOCK) extract_narrow_kernel(const ExtractP
     const uint64_t I1 = ((uint64_t)s_inv[wbase + 4] << 48) | ((uint64_t)s_inv[wbase + 5] << 32) |
                         ((uint64_t)s_inv[wbase + 6] << 16) | s_inv[wbase + 7];
 
-    KeyT keys[PPT];
+    // validity of my PPT windows first: the tile's count is published as early as possible and
+    // the prefix over the earlier tiles is resolved only after the keys have been built
     uint32_t vf = 0, nwide = 0;
 #pragma unroll
     for (int j = 0; j < PPT; ++j) {
@@ -156,47 +157,48 @@ __global__ void __launch_bounds__(EX_BLOCK) extract_narrow_kernel(const ExtractP
         const bool in_range = pos >= p.win_begin && pos < p.win_end;
         if (in_range && bm == 0) vf |= 1u << j;
         if (in_range && im == 0 && bm != 0) ++nwide;
-        const int s2 = 2 * je;
-        const uint64_t hi = je == 0 ? X0 : ((X0 << s2) | (X1 >> (64 - s2)));
-        if constexpr (sizeof(KeyT) == 8) {
-            keys[j] = hi >> (64 - 2 * k);
-        } else {
-            const uint64_t lo = je == 0 ? X1 : ((X1 << s2) | (X2 >> (64 - s2)));
-            const int s = 128 - 2 * k;
-            u128 kk;
-            if (s == 0) {
-                kk.lo = lo;
-                kk.hi = hi;
-            } else {
-                kk.lo = (lo >> s) | (hi << (64 - s));
-                kk.hi = hi >> s;
-            }
-            keys[j] = kk;
-        }
     }
-
-    // ---- compaction in position order ---------------------------------------------------
     const uint32_t cnt = __popc(vf);
     uint32_t total;
     const uint32_t excl = block_excl_scan<EX_BLOCK, uint32_t>(cnt, s_scan, total);
+    if (t == 0) tile_prefix_publish(p.tile_state, tile, (uint64_t)total * OUT_PER_WIN);
     if (nwide) atomicAdd(&s_wide, nwide);
-    if (t < 32) {
-        const uint64_t e = tile_prefix_exclusive_warp(p.tile_state, gridDim.x, tile, (uint64_t)total * OUT_PER_WIN, p.err);
-        if (t == 0) s_base = e;
-    }
+
+    // ---- keys of the valid windows, compacted in position order into the staging buffer -----
     uint32_t r = excl;
 #pragma unroll
     for (int j = 0; j < PPT; ++j) {
-        if (vf & (1u << j)) {
-            const uint64_t pos = tile_pos + (uint64_t)t * PPT + j + p.pos_offset;
-            s_keys[pad_idx<KB>(r * OUT_PER_WIN)] = keys[j];
-            if constexpr (VAL_BYTES != 0) s_vals[pad_idx<VB>(r * OUT_PER_WIN)] = make_val<ValT>(pos, 0);
-            if constexpr (RC) {
-                s_keys[pad_idx<KB>(r * 2 + 1)] = rc_key(keys[j], k);
-                if constexpr (VAL_BYTES != 0) s_vals[pad_idx<VB>(r * 2 + 1)] = make_val<ValT>(pos, 1);
+        if (!(vf & (1u << j))) continue;
+        const int je = joff + j;
+        const int s2 = 2 * je;
+        const uint64_t hi = je == 0 ? X0 : ((X0 << s2) | (X1 >> (64 - s2)));
+        KeyT key;
+        if constexpr (sizeof(KeyT) == 8) {
+            key = hi >> (64 - 2 * k);
+        } else {
+            const uint64_t lo = je == 0 ? X1 : ((X1 << s2) | (X2 >> (64 - s2)));
+            const int s = 128 - 2 * k;
+            if (s == 0) {
+                key.lo = lo;
+                key.hi = hi;
+            } else {
+                key.lo = (lo >> s) | (hi << (64 - s));
+                key.hi = hi >> s;
             }
-            ++r;
         }
+        const uint64_t pos = tile_pos + (uint64_t)t * PPT + j + p.pos_offset;
+        s_keys[pad_idx<KB>(r * OUT_PER_WIN)] = key;
+        if constexpr (VAL_BYTES != 0) s_vals[pad_idx<VB>(r * OUT_PER_WIN)] = make_val<ValT>(pos, 0);
+        if constexpr (RC) {
+            s_keys[pad_idx<KB>(r * 2 + 1)] = rc_key(key, k);
+            if constexpr (VAL_BYTES != 0) s_vals[pad_idx<VB>(r * 2 + 1)] = make_val<ValT>(pos, 1);
+        }
+        ++r;
+    }
+    __syncthreads();
+    if (t < 32) {
+        const uint64_t e = tile_prefix_resolve_warp(p.tile_state, gridDim.x, tile, (uint64_t)total * OUT_PER_WIN, p.err);
+        if (t == 0) s_base = e;
     }
     __syncthreads();
     const uint64_t base = s_base;

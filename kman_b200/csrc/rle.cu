@@ -6,9 +6,17 @@
 //
 // A warp walks its contiguous chunk 32 keys at a time; "is the key different from its
 // predecessor" becomes one ballot per step, so ranks are popcounts and no shared-memory
-// transposition of the keys is needed.  Tiles are chained with a decoupled look-back that
-// carries (number of run heads, position of the last run head); a run's length is written
-// by the tile that sees the run END, which is what makes the pass single-sweep.
+// transposition of the keys is needed.
+//
+// Three launches, no CTA ever waits for another one:
+//   1. rle_tile_aggregates: per tile, number of run heads, number of singletons and the
+//      position of the last head (reads the keys once);
+//   2. rle_scan_tiles: one block turns them into per-tile output offsets and the "run that is
+//      open when the tile starts" carry;
+//   3. rle_count_kernel / select_singletons_kernel: re-read the keys and emit.
+// A single-sweep version with an in-kernel tile prefix was measured first: with B200's tile
+// rate the CTAs spent 55-66 % of their time waiting at the barrier behind the prefix
+// (profiles/r01_ncu_summary.md); the second read of the keys costs less than that wait.
 #include <type_traits>
 
 #include "common.cuh"
@@ -37,9 +45,13 @@ struct RleParams {
     void* vals_out;
     uint32_t* counts_out;
     unsigned long long* n_out;
-    uint64_t* state_a;  // flag | heads
-    uint64_t* state_b;  // flag | last head position + 1 (0 = none)
-    uint32_t* ticket;
+    uint32_t n_tiles;
+    uint32_t* t_heads;    // [tiles] run heads in the tile
+    uint32_t* t_singles;  // [tiles] singletons in the tile
+    uint32_t* t_last;     // [tiles] tile-local position + 1 of the last head (0 = none)
+    uint64_t* t_hpre;     // [tiles] heads before the tile
+    uint64_t* t_spre;     // [tiles] singletons before the tile
+    uint64_t* t_carry;    // [tiles] position + 1 of the last head before the tile (0 = none)
     uint32_t* err;
 };
 
@@ -87,36 +99,125 @@ __device__ __forceinline__ void load_heads(const KeyT* __restrict__ kin, uint64_
     hnext = __shfl_sync(0xffffffffu, h, 0);
 }
 
+// ---- 1. per-tile aggregates ----------------------------------------------------------------------
 template <typename KeyT, int IPT, bool FULL>
-__device__ __forceinline__ void rle_count_tile(const RleParams& p, const uint32_t tile, uint32_t* s_hpos,
-                                               uint32_t* s_wheads, uint64_t* s_bcast) {
+__device__ __forceinline__ void aggregates_tile(const RleParams& p, const uint32_t tile, uint32_t* s_red) {
+    constexpr int TILE = RLE_BLOCK * IPT;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t tile_base = (uint64_t)tile * TILE;
+    const uint32_t n_local = FULL ? (uint32_t)TILE : (uint32_t)(p.n - tile_base);
+    const uint32_t wfirst = warp * 32 * IPT;
+    const KeyT* kin = reinterpret_cast<const KeyT*>(p.keys_in) + tile_base;
+    KeyT keys[IPT];
+    uint32_t hb[IPT];
+    uint32_t hnext;
+    load_heads<KeyT, IPT, FULL>(kin, tile_base, n_local, tile_base + TILE < p.n, wfirst, keys, hb, hnext);
+    uint32_t heads = 0, singles = 0, last = 0;
+#pragma unroll
+    for (int j = 0; j < IPT; ++j) {
+        const uint32_t vm = FULL ? 0xffffffffu : valid_mask(wfirst + 32 * j, n_local);
+        const uint32_t b = hb[j] & vm;
+        const uint32_t nb = (j + 1 < IPT) ? hb[j + 1 < IPT ? j + 1 : j] : hnext;
+        const uint32_t tb = (hb[j] >> 1) | ((nb & 1u) << 31);
+        heads += __popc(b);
+        singles += __popc(b & tb);
+        if (b) last = wfirst + 32 * j + (31 - __clz(b)) + 1;
+    }
+    if (lane == 0) {
+        s_red[warp] = heads;
+        s_red[RLE_WARPS + warp] = singles;
+        s_red[2 * RLE_WARPS + warp] = last;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t th = 0, ts = 0, tl = 0;
+#pragma unroll
+        for (int w = 0; w < RLE_WARPS; ++w) {
+            th += s_red[w];
+            ts += s_red[RLE_WARPS + w];
+            tl = max(tl, s_red[2 * RLE_WARPS + w]);
+        }
+        p.t_heads[tile] = th;
+        p.t_singles[tile] = ts;
+        p.t_last[tile] = tl;
+    }
+}
+
+template <typename KeyT, int IPT>
+__global__ void __launch_bounds__(RLE_BLOCK) rle_tile_aggregates(const RleParams p) {
+    constexpr int TILE = RLE_BLOCK * IPT;
+    __shared__ uint32_t s_red[3 * RLE_WARPS];
+    const uint32_t tile = blockIdx.x;
+    if ((uint64_t)(tile + 1) * TILE <= p.n) aggregates_tile<KeyT, IPT, true>(p, tile, s_red);
+    else aggregates_tile<KeyT, IPT, false>(p, tile, s_red);
+}
+
+// ---- 2. scan over the tiles (one block) -------------------------------------------------------------
+constexpr int SCAN_BLOCK = 1024;
+__global__ void __launch_bounds__(SCAN_BLOCK) rle_scan_tiles(const RleParams p, uint32_t tile_keys, int want_singles) {
+    __shared__ uint64_t s_h[SCAN_BLOCK / 32 + 1], s_s[SCAN_BLOCK / 32 + 1], s_c[SCAN_BLOCK];
+    const uint32_t t = threadIdx.x;
+    const uint32_t per = (p.n_tiles + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    const uint32_t b = min(t * per, p.n_tiles), e = min(b + per, p.n_tiles);
+    uint64_t h = 0, s = 0, c = 0;
+    for (uint32_t i = b; i < e; ++i) {
+        h += p.t_heads[i];
+        s += p.t_singles[i];
+        const uint32_t l = p.t_last[i];
+        if (l) c = (uint64_t)i * tile_keys + l;
+    }
+    uint64_t htot, stot;
+    uint64_t hx = block_excl_scan<SCAN_BLOCK, uint64_t>(h, s_h, htot);
+    uint64_t sx = block_excl_scan<SCAN_BLOCK, uint64_t>(s, s_s, stot);
+    // carry: position+1 of the last head before my first tile = max over the threads before me
+    s_c[t] = c;
+    __syncthreads();
+    for (uint32_t o = 1; o < SCAN_BLOCK; o <<= 1) {  // inclusive max-scan (positions grow with t)
+        const uint64_t v = t >= o ? s_c[t - o] : 0;
+        __syncthreads();
+        s_c[t] = max(s_c[t], v);
+        __syncthreads();
+    }
+    uint64_t cx = t ? s_c[t - 1] : 0;
+    for (uint32_t i = b; i < e; ++i) {
+        p.t_hpre[i] = hx;
+        p.t_spre[i] = sx;
+        p.t_carry[i] = cx;
+        hx += p.t_heads[i];
+        sx += p.t_singles[i];
+        const uint32_t l = p.t_last[i];
+        if (l) cx = (uint64_t)i * tile_keys + l;
+    }
+    if (t == 0) *p.n_out = want_singles ? stot : htot;
+}
+
+// ---- 3a. count: distinct keys + run lengths ----------------------------------------------------------
+template <typename KeyT, int IPT, bool FULL>
+__device__ __forceinline__ void rle_count_tile(const RleParams& p, const uint32_t tile, uint32_t* s_hpos, uint32_t* s_wheads) {
     constexpr int TILE = RLE_BLOCK * IPT;
     const int t = threadIdx.x;
     const uint32_t lane = t & 31, warp = t >> 5;
     const uint64_t tile_base = (uint64_t)tile * TILE;
     const uint32_t n_local = FULL ? (uint32_t)TILE : (uint32_t)(p.n - tile_base);
-    const bool more_after = tile_base + TILE < p.n;
     const uint32_t wfirst = warp * 32 * IPT;
     const KeyT* kin = reinterpret_cast<const KeyT*>(p.keys_in) + tile_base;
+    const uint64_t excl_heads = p.t_hpre[tile];
+    const uint64_t carry = p.t_carry[tile];  // position+1 of the head of the run open at tile start
 
     KeyT keys[IPT];
     uint32_t hb[IPT];
     uint32_t hnext;
-    load_heads<KeyT, IPT, FULL>(kin, tile_base, n_local, more_after, wfirst, keys, hb, hnext);
+    load_heads<KeyT, IPT, FULL>(kin, tile_base, n_local, tile_base + TILE < p.n, wfirst, keys, hb, hnext);
 
-    // real heads per warp -> tile-local ordinals
     uint32_t wheads = 0;
 #pragma unroll
     for (int j = 0; j < IPT; ++j) wheads += __popc(FULL ? hb[j] : (hb[j] & valid_mask(wfirst + 32 * j, n_local)));
     if (lane == 0) s_wheads[warp] = wheads;
     __syncthreads();
-    uint32_t wexcl = 0, theads = 0;
+    uint32_t wexcl = 0;
 #pragma unroll
-    for (int w = 0; w < RLE_WARPS; ++w) {
-        const uint32_t c = s_wheads[w];
-        if (w < (int)warp) wexcl += c;
-        theads += c;
-    }
+    for (int w = 0; w < RLE_WARPS; ++w)
+        if (w < (int)warp) wexcl += s_wheads[w];
     const uint32_t lt = lanemask_lt();
     {
         uint32_t run = wexcl;
@@ -128,70 +229,8 @@ __device__ __forceinline__ void rle_count_tile(const RleParams& p, const uint32_
         }
     }
     __syncthreads();
-    if (t < 32) {
-        // Two-level prefix (common.cuh) over the pair (number of heads: SUM, position+1 of the
-        // last head: MAX -- positions grow with the tile index, so the nearest preceding head is
-        // the maximum).  Both words carry their own flag; a slot counts when both are set.
-        const uint32_t n_tiles = gridDim.x;
-        const uint32_t g = tile / SC_GROUP, r = tile % SC_GROUP;
-        uint64_t* ginc_a = p.state_a + n_tiles;
-        uint64_t* ginc_b = p.state_b + n_tiles;
-        const uint64_t last_plus1 = theads ? tile_base + s_hpos[theads - 1] + 1 : 0;
-        if (lane == 0) {
-            st_relaxed_u64(&p.state_b[tile], SC_FLAG | last_plus1);
-            st_relaxed_u64(&p.state_a[tile], SC_FLAG | theads);
-        }
-        uint32_t spins = 0;
-        uint64_t ga = SC_FLAG, gb = SC_FLAG;
-        if (lane == 0 && g > 0) {
-            ga = ld_relaxed_u64(&ginc_a[g - 1]);
-            gb = ld_relaxed_u64(&ginc_b[g - 1]);
-        }
-        uint64_t wa[SC_GROUP / 32], wb[SC_GROUP / 32];
-#pragma unroll
-        for (int q = 0; q < (int)(SC_GROUP / 32); ++q) {
-            const uint32_t j = lane + 1 + 32 * q;
-            wa[q] = j <= r ? ld_relaxed_u64(&p.state_a[tile - j]) : SC_FLAG;
-            wb[q] = j <= r ? ld_relaxed_u64(&p.state_b[tile - j]) : SC_FLAG;
-        }
-        uint64_t excl = 0, carry = 0;
-#pragma unroll
-        for (int q = 0; q < (int)(SC_GROUP / 32); ++q) {
-            const uint32_t j = lane + 1 + 32 * q;
-            if (j <= r) {
-                wa[q] = sc_wait(&p.state_a[tile - j], wa[q], spins, p.err);
-                wb[q] = sc_wait(&p.state_b[tile - j], wb[q], spins, p.err);
-            }
-            excl += wa[q] & SC_VALUE_MASK;
-            carry = max(carry, wb[q] & SC_VALUE_MASK);
-        }
-        if (lane == 0 && g > 0) {
-            ga = sc_wait(&ginc_a[g - 1], ga, spins, p.err);
-            gb = sc_wait(&ginc_b[g - 1], gb, spins, p.err);
-        }
-        excl += ga & SC_VALUE_MASK;
-        carry = max(carry, gb & SC_VALUE_MASK);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            excl += __shfl_xor_sync(0xffffffffu, excl, o);
-            carry = max(carry, __shfl_xor_sync(0xffffffffu, carry, o));
-        }
-        if (lane == 0) {
-            if (r == SC_GROUP - 1) {
-                st_relaxed_u64(&ginc_b[g], SC_FLAG | max(carry, last_plus1));
-                st_relaxed_u64(&ginc_a[g], SC_FLAG | (excl + theads));
-            }
-            s_bcast[0] = excl;
-            s_bcast[1] = carry;  // position+1 of the head of the run that is open when the tile starts
-            if (tile == gridDim.x - 1) *p.n_out = excl + theads;
-        }
-    }
-    __syncthreads();
-    const uint64_t excl_heads = s_bcast[0];
-    const uint64_t carry = s_bcast[1];
     KeyT* keys_out = reinterpret_cast<KeyT*>(p.keys_out) + excl_heads;
     uint32_t* counts_out = p.counts_out + excl_heads;  // slot -1 (the run open at tile start) is valid when used
-
     uint32_t run = wexcl;  // heads of the tile before the current step
 #pragma unroll
     for (int j = 0; j < IPT; ++j) {
@@ -222,32 +261,28 @@ __global__ void __launch_bounds__(RLE_BLOCK, 3) rle_count_kernel(const RleParams
     constexpr int TILE = RLE_BLOCK * IPT;
     __shared__ uint32_t s_hpos[TILE];  // local position of the i-th head of the tile
     __shared__ uint32_t s_wheads[RLE_WARPS];
-    __shared__ uint32_t s_tile;
-    __shared__ uint64_t s_bcast[2];
-    if (threadIdx.x == 0) s_tile = atomicAdd(p.ticket, 1u);
-    __syncthreads();
-    const uint32_t tile = s_tile;
-    if ((uint64_t)(tile + 1) * TILE <= p.n) rle_count_tile<KeyT, IPT, true>(p, tile, s_hpos, s_wheads, s_bcast);
-    else rle_count_tile<KeyT, IPT, false>(p, tile, s_hpos, s_wheads, s_bcast);
+    const uint32_t tile = blockIdx.x;
+    if ((uint64_t)(tile + 1) * TILE <= p.n) rle_count_tile<KeyT, IPT, true>(p, tile, s_hpos, s_wheads);
+    else rle_count_tile<KeyT, IPT, false>(p, tile, s_hpos, s_wheads);
 }
 
-// singletons: head && tail, compacted in order, with payload
+// ---- 3b. singletons: head && tail, compacted in order, with payload ------------------------------------
 template <typename KeyT, int VAL_BYTES, int IPT, bool FULL>
-__device__ __forceinline__ void select_tile(const RleParams& p, const uint32_t tile, uint32_t* s_wcnt, uint64_t* s_bcast) {
+__device__ __forceinline__ void select_tile(const RleParams& p, const uint32_t tile, uint32_t* s_wcnt) {
     constexpr int TILE = RLE_BLOCK * IPT;
     using ValT = typename std::conditional<VAL_BYTES == 4, uint32_t, uint64_t>::type;
     const int t = threadIdx.x;
     const uint32_t lane = t & 31, warp = t >> 5;
     const uint64_t tile_base = (uint64_t)tile * TILE;
     const uint32_t n_local = FULL ? (uint32_t)TILE : (uint32_t)(p.n - tile_base);
-    const bool more_after = tile_base + TILE < p.n;
     const uint32_t wfirst = warp * 32 * IPT;
     const KeyT* kin = reinterpret_cast<const KeyT*>(p.keys_in) + tile_base;
+    const uint64_t tile_excl = p.t_spre[tile];
 
     KeyT keys[IPT];
     uint32_t hb[IPT];
     uint32_t hnext;
-    load_heads<KeyT, IPT, FULL>(kin, tile_base, n_local, more_after, wfirst, keys, hb, hnext);
+    load_heads<KeyT, IPT, FULL>(kin, tile_base, n_local, tile_base + TILE < p.n, wfirst, keys, hb, hnext);
 
     uint32_t sb[IPT];  // singleton ballots
     uint32_t wcnt = 0;
@@ -260,22 +295,11 @@ __device__ __forceinline__ void select_tile(const RleParams& p, const uint32_t t
     }
     if (lane == 0) s_wcnt[warp] = wcnt;
     __syncthreads();
-    uint32_t wexcl = 0, total = 0;
+    uint32_t wexcl = 0;
 #pragma unroll
-    for (int w = 0; w < RLE_WARPS; ++w) {
-        const uint32_t c = s_wcnt[w];
-        if (w < (int)warp) wexcl += c;
-        total += c;
-    }
-    if (t < 32) {
-        const uint64_t excl = tile_prefix_exclusive_warp(p.state_a, gridDim.x, tile, total, p.err);
-        if (t == 0) {
-            s_bcast[0] = excl;
-            if (tile == gridDim.x - 1) *p.n_out = excl + total;
-        }
-    }
-    __syncthreads();
-    const uint64_t base = s_bcast[0] + wexcl;
+    for (int w = 0; w < RLE_WARPS; ++w)
+        if (w < (int)warp) wexcl += s_wcnt[w];
+    const uint64_t base = tile_excl + wexcl;
     KeyT* keys_out = reinterpret_cast<KeyT*>(p.keys_out) + base;
     const ValT* vals_in = reinterpret_cast<const ValT*>(p.vals_in) + tile_base;
     ValT* vals_out = reinterpret_cast<ValT*>(p.vals_out) + base;
@@ -296,13 +320,9 @@ template <typename KeyT, int VAL_BYTES, int IPT>
 __global__ void __launch_bounds__(RLE_BLOCK, 3) select_singletons_kernel(const RleParams p) {
     constexpr int TILE = RLE_BLOCK * IPT;
     __shared__ uint32_t s_wcnt[RLE_WARPS];
-    __shared__ uint32_t s_tile;
-    __shared__ uint64_t s_bcast[2];
-    if (threadIdx.x == 0) s_tile = atomicAdd(p.ticket, 1u);
-    __syncthreads();
-    const uint32_t tile = s_tile;
-    if ((uint64_t)(tile + 1) * TILE <= p.n) select_tile<KeyT, VAL_BYTES, IPT, true>(p, tile, s_wcnt, s_bcast);
-    else select_tile<KeyT, VAL_BYTES, IPT, false>(p, tile, s_wcnt, s_bcast);
+    const uint32_t tile = blockIdx.x;
+    if ((uint64_t)(tile + 1) * TILE <= p.n) select_tile<KeyT, VAL_BYTES, IPT, true>(p, tile, s_wcnt);
+    else select_tile<KeyT, VAL_BYTES, IPT, false>(p, tile, s_wcnt);
 }
 
 constexpr int RLE_IPT8 = 16;   // 8-byte keys: 4096-key tiles
@@ -312,28 +332,45 @@ constexpr int RLE_IPT16 = 8;   // 16-byte keys: 2048-key tiles
 
 using namespace kmg;
 
+static size_t rle_tiles_max(uint64_t n) { return n / 2048 + 2; }
+
 extern "C" size_t kmg_rle_workspace_bytes(uint64_t n) {
-    const uint64_t tiles = n / 1024 + 2;
-    return sizeof(WsHeader) + 2 * align_up(sc_state_words(tiles) * sizeof(uint64_t), 256);
+    const size_t t = rle_tiles_max(n);
+    return sizeof(WsHeader) + 3 * align_up(t * sizeof(uint32_t), 256) + 3 * align_up(t * sizeof(uint64_t), 256);
 }
 
-static int rle_setup(RleParams& p, uint64_t n, int key_bytes, void* d_ws, size_t ws_bytes, uint32_t& tiles,
-                     cudaStream_t st) {
+static int rle_setup(RleParams& p, uint64_t n, int key_bytes, void* d_ws, size_t ws_bytes, cudaStream_t st) {
     KMG_REQUIRE(key_bytes == 8 || key_bytes == 16, KMG_ERR_ARG, "key_bytes must be 8 or 16");
     KMG_REQUIRE(d_ws, KMG_ERR_ARG, "null workspace");
     KMG_REQUIRE(ws_bytes >= kmg_rle_workspace_bytes(n), KMG_ERR_WS, "rle workspace too small");
     const uint64_t tile = key_bytes == 8 ? RLE_BLOCK * RLE_IPT8 : RLE_BLOCK * RLE_IPT16;
     const uint64_t nt = (n + tile - 1) / tile;
     KMG_REQUIRE(nt < (1ull << 31), KMG_ERR_RANGE, "too many tiles");
-    tiles = (uint32_t)nt;
-    const size_t arr = align_up(sc_state_words(n / 1024 + 2) * sizeof(uint64_t), 256);
-    KMG_CUDA(cudaMemsetAsync(d_ws, 0, sizeof(WsHeader) + 2 * arr, st));
-    WsHeader* hdr = reinterpret_cast<WsHeader*>(d_ws);
+    KMG_CUDA(cudaMemsetAsync(d_ws, 0, sizeof(WsHeader), st));
+    const size_t t = rle_tiles_max(n);
+    const size_t a32 = align_up(t * sizeof(uint32_t), 256), a64 = align_up(t * sizeof(uint64_t), 256);
+    char* at = (char*)d_ws;
+    WsHeader* hdr = reinterpret_cast<WsHeader*>(at);
+    at += sizeof(WsHeader);
     p.n = n;
-    p.state_a = reinterpret_cast<uint64_t*>(hdr + 1);
-    p.state_b = reinterpret_cast<uint64_t*>((char*)(hdr + 1) + arr);
-    p.ticket = &hdr->ticket;
+    p.n_tiles = (uint32_t)nt;
+    p.t_heads = (uint32_t*)at; at += a32;
+    p.t_singles = (uint32_t*)at; at += a32;
+    p.t_last = (uint32_t*)at; at += a32;
+    p.t_hpre = (uint64_t*)at; at += a64;
+    p.t_spre = (uint64_t*)at; at += a64;
+    p.t_carry = (uint64_t*)at; at += a64;
     p.err = &hdr->err;
+    return KMG_OK;
+}
+
+static int rle_prepass(const RleParams& p, int key_bytes, int want_singles, cudaStream_t st) {
+    if (key_bytes == 8) rle_tile_aggregates<uint64_t, RLE_IPT8><<<p.n_tiles, RLE_BLOCK, 0, st>>>(p);
+    else rle_tile_aggregates<u128, RLE_IPT16><<<p.n_tiles, RLE_BLOCK, 0, st>>>(p);
+    KMG_LAUNCH_CHECK();
+    const uint32_t tile_keys = key_bytes == 8 ? RLE_BLOCK * RLE_IPT8 : RLE_BLOCK * RLE_IPT16;
+    rle_scan_tiles<<<1, SCAN_BLOCK, 0, st>>>(p, tile_keys, want_singles);
+    KMG_LAUNCH_CHECK();
     return KMG_OK;
 }
 
@@ -346,15 +383,16 @@ extern "C" int kmg_rle_count(const void* d_sorted_keys, uint64_t n, int key_byte
     KMG_REQUIRE(d_sorted_keys && d_uniq_keys_out && d_counts_out, KMG_ERR_ARG, "null pointer argument");
     RleParams p;
     memset(&p, 0, sizeof(p));
-    uint32_t tiles = 0;
-    int rcode = rle_setup(p, n, key_bytes, d_ws, ws_bytes, tiles, st);
+    int rcode = rle_setup(p, n, key_bytes, d_ws, ws_bytes, st);
     if (rcode != KMG_OK) return rcode;
     p.keys_in = d_sorted_keys;
     p.keys_out = d_uniq_keys_out;
     p.counts_out = d_counts_out;
     p.n_out = reinterpret_cast<unsigned long long*>(d_n_out);
-    if (key_bytes == 8) rle_count_kernel<uint64_t, RLE_IPT8><<<tiles, RLE_BLOCK, 0, st>>>(p);
-    else rle_count_kernel<u128, RLE_IPT16><<<tiles, RLE_BLOCK, 0, st>>>(p);
+    rcode = rle_prepass(p, key_bytes, 0, st);
+    if (rcode != KMG_OK) return rcode;
+    if (key_bytes == 8) rle_count_kernel<uint64_t, RLE_IPT8><<<p.n_tiles, RLE_BLOCK, 0, st>>>(p);
+    else rle_count_kernel<u128, RLE_IPT16><<<p.n_tiles, RLE_BLOCK, 0, st>>>(p);
     KMG_LAUNCH_CHECK();
     return KMG_OK;
 }
@@ -372,14 +410,16 @@ extern "C" int kmg_select_singletons(const void* d_sorted_keys, const void* d_va
     KMG_REQUIRE(d_sorted_keys && d_keys_out, KMG_ERR_ARG, "null pointer argument");
     RleParams p;
     memset(&p, 0, sizeof(p));
-    uint32_t tiles = 0;
-    int rcode = rle_setup(p, n, key_bytes, d_ws, ws_bytes, tiles, st);
+    int rcode = rle_setup(p, n, key_bytes, d_ws, ws_bytes, st);
     if (rcode != KMG_OK) return rcode;
     p.keys_in = d_sorted_keys;
     p.vals_in = d_vals;
     p.keys_out = d_keys_out;
     p.vals_out = d_vals_out;
     p.n_out = reinterpret_cast<unsigned long long*>(d_n_out);
+    rcode = rle_prepass(p, key_bytes, 1, st);
+    if (rcode != KMG_OK) return rcode;
+    const uint32_t tiles = p.n_tiles;
     if (key_bytes == 8) {
         if (val_bytes == 0) select_singletons_kernel<uint64_t, 0, RLE_IPT8><<<tiles, RLE_BLOCK, 0, st>>>(p);
         else if (val_bytes == 4) select_singletons_kernel<uint64_t, 4, RLE_IPT8><<<tiles, RLE_BLOCK, 0, st>>>(p);
