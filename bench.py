@@ -232,7 +232,7 @@ def main():
             return dc.count(d, K, False)
     else:
         def step():
-            a = eng.sort(eng.extract(d, K, False, val_bytes=0, reuse="bench_"))
+            a = eng.sort(eng.extract(d, K, False, val_bytes=0, reuse="bench_", want_hist=True))
             return eng.rle_count(a, reuse="bench_")
 
     def barrier():

@@ -81,21 +81,25 @@ int kmg_ws_status(void* d_ws, void* stream);
  * d_vals_out may be NULL (val_bytes 0).  `pos_offset` is added to the window start before
  * it is stored in the payload (multi-GPU chunks).
  * d_counts[0] = number of keys emitted, d_counts[1] (narrow only) = number of windows
- * that belong to the wide stream.  Output capacity must be (win_end-win_begin)*(1+rc). */
+ * that belong to the wide stream.  Output capacity must be (win_end-win_begin)*(1+rc).
+ * d_hist_out (optional, narrow stream, k >= 4): uint64[16][256] digit histograms of the emitted
+ * keys for kmg_radix_sort's pass plan over bits [0, 2k), derived from one 4-mer histogram of
+ * the bases; hand it to kmg_radix_sort(d_hist_in) to skip the sort's own histogram sweep. */
 size_t kmg_extract_workspace_bytes(uint64_t n_windows);
 int kmg_extract(const uint8_t* d_bases, uint64_t n_bases, uint64_t win_begin, uint64_t win_end, int k, int rc,
                 int wide, const uint8_t* d_lut256, const uint8_t* d_comp16, void* d_keys_out, int key_bytes,
-                void* d_vals_out, int val_bytes, uint64_t pos_offset, uint64_t* d_counts, void* d_ws,
-                size_t ws_bytes, void* stream);
+                void* d_vals_out, int val_bytes, uint64_t pos_offset, uint64_t* d_counts, uint64_t* d_hist_out,
+                void* d_ws, size_t ws_bytes, void* stream);
 
 /* ---- K3: HBM-resident LSD radix sort (batch.py:156-168 + the merge of join.py:63-93) --
  * Stable, sorts on key bits [begin_bit, end_bit).  Ping-pongs between (keys, keys_alt)
  * [and (vals, vals_alt)]; *h_selector_out (host, written before return) is 0 if the
- * result is in keys/vals, 1 if in keys_alt/vals_alt. */
+ * result is in keys/vals, 1 if in keys_alt/vals_alt.  d_hist_in (optional): the digit histograms
+ * kmg_extract produced for exactly these keys (requires begin_bit 0, end_bit 2k). */
 size_t kmg_radix_sort_workspace_bytes(uint64_t n, int key_bytes, int val_bytes, int begin_bit, int end_bit);
 int kmg_radix_sort(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_alt, uint64_t n, int key_bytes,
-                   int val_bytes, int begin_bit, int end_bit, int* h_selector_out, void* d_ws, size_t ws_bytes,
-                   void* stream);
+                   int val_bytes, int begin_bit, int end_bit, const uint64_t* d_hist_in, int* h_selector_out,
+                   void* d_ws, size_t ws_bytes, void* stream);
 
 /* ---- K4: run-length / unique on sorted keys (join.py:95-130, :265-285, :243-263) ------
  * rle_count: distinct keys ascending + run lengths; *d_n_out = number of runs.

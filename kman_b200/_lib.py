@@ -28,9 +28,9 @@ SIGNATURES = {
     "kmg_build_lut": (i32, [C.c_char_p, C.c_char_p, u8p, u8p]),
     "kmg_ws_status": (i32, [vp, vp]),
     "kmg_extract_workspace_bytes": (sz, [u64]),
-    "kmg_extract": (i32, [vp, u64, u64, u64, i32, i32, i32, vp, vp, vp, i32, vp, i32, u64, vp, vp, sz, vp]),
+    "kmg_extract": (i32, [vp, u64, u64, u64, i32, i32, i32, vp, vp, vp, i32, vp, i32, u64, vp, vp, vp, sz, vp]),
     "kmg_radix_sort_workspace_bytes": (sz, [u64, i32, i32, i32, i32]),
-    "kmg_radix_sort": (i32, [vp, vp, vp, vp, u64, i32, i32, i32, i32, C.POINTER(i32), vp, sz, vp]),
+    "kmg_radix_sort": (i32, [vp, vp, vp, vp, u64, i32, i32, i32, i32, vp, C.POINTER(i32), vp, sz, vp]),
     "kmg_rle_workspace_bytes": (sz, [u64]),
     "kmg_rle_count": (i32, [vp, u64, i32, vp, vp, vp, vp, sz, vp]),
     "kmg_select_singletons": (i32, [vp, vp, u64, i32, i32, vp, vp, vp, vp, sz, vp]),

@@ -137,6 +137,7 @@ struct kmg_ctx {
     size_t pool_bytes;
     uint8_t* d_lut;
     uint64_t* d_small;  // counters
+    uint64_t* d_hist;   // [16][256] digit histograms handed from extract to sort
 };
 
 extern "C" int kmg_ctx_create(int device, kmg_ctx** out) {
@@ -151,6 +152,7 @@ extern "C" int kmg_ctx_create(int device, kmg_ctx** out) {
     KMG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     KMG_CUDA(cudaMalloc(&c->d_lut, 256));
     KMG_CUDA(cudaMalloc(&c->d_small, 64));
+    KMG_CUDA(cudaMalloc(&c->d_hist, sizeof(uint64_t) * 16 * 256));
     *out = c;
     return KMG_OK;
 }
@@ -161,6 +163,7 @@ extern "C" void kmg_ctx_destroy(kmg_ctx* c) {
     if (c->pool) cudaFree(c->pool);
     cudaFree(c->d_lut);
     cudaFree(c->d_small);
+    cudaFree(c->d_hist);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -241,8 +244,9 @@ static int run_host(kmg_ctx* c, int mode, const uint8_t* h_bases, uint64_t n_bas
 
     KMG_CUDA(cudaMemcpyAsync(c->d_lut, h_lut256, 256, cudaMemcpyHostToDevice, st));
     KMG_CUDA(cudaMemcpyAsync(d_bases, h_bases, n_bases, cudaMemcpyHostToDevice, st));
+    uint64_t* d_hist = k >= 4 ? c->d_hist : nullptr;
     int rcode = kmg_extract(d_bases, n_bases, 0, n_win, k, rc, 0, c->d_lut, nullptr, d_keys, kb, d_vals, vb, 0,
-                            c->d_small, d_ws, ws_bytes, st);
+                            c->d_small, d_hist, d_ws, ws_bytes, st);
     if (rcode != KMG_OK) return rcode;
     uint64_t h_counts[2] = {0, 0};
     KMG_CUDA(cudaMemcpyAsync(h_counts, c->d_small, 16, cudaMemcpyDeviceToHost, st));
@@ -254,7 +258,7 @@ static int run_host(kmg_ctx* c, int mode, const uint8_t* h_bases, uint64_t n_bas
     const uint64_t n = h_counts[0];
     if (n == 0) return KMG_OK;
     int sel = 0;
-    rcode = kmg_radix_sort(d_keys, d_keys_alt, d_vals, d_vals_alt, n, kb, vb, 0, 2 * k, &sel, d_ws, ws_bytes, st);
+    rcode = kmg_radix_sort(d_keys, d_keys_alt, d_vals, d_vals_alt, n, kb, vb, 0, 2 * k, d_hist, &sel, d_ws, ws_bytes, st);
     if (rcode != KMG_OK) return rcode;
     char* sk = sel ? d_keys_alt : d_keys;
     char* ok = sel ? d_keys : d_keys_alt;  // the other buffer receives the compacted output

@@ -44,6 +44,33 @@ void bump_launches(int n = 1);
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// ---- radix pass plan (shared by the sort and by the extract kernel's fused histograms) -------------
+constexpr int MAX_PASSES = 16;
+constexpr int SORT_RADIX_BITS = 8;
+constexpr int SORT_RADIX = 1 << SORT_RADIX_BITS;
+
+struct PassPlan {
+    int num_passes;
+    int shift[MAX_PASSES];
+    int bits[MAX_PASSES];
+};
+
+// Full 8-bit digits from `begin_bit` upwards; the top pass takes what is left.  Packed keys hold
+// 2 bits per base, so with begin_bit = 0 every digit is a whole number of bases -- which is what
+// lets kmg_extract derive all digit histograms from ONE 4-mer histogram (extract.cu).
+static inline PassPlan make_plan(int begin_bit, int end_bit) {
+    PassPlan plan;
+    memset(&plan, 0, sizeof(plan));
+    const int bits = end_bit - begin_bit;
+    const int np = (bits + SORT_RADIX_BITS - 1) / SORT_RADIX_BITS;
+    plan.num_passes = np;
+    for (int i = 0; i < np; ++i) {
+        plan.shift[i] = begin_bit + i * SORT_RADIX_BITS;
+        plan.bits[i] = i + 1 < np ? SORT_RADIX_BITS : bits - i * SORT_RADIX_BITS;
+    }
+    return plan;
+}
+
 // ---- 128-bit key ------------------------------------------------------------------------
 struct __align__(16) u128 {
     uint64_t lo, hi;

@@ -31,7 +31,31 @@ struct ExtractParams {
     uint64_t* tile_state;
     uint32_t* ticket;
     uint32_t* err;
+    // fused digit histograms (narrow stream): hs[o][x] counts the plain 4-mers x found at window
+    // start + hist_off[o]; hs[n_off] is the unshifted 4-mer histogram G (see hist_finalize_kernel)
+    unsigned long long* hs;
+    int n_off;
+    int hist_off[2 * MAX_PASSES];
 };
+
+constexpr int EX_MAX_OFF = 2 * MAX_PASSES;
+
+// 4 consecutive bases starting at base e (0 <= e <= 92) of the 96-base big-endian string X0:X1:X2
+__device__ __forceinline__ uint32_t mer4_at(uint64_t X0, uint64_t X1, uint64_t X2, int e) {
+    const int w = e >> 5, off = 2 * (e & 31);
+    const uint64_t a = w == 0 ? X0 : (w == 1 ? X1 : X2);
+    const uint64_t b = w == 0 ? X1 : (w == 1 ? X2 : 0ull);
+    const uint64_t v = off == 0 ? a : ((a << off) | (b >> (64 - off)));
+    return (uint32_t)(v >> 56);
+}
+// are the 4 bases starting at base e (0 <= e <= 124) of the 128-base mask string B0:B1 all plain?
+__device__ __forceinline__ bool plain4_at(uint64_t B0, uint64_t B1, int e) {
+    uint64_t v;
+    if (e == 0) v = B0;
+    else if (e < 64) v = (B0 << e) | (B1 >> (64 - e));
+    else v = B1 << (e - 64);
+    return (v >> 60) == 0;
+}
 
 __device__ __forceinline__ uint64_t rev2_64(uint64_t x) {
     x = __brevll(x);
@@ -58,7 +82,7 @@ __device__ __forceinline__ ValT make_val(uint64_t pos, uint32_t strand) {
 }
 
 // KeyT: uint64_t (k<=32) or u128 (33<=k<=64).  PPT: window starts per thread (8 or 16).
-template <typename KeyT, int PPT, bool RC, int VAL_BYTES>
+template <typename KeyT, int PPT, bool RC, int VAL_BYTES, bool HIST>
 __global__ void __launch_bounds__(EX_BLOCK) extract_narrow_kernel(const ExtractParams p) {
     constexpr int TILE = EX_BLOCK * PPT;
     constexpr int WORDS = TILE / 16 + EX_HALO_WORDS;
@@ -80,12 +104,18 @@ __global__ void __launch_bounds__(EX_BLOCK) extract_narrow_kernel(const ExtractP
     __shared__ uint32_t s_tile;
     __shared__ uint64_t s_base;
     __shared__ uint32_t s_wide;
+    __shared__ uint32_t s_g[HIST ? 256 : 1];                 // 4-mer histogram of the tile's window starts
+    uint32_t* s_c = reinterpret_cast<uint32_t*>(smem_raw);  // [n_off][256] corrections for skipped windows;
+                                                            // aliases the key staging buffer, used before it
+    __shared__ uint32_t s_any_skipped;
 
     const int t = threadIdx.x;
     if (t == 0) {
         s_tile = atomicAdd(p.ticket, 1u);
         s_wide = 0;
+        s_any_skipped = 0;
     }
+    if (HIST) s_g[t] = 0;
     s_lut[t] = p.lut[t];
     __syncthreads();
     const uint32_t tile = s_tile;
@@ -163,6 +193,49 @@ __global__ void __launch_bounds__(EX_BLOCK) extract_narrow_kernel(const ExtractP
     const uint32_t excl = block_excl_scan<EX_BLOCK, uint32_t>(cnt, s_scan, total);
     if (t == 0) tile_prefix_publish(p.tile_state, tile, (uint64_t)total * OUT_PER_WIN);
     if (nwide) atomicAdd(&s_wide, nwide);
+
+    if constexpr (HIST) {
+        // G: one count per window start whose first 4 bases are plain.  Digit p of a valid
+        // window's key IS the 4-mer at window start + (k-4-4p), so every pass' histogram is G
+        // over a shifted range minus the contributions of the skipped windows.
+        uint32_t in_range_mask = 0;
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+            const uint64_t pos = tile_pos + (uint64_t)t * PPT + j;
+            if (pos >= p.win_begin && pos < p.win_end) in_range_mask |= 1u << j;
+        }
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+            const int je = joff + j;
+            if (((in_range_mask >> j) & 1u) && plain4_at(B0, B1, je)) atomicAdd(&s_g[mer4_at(X0, X1, X2, je)], 1u);
+        }
+        const uint32_t skipped = in_range_mask & ~vf;
+        if (skipped) s_any_skipped = 1;  // the correction table is zeroed lazily: most tiles never touch it
+        __syncthreads();
+        if (s_any_skipped) {
+            for (int i = t; i < p.n_off * 256; i += EX_BLOCK) s_c[i] = 0;
+            __syncthreads();
+            if (skipped) {
+                for (int j = 0; j < PPT; ++j) {
+                    if (!((skipped >> j) & 1u)) continue;
+                    for (int o = 0; o < p.n_off; ++o) {
+                        const int e = joff + j + p.hist_off[o];
+                        if (plain4_at(B0, B1, e)) atomicAdd(&s_c[o * 256 + mer4_at(X0, X1, X2, e)], 1u);
+                    }
+                }
+            }
+            __syncthreads();
+            for (int i = t; i < p.n_off * 256; i += EX_BLOCK) {
+                const uint32_t c = s_c[i];
+                if (c) atomicAdd(&p.hs[i], 0ull - (unsigned long long)c);
+            }
+            __syncthreads();  // the staging buffer is about to be reused for the keys
+        }
+        {
+            const uint32_t c = s_g[t];
+            if (c) atomicAdd(&p.hs[p.n_off * 256 + t], (unsigned long long)c);
+        }
+    }
 
     // ---- keys of the valid windows, compacted in position order into the staging buffer -----
     uint32_t r = excl;
@@ -304,29 +377,96 @@ __global__ void __launch_bounds__(EXW_BLOCK) extract_wide_kernel(const ExtractPa
     if (t == 0 && tile == gridDim.x - 1) p.counts[0] = base + (uint64_t)total * OUT_PER_WIN;
 }
 
-template <typename KeyT, int PPT, bool RC, int VB>
+template <typename KeyT, int PPT, bool RC, int VB, bool HIST>
 static int launch_narrow(const ExtractParams& p, uint32_t n_tiles, cudaStream_t st) {
     constexpr int TILE = EX_BLOCK * PPT;
     constexpr uint32_t STAGE = TILE * (RC ? 2 : 1);
     constexpr uint32_t STAGE_PAD = STAGE + STAGE / 8 + 8;
     const size_t smem = (sizeof(KeyT) + (VB == 4 ? 4 : (VB == 8 ? 8 : 0))) * (size_t)STAGE_PAD;
-    auto kern = extract_narrow_kernel<KeyT, PPT, RC, VB>;
+    auto kern = extract_narrow_kernel<KeyT, PPT, RC, VB, HIST>;
     KMG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<n_tiles, EX_BLOCK, smem, st>>>(p);
     KMG_LAUNCH_CHECK();
     return KMG_OK;
 }
 
-template <typename KeyT, int PPT>
-static int dispatch_narrow(const ExtractParams& p, uint32_t n_tiles, int rc, int vb, cudaStream_t st) {
+template <typename KeyT, int PPT, bool HIST>
+static int dispatch_narrow2(const ExtractParams& p, uint32_t n_tiles, int rc, int vb, cudaStream_t st) {
     if (rc) {
-        if (vb == 0) return launch_narrow<KeyT, PPT, true, 0>(p, n_tiles, st);
-        if (vb == 4) return launch_narrow<KeyT, PPT, true, 4>(p, n_tiles, st);
-        return launch_narrow<KeyT, PPT, true, 8>(p, n_tiles, st);
+        if (vb == 0) return launch_narrow<KeyT, PPT, true, 0, HIST>(p, n_tiles, st);
+        if (vb == 4) return launch_narrow<KeyT, PPT, true, 4, HIST>(p, n_tiles, st);
+        return launch_narrow<KeyT, PPT, true, 8, HIST>(p, n_tiles, st);
     }
-    if (vb == 0) return launch_narrow<KeyT, PPT, false, 0>(p, n_tiles, st);
-    if (vb == 4) return launch_narrow<KeyT, PPT, false, 4>(p, n_tiles, st);
-    return launch_narrow<KeyT, PPT, false, 8>(p, n_tiles, st);
+    if (vb == 0) return launch_narrow<KeyT, PPT, false, 0, HIST>(p, n_tiles, st);
+    if (vb == 4) return launch_narrow<KeyT, PPT, false, 4, HIST>(p, n_tiles, st);
+    return launch_narrow<KeyT, PPT, false, 8, HIST>(p, n_tiles, st);
+}
+template <typename KeyT, int PPT>
+static int dispatch_narrow(const ExtractParams& p, uint32_t n_tiles, int rc, int vb, bool hist, cudaStream_t st) {
+    return hist ? dispatch_narrow2<KeyT, PPT, true>(p, n_tiles, rc, vb, st)
+                : dispatch_narrow2<KeyT, PPT, false>(p, n_tiles, rc, vb, st);
+}
+
+// ---- fused digit histograms: edges and final assembly -----------------------------------------------
+__device__ __forceinline__ uint32_t rc4(uint32_t x) {  // reverse complement of a packed 4-mer
+    x = ~x & 0xFFu;
+    return ((x & 3u) << 6) | ((x & 0xCu) << 2) | ((x >> 2) & 0xCu) | (x >> 6);
+}
+
+// hs[o] so far = G over [win_begin, win_end) minus the skipped windows' 4-mers at offset o.  The
+// histogram over the SHIFTED range [win_begin+o, win_end+o) differs from G by the two edges.
+__global__ void hist_edges_kernel(const ExtractParams p) {
+    __shared__ uint8_t s_lut[256];
+    s_lut[threadIdx.x] = p.lut[threadIdx.x];
+    __syncthreads();
+    for (int o = 0; o < p.n_off; ++o) {
+        const int off = p.hist_off[o];
+        for (int j = threadIdx.x; j < 2 * off; j += blockDim.x) {
+            const bool tail = j >= off;  // + 4-mers at [win_end, win_end+off), - those at [win_begin, win_begin+off)
+            const uint64_t q = (tail ? p.win_end : p.win_begin) + (uint64_t)(tail ? j - off : j);
+            if (q + 4 > p.n_bases) continue;
+            uint32_t x = 0;
+            bool plain = true;
+            for (int b = 0; b < 4; ++b) {
+                const uint32_t e = s_lut[p.bases[q + b]];
+                plain = plain && !(e & 0xC0u);
+                x = (x << 2) | (e & 3u);
+            }
+            if (plain) atomicAdd(&p.hs[o * 256 + x], tail ? 1ull : 0ull - 1ull);
+        }
+    }
+}
+
+// digit histograms of the sort plan for 2k key bits from the per-offset 4-mer histograms
+//   forward key, full digit p : 4-mer at window offset k-4-4p;   top digit (b bits): first b/2 bases
+//   rc key,      full digit p : rc4 of the 4-mer at offset 4p;    top digit: rc of the last b/2 bases
+__global__ void hist_finalize_kernel(const unsigned long long* __restrict__ hs, int n_off, int k, int rc,
+                                     unsigned long long* __restrict__ hist_out) {
+    const int P = (2 * k + 7) / 8;
+    const int b = 2 * k - 8 * (P - 1);  // bits of the top digit: 2, 4, 6 or 8
+    const unsigned long long* G = hs + (size_t)n_off * 256;
+    const int x = threadIdx.x;  // 256 threads
+    for (int pss = 0; pss < P; ++pss) hist_out[pss * 256 + x] = 0;
+    __syncthreads();
+    // offsets were laid out by the host as: [0 .. P-2] forward full digits, [P-1] forward top (offset 0),
+    // then, if rc: [P .. 2P-2] rc full digits (offset 4p), [2P-1] rc top (offset k-4)
+    for (int pss = 0; pss < P - 1; ++pss) {
+        unsigned long long v = G[x] + hs[(size_t)pss * 256 + x];
+        if (rc) v += G[rc4(x)] + hs[(size_t)(P + pss) * 256 + rc4(x)];
+        hist_out[pss * 256 + x] = v;
+    }
+    // top digit: marginalise
+    {
+        const unsigned long long v = G[x] + hs[(size_t)(P - 1) * 256 + x];
+        atomicAdd(&hist_out[(P - 1) * 256 + (x >> (8 - b))], v);
+        if (rc) {
+            const unsigned long long w = G[x] + hs[(size_t)(2 * P - 1) * 256 + x];
+            // last b/2 bases of the window = low b bits of x; their reverse complement is the rc key's top digit
+            const uint32_t low = x & ((1u << b) - 1u);
+            const uint32_t r = rc4(low << (8 - b)) & ((1u << b) - 1u);
+            atomicAdd(&hist_out[(P - 1) * 256 + r], w);
+        }
+    }
 }
 
 template <bool RC>
@@ -346,14 +486,15 @@ using namespace kmg;
 static constexpr uint64_t EX_MIN_TILE = 1024;
 
 extern "C" size_t kmg_extract_workspace_bytes(uint64_t n_windows) {
-    // header + tile states (+2 tiles for the unaligned head/tail)
-    return sizeof(WsHeader) + align_up(sc_state_words(n_windows / EX_MIN_TILE + 3) * sizeof(uint64_t), 256);
+    // header + tile states (+2 tiles for the unaligned head/tail) + per-offset 4-mer histograms
+    return sizeof(WsHeader) + align_up(sc_state_words(n_windows / EX_MIN_TILE + 3) * sizeof(uint64_t), 256) +
+           (size_t)(EX_MAX_OFF + 1) * 256 * sizeof(uint64_t);
 }
 
 extern "C" int kmg_extract(const uint8_t* d_bases, uint64_t n_bases, uint64_t win_begin, uint64_t win_end, int k,
                            int rc, int wide, const uint8_t* d_lut256, const uint8_t* d_comp16, void* d_keys_out,
                            int key_bytes, void* d_vals_out, int val_bytes, uint64_t pos_offset,
-                           uint64_t* d_counts, void* d_ws, size_t ws_bytes, void* stream) {
+                           uint64_t* d_counts, uint64_t* d_hist_out, void* d_ws, size_t ws_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     KMG_REQUIRE(k >= 2, KMG_ERR_ARG, "k must be >= 2, got %d", k);  // batcher.py:477-478
     KMG_REQUIRE(k <= 64, KMG_ERR_RANGE, "k=%d: this build supports k <= 64 (no CPU fallback)", k);
@@ -370,9 +511,11 @@ extern "C" int kmg_extract(const uint8_t* d_bases, uint64_t n_bases, uint64_t wi
     if (val_bytes == 4)
         KMG_REQUIRE(((pos_offset + n_bases) << 1) < (1ull << 32), KMG_ERR_RANGE, "val_bytes=4 needs < 2^31 positions");
     KMG_REQUIRE(ws_bytes >= kmg_extract_workspace_bytes(win_end - win_begin), KMG_ERR_WS, "extract workspace too small");
+    KMG_REQUIRE(!d_hist_out || (!wide && k >= 4), KMG_ERR_ARG, "fused digit histograms need the narrow stream and k >= 4");
 
     KMG_CUDA(cudaMemsetAsync(d_counts, 0, 2 * sizeof(uint64_t), st));
     KMG_CUDA(cudaMemsetAsync(d_ws, 0, sizeof(WsHeader), st));
+    if (d_hist_out) KMG_CUDA(cudaMemsetAsync(d_hist_out, 0, sizeof(uint64_t) * MAX_PASSES * 256, st));
     if (win_end == win_begin) return KMG_OK;
 
     const uint64_t tile = wide ? (uint64_t)EXW_TILE : (uint64_t)(EX_BLOCK * (key_bytes == 8 ? 16 : 8));
@@ -380,7 +523,9 @@ extern "C" int kmg_extract(const uint8_t* d_bases, uint64_t n_bases, uint64_t wi
     const uint64_t n_tiles = (win_end + tile - 1) / tile - first_tile;
     KMG_REQUIRE(n_tiles < (1ull << 31), KMG_ERR_RANGE, "too many tiles");
     const size_t state_bytes = align_up(sc_state_words(n_tiles) * sizeof(uint64_t), 256);
-    KMG_CUDA(cudaMemsetAsync(d_ws, 0, sizeof(WsHeader) + state_bytes, st));
+    const size_t hs_bytes = (size_t)(EX_MAX_OFF + 1) * 256 * sizeof(uint64_t);
+    KMG_REQUIRE(ws_bytes >= sizeof(WsHeader) + state_bytes + hs_bytes, KMG_ERR_WS, "extract workspace too small");
+    KMG_CUDA(cudaMemsetAsync(d_ws, 0, sizeof(WsHeader) + state_bytes + (d_hist_out ? hs_bytes : 0), st));
     WsHeader* hdr = reinterpret_cast<WsHeader*>(d_ws);
 
     ExtractParams p;
@@ -399,9 +544,29 @@ extern "C" int kmg_extract(const uint8_t* d_bases, uint64_t n_bases, uint64_t wi
     p.tile_state = reinterpret_cast<uint64_t*>(hdr + 1);
     p.ticket = &hdr->ticket;
     p.err = &hdr->err;
+    p.hs = reinterpret_cast<unsigned long long*>((char*)d_ws + sizeof(WsHeader) + state_bytes);
+    p.n_off = 0;
+    if (d_hist_out) {
+        const int P = (2 * k + 7) / 8;
+        for (int q = 0; q < P - 1; ++q) p.hist_off[q] = k - 4 - 4 * q;
+        p.hist_off[P - 1] = 0;
+        p.n_off = P;
+        if (rc) {
+            for (int q = 0; q < P - 1; ++q) p.hist_off[P + q] = 4 * q;
+            p.hist_off[2 * P - 1] = k - 4;
+            p.n_off = 2 * P;
+        }
+    }
 
     if (wide) return rc ? dispatch_wide<true>(p, (uint32_t)n_tiles, val_bytes, st)
                         : dispatch_wide<false>(p, (uint32_t)n_tiles, val_bytes, st);
-    if (key_bytes == 8) return dispatch_narrow<uint64_t, 16>(p, (uint32_t)n_tiles, rc, val_bytes, st);
-    return dispatch_narrow<u128, 8>(p, (uint32_t)n_tiles, rc, val_bytes, st);
+    int rcode;
+    if (key_bytes == 8) rcode = dispatch_narrow<uint64_t, 16>(p, (uint32_t)n_tiles, rc, val_bytes, d_hist_out != nullptr, st);
+    else rcode = dispatch_narrow<u128, 8>(p, (uint32_t)n_tiles, rc, val_bytes, d_hist_out != nullptr, st);
+    if (rcode != KMG_OK || !d_hist_out) return rcode;
+    hist_edges_kernel<<<1, 256, 0, st>>>(p);
+    KMG_LAUNCH_CHECK();
+    hist_finalize_kernel<<<1, 256, 0, st>>>(p.hs, p.n_off, k, rc, reinterpret_cast<unsigned long long*>(d_hist_out));
+    KMG_LAUNCH_CHECK();
+    return KMG_OK;
 }

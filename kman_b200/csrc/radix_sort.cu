@@ -22,14 +22,6 @@
 
 namespace kmg {
 
-constexpr int MAX_PASSES = 16;
-
-struct PassPlan {
-    int num_passes;
-    int shift[MAX_PASSES];
-    int bits[MAX_PASSES];
-};
-
 // ---- digit functions --------------------------------------------------------------------
 struct ShiftDigit {
     int shift;
@@ -181,14 +173,19 @@ __device__ __forceinline__ uint32_t lookback_two_level(const uint32_t* __restric
 }
 
 // MIX: how a warp finds the lanes that hold the same digit
-//   0 = 8 ballots per key (ALU), 1 = shared-memory lane-mask table (LSU), 2 = alternate per item
+//   0 = 8 ballots per key (ALU), 1 = shared-memory lane-mask table (LSU), 2 = alternate per item,
+//   3 = table for every 4th item, 4 = table for 3 items out of 4
+__host__ __device__ constexpr bool mix_uses_table(int mix, int i) {
+    return mix == 1 || (mix == 2 && (i & 1)) || (mix == 3 && (i & 3) == 3) || (mix == 4 && (i & 3) != 0);
+}
+__host__ __device__ constexpr int mix_tables(int mix) { return mix == 0 ? 0 : ((mix == 1 || mix == 4) ? 2 : 1); }
 template <typename KeyT, int VAL_BYTES, int RADIX_BITS, int BLOCK, int IPT, int MIX, typename DigitOp, bool FULL>
 __device__ __forceinline__ void onesweep_tile(const OnesweepParams& p, const DigitOp& digit_of, unsigned char* smem_raw,
                                               uint32_t* s_scan, const uint32_t tile, const uint32_t n_valid) {
     constexpr int RADIX = 1 << RADIX_BITS;
     constexpr int WARPS = BLOCK / 32;
     constexpr int TILE = BLOCK * IPT;
-    constexpr int NTBL = MIX == 0 ? 0 : (MIX == 1 ? 2 : 1);
+    constexpr int NTBL = mix_tables(MIX);
     static_assert(RADIX <= BLOCK, "one thread per digit in the prefix / look-back phases");
     using ValT = typename ValType<VAL_BYTES>::type;
     constexpr int ITEM_BYTES = sizeof(KeyT) > sizeof(ValT) ? sizeof(KeyT) : sizeof(ValT);
@@ -271,10 +268,10 @@ __device__ __forceinline__ void onesweep_tile(const OnesweepParams& p, const Dig
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
         const uint32_t dd = dg[i];
-        const bool use_table = MIX == 1 || (MIX == 2 && (i & 1));
+        const bool use_table = mix_uses_table(MIX, i);
         uint32_t m, cur;
         if (use_table) {
-            uint32_t* tbl = s_tbl + ((MIX == 1 ? (i & 1) : 0) * WARPS + warp) * RADIX;
+            uint32_t* tbl = s_tbl + ((NTBL == 2 ? (i & 1) : 0) * WARPS + warp) * RADIX;
             atomicOr(&tbl[dd], my_bit);
             __syncwarp();
             m = tbl[dd];
@@ -354,7 +351,7 @@ __global__ void __launch_bounds__(BLOCK, min_ctas(BLOCK, IPT)) onesweep_kernel(c
     constexpr int RADIX = 1 << RADIX_BITS;
     constexpr int WARPS = BLOCK / 32;
     constexpr int TILE = BLOCK * IPT;
-    constexpr int NTBL = MIX == 0 ? 0 : (MIX == 1 ? 2 : 1);
+    constexpr int NTBL = mix_tables(MIX);
     using ValT = typename ValType<VAL_BYTES>::type;
     constexpr int ITEM_BYTES = sizeof(KeyT) > sizeof(ValT) ? sizeof(KeyT) : sizeof(ValT);
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -381,7 +378,8 @@ struct SortTile {
 };
 // index = kmg_set_option("sort_config", i)
 static const SortTile kSortTiles[] = {
-    {256, 16, 2}, {256, 16, 0}, {256, 16, 1}, {256, 24, 2}, {512, 16, 2}, {512, 16, 0}, {384, 16, 2}, {256, 24, 0},
+    {256, 16, 2}, {256, 16, 0}, {256, 16, 1}, {256, 24, 2}, {512, 16, 2}, {256, 16, 3}, {384, 16, 2}, {256, 16, 4},
+    {256, 24, 3}, {256, 20, 2},
 };
 constexpr int kNumSortTiles = sizeof(kSortTiles) / sizeof(kSortTiles[0]);
 
@@ -389,7 +387,7 @@ template <typename KeyT, int VB, int RB, int BLOCK, int IPT, int MIX>
 static size_t onesweep_smem() {
     using ValT = typename ValType<VB>::type;
     const size_t item = sizeof(KeyT) > (VB ? sizeof(ValT) : 0) ? sizeof(KeyT) : sizeof(ValT);
-    const int ntbl = MIX == 0 ? 0 : (MIX == 1 ? 2 : 1);
+    const int ntbl = mix_tables(MIX);
     return item * BLOCK * IPT + (size_t)(1 + ntbl) * (BLOCK / 32) * (1 << RB) * 4 + (size_t)(1 << RB) * 8;
 }
 
@@ -411,9 +409,11 @@ static int dispatch_tile(int cfg, const OnesweepParams& p, const ShiftDigit& op,
         case 2: return launch_onesweep<KeyT, VB, 8, 256, 16, 1>(p, op, st);
         case 3: return launch_onesweep<KeyT, VB, 8, 256, 24, 2>(p, op, st);
         case 4: return launch_onesweep<KeyT, VB, 8, 512, 16, 2>(p, op, st);
-        case 5: return launch_onesweep<KeyT, VB, 8, 512, 16, 0>(p, op, st);
+        case 5: return launch_onesweep<KeyT, VB, 8, 256, 16, 3>(p, op, st);
         case 6: return launch_onesweep<KeyT, VB, 8, 384, 16, 2>(p, op, st);
-        case 7: return launch_onesweep<KeyT, VB, 8, 256, 24, 0>(p, op, st);
+        case 7: return launch_onesweep<KeyT, VB, 8, 256, 16, 4>(p, op, st);
+        case 8: return launch_onesweep<KeyT, VB, 8, 256, 24, 3>(p, op, st);
+        case 9: return launch_onesweep<KeyT, VB, 8, 256, 20, 2>(p, op, st);
         default: return launch_onesweep<KeyT, VB, 8, 256, 16, 2>(p, op, st);
     }
 }
@@ -437,7 +437,7 @@ static int dispatch_onesweep(int cfg, int key_bytes, int val_bytes, const Oneswe
     return launch_onesweep<u128, 8, 8, 256, 8, 2>(p, op, st);
 }
 
-int g_sort_config = 0;
+int g_sort_config = 3;  // 256 threads x 24 keys, alternating ballot / lane-mask ranking: best measured on B200
 int g_time_passes = 0;  // kmg_set_option("time_passes", 1): bracket every pass launch with events
 thread_local int64_t g_stat_sort_passes = 0;
 
@@ -485,27 +485,8 @@ static int tile_items(int cfg, int key_bytes) {
     return kSortTiles[cfg].block * kSortTiles[cfg].ipt;
 }
 
-static PassPlan make_plan(int begin_bit, int end_bit, int radix_bits) {
-    PassPlan plan;
-    memset(&plan, 0, sizeof(plan));
-    const int bits = end_bit - begin_bit;
-    const int np = (bits + radix_bits - 1) / radix_bits;
-    plan.num_passes = np;
-    int at = begin_bit;
-    for (int i = 0; i < np; ++i) {
-        // spread the bits evenly: the first (bits % np) passes get one more bit
-        const int b = bits / np + (i < bits % np ? 1 : 0);
-        plan.shift[i] = at;
-        plan.bits[i] = b;
-        at += b;
-    }
-    return plan;
-}
-
-constexpr int SORT_RADIX_BITS = 8;
-constexpr int SORT_RADIX = 1 << SORT_RADIX_BITS;
 // keys per look-back part: 30-bit counts, multiple of every tile size (lcm of tiles | 2^k*3)
-constexpr uint64_t PART_MAX = ((1ull << 30) - 1) / (4096ull * 3 * 3) * (4096ull * 3 * 3);
+constexpr uint64_t PART_MAX = ((1ull << 30) - 1) / (4096ull * 3 * 3 * 5) * (4096ull * 3 * 3 * 5);
 
 struct SortWs {
     WsHeader* hdr;
@@ -546,8 +527,8 @@ extern "C" size_t kmg_radix_sort_workspace_bytes(uint64_t n, int key_bytes, int 
 }
 
 extern "C" int kmg_radix_sort(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_alt, uint64_t n,
-                              int key_bytes, int val_bytes, int begin_bit, int end_bit, int* h_selector_out,
-                              void* d_ws, size_t ws_bytes, void* stream) {
+                              int key_bytes, int val_bytes, int begin_bit, int end_bit, const uint64_t* d_hist_in,
+                              int* h_selector_out, void* d_ws, size_t ws_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     KMG_REQUIRE(key_bytes == 8 || key_bytes == 16, KMG_ERR_ARG, "key_bytes must be 8 or 16");
     KMG_REQUIRE(val_bytes == 0 || val_bytes == 4 || val_bytes == 8, KMG_ERR_ARG, "val_bytes must be 0, 4 or 8");
@@ -565,7 +546,7 @@ extern "C" int kmg_radix_sort(void* d_keys, void* d_keys_alt, void* d_vals, void
     SortWs w = carve_sort_ws(d_ws, n, key_bytes);
     KMG_REQUIRE(ws_bytes >= w.total, KMG_ERR_WS, "sort workspace too small: %zu < %zu", ws_bytes, w.total);
 
-    const PassPlan plan = make_plan(begin_bit, end_bit, SORT_RADIX_BITS);
+    const PassPlan plan = make_plan(begin_bit, end_bit);
     const int np = plan.num_passes;
     const int cfg = g_sort_config;
     const uint64_t n_parts = (n + PART_MAX - 1) / PART_MAX;
@@ -576,7 +557,11 @@ extern "C" int kmg_radix_sort(void* d_keys, void* d_keys_alt, void* d_vals, void
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    {
+    const unsigned long long* hist = w.hist;
+    if (d_hist_in) {
+        // digit histograms of exactly these keys and this plan, produced by kmg_extract
+        hist = reinterpret_cast<const unsigned long long*>(d_hist_in);
+    } else {
         const int grid = (int)std::min<uint64_t>((n + 511) / 512, (uint64_t)sms * 4);
         const size_t smem = (size_t)np * SORT_RADIX * sizeof(uint32_t);
         if (key_bytes == 8)
@@ -584,9 +569,9 @@ extern "C" int kmg_radix_sort(void* d_keys, void* d_keys_alt, void* d_vals, void
         else
             radix_hist_kernel<u128, SORT_RADIX_BITS><<<grid, 512, smem, st>>>((const u128*)d_keys, n, plan, w.hist);
         KMG_LAUNCH_CHECK();
-        radix_scan_kernel<<<np, 32, 0, st>>>(w.hist, w.bins, SORT_RADIX, 2 * SORT_RADIX, nullptr);
-        KMG_LAUNCH_CHECK();
     }
+    radix_scan_kernel<<<np, 32, 0, st>>>(hist, w.bins, SORT_RADIX, 2 * SORT_RADIX, nullptr);
+    KMG_LAUNCH_CHECK();
 
     char* kin = (char*)d_keys;
     char* kout = (char*)d_keys_alt;

@@ -64,6 +64,7 @@ class KeyArray:
     wide: bool
     n_other: int = 0  # narrow extraction: windows that belong to the wide stream
     is_sorted: bool = False
+    hist: Optional[torch.Tensor] = None  # digit histograms of exactly these keys (from kmg_extract)
 
     @property
     def key_bits(self) -> int:
@@ -163,7 +164,8 @@ class Engine:
 
     # ---- K1+K2 ------------------------------------------------------------------------------
     def extract(self, d: DeviceInput, k: int, rc: bool = False, wide: bool = False, val_bytes: int = 0,
-                win_begin: int = 0, win_end: Optional[int] = None, reuse: Optional[str] = None) -> KeyArray:
+                win_begin: int = 0, win_end: Optional[int] = None, reuse: Optional[str] = None,
+                want_hist: bool = False) -> KeyArray:
         """Keys (and payload) of the windows starting in [win_begin, win_end), emission order.
 
         `reuse`: name prefix of engine-owned scratch buffers to place the output in (the
@@ -185,16 +187,21 @@ class Engine:
         vals_alt = mk("vals_alt", cap * val_bytes) if val_bytes else None
         ws_bytes = self.lib.kmg_extract_workspace_bytes(n_win)
         ws = self._buf("ws_extract", ws_bytes)
+        # fused digit histograms for the sort that follows (narrow stream only)
+        hist = None
+        if want_hist and not wide and k >= 4:
+            hist = self._buf((reuse or "") + "hist", 16 * 256 * 8) if reuse else self._new(16 * 256 * 8)
         _lib.check(
             self.lib.kmg_extract(
                 d.bases.data_ptr(), d.n_bases, win_begin, win_end, k, int(rc), int(wide), d.lut.data_ptr(),
                 d.comp16.data_ptr(), keys.data_ptr(), kb, _ptr(vals), val_bytes, d.pos_offset,
-                self._small.data_ptr(), ws.data_ptr(), ws_bytes, self._stream(),
+                self._small.data_ptr(), _ptr(hist), ws.data_ptr(), ws_bytes, self._stream(),
             )
         )
         self._status(ws)
         cnt = self._small[:2].cpu().numpy().view(np.uint64)
-        return KeyArray(keys, keys_alt, vals, vals_alt, int(cnt[0]), kb, val_bytes, k, wide, n_other=int(cnt[1]))
+        return KeyArray(keys, keys_alt, vals, vals_alt, int(cnt[0]), kb, val_bytes, k, wide, n_other=int(cnt[1]),
+                        hist=hist)
 
     # ---- K3 -----------------------------------------------------------------------------------
     def sort(self, a: KeyArray, begin_bit: int = 0, end_bit: Optional[int] = None) -> KeyArray:
@@ -203,12 +210,14 @@ class Engine:
             ws_bytes = self.lib.kmg_radix_sort_workspace_bytes(a.n, a.key_bytes, a.val_bytes, begin_bit, end_bit)
             ws = self._buf("ws_sort", ws_bytes)
             sel = C.c_int(0)
+            hist = a.hist if (begin_bit == 0 and end_bit == a.key_bits) else None
             _lib.check(
                 self.lib.kmg_radix_sort(
                     a.keys.data_ptr(), a.keys_alt.data_ptr(), _ptr(a.vals), _ptr(a.vals_alt), a.n, a.key_bytes,
-                    a.val_bytes, begin_bit, end_bit, C.byref(sel), ws.data_ptr(), ws_bytes, self._stream(),
+                    a.val_bytes, begin_bit, end_bit, _ptr(hist), C.byref(sel), ws.data_ptr(), ws_bytes, self._stream(),
                 )
             )
+            a.hist = None
             self._last_sort_ws = ws
             if sel.value:
                 a.keys, a.keys_alt = a.keys_alt, a.keys
@@ -316,7 +325,7 @@ class Engine:
     # ---- whole path on one GPU ------------------------------------------------------------------
     def sorted_streams(self, d: DeviceInput, k: int, rc: bool, val_bytes: int) -> List[KeyArray]:
         """[narrow] or [narrow, wide]: extracted and sorted key arrays of the input."""
-        narrow = self.sort(self.extract(d, k, rc, wide=False, val_bytes=val_bytes))
+        narrow = self.sort(self.extract(d, k, rc, wide=False, val_bytes=val_bytes, want_hist=True))
         out = [narrow]
         if narrow.n_other:
             if k > 32:

@@ -116,7 +116,7 @@ def _sort_case(eng, n, kb, vb, bits, seed, cfg=0, dup=False):
         a = eng.sort(a, 0, bits)
         eng._status(eng._last_sort_ws) if n > 1 else None
     finally:
-        eng.lib.kmg_set_option(b"sort_config", 0)
+        eng.lib.kmg_set_option(b"sort_config", 3)
     if limbs == 1:
         order = np.argsort(raw[:, 0], kind="stable")
         want = raw[order, 0]
@@ -139,7 +139,7 @@ def test_radix_sort_u64_bit_ranges(eng, bits):
     _sort_case(eng, 300_000, 8, 4, bits, seed=bits, dup=True)
 
 
-@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9])
 @pytest.mark.parametrize("vb", [0, 4, 8])
 def test_radix_sort_u64_tile_configs(eng, cfg, vb):
     _sort_case(eng, 500_009, 8, vb, 62, seed=cfg * 10 + vb, cfg=cfg, dup=True)
@@ -365,3 +365,38 @@ def test_cfg2_properties_100mbp(eng):
     a = eng.extract(d, k)
     all_keys = a.keys[: a.n * 8].view(torch.int64)
     assert int((keys * counts.to(torch.int64)).sum()) == int(all_keys.sum())
+
+
+# ---- fused digit histograms (extract -> sort hand-off) ------------------------------------------------
+@pytest.mark.parametrize("k", [4, 5, 7, 8, 16, 21, 31, 32, 33, 45, 64])
+@pytest.mark.parametrize("rc", [False, True])
+def test_extract_fused_histograms_match_key_digits(eng, k, rc):
+    """kmg_extract derives every radix pass' digit histogram from one 4-mer histogram of the bases
+    (+ edge / skipped-window corrections); it must equal the histogram of the emitted keys."""
+    rng = np.random.default_rng(900 + k)
+    recs = _rand_records(rng, 4, 12000, p_other=0.01) + [("tiny", "ACG"), ("short", "ACGTAC")]
+    d = eng.upload(_flat(recs))
+    n_win = d.n_bases - k + 1
+    for (wb, we) in ((0, None), (3, n_win - 5), (4096, 4096 + 5000)):
+        a = eng.extract(d, k, rc, val_bytes=0, win_begin=wb, win_end=we, want_hist=True)
+        assert a.hist is not None
+        hist = a.hist.cpu().numpy().view(np.uint64).reshape(16, 256)
+        keys = a.keys_host()
+        P = (2 * k + 7) // 8
+        for p in range(P):
+            bits = 8 if p + 1 < P else 2 * k - 8 * (P - 1)
+            sh = 8 * p
+            if keys.ndim == 1:
+                dig = (keys >> np.uint64(sh)) & np.uint64((1 << bits) - 1)
+            else:
+                lo, hi = keys[:, 0], keys[:, 1]
+                if sh >= 64:
+                    v = hi >> np.uint64(sh - 64)
+                elif sh == 0:
+                    v = lo
+                else:
+                    v = (lo >> np.uint64(sh)) | (hi << np.uint64(64 - sh))
+                dig = v & np.uint64((1 << bits) - 1)
+            want = np.bincount(dig.astype(np.int64), minlength=256).astype(np.uint64)
+            assert first_diff(hist[p], want) == "equal", (k, rc, wb, we, p)
+        assert not hist[P:].any()

@@ -36,7 +36,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=100_000_000)
     ap.add_argument("--k", type=int, default=31)
-    ap.add_argument("--configs", default="0,1,2,3,4,5,6,7")
+    ap.add_argument("--configs", default="0,1,2,3,4,5,6,7,8,9")
     ap.add_argument("--vb", type=int, default=0)
     ap.add_argument("--yardstick", action="store_true")
     args = ap.parse_args()
@@ -54,7 +54,7 @@ def main():
         pass
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     res = {}
-    med, mn = timed(lambda: eng.extract(d, k, False, val_bytes=args.vb, reuse="b_"), flush=flush)
+    med, mn = timed(lambda: eng.extract(d, k, False, val_bytes=args.vb, reuse="b_", want_hist=True), flush=flush)
     W = 8 if k <= 32 else 16
     print(f"extract        : {med:8.3f} ms (min {mn:.3f})  {N/med/1e6:8.2f} G kmers/s   alg {(1+W+args.vb)*N/med/1e6:8.1f} GB/s")
     res["extract_ms"] = med
@@ -63,7 +63,7 @@ def main():
         eng.lib.kmg_set_option(b"sort_config", cfg)
 
         def run():
-            a = eng.extract(d, k, False, val_bytes=args.vb, reuse="b_")
+            a = eng.extract(d, k, False, val_bytes=args.vb, reuse="b_", want_hist=True)
             return eng.sort(a)
 
         med_all, _ = timed(run, flush=flush)
@@ -71,17 +71,17 @@ def main():
         alg = N * (W * (2 * P8 + 1) + 2 * P8 * args.vb)
         print(f"sort cfg {cfg}     : {srt:8.3f} ms  {N/srt/1e6:8.2f} G keys/s  model {alg/srt/1e6:8.1f} GB/s = {alg/srt/1e6/peak:5.3f} of measured peak")
         res[f"sort_cfg{cfg}_ms"] = srt
-    eng.lib.kmg_set_option(b"sort_config", 0)
+    eng.lib.kmg_set_option(b"sort_config", 3)
 
     def full():
-        a = eng.sort(eng.extract(d, k, False, val_bytes=0, reuse="b_"))
+        a = eng.sort(eng.extract(d, k, False, val_bytes=0, reuse="b_", want_hist=True))
         return eng.rle_count(a, reuse="b_")
 
     med_full, mn_full = timed(full, flush=flush)
     print(f"full count     : {med_full:8.3f} ms (min {mn_full:.3f})  {N/med_full/1e6:8.2f} G kmers/s")
     res["full_ms"] = med_full
     if args.yardstick:
-        a = eng.extract(d, k, False, val_bytes=0, reuse="b_")
+        a = eng.extract(d, k, False, val_bytes=0, reuse="b_", want_hist=True)
         keys = a.keys[: a.n * 8].view(torch.int64)
         med, mn = timed(lambda: torch.sort(keys), flush=flush)
         print(f"torch.sort (library yardstick): {med:8.3f} ms  {N/med/1e6:8.2f} G keys/s")
