@@ -61,48 +61,62 @@ def peak_hbm_gbs():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled every 200 ms while the timed region runs."""
+    """SM clock + throttle reasons sampled every ~10 ms WHILE the timed region runs (NVML in a
+    thread; falls back to one `nvidia-smi` query if NVML is unavailable)."""
 
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index: int):
-        self.proc = None
+        import threading
+
+        self.index = index
+        self.samples, self.reason_bits, self.max_mhz = [], 0, None
+        self._stop = threading.Event()
+        self._thread = None
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            import pynvml
+
+            pynvml.nvmlInit()
+            # honour CUDA_VISIBLE_DEVICES-style remapping when the UUID is available through torch
+            import torch
+
+            uuid = str(torch.cuda.get_device_properties(index).uuid)
+            try:
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nv = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
         except Exception:
-            self.proc = None
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:
+                pass
+            self._stop.wait(0.01)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join(timeout=2)
+            sm = sorted(self.samples)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(v for b, v in self.REASONS.items() if self.reason_bits & b),
+                    "samples": len(sm), "source": "nvml, 10 ms period, timed region only"}
         try:
-            out, _ = self.proc.communicate(timeout=5)
+            out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm",
+                                  "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
+            a, b = [float(x) for x in out.strip().split(",")[:2]]
+            return {"sm_mhz": a, "sm_max_mhz": b, "reasons": [], "samples": 1, "source": "nvidia-smi after the run"}
         except Exception:
-            self.proc.kill()
-            out = ""
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in out.splitlines():
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        # the busiest samples are the ones under load
-        sm_sorted = sorted(sm)
-        med = sm_sorted[len(sm_sorted) // 2] if sm_sorted else None
-        return {"sm_mhz": med, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"], "samples": 0}
 
 
 # ---- reference arm / cpu baseline -------------------------------------------------------------------
@@ -167,7 +181,7 @@ def workload_config(args, sample_note=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="kmg", choices=["kmg", "reference"])
     ap.add_argument("--workload", default="auto", choices=["auto", "cfg2", "cfg3"])

@@ -152,43 +152,76 @@ __global__ void __launch_bounds__(RLE_BLOCK) rle_tile_aggregates(const RleParams
     else aggregates_tile<KeyT, IPT, false>(p, tile, s_red);
 }
 
-// ---- 2. scan over the tiles (one block) -------------------------------------------------------------
+// ---- 2. scan over the tiles (one block of 32 warps; warp w owns a contiguous segment) ----------------
 constexpr int SCAN_BLOCK = 1024;
+
+__device__ __forceinline__ uint64_t warp_incl_max(uint64_t v) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint64_t t = __shfl_up_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) >= (uint32_t)o) v = max(v, t);
+    }
+    return v;
+}
+
 __global__ void __launch_bounds__(SCAN_BLOCK) rle_scan_tiles(const RleParams p, uint32_t tile_keys, int want_singles) {
-    __shared__ uint64_t s_h[SCAN_BLOCK / 32 + 1], s_s[SCAN_BLOCK / 32 + 1], s_c[SCAN_BLOCK];
-    const uint32_t t = threadIdx.x;
-    const uint32_t per = (p.n_tiles + SCAN_BLOCK - 1) / SCAN_BLOCK;
-    const uint32_t b = min(t * per, p.n_tiles), e = min(b + per, p.n_tiles);
+    __shared__ uint64_t s_h[33], s_s[33], s_c[33];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t per = ((p.n_tiles + 31) / 32 + 31) / 32 * 32;  // tiles per warp, multiple of 32
+    const uint32_t b = min(warp * per, p.n_tiles), e = min(b + per, p.n_tiles);
+    // pass 1: the segment's totals
     uint64_t h = 0, s = 0, c = 0;
-    for (uint32_t i = b; i < e; ++i) {
+    for (uint32_t i = b + lane; i < e; i += 32) {
         h += p.t_heads[i];
         s += p.t_singles[i];
         const uint32_t l = p.t_last[i];
-        if (l) c = (uint64_t)i * tile_keys + l;
+        if (l) c = max(c, (uint64_t)i * tile_keys + l);
     }
-    uint64_t htot, stot;
-    uint64_t hx = block_excl_scan<SCAN_BLOCK, uint64_t>(h, s_h, htot);
-    uint64_t sx = block_excl_scan<SCAN_BLOCK, uint64_t>(s, s_s, stot);
-    // carry: position+1 of the last head before my first tile = max over the threads before me
-    s_c[t] = c;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        h += __shfl_xor_sync(0xffffffffu, h, o);
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        c = max(c, __shfl_xor_sync(0xffffffffu, c, o));
+    }
+    if (lane == 0) {
+        s_h[warp] = h;
+        s_s[warp] = s;
+        s_c[warp] = c;
+    }
     __syncthreads();
-    for (uint32_t o = 1; o < SCAN_BLOCK; o <<= 1) {  // inclusive max-scan (positions grow with t)
-        const uint64_t v = t >= o ? s_c[t - o] : 0;
-        __syncthreads();
-        s_c[t] = max(s_c[t], v);
-        __syncthreads();
+    if (warp == 0) {  // exclusive scan of the 32 segment totals
+        const uint64_t hv = s_h[lane], sv = s_s[lane], cv = s_c[lane];
+        const uint64_t hi = warp_incl_scan(hv), si = warp_incl_scan(sv), ci = warp_incl_max(cv);
+        const uint64_t cprev = __shfl_up_sync(0xffffffffu, ci, 1);
+        s_h[lane] = hi - hv;
+        s_s[lane] = si - sv;
+        s_c[lane] = lane ? cprev : 0;
+        if (lane == 31) {
+            s_h[32] = hi;
+            s_s[32] = si;
+        }
     }
-    uint64_t cx = t ? s_c[t - 1] : 0;
-    for (uint32_t i = b; i < e; ++i) {
-        p.t_hpre[i] = hx;
-        p.t_spre[i] = sx;
-        p.t_carry[i] = cx;
-        hx += p.t_heads[i];
-        sx += p.t_singles[i];
-        const uint32_t l = p.t_last[i];
-        if (l) cx = (uint64_t)i * tile_keys + l;
+    __syncthreads();
+    // pass 2: prefixes inside the segment, 32 tiles per step
+    uint64_t hrun = s_h[warp], srun = s_s[warp], crun = s_c[warp];
+    for (uint32_t i0 = b; i0 < e; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        const bool ok = i < e;
+        const uint64_t hv = ok ? p.t_heads[i] : 0, sv = ok ? p.t_singles[i] : 0;
+        const uint32_t l = ok ? p.t_last[i] : 0;
+        const uint64_t cv = l ? (uint64_t)i * tile_keys + l : 0;
+        const uint64_t hi = warp_incl_scan(hv), si = warp_incl_scan(sv), ci = warp_incl_max(cv);
+        const uint64_t cprev = __shfl_up_sync(0xffffffffu, ci, 1);
+        if (ok) {
+            p.t_hpre[i] = hrun + hi - hv;
+            p.t_spre[i] = srun + si - sv;
+            p.t_carry[i] = max(crun, lane ? cprev : (uint64_t)0);
+        }
+        hrun += __shfl_sync(0xffffffffu, hi, 31);
+        srun += __shfl_sync(0xffffffffu, si, 31);
+        crun = max(crun, __shfl_sync(0xffffffffu, ci, 31));
     }
-    if (t == 0) *p.n_out = want_singles ? stot : htot;
+    if (threadIdx.x == 0) *p.n_out = want_singles ? s_s[32] : s_h[32];
 }
 
 // ---- 3a. count: distinct keys + run lengths ----------------------------------------------------------

@@ -16,7 +16,8 @@ n = int(os.environ.get("KMG_PROF_N", "100000000"))
 k = int(os.environ.get("KMG_PROF_K", "31"))
 vb = int(os.environ.get("KMG_PROF_VB", "0"))
 eng = get_engine(0)
-eng.lib.kmg_set_option(b"sort_config", int(os.environ.get("KMG_SORT_CONFIG", "0")))
+if "KMG_SORT_CONFIG" in os.environ:
+    eng.lib.kmg_set_option(b"sort_config", int(os.environ["KMG_SORT_CONFIG"]))
 rng = np.random.default_rng(1234)
 bases = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, size=n, dtype=np.uint8)]
 flat = fasta.FlatInput(np.concatenate([bases, np.array([10], np.uint8)]), np.array([0, n + 1], np.uint64), ["chr1"], ["chr1"])
