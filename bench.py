@@ -169,7 +169,9 @@ def workload_config(args, sample_note=None):
         wl = f"config 2: {CFG2_BASES} bp synthetic random-ACGT single record (seed 1234), k={K}, count"
     else:
         wl = (f"config 2 x {n} (weak): {n}x{CFG2_BASES} bp synthetic random-ACGT genome, one {CFG2_BASES} bp chunk per GPU "
-              f"with k-1 overlap, range partition + one all-to-all, k={K}, count")
+              f"with k-1 overlap, range partition by the top key bits, k={K}, count; exchange: "
+              + ("NCCL all-to-all of the partitioned keys" if os.environ.get("KMG_DIST_P2P", "1") == "0"
+                 else "fused extract+partition kernel storing into the owners' buffers over NVLink (CUDA IPC peer memory)"))
     cfg = {"workload": wl, "k": K, "mode": "count", "alphabet": "ACGT",
            "l2": "working set per step (keys 2x0.8 GB + table 1.2 GB per GPU) >> 126 MB L2; no explicit flush"}
     if sample_note:

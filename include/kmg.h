@@ -121,6 +121,24 @@ int kmg_range_partition(const void* d_keys, const void* d_vals, uint64_t n, int 
                         int key_bits, int n_parts, void* d_keys_out, void* d_vals_out, uint64_t* d_part_counts,
                         void* d_ws, size_t ws_bytes, void* stream);
 
+/* ---- K5b: fused extraction + range partition + peer-memory exchange (multi-GPU) --------
+ * Same extraction as kmg_extract (narrow stream), but every key is stored straight into the
+ * receive buffer of the GPU that owns its key range (part as in kmg_range_partition, with
+ * key_bits = 2k; needs k >= 8): d_dest_keys / d_dest_vals are DEVICE arrays of n_parts
+ * pointers (peer-mapped, e.g. from kmg_ipc_open), d_cursors[n_parts] holds, per destination,
+ * the first free element of THIS source's region and is advanced atomically.  With
+ * count_only != 0 nothing is written: d_counts[0..n_parts) receives the number of keys per
+ * destination and d_counts[n_parts] the number of windows that belong to the wide stream. */
+int kmg_extract_scatter(const uint8_t* d_bases, uint64_t n_bases, uint64_t win_begin, uint64_t win_end, int k, int rc,
+                        const uint8_t* d_lut256, int n_parts, void* const* d_dest_keys, void* const* d_dest_vals,
+                        int key_bytes, int val_bytes, uint64_t pos_offset, uint64_t* d_cursors, uint64_t* d_counts,
+                        int count_only, void* stream);
+/* Device memory that other processes of the same box can map (CUDA IPC, 64-byte handle). */
+int kmg_ipc_alloc(size_t bytes, void** d_ptr_out, uint8_t* h_handle64);
+int kmg_ipc_open(const uint8_t* h_handle64, void** d_ptr_out);
+int kmg_ipc_close(void* d_ptr);
+int kmg_ipc_free(void* d_ptr);
+
 /* ---- K6: text emission (join.py:262,284; seq.py:103-104,489-495) ----------------------
  * count lines "SEQ\tCOUNT\n"; *d_bytes_out = total bytes; d_text_out capacity must be
  * n*(k+12).  Symbols: narrow keys decode through "ACGT"/"ACGU" (rna != 0), wide keys

@@ -99,14 +99,122 @@ class RankShard:
     n_windows_global: int
 
 
-class DistributedCounter:
-    """`kmer count` / `kmer uniq` across the GPUs of one box."""
+class _DevMem:
+    """A raw device allocation exposed to torch through __cuda_array_interface__ (no copy)."""
 
-    def __init__(self, engine, group=None):
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+class PeerBuffers:
+    """Receive buffers of all ranks, mapped into this process with CUDA IPC.
+
+    Every rank allocates its receive buffer through libkmg (kmg_ipc_alloc), the 64-byte handles
+    are all-gathered, and each rank maps its peers' buffers (kmg_ipc_open).  `ptr_table` is the
+    device array of per-destination base pointers the scatter kernel indexes."""
+
+    def __init__(self, engine, nbytes: int, group=None):
+        import ctypes as C
+
+        from kman_b200 import _lib
+
+        self.eng, self.lib, self.group = engine, engine.lib, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.nbytes = int(nbytes)
+        ptr = C.c_void_p()
+        handle = (C.c_uint8 * 64)()
+        _lib.check(self.lib.kmg_ipc_alloc(self.nbytes, C.byref(ptr), handle))
+        self.local_ptr = ptr.value
+        self.local = torch.as_tensor(_DevMem(self.local_ptr, self.nbytes), device=engine.device)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        self.peer_ptrs = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                self.peer_ptrs.append(self.local_ptr)
+                continue
+            q = C.c_void_p()
+            hb = (C.c_uint8 * 64).from_buffer_copy(h)
+            _lib.check(self.lib.kmg_ipc_open(hb, C.byref(q)))
+            self.peer_ptrs.append(q.value)
+        self.ptr_table = torch.tensor(self.peer_ptrs, dtype=torch.int64, device=engine.device)
+
+    def close(self):
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        for r, q in enumerate(self.peer_ptrs):
+            if r != self.rank:
+                self.lib.kmg_ipc_close(q)
+        self.local = None
+        self.lib.kmg_ipc_free(self.local_ptr)
+        self.peer_ptrs = []
+
+
+class DistributedCounter:
+    """`kmer count` / `kmer uniq` across the GPUs of one box.
+
+    Two exchange paths: `p2p=True` (default when CUDA IPC works) fuses extraction, range partition
+    and the transfer into ONE kernel that stores keys into the owners' receive buffers over NVLink;
+    `p2p=False` is the plain path: extract -> range partition pass -> NCCL all-to-all."""
+
+    def __init__(self, engine, group=None, p2p: Optional[bool] = None):
         self.eng = engine
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
+        import os
+
+        self.p2p = (os.environ.get("KMG_DIST_P2P", "1") != "0") if p2p is None else p2p
+        self._peer_keys: Optional[PeerBuffers] = None
+        self._peer_vals: Optional[PeerBuffers] = None
+
+    # ---- fused extraction + partition + peer stores ---------------------------------------------
+    def _ensure_peer(self, which: str, nbytes: int) -> PeerBuffers:
+        """(Re)allocate the mapped receive buffers.  `nbytes` comes from the all-gathered count
+        matrix, so every rank takes the same decision without further communication."""
+        cur = getattr(self, which)
+        if cur is not None and cur.nbytes >= nbytes:
+            return cur
+        if cur is not None:
+            cur.close()
+        cur = PeerBuffers(self.eng, int(nbytes * 1.1) + 4096, self.group)
+        setattr(self, which, cur)
+        return cur
+
+    def _extract_exchange_p2p(self, d, k: int, rc: bool, with_vals: bool):
+        """extract_scatter: size the regions (count-only launch), agree on offsets, then one kernel
+        extracts the keys and stores them into the owning GPUs' receive buffers."""
+        from kman_b200 import _lib
+        from kman_b200.engine import KeyArray
+
+        eng, lib, G = self.eng, self.eng.lib, self.world
+        kb = 8 if k <= 32 else 16
+        vb = 8 if with_vals else 0
+        n_win = max(0, d.n_bases - k + 1)
+        counts = torch.zeros(G + 1, dtype=torch.int64, device=eng.device)
+        _lib.check(lib.kmg_extract_scatter(d.bases.data_ptr(), d.n_bases, 0, n_win, k, int(rc), d.lut.data_ptr(), G, None,
+                                           None, kb, 0, d.pos_offset, None, counts.data_ptr(), 1, eng._stream()))
+        allc = torch.empty(G * (G + 1), dtype=torch.int64, device=eng.device)
+        dist.all_gather_into_tensor(allc, counts, group=self.group)
+        M = allc.cpu().numpy().reshape(G, G + 1)
+        if int(M[:, G].sum()):
+            raise ValueError("distributed path handles the narrow (plain ACGT) stream only in this build; "
+                             f"input holds {int(M[:, G].sum())} windows with other alphabet symbols")
+        M = M[:, :G]
+        n_recv = int(M[:, self.rank].sum())
+        recv_max = int(M.sum(axis=0).max())
+        pk = self._ensure_peer("_peer_keys", recv_max * kb)
+        pv = self._ensure_peer("_peer_vals", recv_max * vb) if with_vals else None
+        # my region inside destination dst starts after the regions of the sources before me
+        cursors = torch.from_numpy(np.ascontiguousarray(M[: self.rank, :].sum(axis=0), dtype=np.int64)).to(eng.device)
+        dist.barrier(group=self.group)  # nobody still reads the receive buffers of the previous step
+        _lib.check(lib.kmg_extract_scatter(d.bases.data_ptr(), d.n_bases, 0, n_win, k, int(rc), d.lut.data_ptr(), G,
+                                           pk.ptr_table.data_ptr(), pv.ptr_table.data_ptr() if pv else None, kb, vb,
+                                           d.pos_offset, cursors.data_ptr(), None, 0, eng._stream()))
+        dist.barrier(group=self.group)  # every rank's peer stores (stream-ordered before its barrier) have landed
+        alt = eng._buf("p2p_keys_alt", max(n_recv, 1) * kb)
+        valt = eng._buf("p2p_vals_alt", max(n_recv, 1) * vb) if with_vals else None
+        return KeyArray(pk.local, alt, pv.local if pv else None, valt, n_recv, kb, vb, k, False)
 
     def shard(self, flat, k: int, alphabet: Optional[str] = None, natype=None):
         """Upload this rank's chunk of a host-resident flat input (k-1 overlap)."""
@@ -149,6 +257,10 @@ class DistributedCounter:
 
     def count(self, d, k: int, rc: bool = False):
         """This rank's slice (key range `rank`) of the global count table, narrow stream."""
+        if self.p2p and k >= 8:
+            r = self._extract_exchange_p2p(d, k, rc, with_vals=False)
+            r = self.eng.sort(r, 0, sort_bits_after_partition(r.key_bits, self.world))
+            return self.eng.rle_count(r, reuse="p2p_")
         a = self.eng.extract(d, k, rc, wide=False, val_bytes=0)
         n_other = torch.tensor([a.n_other], dtype=torch.int64, device=a.keys.device)
         dist.all_reduce(n_other, group=self.group)
@@ -159,8 +271,19 @@ class DistributedCounter:
         r = self.eng.sort(r, 0, sort_bits_after_partition(r.key_bits, self.world))
         return self.eng.rle_count(r)
 
+    def close(self):
+        for which in ("_peer_keys", "_peer_vals"):
+            cur = getattr(self, which)
+            if cur is not None:
+                cur.close()
+                setattr(self, which, None)
+
     def uniq(self, d, k: int, rc: bool = False):
         """This rank's slice of the global singleton list (keys + (pos<<1|strand) payload)."""
+        if self.p2p and k >= 8:
+            r = self._extract_exchange_p2p(d, k, rc, with_vals=True)
+            r = self.eng.sort(r, 0, sort_bits_after_partition(r.key_bits, self.world))
+            return self.eng.singletons(r)
         a = self.eng.extract(d, k, rc, wide=False, val_bytes=8)
         n_other = torch.tensor([a.n_other], dtype=torch.int64, device=a.keys.device)
         dist.all_reduce(n_other, group=self.group)

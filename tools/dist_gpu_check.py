@@ -21,6 +21,7 @@ torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 eng = get_engine(lr)
 dc = DistributedCounter(eng)
+print("p2p path:", dc.p2p, flush=True) if rank == 0 else None
 ok = True
 for k, rc in ((31, False), (21, True), (45, False)):
     seq = ko.synth_bases(3_000_000, 77).decode()
