@@ -14,6 +14,7 @@ static thread_local char g_err[512] = "";
 static thread_local int64_t g_launches = 0;
 extern int g_sort_config;
 extern int g_time_passes;
+extern int g_lb_group;
 extern thread_local int64_t g_stat_sort_passes;
 void timing_collect();
 double timing_total_ms();
@@ -50,6 +51,11 @@ extern "C" int kmg_set_option(const char* name, int64_t value) {
     KMG_REQUIRE(name, KMG_ERR_ARG, "option name is null");
     if (!strcmp(name, "sort_config")) {
         g_sort_config = (int)value;
+        return KMG_OK;
+    }
+    if (!strcmp(name, "lb_group")) {
+        KMG_REQUIRE(value >= 8 && value <= 4096, KMG_ERR_ARG, "lb_group must be in [8,4096]");
+        g_lb_group = (int)value;
         return KMG_OK;
     }
     if (!strcmp(name, "time_passes")) {

@@ -114,6 +114,7 @@ struct OnesweepParams {
     uint32_t* lb_ginc;        // [groups][RADIX]  tag | digit count of all tiles up to the END of the group
     uint32_t* ticket;
     uint32_t* err;
+    uint32_t lb_group;  // tiles per look-back group
     uint32_t tag;  // (epoch 1..3) << 30: words carrying another tag are "not written yet", so the
                    // arrays need no re-zeroing between the passes of one sort
 };
@@ -133,13 +134,14 @@ struct ValType<4> {
 // only dependency chain runs over the groups' last tiles, which resolve their prefix EARLY
 // (right after publishing their counts): one link per LB_GROUP tiles instead of one per tile.
 // Every word carries the launch's 2-bit tag; a word with another tag has not been written yet.
-constexpr uint32_t LB_GROUP = 32;
-constexpr int LB_BATCH = 16;  // loads a thread keeps in flight
+constexpr uint32_t LB_GROUP_MIN = 8;   // workspace sizing
+constexpr int LB_BATCH = 16;           // loads a thread keeps in flight
 
 __device__ __forceinline__ uint32_t lookback_two_level(const uint32_t* __restrict__ lb_agg,
-                                                       const uint32_t* __restrict__ lb_ginc, uint32_t tile, int d,
-                                                       int radix, uint32_t tag, uint32_t* err) {
-    const uint32_t g = tile / LB_GROUP, r = tile % LB_GROUP;
+                                                       const uint32_t* __restrict__ lb_ginc, uint32_t tile,
+                                                       uint32_t lb_group, int d, int radix, uint32_t tag,
+                                                       uint32_t* err) {
+    const uint32_t g = tile / lb_group, r = tile % lb_group;
     uint32_t excl = 0, spins = 0;
     const uint32_t* gsrc = lb_ginc + (size_t)(g ? g - 1 : 0) * radix + d;
     uint32_t gw = g ? ld_relaxed_u32(gsrc) : tag;  // issued first: it is the one that may lag
@@ -242,7 +244,8 @@ __device__ __forceinline__ void onesweep_tile(const OnesweepParams& p, const Dig
     }
     uint32_t total;
     const uint32_t bin_excl = block_excl_scan<BLOCK, uint32_t>(cnt, s_scan, total);
-    const bool group_end = tile % LB_GROUP == LB_GROUP - 1;
+    const uint32_t lb_group = p.lb_group;
+    const bool group_end = tile % lb_group == lb_group - 1;
     uint32_t excl = 0;
     if (d < RADIX) {
         // fold the digit's tile-local base into every warp's running offset
@@ -251,8 +254,8 @@ __device__ __forceinline__ void onesweep_tile(const OnesweepParams& p, const Dig
         if (group_end) {  // the chain link: resolve and publish the group's inclusive prefix now
             uint32_t c = cnt;
             if (!FULL && d == RADIX - 1) c -= padding;
-            excl = lookback_two_level(p.lb_agg, p.lb_ginc, tile, d, RADIX, tag, p.err);
-            st_relaxed_u32(p.lb_ginc + (size_t)(tile / LB_GROUP) * RADIX + d, tag | (excl + c));
+            excl = lookback_two_level(p.lb_agg, p.lb_ginc, tile, lb_group, d, RADIX, tag, p.err);
+            st_relaxed_u32(p.lb_ginc + (size_t)(tile / lb_group) * RADIX + d, tag | (excl + c));
         }
     }
     __syncthreads();
@@ -302,7 +305,7 @@ __device__ __forceinline__ void onesweep_tile(const OnesweepParams& p, const Dig
     if (d < RADIX) {
         uint32_t c = cnt;
         if (!FULL && d == RADIX - 1) c -= padding;
-        if (!group_end && tile != 0) excl = lookback_two_level(p.lb_agg, p.lb_ginc, tile, d, RADIX, tag, p.err);
+        if (!group_end && tile != 0) excl = lookback_two_level(p.lb_agg, p.lb_ginc, tile, lb_group, d, RADIX, tag, p.err);
         const uint64_t gbase = p.bins_in[d];
         // destination of local sorted slot s holding digit d:  s_goff[d] + s
         s_goff[d] = gbase + excl - bin_excl;
@@ -361,7 +364,10 @@ __global__ void __launch_bounds__(BLOCK, min_ctas(BLOCK, IPT)) onesweep_kernel(c
 
     const int t = threadIdx.x;
     if (t == 0) s_tile = atomicAdd(p.ticket, 1u);
-    for (int i = t; i < (1 + NTBL) * WARPS * RADIX; i += BLOCK) s_whist[i] = 0;  // warp histograms + match tables
+    {   // warp histograms + match tables, 16 bytes per store
+        uint4* z = reinterpret_cast<uint4*>(s_whist);
+        for (int i = t; i < (1 + NTBL) * WARPS * RADIX / 4; i += BLOCK) z[i] = make_uint4(0, 0, 0, 0);
+    }
     __syncthreads();
     const uint32_t tile = s_tile;
     if (t == 0 && tile == gridDim.x - 1) *p.ticket = 0;  // every ticket of this launch is taken
@@ -438,6 +444,7 @@ static int dispatch_onesweep(int cfg, int key_bytes, int val_bytes, const Oneswe
 }
 
 int g_sort_config = 3;  // 256 threads x 24 keys, alternating ballot / lane-mask ranking: best measured on B200
+int g_lb_group = 32;   // tiles per look-back group (kmg_set_option("lb_group", n), n >= 32)
 int g_time_passes = 0;  // kmg_set_option("time_passes", 1): bracket every pass launch with events
 thread_local int64_t g_stat_sort_passes = 0;
 
@@ -511,7 +518,7 @@ static SortWs carve_sort_ws(void* ws, uint64_t n, int key_bytes) {
     const uint64_t min_tile = key_bytes == 16 ? 2048 : 4096;  // smallest tile of any configuration
     const uint64_t tiles = (part + min_tile - 1) / min_tile + 1;
     w.lb_words = align_up(tiles * SORT_RADIX * sizeof(uint32_t), 256) / sizeof(uint32_t);
-    p += w.lb_words * sizeof(uint32_t) + align_up((tiles / LB_GROUP + 2) * SORT_RADIX * sizeof(uint32_t), 256);
+    p += w.lb_words * sizeof(uint32_t) + align_up((tiles / LB_GROUP_MIN + 2) * SORT_RADIX * sizeof(uint32_t), 256);
     w.total = p - (char*)ws;
     return w;
 }
@@ -593,6 +600,8 @@ extern "C" int kmg_radix_sort(void* d_keys, void* d_keys_alt, void* d_vals, void
             p.bins_out = (part + 1 < n_parts) ? bins + ((part + 1) & 1) * SORT_RADIX : nullptr;
             p.lb_agg = w.lookback;
             p.lb_ginc = w.lookback + w.lb_words;
+        p.lb_group = (uint32_t)g_lb_group;
+            p.lb_group = (uint32_t)g_lb_group;
             p.ticket = &w.hdr->ticket;
             p.err = &w.hdr->err;
             if (n_parts > 1) {
@@ -665,6 +674,7 @@ extern "C" int kmg_range_partition(const void* d_keys, const void* d_vals, uint6
         p.bins_out = (part + 1 < n_lb_parts) ? w.bins + ((part + 1) & 1) * SORT_RADIX : nullptr;
         p.lb_agg = w.lookback;
         p.lb_ginc = w.lookback + w.lb_words;
+        p.lb_group = (uint32_t)g_lb_group;
         p.ticket = &w.hdr->ticket;
         p.err = &w.hdr->err;
         p.tag = 1u << 30;

@@ -400,3 +400,44 @@ def test_extract_fused_histograms_match_key_digits(eng, k, rc):
             want = np.bincount(dig.astype(np.int64), minlength=256).astype(np.uint64)
             assert first_diff(hist[p], want) == "equal", (k, rc, wb, we, p)
         assert not hist[P:].any()
+
+
+@pytest.mark.parametrize("pattern", ["all_equal", "two_values", "sorted", "reversed", "low_bits_only", "poly_a_genome"])
+def test_radix_sort_adversarial_distributions(eng, pattern):
+    """Skewed digit distributions: every lane of a warp in the same bin, presorted input, ..."""
+    import torch
+
+    from kman_b200.engine import KeyArray
+
+    n = 700_001
+    rng = np.random.default_rng(11)
+    if pattern == "all_equal":
+        raw = np.full(n, 0x2AAAAAAAAAAAAAAA, np.uint64)
+    elif pattern == "two_values":
+        raw = np.where(rng.random(n) < 0.5, np.uint64(3), np.uint64(0x3FFFFFFFFFFFFFFF)).astype(np.uint64)
+    elif pattern == "sorted":
+        raw = np.sort(rng.integers(0, 1 << 62, size=n, dtype=np.uint64))
+    elif pattern == "reversed":
+        raw = np.sort(rng.integers(0, 1 << 62, size=n, dtype=np.uint64))[::-1].copy()
+    elif pattern == "low_bits_only":
+        raw = rng.integers(0, 7, size=n, dtype=np.uint64)
+    else:
+        raw = None
+    if raw is not None:
+        vals = np.arange(n, dtype=np.uint64)
+        t = lambda x: torch.from_numpy(x.view(np.uint8).reshape(-1).copy()).to(eng.device)  # noqa: E731
+        a = KeyArray(t(raw), t(np.zeros_like(raw)), t(vals), t(np.zeros_like(vals)), n, 8, 8, 31, False)
+        a = eng.sort(a, 0, 62)
+        order = np.argsort(raw, kind="stable")
+        assert first_diff(a.keys_host(), raw[order]) == "equal"
+        assert first_diff(a.vals_host(), vals[order]) == "equal"  # stable
+        return
+    # low-complexity genome: long homopolymer and dinucleotide runs through the whole path
+    from kman_b200 import fasta
+
+    s = "A" * 200_000 + "ACGT" * 10 + "T" * 150_000 + "AC" * 100_000 + ko.synth_bases(50_000, 5).decode() + "A" * 5000
+    recs = [("low complexity", s), ("again", s[100_000:400_000])]
+    d = eng.upload(fasta.from_records(recs), alphabet="ACGT")
+    for k, rc in ((31, False), (31, True), (12, False)):
+        assert eng.count_text(d, k, rc) == ko.count_text_np(recs, k, rc, "ACGT"), (k, rc)
+        assert eng.uniq_text(d, k, rc) == ko.uniq_text_np(recs, k, rc, "ACGT"), (k, rc)

@@ -39,6 +39,7 @@ def main():
     ap.add_argument("--configs", default="0,1,2,3,4,5,6,7,8,9")
     ap.add_argument("--vb", type=int, default=0)
     ap.add_argument("--yardstick", action="store_true")
+    ap.add_argument("--lb-groups", default="")
     args = ap.parse_args()
     eng = get_engine(0)
     rng = np.random.default_rng(1234)
@@ -72,6 +73,18 @@ def main():
         print(f"sort cfg {cfg}     : {srt:8.3f} ms  {N/srt/1e6:8.2f} G keys/s  model {alg/srt/1e6:8.1f} GB/s = {alg/srt/1e6/peak:5.3f} of measured peak")
         res[f"sort_cfg{cfg}_ms"] = srt
     eng.lib.kmg_set_option(b"sort_config", 3)
+    for g in [int(x) for x in args.lb_groups.split(",") if x]:
+        eng.lib.kmg_set_option(b"lb_group", g)
+
+        def run_g():
+            a = eng.extract(d, k, False, val_bytes=args.vb, reuse="b_", want_hist=True)
+            return eng.sort(a)
+
+        med_all, _ = timed(run_g, flush=flush)
+        srt = med_all - res["extract_ms"]
+        print(f"lb_group {g:4d} (cfg 3): sort {srt:8.3f} ms  {N/srt/1e6:8.2f} G keys/s")
+        res[f"sort_lbg{g}_ms"] = srt
+    eng.lib.kmg_set_option(b"lb_group", 32)
 
     def full():
         a = eng.sort(eng.extract(d, k, False, val_bytes=0, reuse="b_", want_hist=True))
