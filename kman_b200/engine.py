@@ -147,7 +147,8 @@ class Engine:
         n = int(flat.bases.shape[0])
         bases = torch.empty(((n + 15) // 16 + 1) * 16, dtype=torch.uint8, device=self.device)
         if n:
-            bases[:n].copy_(torch.from_numpy(np.ascontiguousarray(flat.bases)), non_blocking=False)
+            src = flat.bases if flat.bases.flags.writeable and flat.bases.flags.c_contiguous else np.array(flat.bases)
+            bases[:n].copy_(torch.from_numpy(src), non_blocking=False)
         d = DeviceInput(bases, n, flat, alphabet, natype, lut, c16)
         if with_names:
             self._upload_names(d)

@@ -441,3 +441,56 @@ def test_radix_sort_adversarial_distributions(eng, pattern):
     for k, rc in ((31, False), (31, True), (12, False)):
         assert eng.count_text(d, k, rc) == ko.count_text_np(recs, k, rc, "ACGT"), (k, rc)
         assert eng.uniq_text(d, k, rc) == ko.uniq_text_np(recs, k, rc, "ACGT"), (k, rc)
+
+
+# ---- fused extract + range partition + (peer) stores, emulated on one GPU -----------------------------
+@pytest.mark.parametrize("k,rc,n_parts", [(31, False, 8), (21, True, 4), (45, False, 3), (12, True, 2), (8, False, 5)])
+def test_extract_scatter_partitions_like_extract_plus_range_partition(eng, k, rc, n_parts):
+    """kmg_extract_scatter with all destination buffers on this GPU: every destination must receive
+    exactly the keys (and payloads) of its key range -- as a multiset, the order inside a
+    destination is not defined -- and the count-only launch must size the regions exactly."""
+    import torch
+
+    from kman_b200 import _lib
+
+    rng = np.random.default_rng(500 + k)
+    recs = _rand_records(rng, 3, 40000, p_other=0.002)
+    ex = ko.extract_np(recs, k, rc, "ACGT")
+    d = eng.upload(_flat(recs), alphabet="ACGT")
+    lib = eng.lib
+    kb = 8 if k <= 32 else 16
+    n_win = d.n_bases - k + 1
+    counts = torch.zeros(n_parts + 1, dtype=torch.int64, device=eng.device)
+    _lib.check(lib.kmg_extract_scatter(d.bases.data_ptr(), d.n_bases, 0, n_win, k, int(rc), d.lut.data_ptr(), n_parts, None,
+                                       None, kb, 0, 0, None, counts.data_ptr(), 1, eng._stream()))
+    cnt = counts.cpu().numpy()
+    limbs = ex["narrow"]["keys"]
+    top16 = (limbs[0] >> np.uint64(2 * k - 16 - (64 if len(limbs) == 2 else 0))) if (len(limbs) == 1 or 2 * k - 16 >= 64) else None
+    if top16 is None:  # 128-bit key whose top 16 bits straddle the limbs
+        sh = 2 * k - 16
+        top16 = ((limbs[1] >> np.uint64(sh)) | (limbs[0] << np.uint64(64 - sh))) & np.uint64(0xFFFF)
+    top16 = top16 & np.uint64(0xFFFF)
+    part = ((top16 * np.uint64(n_parts)) >> np.uint64(16)).astype(np.int64)
+    want_counts = np.bincount(part, minlength=n_parts)
+    assert list(cnt[:n_parts]) == list(want_counts)
+    assert cnt[n_parts] == 0
+    bufs = [torch.zeros(max(int(c), 1) * kb, dtype=torch.uint8, device=eng.device) for c in want_counts]
+    vbufs = [torch.zeros(max(int(c), 1) * 8, dtype=torch.uint8, device=eng.device) for c in want_counts]
+    ptrs = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device=eng.device)
+    vptrs = torch.tensor([b.data_ptr() for b in vbufs], dtype=torch.int64, device=eng.device)
+    cursors = torch.zeros(n_parts, dtype=torch.int64, device=eng.device)
+    _lib.check(lib.kmg_extract_scatter(d.bases.data_ptr(), d.n_bases, 0, n_win, k, int(rc), d.lut.data_ptr(), n_parts,
+                                       ptrs.data_ptr(), vptrs.data_ptr(), kb, 8, 0, cursors.data_ptr(), None, 0, eng._stream()))
+    torch.cuda.synchronize()
+    assert list(cursors.cpu().numpy()) == list(want_counts)
+    rows = limbs_to_rows(limbs)
+    wv = (ex["narrow"]["pos"].astype(np.uint64) << np.uint64(1)) | ex["narrow"]["strand"].astype(np.uint64)
+    for p in range(n_parts):
+        c = int(want_counts[p])
+        got_k = bufs[p][: c * kb].cpu().numpy().view(np.uint64)
+        got_k = got_k if kb == 8 else got_k.reshape(-1, 2)
+        got_v = vbufs[p][: c * 8].cpu().numpy().view(np.uint64)
+        sel = part == p
+        o_got, o_want = np.argsort(got_v), np.argsort(wv[sel])  # payloads are unique: align by them
+        assert first_diff(got_v[o_got], wv[sel][o_want]) == "equal", p
+        assert first_diff(got_k[o_got], rows[sel][o_want]) == "equal", p
