@@ -297,9 +297,11 @@ def main():
     if pass_cnt:
         avg_pass_ms = pass_ns / 1e6 / pass_cnt
         n_keys = n_local if world == 1 else n_win_global / world
-        alg_bytes = 2 * W * n_keys
-        achieved = alg_bytes / (avg_pass_ms / 1e3) / 1e9
         passes_per_sort = pass_cnt / args.steps
+        # sorts of more than 2^30 keys run every pass in several launches (30-bit look-back counts)
+        launches_per_pass = max(1.0, passes_per_sort / P8)
+        alg_bytes = 2 * W * n_keys / launches_per_pass
+        achieved = alg_bytes / (avg_pass_ms / 1e3) / 1e9
         sort_ms = avg_pass_ms * passes_per_sort
         roofline = {
             "bound": "hbm", "kernel": "kmg::onesweep_kernel (one radix pass: read + write of every key)",
