@@ -183,7 +183,8 @@ __host__ __device__ constexpr bool mix_uses_table(int mix, int i) {
 __host__ __device__ constexpr int mix_tables(int mix) { return mix == 0 ? 0 : ((mix == 1 || mix == 4) ? 2 : 1); }
 template <typename KeyT, int VAL_BYTES, int RADIX_BITS, int BLOCK, int IPT, int MIX, typename DigitOp, bool FULL>
 __device__ __forceinline__ void onesweep_tile(const OnesweepParams& p, const DigitOp& digit_of, unsigned char* smem_raw,
-                                              uint32_t* s_scan, const uint32_t tile, const uint32_t n_valid) {
+                                              uint32_t* s_scan, uint64_t* s_bar, const uint32_t tile,
+                                              const uint32_t n_valid) {
     constexpr int RADIX = 1 << RADIX_BITS;
     constexpr int WARPS = BLOCK / 32;
     constexpr int TILE = BLOCK * IPT;
@@ -209,11 +210,20 @@ __device__ __forceinline__ void onesweep_tile(const OnesweepParams& p, const Dig
     const KeyT* keys_in = reinterpret_cast<const KeyT*>(p.keys_in) + tile_base;
     KeyT keys[IPT];
     const uint32_t wbase = warp * 32 * IPT + lane;
+    if constexpr (FULL) {
+        // TMA-staged tile: the bulk copies into the (still idle) staging buffer were issued by
+        // thread 0 at kernel entry (onesweep_kernel); wait for them, then pick the keys up
+        // warp-striped from shared memory (conflict-free)
+        mbar_wait(s_bar, 0);
 #pragma unroll
-    for (int i = 0; i < IPT; ++i) {
-        const uint32_t idx = wbase + i * 32;
-        if (FULL) keys[i] = keys_in[idx];
-        else keys[i] = idx < n_valid ? keys_in[idx] : key_all_ones(KeyT{});
+        for (int i = 0; i < IPT; ++i) keys[i] = s_keys[wbase + i * 32];
+        // (the barriers of phases 1-3 separate these reads from the scatter into the same buffer)
+    } else {
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) {
+            const uint32_t idx = wbase + i * 32;
+            keys[i] = idx < n_valid ? keys_in[idx] : key_all_ones(KeyT{});
+        }
     }
     uint32_t dg[IPT];
 #pragma unroll
@@ -357,13 +367,27 @@ __global__ void __launch_bounds__(BLOCK, min_ctas(BLOCK, IPT)) onesweep_kernel(c
     constexpr int NTBL = mix_tables(MIX);
     using ValT = typename ValType<VAL_BYTES>::type;
     constexpr int ITEM_BYTES = sizeof(KeyT) > sizeof(ValT) ? sizeof(KeyT) : sizeof(ValT);
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     uint32_t* s_whist = reinterpret_cast<uint32_t*>(smem_raw + (size_t)ITEM_BYTES * TILE);
     __shared__ uint32_t s_scan[WARPS + 1];
     __shared__ uint32_t s_tile;
 
+    __shared__ __align__(8) uint64_t s_bar;
     const int t = threadIdx.x;
-    if (t == 0) s_tile = atomicAdd(p.ticket, 1u);
+    if (t == 0) {
+        s_tile = atomicAdd(p.ticket, 1u);
+        mbar_init(&s_bar, 1);
+        // full tile: start the TMA bulk load of the keys right away, it overlaps the set-up below
+        const uint32_t my_tile = s_tile;
+        if ((uint64_t)(my_tile + 1) * TILE <= p.n) {
+            constexpr uint32_t BYTES = (uint32_t)TILE * sizeof(KeyT);
+            constexpr uint32_t CHUNK = 16384;
+            mbar_expect_tx(&s_bar, BYTES);
+            const char* src = reinterpret_cast<const char*>(p.keys_in) + (size_t)my_tile * BYTES;
+            for (uint32_t o = 0; o < BYTES; o += CHUNK)
+                tma_load_1d(smem_raw + o, src + o, BYTES - o < CHUNK ? BYTES - o : CHUNK, &s_bar);
+        }
+    }
     {   // warp histograms + match tables, 16 bytes per store
         uint4* z = reinterpret_cast<uint4*>(s_whist);
         for (int i = t; i < (1 + NTBL) * WARPS * RADIX / 4; i += BLOCK) z[i] = make_uint4(0, 0, 0, 0);
@@ -373,9 +397,9 @@ __global__ void __launch_bounds__(BLOCK, min_ctas(BLOCK, IPT)) onesweep_kernel(c
     if (t == 0 && tile == gridDim.x - 1) *p.ticket = 0;  // every ticket of this launch is taken
     const uint32_t n_valid = min((uint32_t)TILE, p.n - tile * (uint32_t)TILE);
     if (n_valid == (uint32_t)TILE)
-        onesweep_tile<KeyT, VAL_BYTES, RADIX_BITS, BLOCK, IPT, MIX, DigitOp, true>(p, digit_of, smem_raw, s_scan, tile, n_valid);
+        onesweep_tile<KeyT, VAL_BYTES, RADIX_BITS, BLOCK, IPT, MIX, DigitOp, true>(p, digit_of, smem_raw, s_scan, &s_bar, tile, n_valid);
     else
-        onesweep_tile<KeyT, VAL_BYTES, RADIX_BITS, BLOCK, IPT, MIX, DigitOp, false>(p, digit_of, smem_raw, s_scan, tile, n_valid);
+        onesweep_tile<KeyT, VAL_BYTES, RADIX_BITS, BLOCK, IPT, MIX, DigitOp, false>(p, digit_of, smem_raw, s_scan, &s_bar, tile, n_valid);
 }
 
 // ---- tile configurations ----------------------------------------------------------------------
