@@ -15,6 +15,7 @@ static thread_local int64_t g_launches = 0;
 extern int g_sort_config;
 extern int g_time_passes;
 extern int g_lb_group;
+extern int g_prefetch_tiles;
 extern thread_local int64_t g_stat_sort_passes;
 void timing_collect();
 double timing_total_ms();
@@ -51,6 +52,11 @@ extern "C" int kmg_set_option(const char* name, int64_t value) {
     KMG_REQUIRE(name, KMG_ERR_ARG, "option name is null");
     if (!strcmp(name, "sort_config")) {
         g_sort_config = (int)value;
+        return KMG_OK;
+    }
+    if (!strcmp(name, "prefetch_tiles")) {
+        KMG_REQUIRE(value >= 0 && value <= 65536, KMG_ERR_ARG, "prefetch_tiles must be in [0,65536]");
+        g_prefetch_tiles = (int)value;
         return KMG_OK;
     }
     if (!strcmp(name, "lb_group")) {

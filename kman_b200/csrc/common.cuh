@@ -261,6 +261,11 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
                  : "memory");
 }
 
+// hint: pull a range into L2 ahead of its consumer (no shared memory involved)
+__device__ __forceinline__ void tma_prefetch_l2(const void* gmem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
+}
+
 // ---- warp helpers ---------------------------------------------------------------------
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ uint32_t lanemask_lt() {

@@ -114,6 +114,7 @@ struct OnesweepParams {
     uint32_t* lb_ginc;        // [groups][RADIX]  tag | digit count of all tiles up to the END of the group
     uint32_t* ticket;
     uint32_t* err;
+    uint32_t prefetch_tiles;  // L2 prefetch distance in tiles (0 = off)
     uint32_t lb_group;  // tiles per look-back group
     uint32_t tag;  // (epoch 1..3) << 30: words carrying another tag are "not written yet", so the
                    // arrays need no re-zeroing between the passes of one sort
@@ -386,6 +387,12 @@ __global__ void __launch_bounds__(BLOCK, min_ctas(BLOCK, IPT)) onesweep_kernel(c
             const char* src = reinterpret_cast<const char*>(p.keys_in) + (size_t)my_tile * BYTES;
             for (uint32_t o = 0; o < BYTES; o += CHUNK)
                 tma_load_1d(smem_raw + o, src + o, BYTES - o < CHUNK ? BYTES - o : CHUNK, &s_bar);
+            // pull the tile a later CTA will work on into L2 (DRAM has headroom, latency does not)
+            const uint64_t ahead = (uint64_t)my_tile + p.prefetch_tiles;
+            if (p.prefetch_tiles && (ahead + 1) * TILE <= p.n) {
+                const char* nxt = reinterpret_cast<const char*>(p.keys_in) + (size_t)ahead * BYTES;
+                for (uint32_t o = 0; o < BYTES; o += CHUNK) tma_prefetch_l2(nxt + o, BYTES - o < CHUNK ? BYTES - o : CHUNK);
+            }
         }
     }
     {   // warp histograms + match tables, 16 bytes per store
@@ -469,6 +476,7 @@ static int dispatch_onesweep(int cfg, int key_bytes, int val_bytes, const Oneswe
 
 int g_sort_config = 3;  // 256 threads x 24 keys, alternating ballot / lane-mask ranking: best measured on B200
 int g_lb_group = 32;   // tiles per look-back group (kmg_set_option("lb_group", n), n >= 32)
+int g_prefetch_tiles = 192;  // L2 prefetch distance in tiles (kmg_set_option("prefetch_tiles", n)); 148-296 measured best
 int g_time_passes = 0;  // kmg_set_option("time_passes", 1): bracket every pass launch with events
 thread_local int64_t g_stat_sort_passes = 0;
 
@@ -625,7 +633,10 @@ extern "C" int kmg_radix_sort(void* d_keys, void* d_keys_alt, void* d_vals, void
             p.lb_agg = w.lookback;
             p.lb_ginc = w.lookback + w.lb_words;
         p.lb_group = (uint32_t)g_lb_group;
+        p.prefetch_tiles = (uint32_t)g_prefetch_tiles;
             p.lb_group = (uint32_t)g_lb_group;
+        p.prefetch_tiles = (uint32_t)g_prefetch_tiles;
+            p.prefetch_tiles = (uint32_t)g_prefetch_tiles;
             p.ticket = &w.hdr->ticket;
             p.err = &w.hdr->err;
             if (n_parts > 1) {
@@ -699,6 +710,7 @@ extern "C" int kmg_range_partition(const void* d_keys, const void* d_vals, uint6
         p.lb_agg = w.lookback;
         p.lb_ginc = w.lookback + w.lb_words;
         p.lb_group = (uint32_t)g_lb_group;
+        p.prefetch_tiles = (uint32_t)g_prefetch_tiles;
         p.ticket = &w.hdr->ticket;
         p.err = &w.hdr->err;
         p.tag = 1u << 30;

@@ -40,6 +40,7 @@ def main():
     ap.add_argument("--vb", type=int, default=0)
     ap.add_argument("--yardstick", action="store_true")
     ap.add_argument("--lb-groups", default="")
+    ap.add_argument("--prefetch", default="")
     args = ap.parse_args()
     eng = get_engine(0)
     rng = np.random.default_rng(1234)
@@ -85,6 +86,18 @@ def main():
         print(f"lb_group {g:4d} (cfg 3): sort {srt:8.3f} ms  {N/srt/1e6:8.2f} G keys/s")
         res[f"sort_lbg{g}_ms"] = srt
     eng.lib.kmg_set_option(b"lb_group", 32)
+    for g in [int(x) for x in args.prefetch.split(",") if x]:
+        eng.lib.kmg_set_option(b"prefetch_tiles", g)
+
+        def run_p():
+            a = eng.extract(d, k, False, val_bytes=args.vb, reuse="b_", want_hist=True)
+            return eng.sort(a)
+
+        med_all, _ = timed(run_p, flush=flush)
+        srt = med_all - res["extract_ms"]
+        print(f"prefetch {g:5d} tiles (cfg 3): sort {srt:8.3f} ms  {N/srt/1e6:8.2f} G keys/s")
+        res[f"sort_pf{g}_ms"] = srt
+    eng.lib.kmg_set_option(b"prefetch_tiles", 192)
 
     def full():
         a = eng.sort(eng.extract(d, k, False, val_bytes=0, reuse="b_", want_hist=True))
