@@ -143,15 +143,16 @@ __global__ void __launch_bounds__(EX_BLOCK) extract_narrow_kernel(const ExtractP
                 b[q] = x;
             }
         }
+        const int nvalid = pos + 16 <= p.n_bases ? 16 : (pos < p.n_bases ? (int)(p.n_bases - pos) : 0);
         uint32_t codes = 0, bad = 0, inv = 0;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             const uint32_t byte = (b[j >> 2] >> (8 * (j & 3))) & 0xFFu;
             uint32_t e = s_lut[byte];
-            if (pos + j >= p.n_bases) e = KMG_LUT_INVALID;
+            if (j >= nvalid) e = KMG_LUT_INVALID;
             codes |= (e & 3u) << (30 - 2 * j);
-            bad |= ((e & 0xC0u) ? 1u : 0u) << (15 - j);
-            inv |= ((e & 0x80u) ? 1u : 0u) << (15 - j);
+            bad |= ((e >> 6) ? 1u : 0u) << (15 - j);
+            inv |= (e >> 7) << (15 - j);
         }
         s_codes[w] = codes;
         s_bad[w] = (uint16_t)bad;
@@ -177,16 +178,35 @@ __global__ void __launch_bounds__(EX_BLOCK) extract_narrow_kernel(const ExtractP
 
     // validity of my PPT windows first: the tile's count is published as early as possible and
     // the prefix over the earlier tiles is resolved only after the keys have been built
+    const uint64_t first_pos = tile_pos + (uint64_t)t * PPT;
+    uint32_t in_range_mask;
+    {   // window starts [win_begin, win_end) among my PPT positions
+        const uint64_t lo = p.win_begin > first_pos ? p.win_begin - first_pos : 0;
+        const uint64_t hi = p.win_end > first_pos ? p.win_end - first_pos : 0;
+        const uint32_t l = lo < PPT ? (uint32_t)lo : PPT, h = hi < PPT ? (uint32_t)hi : PPT;
+        in_range_mask = h > l ? (((1u << (h - l)) - 1u) << l) : 0u;
+    }
+    // fast path: no base that is bad for the narrow stream among the PPT+k-1 bases my windows span
+    bool span_clean;
+    {
+        const uint64_t W0 = joff == 0 ? B0 : ((B0 << joff) | (B1 >> (64 - joff)));
+        const int span = PPT + k - 1;  // 17 .. 79
+        if (span <= 64) span_clean = (W0 >> (64 - span)) == 0;
+        else span_clean = W0 == 0 && ((B1 << joff) >> (128 - span)) == 0;
+    }
     uint32_t vf = 0, nwide = 0;
+    if (span_clean) {
+        vf = in_range_mask;
+    } else {
 #pragma unroll
-    for (int j = 0; j < PPT; ++j) {
-        const int je = joff + j;  // 0..15
-        const uint64_t pos = tile_pos + (uint64_t)t * PPT + j;
-        const uint64_t bm = (je == 0 ? B0 : ((B0 << je) | (B1 >> (64 - je)))) >> (64 - k);
-        const uint64_t im = (je == 0 ? I0 : ((I0 << je) | (I1 >> (64 - je)))) >> (64 - k);
-        const bool in_range = pos >= p.win_begin && pos < p.win_end;
-        if (in_range && bm == 0) vf |= 1u << j;
-        if (in_range && im == 0 && bm != 0) ++nwide;
+        for (int j = 0; j < PPT; ++j) {
+            const int je = joff + j;  // 0..15
+            const uint64_t bm = (je == 0 ? B0 : ((B0 << je) | (B1 >> (64 - je)))) >> (64 - k);
+            const uint64_t im = (je == 0 ? I0 : ((I0 << je) | (I1 >> (64 - je)))) >> (64 - k);
+            const bool in_range = (in_range_mask >> j) & 1u;
+            if (in_range && bm == 0) vf |= 1u << j;
+            if (in_range && im == 0 && bm != 0) ++nwide;
+        }
     }
     const uint32_t cnt = __popc(vf);
     uint32_t total;
@@ -198,16 +218,11 @@ __global__ void __launch_bounds__(EX_BLOCK) extract_narrow_kernel(const ExtractP
         // G: one count per window start whose first 4 bases are plain.  Digit p of a valid
         // window's key IS the 4-mer at window start + (k-4-4p), so every pass' histogram is G
         // over a shifted range minus the contributions of the skipped windows.
-        uint32_t in_range_mask = 0;
-#pragma unroll
-        for (int j = 0; j < PPT; ++j) {
-            const uint64_t pos = tile_pos + (uint64_t)t * PPT + j;
-            if (pos >= p.win_begin && pos < p.win_end) in_range_mask |= 1u << j;
-        }
 #pragma unroll
         for (int j = 0; j < PPT; ++j) {
             const int je = joff + j;
-            if (((in_range_mask >> j) & 1u) && plain4_at(B0, B1, je)) atomicAdd(&s_g[mer4_at(X0, X1, X2, je)], 1u);
+            if (((in_range_mask >> j) & 1u) && (span_clean || plain4_at(B0, B1, je)))
+                atomicAdd(&s_g[mer4_at(X0, X1, X2, je)], 1u);
         }
         const uint32_t skipped = in_range_mask & ~vf;
         if (skipped) s_any_skipped = 1;  // the correction table is zeroed lazily: most tiles never touch it
