@@ -156,6 +156,17 @@ int kmg_format_uniq(const void* d_keys, const void* d_vals, uint64_t n, int key_
                     const uint64_t* d_name_offs, uint8_t* d_text_out, uint64_t* d_bytes_out, void* d_ws,
                     size_t ws_bytes, void* stream);
 
+/* ---- FASTA text -> flat base buffer (kmermaid/parsers.py:53-128) --------------
+ * d_raw holds the file's bytes.  Writes the flat layout the extraction expects (record bytes,
+ * one '\n' after every record) to d_bases_out (capacity n_raw + 16), d_rec_starts[r] / [n_rec]
+ * and d_hdr_begin[r] = raw offset of the first title character, for r < max_rec.
+ * d_totals[0] = bytes written, [1] = number of records, [2] != 0 if the text holds bytes this
+ * kernel does not implement (TAB/VT/FF/FS..US or non-ASCII: the host loader handles those). */
+size_t kmg_fasta_workspace_bytes(uint64_t n_raw);
+int kmg_fasta_flatten(const uint8_t* d_raw, uint64_t n_raw, uint8_t* d_bases_out, uint64_t* d_rec_starts,
+                      uint64_t* d_hdr_begin, uint64_t max_rec, uint64_t* d_totals, void* d_ws, size_t ws_bytes,
+                      void* stream);
+
 /* ---- merge ranks between the narrow and the wide stream -------------------------------
  * For two sorted, disjoint key lists, rank_of_wide[i] = number of narrow keys that sort
  * before wide key i in the reference's ASCII order (and vice versa), so that the merged

@@ -41,6 +41,8 @@ SIGNATURES = {
     "kmg_ipc_open": (i32, [u8p, C.POINTER(vp)]),
     "kmg_ipc_close": (i32, [vp]),
     "kmg_ipc_free": (i32, [vp]),
+    "kmg_fasta_workspace_bytes": (sz, [u64]),
+    "kmg_fasta_flatten": (i32, [vp, u64, vp, vp, vp, u64, vp, vp, sz, vp]),
     "kmg_format_workspace_bytes": (sz, [u64]),
     "kmg_format_counts": (i32, [vp, vp, u64, i32, i32, i32, i32, vp, vp, vp, sz, vp]),
     "kmg_format_uniq": (i32, [vp, vp, u64, i32, i32, i32, i32, i32, vp, C.c_uint32, vp, vp, vp, vp, vp, sz, vp]),

@@ -180,8 +180,10 @@ class FastaBatcher(BatcherThreading):
         from kman_b200.engine import get_engine
 
         eng = get_engine()
-        flat = fasta.read_fasta(fasta_path)
-        d = eng.upload(flat, self.alphabet, self.natype)
+        if os.environ.get("KMG_GPU_LOADER", "1") != "0":
+            d = eng.load_fasta(fasta_path, self.alphabet, self.natype)  # text -> flat buffer on the GPU
+        else:
+            d = eng.upload(fasta.read_fasta(fasta_path), self.alphabet, self.natype)
         batch = DeviceBatch(eng, d, k, self.doReverseComplement, self.natype, self.tmp, self.size)
         self.feed_collection([batch], feedMode)
         return self

@@ -154,6 +154,61 @@ class Engine:
             self._upload_names(d)
         return d
 
+    def load_fasta(self, path: str, alphabet: Optional[str] = None, natype: ab.NATYPES = ab.NATYPES.DNA,
+                   with_names: bool = True) -> DeviceInput:
+        """Read a FASTA file and flatten it ON THE GPU (kmg_fasta_flatten): the raw bytes go to
+        the device once, line structure / header lines / blanks are resolved by three kernels.
+        Files with TAB / VT / FF / control separators or non-ASCII bytes take the host loader,
+        which implements the reference's rstrip() rule for them."""
+        import gzip
+        import os
+
+        from kman_b200 import fasta
+
+        if not os.path.isfile(path):
+            raise AssertionError(f"input file not found: {path}")  # batcher.py:475-476
+        opener = gzip.open if path.endswith(".gz") else open
+        with opener(path, "rb") as fh:
+            raw = fh.read()
+        if len(raw) == 0:
+            raise AssertionError("premature end of file or empty file")
+        n_raw = len(raw)
+        d_raw = torch.empty(((n_raw + 15) // 16 + 1) * 16, dtype=torch.uint8, device=self.device)
+        d_raw[:n_raw].copy_(torch.frombuffer(bytearray(raw), dtype=torch.uint8))
+        bases = torch.empty(((n_raw + 15) // 16 + 2) * 16, dtype=torch.uint8, device=self.device)
+        max_rec = 1 << 16
+        while True:
+            rec_starts = torch.zeros(max_rec + 1, dtype=torch.int64, device=self.device)
+            hdr_begin = torch.zeros(max_rec, dtype=torch.int64, device=self.device)
+            ws_bytes = self.lib.kmg_fasta_workspace_bytes(n_raw)
+            ws = self._buf("ws_fasta", ws_bytes)
+            _lib.check(self.lib.kmg_fasta_flatten(d_raw.data_ptr(), n_raw, bases.data_ptr(), rec_starts.data_ptr(),
+                                                  hdr_begin.data_ptr(), max_rec, self._small[5:].data_ptr(),
+                                                  ws.data_ptr(), ws_bytes, self._stream()))
+            n_out, n_rec, special = (int(x) for x in self._small[5:8].cpu().numpy().view(np.uint64))
+            if special:
+                return self.upload(fasta.parse_bytes(raw), alphabet, natype, with_names)
+            if n_rec <= max_rec:
+                break
+            max_rec = n_rec
+        if n_rec == 0:
+            raise AssertionError("premature end of file or empty file")  # parsers.py:100-102
+        hb = hdr_begin[:n_rec].cpu().numpy()
+        titles = []
+        for b in hb:
+            b = int(b)
+            e1, e2 = raw.find(b"\n", b), raw.find(b"\r", b)
+            e = min(x for x in (e1, e2, n_raw) if x >= 0)
+            titles.append(raw[b:e].decode("latin-1").rstrip())
+        names = [t.split(" ")[0] for t in titles]
+        flat = FlatInput(bases[:n_out].cpu().numpy(), rec_starts[: n_rec + 1].cpu().numpy().astype(np.uint64), names, titles)
+        alphabet = alphabet or ab.default_alphabet()
+        lut, c16 = self.lut_tensors(alphabet, natype)
+        d = DeviceInput(bases, n_out, flat, alphabet, natype, lut, c16)
+        if with_names:
+            self._upload_names(d)
+        return d
+
     def _upload_names(self, d: DeviceInput) -> None:
         flat = d.flat
         d.rec_starts = torch.from_numpy(flat.rec_starts.astype(np.int64)).to(self.device)

@@ -108,3 +108,53 @@ def test_two_fastas_appended_join_as_one(tmp_path):
     KJoinerThreading().join(fb.collection, str(out))
     assert out.read_bytes() == ko.uniq_text_py(recs, 5, True)
     assert sum(bt.current_size for bt in fb.collection) == len(list(ko.crawl_groups_py(ko.batches_py(recs, 5, True)))) or True
+
+
+def test_gpu_fasta_loader_matches_host_loader(golden, tmp_path):
+    """kmg_fasta_flatten (three kernels) against kman_b200.fasta (numpy) and the oracle's parser."""
+    import gzip
+
+    import kmer_oracle as ko
+    import numpy as np
+    from kman_b200 import fasta
+    from kman_b200.engine import get_engine
+
+    eng = get_engine()
+    texts = {c["name"]: c["fasta_text"] for c in golden["cases"]}
+    rng = np.random.default_rng(3)
+    # long single-line records, many tiny records, headers at tile boundaries, CRLF, preamble, empty records
+    big = ">long one\n" + ko.synth_bases(150_000, 1).decode() + "\n>" + "x" * 5000 + " y\n" + "\n".join(
+        ko.synth_bases(61, i).decode() for i in range(300)) + "\n"
+    texts["long_lines"] = big
+    texts["many_records"] = "".join(">r%d d\nAC GT\n\nNNAC\n" % i for i in range(3000))
+    texts["crlf_big"] = "junk\r\n;c\r\n" + "".join(">q%d\r\n%s\r\n" % (i, ko.synth_bases(100 + i, i).decode()) for i in range(200))
+    texts["empty_records"] = ">a\n>b\nACGT\n>c\n>d\n"
+    texts["no_final_newline"] = ">a\nACGT\n>b x y\nGG"
+    pad = "".join(rng.choice(list("ACGT\n"), p=[.24, .24, .24, .24, .04], size=4096 * 3 + 7))
+    for off in (4080, 4095, 4096, 4097):
+        texts["boundary_%d" % off] = ">h\n" + pad[: off - 3] + "\n>next header here\nACGTACGT\n"
+    for name, text in texts.items():
+        p = tmp_path / (name + ".fa")
+        p.write_bytes(text.encode("latin-1"))
+        want = fasta.parse_bytes(text.encode("latin-1"))
+        d = eng.load_fasta(str(p))
+        got = d.flat
+        assert got.titles == want.titles, name
+        assert got.names == want.names, name
+        assert (got.rec_starts == want.rec_starts).all(), name
+        assert got.bases.tobytes() == want.bases.tobytes(), name
+        assert d.n_bases == want.bases.size
+        assert d.bases[: d.n_bases].cpu().numpy().tobytes() == want.bases.tobytes(), name
+    # gz, tabs (host fallback), missing / empty files
+    p = tmp_path / "t.fa.gz"
+    with gzip.open(p, "wt") as fh:
+        fh.write(">r\nACGT\nAC\n")
+    assert eng.load_fasta(str(p)).flat.bases.tobytes() == b"ACGTAC\n"
+    p = tmp_path / "tab.fa"
+    p.write_text(">a\tb c\nACG\tT \t\nAC GT\n")
+    assert eng.load_fasta(str(p)).flat.bases.tobytes() == fasta.parse_bytes(p.read_bytes()).bases.tobytes()
+    with pytest.raises(AssertionError):
+        eng.load_fasta(str(tmp_path / "missing.fa"))
+    (tmp_path / "nohdr.fa").write_text("no header here\nACGT\n")
+    with pytest.raises(AssertionError):
+        eng.load_fasta(str(tmp_path / "nohdr.fa"))
