@@ -161,8 +161,10 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def workload_config(args, sample_note=None):
+def workload_config(args, sample_note=None, p2p=None):
     n = args.gpus
+    if p2p is None:
+        p2p = os.environ.get("KMG_DIST_P2P", "1") != "0"
     if args.workload == "cfg3":
         wl = f"config 3: {CFG3_BASES} bp synthetic random-ACGT genome, k={K}, count, strong scaling over {n} GPU(s)"
     elif n == 1:
@@ -170,8 +172,8 @@ def workload_config(args, sample_note=None):
     else:
         wl = (f"config 2 x {n} (weak): {n}x{CFG2_BASES} bp synthetic random-ACGT genome, one {CFG2_BASES} bp chunk per GPU "
               f"with k-1 overlap, range partition by the top key bits, k={K}, count; exchange: "
-              + ("NCCL all-to-all of the partitioned keys" if os.environ.get("KMG_DIST_P2P", "1") == "0"
-                 else "fused extract+partition kernel storing into the owners' buffers over NVLink (CUDA IPC peer memory)"))
+              + ("fused extract+partition kernel storing into the owners' buffers over NVLink (CUDA IPC peer memory)"
+                 if p2p else "range partition pass + NCCL all-to-all of the partitioned keys"))
     cfg = {"workload": wl, "k": K, "mode": "count", "alphabet": "ACGT",
            "l2": "working set per step (keys 2x0.8 GB + table 1.2 GB per GPU) >> 126 MB L2; no explicit flush"}
     if sample_note:
@@ -382,7 +384,8 @@ def main():
             "metric": METRIC, "value": value, "unit": "k-mers/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong" if args.workload == "cfg3" else "weak", "vs_baseline": None, "dtype": "u64",
-            "data": "synthetic", "config": workload_config(args), "clocks": clocks, "e2e": e2e,
+            "data": "synthetic", "config": workload_config(args, p2p=(dc.p2p if world > 1 else None)), "clocks": clocks,
+            "e2e": e2e,
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "wall_ms_per_step": t_wall / args.steps * 1e3, "kmers_per_step": n_win_global,
         }

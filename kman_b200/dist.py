@@ -99,6 +99,10 @@ class RankShard:
     n_windows_global: int
 
 
+class _PeerUnavailable(RuntimeError):
+    """CUDA IPC peer mapping failed on at least one rank: every rank falls back to NCCL together."""
+
+
 class _DevMem:
     """A raw device allocation exposed to torch through __cuda_array_interface__ (no copy)."""
 
@@ -177,7 +181,18 @@ class DistributedCounter:
             return cur
         if cur is not None:
             cur.close()
-        cur = PeerBuffers(self.eng, int(nbytes * 1.1) + 4096, self.group)
+            setattr(self, which, None)
+        try:
+            cur = PeerBuffers(self.eng, int(nbytes * 1.1) + 4096, self.group)
+            ok = 1
+        except Exception as exc:  # CUDA IPC unavailable (container policy, no peer access, ...)
+            cur, ok, self._p2p_error = None, 0, repr(exc)
+        flag = torch.tensor([ok], dtype=torch.int64, device=self.eng.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:
+            if cur is not None:
+                cur.close()
+            raise _PeerUnavailable(getattr(self, "_p2p_error", "a peer could not map the receive buffers"))
         setattr(self, which, cur)
         return cur
 
@@ -258,9 +273,13 @@ class DistributedCounter:
     def count(self, d, k: int, rc: bool = False):
         """This rank's slice (key range `rank`) of the global count table, narrow stream."""
         if self.p2p and k >= 8:
-            r = self._extract_exchange_p2p(d, k, rc, with_vals=False)
-            r = self.eng.sort(r, 0, sort_bits_after_partition(r.key_bits, self.world))
-            return self.eng.rle_count(r, reuse="p2p_")
+            try:
+                r = self._extract_exchange_p2p(d, k, rc, with_vals=False)
+            except _PeerUnavailable as exc:
+                self._fall_back(exc)
+            else:
+                r = self.eng.sort(r, 0, sort_bits_after_partition(r.key_bits, self.world))
+                return self.eng.rle_count(r, reuse="p2p_")
         a = self.eng.extract(d, k, rc, wide=False, val_bytes=0)
         n_other = torch.tensor([a.n_other], dtype=torch.int64, device=a.keys.device)
         dist.all_reduce(n_other, group=self.group)
@@ -270,6 +289,14 @@ class DistributedCounter:
         r = self._partition_exchange(a, with_vals=False)
         r = self.eng.sort(r, 0, sort_bits_after_partition(r.key_bits, self.world))
         return self.eng.rle_count(r)
+
+    def _fall_back(self, exc) -> None:
+        """Every rank raised together (the failure flag is all-reduced): use the NCCL all-to-all path."""
+        import warnings
+
+        self.p2p = False
+        if self.rank == 0:
+            warnings.warn(f"CUDA IPC peer buffers unavailable ({exc}); using the NCCL all-to-all exchange")
 
     def close(self):
         for which in ("_peer_keys", "_peer_vals"):
@@ -281,9 +308,13 @@ class DistributedCounter:
     def uniq(self, d, k: int, rc: bool = False):
         """This rank's slice of the global singleton list (keys + (pos<<1|strand) payload)."""
         if self.p2p and k >= 8:
-            r = self._extract_exchange_p2p(d, k, rc, with_vals=True)
-            r = self.eng.sort(r, 0, sort_bits_after_partition(r.key_bits, self.world))
-            return self.eng.singletons(r)
+            try:
+                r = self._extract_exchange_p2p(d, k, rc, with_vals=True)
+            except _PeerUnavailable as exc:
+                self._fall_back(exc)
+            else:
+                r = self.eng.sort(r, 0, sort_bits_after_partition(r.key_bits, self.world))
+                return self.eng.singletons(r)
         a = self.eng.extract(d, k, rc, wide=False, val_bytes=8)
         n_other = torch.tensor([a.n_other], dtype=torch.int64, device=a.keys.device)
         dist.all_reduce(n_other, group=self.group)
