@@ -125,15 +125,16 @@ __global__ void __launch_bounds__(DX_BLOCK) extract_scatter_kernel(const Scatter
                 b[q] = x;
             }
         }
+        const int nvalid = pos + 16 <= p.n_bases ? 16 : (pos < p.n_bases ? (int)(p.n_bases - pos) : 0);
         uint32_t codes = 0, bad = 0, inv = 0;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             const uint32_t byte = (b[j >> 2] >> (8 * (j & 3))) & 0xFFu;
             uint32_t e = s_lut[byte];
-            if (pos + j >= p.n_bases) e = KMG_LUT_INVALID;
+            if (j >= nvalid) e = KMG_LUT_INVALID;
             codes |= (e & 3u) << (30 - 2 * j);
-            bad |= ((e & 0xC0u) ? 1u : 0u) << (15 - j);
-            inv |= ((e & 0x80u) ? 1u : 0u) << (15 - j);
+            bad |= ((e >> 6) ? 1u : 0u) << (15 - j);
+            inv |= (e >> 7) << (15 - j);
         }
         s_codes[w] = codes;
         s_bad[w] = (uint16_t)bad;
@@ -160,6 +161,14 @@ __global__ void __launch_bounds__(DX_BLOCK) extract_scatter_kernel(const Scatter
     int part_bits = 0;
     while ((1 << part_bits) < p.n_parts) ++part_bits;
 
+    // fast path: no base that is bad for the narrow stream among the PPT+k-1 bases my windows span
+    bool span_clean;
+    {
+        const uint64_t W0 = joff == 0 ? B0 : ((B0 << joff) | (B1 >> (64 - joff)));
+        const int span = PPT + k - 1;
+        if (span <= 64) span_clean = (W0 >> (64 - span)) == 0;
+        else span_clean = W0 == 0 && ((B1 << joff) >> (128 - span)) == 0;
+    }
     // slot of every emitted key inside its destination group of the tile: (part << 20) | rank
     uint32_t where[PPT * OUT_PER_WIN];
     KeyT keys[PPT];
@@ -168,12 +177,15 @@ __global__ void __launch_bounds__(DX_BLOCK) extract_scatter_kernel(const Scatter
     for (int j = 0; j < PPT; ++j) {
         const int je = joff + j;
         const uint64_t pos = tile_pos + (uint64_t)t * PPT + j;
-        const uint64_t bm = (je == 0 ? B0 : ((B0 << je) | (B1 >> (64 - je)))) >> (64 - k);
-        const uint64_t im = (je == 0 ? I0 : ((I0 << je) | (I1 >> (64 - je)))) >> (64 - k);
         const bool in_range = pos >= p.win_begin && pos < p.win_end;
-        const bool valid = in_range && bm == 0;
+        bool valid = in_range;
+        if (!span_clean) {
+            const uint64_t bm = (je == 0 ? B0 : ((B0 << je) | (B1 >> (64 - je)))) >> (64 - k);
+            const uint64_t im = (je == 0 ? I0 : ((I0 << je) | (I1 >> (64 - je)))) >> (64 - k);
+            valid = in_range && bm == 0;
+            if (in_range && im == 0 && bm != 0) ++nwide;
+        }
         if (valid) vf |= 1u << j;
-        if (in_range && im == 0 && bm != 0) ++nwide;
         const int s2 = 2 * je;
         const uint64_t hi = je == 0 ? X0 : ((X0 << s2) | (X1 >> (64 - s2)));
         KeyT key;
