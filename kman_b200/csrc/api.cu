@@ -15,6 +15,9 @@ static thread_local int64_t g_launches = 0;
 extern int g_sort_config;
 extern int g_time_passes;
 extern int g_lb_group;
+extern int g_hybrid;
+extern int g_hybrid_pb;
+extern thread_local int64_t g_stat_hybrid_irregular;
 extern int g_prefetch_tiles;
 extern thread_local int64_t g_stat_sort_passes;
 void timing_collect();
@@ -54,6 +57,14 @@ extern "C" int kmg_set_option(const char* name, int64_t value) {
         g_sort_config = (int)value;
         return KMG_OK;
     }
+    if (!strcmp(name, "hybrid_pb")) {
+        g_hybrid_pb = (int)value;
+        return KMG_OK;
+    }
+    if (!strcmp(name, "hybrid")) {
+        g_hybrid = value != 0;
+        return KMG_OK;
+    }
     if (!strcmp(name, "prefetch_tiles")) {
         KMG_REQUIRE(value >= 0 && value <= 65536, KMG_ERR_ARG, "prefetch_tiles must be in [0,65536]");
         g_prefetch_tiles = (int)value;
@@ -77,6 +88,7 @@ extern "C" int64_t kmg_get_stat(const char* name) {
     if (!name) return -1;
     if (!strcmp(name, "launches")) return g_launches;
     if (!strcmp(name, "sort_passes")) return g_stat_sort_passes;
+    if (!strcmp(name, "hybrid_irregular")) return g_stat_hybrid_irregular;
     if (!strcmp(name, "sort_pass_ns")) {  // total device time of the timed onesweep launches
         timing_collect();
         return (int64_t)(timing_total_ms() * 1e6);

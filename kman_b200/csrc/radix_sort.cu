@@ -409,6 +409,216 @@ __global__ void __launch_bounds__(BLOCK, min_ctas(BLOCK, IPT)) onesweep_kernel(c
         onesweep_tile<KeyT, VAL_BYTES, RADIX_BITS, BLOCK, IPT, MIX, DigitOp, false>(p, digit_of, smem_raw, s_scan, &s_bar, tile, n_valid);
 }
 
+// ---- hybrid finish: after the keys are sorted by their top PB bits ---------------------------------
+// Every LSD pass pays the full per-key ranking cost again.  For key-only sorts the tail can be
+// cheaper: once the top PB = 16 or 24 bits are in order (2-3 ordinary passes), equal-prefix
+// buckets are contiguous and small, and a tile of ~4096 keys can finish ALL remaining bits at
+// once in shared memory: a counting sort into up to 8192 cells (bucket x next few bits, plain
+// shared atomics -- no stability needed) followed by ranking inside the 1-3 key cells.  Tiles
+// whose buckets do not fit the scheme (long runs of one prefix, huge cells: repeats) are flagged
+// and the caller falls back to the plain LSD sort, so correctness never depends on the data.
+constexpr int LS_BLOCK = 512;
+constexpr int LS_IPT = 16;
+constexpr int LS_CAP = LS_BLOCK * LS_IPT;  // keys a tile can own
+constexpr int LS_T = 4096;                 // positions per tile (a tile owns the buckets starting in it)
+constexpr int LS_CELLS = 8192;
+constexpr int LS_CPT = LS_CELLS / LS_BLOCK;  // consecutive cells per thread in the prefix / cell-sort phases
+static_assert(LS_CPT == 16, "the cell phases move 4 x uint4 per thread");
+constexpr int LS_SORT_BUDGET = 4096;       // insertion-sort moves one thread may spend before the tile gives up
+// cell counters are padded (4 words per 16) so that one thread's 16 consecutive cells are four
+// conflict-free 128-bit accesses: thread stride 20 words
+__device__ __forceinline__ uint32_t pc(uint32_t c) { return c + ((c >> 4) << 2); }
+constexpr int LS_CELL_WORDS = LS_CELLS + LS_CELLS / 4 + 4;
+
+struct HybridParams {
+    const uint64_t* keys_in;
+    uint64_t* keys_out;
+    uint64_t n;
+    uint64_t key_mask;      // bits [0, key_bits)
+    uint32_t n_tiles;
+    int key_bits, pb;
+    unsigned long long* irregular;  // number of tiles the local scheme could not handle
+};
+
+// First i in [lo, hi) whose prefix differs from `ref`, or hi; the prefixes are non-decreasing.
+// Whole-warp 32-ary search: the common case (buckets of a few keys) ends after one probe round.
+__device__ __forceinline__ uint64_t prefix_run_end(const uint64_t* __restrict__ keys, uint64_t lo, uint64_t hi,
+                                                   uint64_t ref, uint64_t mask, int sh) {
+    const uint32_t lane = threadIdx.x & 31u;
+    uint64_t step = 1;  // first round: 32 consecutive keys
+    while (lo < hi) {
+        const uint64_t i = lo + lane * step;
+        const bool ne = i < hi ? ((keys[i] & mask) >> sh) != ref : true;
+        const uint32_t bal = __ballot_sync(0xffffffffu, ne);
+        const uint32_t first = bal ? __ffs(bal) - 1 : 32u;  // 32: all probes still match
+        if (first == 0) return lo;
+        if (step == 1) {
+            if (first < 32) return min(lo + first, hi);
+            lo += 32;
+        } else {
+            const uint64_t nlo = lo + (uint64_t)(first - 1) * step + 1;
+            hi = first < 32 ? min(hi, lo + (uint64_t)first * step) : hi;
+            lo = nlo;
+        }
+        const uint64_t span = hi - lo;
+        step = span <= 32 ? 1 : (span + 31) / 32;
+    }
+    return hi;
+}
+
+// monotone map key -> cell of the tile's counting sort (see local_sort_kernel)
+struct CellMap {
+    uint64_t base;   // b_lo << w
+    uint32_t inv;    // 0: cell = x, else cell = umulhi(x, inv)
+    int sh;          // x = (key >> sh) - base
+    __device__ __forceinline__ uint32_t operator()(uint64_t key) const {
+        const uint32_t x = (uint32_t)((key >> sh) - base);
+        return inv ? __umulhi(x, inv) : x;
+    }
+};
+
+__global__ void __launch_bounds__(LS_BLOCK, 2) local_sort_kernel(const HybridParams p) {
+    extern __shared__ __align__(16) unsigned char ls_smem[];
+    uint64_t* s_stage = reinterpret_cast<uint64_t*>(ls_smem);                             // [LS_CAP]
+    uint32_t* s_cell = reinterpret_cast<uint32_t*>(ls_smem + sizeof(uint64_t) * LS_CAP);  // [LS_CELL_WORDS]
+    __shared__ uint32_t s_scan[LS_BLOCK / 32 + 1];
+    __shared__ uint64_t s_bounds[2];
+    __shared__ int s_bad;
+    const int t = threadIdx.x;
+    const uint32_t tile = blockIdx.x;
+    const int sh_pref = p.key_bits - p.pb;
+
+    // the tile owns the prefix buckets that START inside its LS_T positions: [s, e)
+    if (t < 64) {
+        const uint32_t lane = t & 31u;
+        const uint64_t pos = min((uint64_t)(tile + (t >> 5)) * LS_T, p.n);
+        uint64_t r = pos;
+        if (pos > 0 && pos < p.n) {
+            // a run that reaches past pos + LS_T + LS_CAP makes both this tile and its owner irregular
+            const uint64_t hi = min(p.n, pos + LS_T + LS_CAP + 1);
+            // one round trip in the common case: keys[pos-1 .. pos+30]
+            const uint64_t i = pos - 1 + lane;
+            const uint64_t v = i < hi ? (p.keys_in[i] & p.key_mask) >> sh_pref : ~0ull;
+            const uint64_t ref = __shfl_sync(0xffffffffu, v, 0);
+            const uint32_t bal = __ballot_sync(0xffffffffu, v != ref);
+            r = bal ? min(pos - 1 + (uint64_t)(__ffs(bal) - 1), hi)
+                    : prefix_run_end(p.keys_in, pos + 31, hi, ref, p.key_mask, sh_pref);
+        }
+        if (lane == 0) s_bounds[t >> 5] = r;
+    }
+    if (t == 0) s_bad = 0;
+    {
+        uint4* z = reinterpret_cast<uint4*>(s_cell);
+        for (uint32_t i = t; i < (uint32_t)LS_CELL_WORDS / 4; i += LS_BLOCK) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
+    const uint64_t s = s_bounds[0], e = s_bounds[1];
+    if (s >= min((uint64_t)(tile + 1) * LS_T, p.n) || e <= s) return;  // no bucket starts in this tile
+    const uint64_t m64 = e - s;
+    if (m64 > LS_CAP) {
+        if (t == 0) atomicAdd(p.irregular, 1ull);
+        return;
+    }
+    const uint32_t m = (uint32_t)m64;
+    const uint64_t* kin = p.keys_in + s;
+    const uint64_t k_first = kin[0] & p.key_mask, k_last = kin[m - 1] & p.key_mask;
+    uint64_t keys[LS_IPT];
+#pragma unroll
+    for (int j = 0; j < LS_IPT; ++j) {
+        const uint32_t idx = t + j * LS_BLOCK;
+        keys[j] = idx < m ? kin[idx] & p.key_mask : 0;
+    }
+    // Counting sort into <= LS_CELLS cells through a monotone map of the key: the w bits after
+    // the prefix, relative to the tile's first bucket, scaled down to the cell range when the
+    // tile spans more than LS_CELLS such values.  Monotone, so sorting inside cells finishes it.
+    CellMap cm;
+    {
+        const uint64_t b_lo = k_first >> sh_pref;
+        const uint64_t R = (k_last >> sh_pref) - b_lo + 1;  // <= 2^24
+        int w = min(13, sh_pref);
+        w = min(w, 30 - (63 - __clzll((long long)R)));     // (R << w) < 2^31
+        cm.sh = sh_pref - w;
+        cm.base = b_lo << w;
+        const uint64_t range = R << w;
+        cm.inv = range <= (uint64_t)LS_CELLS ? 0u : (uint32_t)((((uint64_t)LS_CELLS) << 32) / range);
+    }
+    uint32_t meta[LS_IPT];  // cell | slot inside the cell << 13
+#pragma unroll
+    for (int j = 0; j < LS_IPT; ++j) {
+        const uint32_t idx = t + j * LS_BLOCK;
+        if (idx < m) {
+            const uint32_t c = cm(keys[j]);
+            meta[j] = c | (atomicAdd(&s_cell[pc(c)], 1u) << 13);
+        }
+    }
+    __syncthreads();
+    // exclusive prefix over the cells: 16 consecutive cells per thread
+    uint4* cv = reinterpret_cast<uint4*>(s_cell + pc(t * LS_CPT));
+    uint4 q0 = cv[0], q1 = cv[1], q2 = cv[2], q3 = cv[3];
+    const uint32_t sum = q0.x + q0.y + q0.z + q0.w + q1.x + q1.y + q1.z + q1.w + q2.x + q2.y + q2.z + q2.w + q3.x + q3.y +
+                         q3.z + q3.w;
+    uint32_t total;
+    uint32_t run = block_excl_scan<LS_BLOCK, uint32_t>(sum, s_scan, total);
+    {
+        uint32_t v;
+#define KMG_LS_STEP(f) v = f; f = run; run += v;
+        KMG_LS_STEP(q0.x) KMG_LS_STEP(q0.y) KMG_LS_STEP(q0.z) KMG_LS_STEP(q0.w)
+        KMG_LS_STEP(q1.x) KMG_LS_STEP(q1.y) KMG_LS_STEP(q1.z) KMG_LS_STEP(q1.w)
+        KMG_LS_STEP(q2.x) KMG_LS_STEP(q2.y) KMG_LS_STEP(q2.z) KMG_LS_STEP(q2.w)
+        KMG_LS_STEP(q3.x) KMG_LS_STEP(q3.y) KMG_LS_STEP(q3.z) KMG_LS_STEP(q3.w)
+#undef KMG_LS_STEP
+    }
+    cv[0] = q0; cv[1] = q1; cv[2] = q2; cv[3] = q3;
+    asm volatile("" ::: "memory");
+    if (t == LS_BLOCK - 1) s_cell[pc(LS_CELLS)] = run;  // sentinel: end of the last cell
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < LS_IPT; ++j) {
+        const uint32_t idx = t + j * LS_BLOCK;
+        if (idx < m) s_stage[s_cell[pc(meta[j] & 8191u)] + (meta[j] >> 13)] = keys[j];
+    }
+    __syncthreads();
+    // order every cell in place: insertion sort (cells hold ~1 key; equal keys cost one compare each)
+    {
+        const uint32_t endc = s_cell[pc((t + 1) * LS_CPT)];
+        q0 = cv[0]; q1 = cv[1]; q2 = cv[2]; q3 = cv[3];  // (reloaded: keeping them live across the placement spills)
+        const uint32_t st[LS_CPT + 1] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x,
+                                         q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w, endc};
+        int budget = LS_SORT_BUDGET;
+#pragma unroll
+        for (int c = 0; c < LS_CPT; ++c) {
+            const uint32_t cs = st[c], ce = st[c + 1];
+            if (ce - cs < 2) continue;
+            for (uint32_t i = cs + 1; i < ce; ++i) {
+                const uint64_t key = s_stage[i];
+                uint32_t q = i;
+                while (q > cs) {
+                    const uint64_t o = s_stage[q - 1];
+                    if (o <= key) break;
+                    s_stage[q] = o;
+                    --q;
+                    --budget;
+                }
+                s_stage[q] = key;
+                if (budget < 0) break;
+            }
+            if (budget < 0) break;
+        }
+        if (budget < 0) s_bad = 1;
+    }
+    __syncthreads();
+    if (s_bad) {  // too many distinct keys crowded into one cell: leave the tile to the fallback
+        if (t == 0) atomicAdd(p.irregular, 1ull);
+        return;
+    }
+    uint64_t* kout = p.keys_out + s;
+#pragma unroll
+    for (int j = 0; j < LS_IPT; ++j) {
+        const uint32_t idx = t + j * LS_BLOCK;
+        if (idx < m) kout[idx] = s_stage[idx];
+    }
+}
+
 // ---- tile configurations ----------------------------------------------------------------------
 struct SortTile {
     int block, ipt, mix;
@@ -479,6 +689,7 @@ int g_lb_group = 32;   // tiles per look-back group (kmg_set_option("lb_group", 
 int g_prefetch_tiles = 192;  // L2 prefetch distance in tiles (kmg_set_option("prefetch_tiles", n)); 148-296 measured best
 int g_time_passes = 0;  // kmg_set_option("time_passes", 1): bracket every pass launch with events
 thread_local int64_t g_stat_sort_passes = 0;
+thread_local int64_t g_stat_hybrid_irregular = -1;
 
 // live per-launch timing of the dominant kernel (bench.py's roofline): event pairs recorded
 // on the caller's stream around each onesweep launch, read back by kmg_get_stat().
@@ -533,8 +744,22 @@ struct SortWs {
     uint64_t* bins;            // [MAX_PASSES][2][RADIX]
     uint32_t* lookback;        // [tiles_per_part][RADIX] tile counts, then [groups][RADIX] group prefixes
     size_t lb_words;           // words of the tile-count array
+    int hyb_pb;                // prefix bits of the hybrid finish (0: not applicable)
     size_t total;
 };
+
+// Prefix bits the hybrid finish sorts with ordinary passes before the local sort takes over: the
+// average bucket (n / 2^pb keys) has to stay well under a tile.  0 = do not use the hybrid.
+int g_hybrid = 1;  // kmg_set_option("hybrid", 0/1)
+int g_hybrid_rows = 0;  // d_hist_in carries rows 14 / 15 (top two bytes)
+int g_hybrid_pb = 0;    // kmg_set_option("hybrid_pb", 0 | 16 | 24): force the prefix width (0 = by n)
+static int hybrid_prefix_bits(uint64_t n) {
+    if (!g_hybrid || n < (1ull << 20)) return 0;
+    if (g_hybrid_pb == 16 || g_hybrid_pb == 24) return g_hybrid_pb;
+    if (n <= 112ull << 20) return 16;      // <= ~1790 keys per bucket
+    if (n <= (112ull << 20) * 256) return 24;
+    return 0;
+}
 
 static SortWs carve_sort_ws(void* ws, uint64_t n, int key_bytes) {
     SortWs w;
@@ -551,6 +776,7 @@ static SortWs carve_sort_ws(void* ws, uint64_t n, int key_bytes) {
     const uint64_t tiles = (part + min_tile - 1) / min_tile + 1;
     w.lb_words = align_up(tiles * SORT_RADIX * sizeof(uint32_t), 256) / sizeof(uint32_t);
     p += w.lb_words * sizeof(uint32_t) + align_up((tiles / LB_GROUP_MIN + 2) * SORT_RADIX * sizeof(uint32_t), 256);
+    w.hyb_pb = key_bytes == 8 ? hybrid_prefix_bits(n) : 0;
     w.total = p - (char*)ws;
     return w;
 }
@@ -585,21 +811,43 @@ extern "C" int kmg_radix_sort(void* d_keys, void* d_keys_alt, void* d_vals, void
     SortWs w = carve_sort_ws(d_ws, n, key_bytes);
     KMG_REQUIRE(ws_bytes >= w.total, KMG_ERR_WS, "sort workspace too small: %zu < %zu", ws_bytes, w.total);
 
-    const PassPlan plan = make_plan(begin_bit, end_bit);
-    const int np = plan.num_passes;
+    PassPlan plan = make_plan(begin_bit, end_bit);
+    int np = plan.num_passes;
     const int cfg = g_sort_config;
     const uint64_t n_parts = (n + PART_MAX - 1) / PART_MAX;
 
     // header + hist zero; look-back words zero once per sort -- see OnesweepParams::tag
     KMG_CUDA(cudaMemsetAsync(d_ws, 0, w.total, st));
 
+    // Hybrid finish (key-only 8-byte sorts over bits [0, end_bit)): ordinary passes over the top
+    // pb bits only, then local_sort_kernel orders everything below them.  d_hist_in rows 14 / 15
+    // are the histograms of the two top bytes when the keys come from kmg_extract.
+    const int pb = (key_bytes == 8 && val_bytes == 0 && begin_bit == 0 && n_parts == 1) ? w.hyb_pb : 0;
+    const bool hybrid = pb != 0 && end_bit >= pb + 8;
+    const uint64_t* hist_in = d_hist_in;
+    if (hybrid) {
+        memset(&plan, 0, sizeof(plan));
+        np = plan.num_passes = pb / 8;
+        for (int i = 0; i < np; ++i) {
+            plan.shift[i] = end_bit - pb + 8 * i;
+            plan.bits[i] = 8;
+        }
+        if (d_hist_in && pb == 16 && g_hybrid_rows) {
+            KMG_CUDA(cudaMemcpyAsync(w.hist, d_hist_in + 14 * SORT_RADIX, 2 * SORT_RADIX * sizeof(uint64_t),
+                                     cudaMemcpyDeviceToDevice, st));
+            hist_in = reinterpret_cast<const uint64_t*>(w.hist);
+        } else {
+            hist_in = nullptr;  // histogram sweep over the top bytes
+        }
+    }
+
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const unsigned long long* hist = w.hist;
-    if (d_hist_in) {
+    if (hist_in) {
         // digit histograms of exactly these keys and this plan, produced by kmg_extract
-        hist = reinterpret_cast<const unsigned long long*>(d_hist_in);
+        hist = reinterpret_cast<const unsigned long long*>(hist_in);
     } else {
         const int grid = (int)std::min<uint64_t>((n + 511) / 512, (uint64_t)sms * 4);
         const size_t smem = (size_t)np * SORT_RADIX * sizeof(uint32_t);
@@ -632,10 +880,7 @@ extern "C" int kmg_radix_sort(void* d_keys, void* d_keys_alt, void* d_vals, void
             p.bins_out = (part + 1 < n_parts) ? bins + ((part + 1) & 1) * SORT_RADIX : nullptr;
             p.lb_agg = w.lookback;
             p.lb_ginc = w.lookback + w.lb_words;
-        p.lb_group = (uint32_t)g_lb_group;
-        p.prefetch_tiles = (uint32_t)g_prefetch_tiles;
             p.lb_group = (uint32_t)g_lb_group;
-        p.prefetch_tiles = (uint32_t)g_prefetch_tiles;
             p.prefetch_tiles = (uint32_t)g_prefetch_tiles;
             p.ticket = &w.hdr->ticket;
             p.err = &w.hdr->err;
@@ -659,6 +904,43 @@ extern "C" int kmg_radix_sort(void* d_keys, void* d_keys_alt, void* d_vals, void
         std::swap(kin, kout);
         std::swap(vin, vout);
         ++g_stat_sort_passes;
+    }
+    if (hybrid) {
+        // kin now holds the keys ordered by their top pb bits; finish into kout
+        HybridParams hp;
+        hp.keys_in = reinterpret_cast<const uint64_t*>(kin);
+        hp.keys_out = reinterpret_cast<uint64_t*>(kout);
+        hp.n = n;
+        hp.key_mask = end_bit >= 64 ? ~0ull : (1ull << end_bit) - 1ull;
+        hp.n_tiles = (uint32_t)((n + LS_T - 1) / LS_T);
+        hp.key_bits = end_bit;
+        hp.pb = pb;
+        hp.irregular = reinterpret_cast<unsigned long long*>(&w.hdr->pad[0]);  // 8-byte aligned slot of the header
+        const size_t smem = sizeof(uint64_t) * LS_CAP + sizeof(uint32_t) * LS_CELL_WORDS;
+        KMG_CUDA(cudaFuncSetAttribute(local_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        local_sort_kernel<<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);
+        KMG_LAUNCH_CHECK();
+        unsigned long long irregular = 0;
+        KMG_CUDA(cudaMemcpyAsync(&irregular, hp.irregular, sizeof(irregular), cudaMemcpyDeviceToHost, st));
+        KMG_CUDA(cudaStreamSynchronize(st));
+        g_stat_hybrid_irregular = (int64_t)irregular;
+        if (irregular == 0) {
+            *h_selector_out = (np + 1) & 1;
+            return KMG_OK;
+        }
+        // some tile did not fit the local scheme: plain LSD over all bits, starting from whichever
+        // buffer holds the (permuted) keys now
+        const int saved = g_hybrid;
+        g_hybrid = 0;
+        int sel2 = 0;
+        const int rcode = kmg_radix_sort(kin, kout, nullptr, nullptr, n, key_bytes, 0, begin_bit, end_bit, nullptr, &sel2,
+                                         d_ws, ws_bytes, stream);
+        g_hybrid = saved;
+        if (rcode != KMG_OK) return rcode;
+        // kin is d_keys when np is even
+        const int base = np & 1;  // 0: kin == d_keys
+        *h_selector_out = base ^ sel2;
+        return KMG_OK;
     }
     *h_selector_out = np & 1;
     return KMG_OK;

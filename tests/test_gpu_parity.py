@@ -494,3 +494,87 @@ def test_extract_scatter_partitions_like_extract_plus_range_partition(eng, k, rc
         o_got, o_want = np.argsort(got_v), np.argsort(wv[sel])  # payloads are unique: align by them
         assert first_diff(got_v[o_got], wv[sel][o_want]) == "equal", p
         assert first_diff(got_k[o_got], rows[sel][o_want]) == "equal", p
+
+
+# ---- hybrid finish of key-only sorts (top-prefix passes + one shared-memory local sort) ---------------
+def _keyonly_sort(eng, raw, bits):
+    import torch
+
+    from kman_b200.engine import KeyArray
+
+    n = len(raw)
+    t = lambda x: torch.from_numpy(x.view(np.uint8).reshape(-1)).to(eng.device)  # noqa: E731
+    a = KeyArray(t(raw), torch.zeros(n * 8, dtype=torch.uint8, device=eng.device), None, None, n, 8, 0, bits // 2, False)
+    a = eng.sort(a, 0, bits)
+    eng._status(eng._last_sort_ws)
+    return a
+
+
+@pytest.mark.parametrize("n", [1 << 20, 1_300_007, 5_000_011])
+@pytest.mark.parametrize("bits", [24, 40, 62, 64])
+def test_hybrid_sort_random(eng, n, bits):
+    rng = np.random.default_rng(n + bits)
+    raw = rng.integers(0, 2**63, size=n, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=n, dtype=np.uint64)
+    if bits < 64:
+        raw &= np.uint64((1 << bits) - 1)
+    a = _keyonly_sort(eng, raw, bits)
+    assert eng.lib.kmg_get_stat(b"hybrid_irregular") == 0  # the local sort handled every tile
+    assert eng.lib.kmg_get_stat(b"sort_passes") == 2
+    assert first_diff(a.keys_host(), np.sort(raw)) == "equal"
+
+
+@pytest.mark.parametrize("pattern", ["dup50", "dup3", "all_equal", "clustered", "one_big_bucket", "sorted", "ramp"])
+def test_hybrid_sort_skewed_inputs_fall_back_or_finish(eng, pattern):
+    n = 2_000_003
+    rng = np.random.default_rng(5)
+    rnd = rng.integers(0, 1 << 62, size=n, dtype=np.uint64)
+    if pattern == "dup50":
+        raw = rnd[rng.integers(0, n // 50, size=n)]
+    elif pattern == "dup3":
+        raw = rnd[rng.integers(0, n // 3, size=n)]
+    elif pattern == "all_equal":
+        raw = np.full(n, 0x1234567890ABCDE, np.uint64)
+    elif pattern == "clustered":  # two far-apart dense clusters plus a sparse background
+        raw = np.concatenate([rnd[: n // 3] >> np.uint64(30), (rnd[n // 3: 2 * n // 3] >> np.uint64(30)) | np.uint64(1 << 61),
+                              rnd[2 * n // 3:]])
+    elif pattern == "one_big_bucket":  # 5% of the keys share one 16-bit prefix
+        raw = rnd.copy()
+        raw[: n // 20] = (raw[: n // 20] & np.uint64((1 << 46) - 1)) | np.uint64(0x1F3 << 46)
+    elif pattern == "sorted":
+        raw = np.sort(rnd)
+    else:
+        raw = np.arange(n, dtype=np.uint64) * np.uint64(977)
+    a = _keyonly_sort(eng, raw, 62)
+    assert eng.lib.kmg_get_stat(b"hybrid_irregular") >= 0
+    assert first_diff(a.keys_host(), np.sort(raw)) == "equal", pattern
+
+
+def test_hybrid_sort_can_be_switched_off(eng):
+    rng = np.random.default_rng(9)
+    raw = rng.integers(0, 1 << 62, size=1_500_000, dtype=np.uint64)
+    eng.lib.kmg_set_option(b"hybrid", 0)
+    try:
+        a = _keyonly_sort(eng, raw, 62)
+        assert eng.lib.kmg_get_stat(b"sort_passes") == 8
+    finally:
+        eng.lib.kmg_set_option(b"hybrid", 1)
+    assert first_diff(a.keys_host(), np.sort(raw)) == "equal"
+
+
+def test_hybrid_sort_24bit_prefix_large(eng):
+    """n above the 16-bit-prefix range: three prefix passes + local sort; torch.sort is the checker."""
+    import torch
+
+    n = 125_000_000
+    g = torch.Generator(device=eng.device).manual_seed(3)
+    keys = torch.randint(0, 1 << 62, (n,), dtype=torch.int64, device=eng.device, generator=g)
+    want = torch.sort(keys).values
+    from kman_b200.engine import KeyArray
+
+    a = KeyArray(keys.view(torch.uint8), torch.zeros(n * 8, dtype=torch.uint8, device=eng.device), None, None, n, 8, 0, 31, False)
+    a = eng.sort(a, 0, 62)
+    eng._status(eng._last_sort_ws)
+    assert eng.lib.kmg_get_stat(b"hybrid_irregular") == 0
+    assert eng.lib.kmg_get_stat(b"sort_passes") == 3
+    got = a.keys.view(torch.int64)[:n]
+    assert torch.equal(got, want)

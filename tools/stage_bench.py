@@ -74,6 +74,19 @@ def main():
         print(f"sort cfg {cfg}     : {srt:8.3f} ms  {N/srt/1e6:8.2f} G keys/s  model {alg/srt/1e6:8.1f} GB/s = {alg/srt/1e6/peak:5.3f} of measured peak")
         res[f"sort_cfg{cfg}_ms"] = srt
     eng.lib.kmg_set_option(b"sort_config", 3)
+    for hy, pb in ((0, 0), (1, 16), (1, 24), (1, 0)):
+        eng.lib.kmg_set_option(b"hybrid", hy)
+        eng.lib.kmg_set_option(b"hybrid_pb", pb)
+
+        def run_h():
+            a = eng.extract(d, k, False, val_bytes=args.vb, reuse="b_", want_hist=True)
+            return eng.sort(a)
+
+        med_all, _ = timed(run_h, flush=flush)
+        srt = med_all - res["extract_ms"]
+        print(f"hybrid {hy} pb {pb:2d}: sort {srt:8.3f} ms  {N/srt/1e6:8.2f} G keys/s  passes {eng.lib.kmg_get_stat(b'sort_passes')} irregular {eng.lib.kmg_get_stat(b'hybrid_irregular')}")
+        res[f"sort_hy{hy}_pb{pb}_ms"] = srt
+    eng.lib.kmg_set_option(b"hybrid_pb", 0)
     for g in [int(x) for x in args.lb_groups.split(",") if x]:
         eng.lib.kmg_set_option(b"lb_group", g)
 
