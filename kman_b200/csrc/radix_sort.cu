@@ -435,6 +435,7 @@ struct HybridParams {
     uint64_t* keys_out;
     uint64_t n;
     uint64_t key_mask;      // bits [0, key_bits)
+    uint64_t* bounds;       // [n_tiles + 1], see tile_bounds_kernel
     uint32_t n_tiles;
     int key_bits, pb;
     unsigned long long* irregular;  // number of tiles the local scheme could not handle
@@ -466,6 +467,29 @@ __device__ __forceinline__ uint64_t prefix_run_end(const uint64_t* __restrict__ 
     return hi;
 }
 
+// bounds[tile] = first position >= tile * LS_T where a new prefix bucket starts (one warp per tile);
+// tile owns [bounds[tile], bounds[tile + 1])
+__global__ void __launch_bounds__(256) tile_bounds_kernel(const HybridParams p) {
+    const uint32_t tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (tile > p.n_tiles) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    const int sh_pref = p.key_bits - p.pb;
+    const uint64_t pos = min((uint64_t)tile * LS_T, p.n);
+    uint64_t r = pos;
+    if (pos > 0 && pos < p.n) {
+        // a run that reaches past pos + LS_T + LS_CAP makes both this tile and its owner irregular
+        const uint64_t hi = min(p.n, pos + LS_T + LS_CAP + 1);
+        // one round trip in the common case: keys[pos-1 .. pos+30]
+        const uint64_t i = pos - 1 + lane;
+        const uint64_t v = i < hi ? (p.keys_in[i] & p.key_mask) >> sh_pref : ~0ull;
+        const uint64_t ref = __shfl_sync(0xffffffffu, v, 0);
+        const uint32_t bal = __ballot_sync(0xffffffffu, v != ref);
+        r = bal ? min(pos - 1 + (uint64_t)(__ffs(bal) - 1), hi)
+                : prefix_run_end(p.keys_in, pos + 31, hi, ref, p.key_mask, sh_pref);
+    }
+    if (lane == 0) p.bounds[tile] = r;
+}
+
 // monotone map key -> cell of the tile's counting sort (see local_sort_kernel)
 struct CellMap {
     uint64_t base;   // b_lo << w
@@ -482,37 +506,17 @@ __global__ void __launch_bounds__(LS_BLOCK, 2) local_sort_kernel(const HybridPar
     uint64_t* s_stage = reinterpret_cast<uint64_t*>(ls_smem);                             // [LS_CAP]
     uint32_t* s_cell = reinterpret_cast<uint32_t*>(ls_smem + sizeof(uint64_t) * LS_CAP);  // [LS_CELL_WORDS]
     __shared__ uint32_t s_scan[LS_BLOCK / 32 + 1];
-    __shared__ uint64_t s_bounds[2];
     __shared__ int s_bad;
     const int t = threadIdx.x;
     const uint32_t tile = blockIdx.x;
     const int sh_pref = p.key_bits - p.pb;
 
-    // the tile owns the prefix buckets that START inside its LS_T positions: [s, e)
-    if (t < 64) {
-        const uint32_t lane = t & 31u;
-        const uint64_t pos = min((uint64_t)(tile + (t >> 5)) * LS_T, p.n);
-        uint64_t r = pos;
-        if (pos > 0 && pos < p.n) {
-            // a run that reaches past pos + LS_T + LS_CAP makes both this tile and its owner irregular
-            const uint64_t hi = min(p.n, pos + LS_T + LS_CAP + 1);
-            // one round trip in the common case: keys[pos-1 .. pos+30]
-            const uint64_t i = pos - 1 + lane;
-            const uint64_t v = i < hi ? (p.keys_in[i] & p.key_mask) >> sh_pref : ~0ull;
-            const uint64_t ref = __shfl_sync(0xffffffffu, v, 0);
-            const uint32_t bal = __ballot_sync(0xffffffffu, v != ref);
-            r = bal ? min(pos - 1 + (uint64_t)(__ffs(bal) - 1), hi)
-                    : prefix_run_end(p.keys_in, pos + 31, hi, ref, p.key_mask, sh_pref);
-        }
-        if (lane == 0) s_bounds[t >> 5] = r;
-    }
     if (t == 0) s_bad = 0;
     {
         uint4* z = reinterpret_cast<uint4*>(s_cell);
         for (uint32_t i = t; i < (uint32_t)LS_CELL_WORDS / 4; i += LS_BLOCK) z[i] = make_uint4(0, 0, 0, 0);
     }
-    __syncthreads();
-    const uint64_t s = s_bounds[0], e = s_bounds[1];
+    const uint64_t s = p.bounds[tile], e = p.bounds[tile + 1];
     if (s >= min((uint64_t)(tile + 1) * LS_T, p.n) || e <= s) return;  // no bucket starts in this tile
     const uint64_t m64 = e - s;
     if (m64 > LS_CAP) {
@@ -542,6 +546,7 @@ __global__ void __launch_bounds__(LS_BLOCK, 2) local_sort_kernel(const HybridPar
         const uint64_t range = R << w;
         cm.inv = range <= (uint64_t)LS_CELLS ? 0u : (uint32_t)((((uint64_t)LS_CELLS) << 32) / range);
     }
+    __syncthreads();        // cells are zero
     uint32_t meta[LS_IPT];  // cell | slot inside the cell << 13
 #pragma unroll
     for (int j = 0; j < LS_IPT; ++j) {
@@ -578,30 +583,26 @@ __global__ void __launch_bounds__(LS_BLOCK, 2) local_sort_kernel(const HybridPar
         if (idx < m) s_stage[s_cell[pc(meta[j] & 8191u)] + (meta[j] >> 13)] = keys[j];
     }
     __syncthreads();
-    // order every cell in place: insertion sort (cells hold ~1 key; equal keys cost one compare each)
+    // Order every cell in place.  The cells are already in order among themselves, so a thread
+    // simply insertion-sorts the contiguous run of its 16 cells (~11 keys): a key moves only
+    // inside its own cell, equal keys cost one compare each.
     {
-        const uint32_t endc = s_cell[pc((t + 1) * LS_CPT)];
-        q0 = cv[0]; q1 = cv[1]; q2 = cv[2]; q3 = cv[3];  // (reloaded: keeping them live across the placement spills)
-        const uint32_t st[LS_CPT + 1] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x,
-                                         q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w, endc};
+        const uint32_t lo = s_cell[pc(t * LS_CPT)], hi = s_cell[pc((t + 1) * LS_CPT)];
         int budget = LS_SORT_BUDGET;
-#pragma unroll
-        for (int c = 0; c < LS_CPT; ++c) {
-            const uint32_t cs = st[c], ce = st[c + 1];
-            if (ce - cs < 2) continue;
-            for (uint32_t i = cs + 1; i < ce; ++i) {
-                const uint64_t key = s_stage[i];
-                uint32_t q = i;
-                while (q > cs) {
-                    const uint64_t o = s_stage[q - 1];
-                    if (o <= key) break;
-                    s_stage[q] = o;
-                    --q;
-                    --budget;
-                }
-                s_stage[q] = key;
-                if (budget < 0) break;
+        uint64_t prev = 0;
+        for (uint32_t i = lo; i < hi; ++i) {
+            const uint64_t key = s_stage[i];
+            if (key >= prev) {
+                prev = key;
+                continue;
             }
+            uint32_t q = i;
+            do {
+                s_stage[q] = s_stage[q - 1];
+                --q;
+                --budget;
+            } while (q > lo && s_stage[q - 1] > key);
+            s_stage[q] = key;
             if (budget < 0) break;
         }
         if (budget < 0) s_bad = 1;
@@ -745,6 +746,7 @@ struct SortWs {
     uint32_t* lookback;        // [tiles_per_part][RADIX] tile counts, then [groups][RADIX] group prefixes
     size_t lb_words;           // words of the tile-count array
     int hyb_pb;                // prefix bits of the hybrid finish (0: not applicable)
+    uint64_t* hyb_bounds;      // [n / LS_T + 2] tile bounds of the hybrid finish
     size_t total;
 };
 
@@ -777,6 +779,8 @@ static SortWs carve_sort_ws(void* ws, uint64_t n, int key_bytes) {
     w.lb_words = align_up(tiles * SORT_RADIX * sizeof(uint32_t), 256) / sizeof(uint32_t);
     p += w.lb_words * sizeof(uint32_t) + align_up((tiles / LB_GROUP_MIN + 2) * SORT_RADIX * sizeof(uint32_t), 256);
     w.hyb_pb = key_bytes == 8 ? hybrid_prefix_bits(n) : 0;
+    w.hyb_bounds = (uint64_t*)p;
+    if (w.hyb_pb) p += align_up((n / LS_T + 2) * sizeof(uint64_t), 256);
     w.total = p - (char*)ws;
     return w;
 }
@@ -913,9 +917,12 @@ extern "C" int kmg_radix_sort(void* d_keys, void* d_keys_alt, void* d_vals, void
         hp.n = n;
         hp.key_mask = end_bit >= 64 ? ~0ull : (1ull << end_bit) - 1ull;
         hp.n_tiles = (uint32_t)((n + LS_T - 1) / LS_T);
+        hp.bounds = w.hyb_bounds;
         hp.key_bits = end_bit;
         hp.pb = pb;
         hp.irregular = reinterpret_cast<unsigned long long*>(&w.hdr->pad[0]);  // 8-byte aligned slot of the header
+        tile_bounds_kernel<<<(hp.n_tiles + 1 + 7) / 8, 256, 0, st>>>(hp);
+        KMG_LAUNCH_CHECK();
         const size_t smem = sizeof(uint64_t) * LS_CAP + sizeof(uint32_t) * LS_CELL_WORDS;
         KMG_CUDA(cudaFuncSetAttribute(local_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         local_sort_kernel<<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);
