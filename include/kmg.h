@@ -84,7 +84,9 @@ int kmg_ws_status(void* d_ws, void* stream);
  * that belong to the wide stream.  Output capacity must be (win_end-win_begin)*(1+rc).
  * d_hist_out (optional, narrow stream, k >= 4): uint64[16][256] digit histograms of the emitted
  * keys for kmg_radix_sort's pass plan over bits [0, 2k), derived from one 4-mer histogram of
- * the bases; hand it to kmg_radix_sort(d_hist_in) to skip the sort's own histogram sweep. */
+ * the bases; hand it to kmg_radix_sort(d_hist_in) to skip the sort's own histogram sweep.
+ * For 8-byte keys and k >= 12, rows 13..15 additionally hold the histograms of the three top
+ * key bytes (bits [2k-24, 2k)), which the hybrid sort's prefix passes use. */
 size_t kmg_extract_workspace_bytes(uint64_t n_windows);
 int kmg_extract(const uint8_t* d_bases, uint64_t n_bases, uint64_t win_begin, uint64_t win_end, int k, int rc,
                 int wide, const uint8_t* d_lut256, const uint8_t* d_comp16, void* d_keys_out, int key_bytes,
@@ -95,7 +97,15 @@ int kmg_extract(const uint8_t* d_bases, uint64_t n_bases, uint64_t win_begin, ui
  * Stable, sorts on key bits [begin_bit, end_bit).  Ping-pongs between (keys, keys_alt)
  * [and (vals, vals_alt)]; *h_selector_out (host, written before return) is 0 if the
  * result is in keys/vals, 1 if in keys_alt/vals_alt.  d_hist_in (optional): the digit histograms
- * kmg_extract produced for exactly these keys (requires begin_bit 0, end_bit 2k). */
+ * kmg_extract produced for exactly these keys (requires begin_bit 0, end_bit 2k).
+ * Key-only sorts of 8-byte keys over bits [0, end_bit) with 2^20 <= n <= 2^30 take the "hybrid
+ * finish": 2-3 ordinary passes over the top 16/24 bits, then ONE shared-memory local sort per
+ * ~4096-key tile orders all remaining bits (radix_sort.cu: local_sort_kernel).  Tiles the local
+ * scheme cannot hold (a prefix bucket above 8192 keys) make the call fall back to the plain LSD
+ * passes; the result is identical either way.  The call synchronises the stream in that mode.
+ * Keys must have no bits set at or above end_bit in that mode (kmg_extract's keys never do);
+ * such bits would come back cleared.
+ * kmg_set_option("hybrid", 0) switches it off. */
 size_t kmg_radix_sort_workspace_bytes(uint64_t n, int key_bytes, int val_bytes, int begin_bit, int end_bit);
 int kmg_radix_sort(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_alt, uint64_t n, int key_bytes,
                    int val_bytes, int begin_bit, int end_bit, const uint64_t* d_hist_in, int* h_selector_out,

@@ -455,7 +455,10 @@ __global__ void hist_edges_kernel(const ExtractParams p) {
 // digit histograms of the sort plan for 2k key bits from the per-offset 4-mer histograms
 //   forward key, full digit p : 4-mer at window offset k-4-4p;   top digit (b bits): first b/2 bases
 //   rc key,      full digit p : rc4 of the 4-mer at offset 4p;    top digit: rc of the last b/2 bases
-__global__ void hist_finalize_kernel(const unsigned long long* __restrict__ hs, int n_off, int k, int rc,
+// Rows 13..15 (u64 keys, k >= 12): histograms of the three TOP key bytes, i.e. the 4-mers at window
+// offsets 8, 4, 0 (rc: rc4 of those at k-12, k-8, k-4), for the prefix passes of the hybrid sort;
+// top_idx = index of the first of those extra offsets in hs (fwd 4, fwd 8, [rc k-8, rc k-12]) or -1.
+__global__ void hist_finalize_kernel(const unsigned long long* __restrict__ hs, int n_off, int k, int rc, int top_idx,
                                      unsigned long long* __restrict__ hist_out) {
     const int P = (2 * k + 7) / 8;
     const int b = 2 * k - 8 * (P - 1);  // bits of the top digit: 2, 4, 6 or 8
@@ -480,6 +483,18 @@ __global__ void hist_finalize_kernel(const unsigned long long* __restrict__ hs, 
             const uint32_t low = x & ((1u << b) - 1u);
             const uint32_t r = rc4(low << (8 - b)) & ((1u << b) - 1u);
             atomicAdd(&hist_out[(P - 1) * 256 + r], w);
+        }
+    }
+    if (top_idx >= 0) {
+        // byte 15: offset 0 (hs row P-1) / rc k-4 (row 2P-1); bytes 14, 13: the extra offsets
+        for (int j = 0; j < 3; ++j) {
+            const int fi = j == 0 ? P - 1 : top_idx + (j - 1);
+            unsigned long long v = G[x] + hs[(size_t)fi * 256 + x];
+            if (rc) {
+                const int ri = j == 0 ? 2 * P - 1 : top_idx + 2 + (j - 1);
+                v += G[rc4(x)] + hs[(size_t)ri * 256 + rc4(x)];
+            }
+            hist_out[(15 - j) * 256 + x] = v;
         }
     }
 }
@@ -561,6 +576,7 @@ extern "C" int kmg_extract(const uint8_t* d_bases, uint64_t n_bases, uint64_t wi
     p.err = &hdr->err;
     p.hs = reinterpret_cast<unsigned long long*>((char*)d_ws + sizeof(WsHeader) + state_bytes);
     p.n_off = 0;
+    int top_idx = -1;
     if (d_hist_out) {
         const int P = (2 * k + 7) / 8;
         for (int q = 0; q < P - 1; ++q) p.hist_off[q] = k - 4 - 4 * q;
@@ -570,6 +586,15 @@ extern "C" int kmg_extract(const uint8_t* d_bases, uint64_t n_bases, uint64_t wi
             for (int q = 0; q < P - 1; ++q) p.hist_off[P + q] = 4 * q;
             p.hist_off[2 * P - 1] = k - 4;
             p.n_off = 2 * P;
+        }
+        if (key_bytes == 8 && k >= 12) {
+            top_idx = p.n_off;
+            p.hist_off[p.n_off++] = 4;
+            p.hist_off[p.n_off++] = 8;
+            if (rc) {
+                p.hist_off[p.n_off++] = k - 8;
+                p.hist_off[p.n_off++] = k - 12;
+            }
         }
     }
 
@@ -581,7 +606,7 @@ extern "C" int kmg_extract(const uint8_t* d_bases, uint64_t n_bases, uint64_t wi
     if (rcode != KMG_OK || !d_hist_out) return rcode;
     hist_edges_kernel<<<1, 256, 0, st>>>(p);
     KMG_LAUNCH_CHECK();
-    hist_finalize_kernel<<<1, 256, 0, st>>>(p.hs, p.n_off, k, rc, reinterpret_cast<unsigned long long*>(d_hist_out));
+    hist_finalize_kernel<<<1, 256, 0, st>>>(p.hs, p.n_off, k, rc, top_idx, reinterpret_cast<unsigned long long*>(d_hist_out));
     KMG_LAUNCH_CHECK();
     return KMG_OK;
 }

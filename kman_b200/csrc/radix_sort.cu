@@ -753,7 +753,6 @@ struct SortWs {
 // Prefix bits the hybrid finish sorts with ordinary passes before the local sort takes over: the
 // average bucket (n / 2^pb keys) has to stay well under a tile.  0 = do not use the hybrid.
 int g_hybrid = 1;  // kmg_set_option("hybrid", 0/1)
-int g_hybrid_rows = 0;  // d_hist_in carries rows 14 / 15 (top two bytes)
 int g_hybrid_pb = 0;    // kmg_set_option("hybrid_pb", 0 | 16 | 24): force the prefix width (0 = by n)
 static int hybrid_prefix_bits(uint64_t n) {
     if (!g_hybrid || n < (1ull << 20)) return 0;
@@ -836,9 +835,10 @@ extern "C" int kmg_radix_sort(void* d_keys, void* d_keys_alt, void* d_vals, void
             plan.shift[i] = end_bit - pb + 8 * i;
             plan.bits[i] = 8;
         }
-        if (d_hist_in && pb == 16 && g_hybrid_rows) {
-            KMG_CUDA(cudaMemcpyAsync(w.hist, d_hist_in + 14 * SORT_RADIX, 2 * SORT_RADIX * sizeof(uint64_t),
-                                     cudaMemcpyDeviceToDevice, st));
+        if (d_hist_in && end_bit >= 24 && (end_bit & 1) == 0) {
+            // kmg_extract's rows 13..15: the three top key bytes (k >= 12)
+            KMG_CUDA(cudaMemcpyAsync(w.hist, d_hist_in + (size_t)(16 - np) * SORT_RADIX,
+                                     (size_t)np * SORT_RADIX * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
             hist_in = reinterpret_cast<const uint64_t*>(w.hist);
         } else {
             hist_in = nullptr;  // histogram sweep over the top bytes

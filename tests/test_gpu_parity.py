@@ -368,7 +368,7 @@ def test_cfg2_properties_100mbp(eng):
 
 
 # ---- fused digit histograms (extract -> sort hand-off) ------------------------------------------------
-@pytest.mark.parametrize("k", [4, 5, 7, 8, 16, 21, 31, 32, 33, 45, 64])
+@pytest.mark.parametrize("k", [4, 5, 7, 8, 11, 12, 13, 16, 21, 31, 32, 33, 45, 64])
 @pytest.mark.parametrize("rc", [False, True])
 def test_extract_fused_histograms_match_key_digits(eng, k, rc):
     """kmg_extract derives every radix pass' digit histogram from one 4-mer histogram of the bases
@@ -399,7 +399,15 @@ def test_extract_fused_histograms_match_key_digits(eng, k, rc):
                 dig = v & np.uint64((1 << bits) - 1)
             want = np.bincount(dig.astype(np.int64), minlength=256).astype(np.uint64)
             assert first_diff(hist[p], want) == "equal", (k, rc, wb, we, p)
-        assert not hist[P:].any()
+        if keys.ndim == 1 and k >= 12:
+            # rows 13..15: the three top key bytes (prefix passes of the hybrid sort)
+            for j in range(3):
+                dig = (keys >> np.uint64(2 * k - 8 * (j + 1))) & np.uint64(0xFF)
+                want = np.bincount(dig.astype(np.int64), minlength=256).astype(np.uint64)
+                assert first_diff(hist[15 - j], want) == "equal", (k, rc, wb, we, "top", j)
+            assert not hist[P:13].any()
+        else:
+            assert not hist[P:].any()
 
 
 @pytest.mark.parametrize("pattern", ["all_equal", "two_values", "sorted", "reversed", "low_bits_only", "poly_a_genome"])
