@@ -14,8 +14,9 @@ A "step" is one pass of the hot path over one synthetic input:
            distributed Python API (N>1), pinned host memory, H2D of the bases and D2H of the
            (k-mer, count) table inside the timed region
 `roofline`: onesweep pass kernel, algorithmic bytes 2*W per key per launch, live CUDA-event
-           timing of every launch inside the timed region; `sort_model_frac` is SURVEY.md §8d's
-           fixed 8-bit-digit model N*W*(2*P8+1) over the whole sort
+           timing of every launch inside the timed region; `local_sort` is the same for the hybrid
+           finish's kernel; `sort_model_frac` = 2*W bytes per key per launch over the whole sort,
+           `sort_lsd8_model_frac` = SURVEY.md §8d's fixed 8-bit LSD model N*W*(2*P8+1) over the same time
 `cpu_baseline` / --impl reference: the oracle's numpy port of the reference algorithm on the
            host cores (bounded sample) -- a reported baseline, not the target.
 """
@@ -250,8 +251,7 @@ def main():
             return dc.count(d, K, False)
     else:
         def step():
-            a = eng.sort(eng.extract(d, K, False, val_bytes=0, reuse="bench_", want_hist=True))
-            return eng.rle_count(a, reuse="bench_")
+            return eng.sort_count(eng.extract(d, K, False, val_bytes=0, reuse="bench_", want_hist=True), reuse="bench_")
 
     def barrier():
         if world > 1:
@@ -282,6 +282,8 @@ def main():
     launches = int(lib.kmg_get_stat(b"launches"))
     pass_ns = int(lib.kmg_get_stat(b"sort_pass_ns"))
     pass_cnt = int(lib.kmg_get_stat(b"sort_pass_count"))
+    ls_ns = int(lib.kmg_get_stat(b"local_sort_ns"))
+    ls_cnt = int(lib.kmg_get_stat(b"local_sort_count"))
     lib.kmg_set_option(b"time_passes", 0)
     dev_ms = sum(a.elapsed_time(b_) for a, b_ in ev)
     tmax = torch.tensor([dev_ms], dtype=torch.float64, device=eng.device)
@@ -300,20 +302,33 @@ def main():
         avg_pass_ms = pass_ns / 1e6 / pass_cnt
         n_keys = n_local if world == 1 else n_win_global / world
         passes_per_sort = pass_cnt / args.steps
-        # sorts of more than 2^30 keys run every pass in several launches (30-bit look-back counts)
-        launches_per_pass = max(1.0, passes_per_sort / P8)
+        local_per_sort = ls_cnt / args.steps
+        avg_local_ms = ls_ns / 1e6 / ls_cnt if ls_cnt else 0.0
+        # plain LSD: P8 passes (a sort of more than 2^30 keys runs every pass in several launches);
+        # hybrid finish: 2-3 prefix passes + one local-sort launch, every one a read + write of the keys
+        launches_per_pass = max(1.0, passes_per_sort / P8) if not ls_cnt else 1.0
         alg_bytes = 2 * W * n_keys / launches_per_pass
         achieved = alg_bytes / (avg_pass_ms / 1e3) / 1e9
-        sort_ms = avg_pass_ms * passes_per_sort
+        sort_ms = avg_pass_ms * passes_per_sort + avg_local_ms * local_per_sort
+        model_launches = passes_per_sort / launches_per_pass + local_per_sort
         roofline = {
             "bound": "hbm", "kernel": "kmg::onesweep_kernel (one radix pass: read + write of every key)",
             "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
             "traffic": None, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_pass_ms,
             "launches_per_step": passes_per_sort,
-            "sort_model_bytes_per_kmer": W * (2 * P8 + 1),
-            "sort_model_frac": (W * (2 * P8 + 1) * n_keys) / (sort_ms / 1e3) / 1e9 / peak,
-            "sort_passes_ms_per_step": sort_ms,
+            "sort_model_bytes_per_kmer": 2 * W * model_launches,
+            "sort_model_frac": (2 * W * model_launches * n_keys) / (sort_ms / 1e3) / 1e9 / peak,
+            "sort_ms_per_step": sort_ms,
+            # SURVEY.md 8d's fixed 8-bit LSD model (W*(2*P8+1) bytes per key) over the same time: above 1
+            # means the sort moved fewer bytes than that model (the hybrid finish does)
+            "sort_lsd8_model_bytes_per_kmer": W * (2 * P8 + 1),
+            "sort_lsd8_model_frac": (W * (2 * P8 + 1) * n_keys) / (sort_ms / 1e3) / 1e9 / peak,
         }
+        if ls_cnt:
+            ls_ach = 2 * W * n_keys / (avg_local_ms / 1e3) / 1e9
+            roofline["local_sort"] = {"kernel": "kmg::local_sort_kernel (hybrid finish: read + write of every key)",
+                                      "avg_launch_ms": avg_local_ms, "launches_per_step": local_per_sort,
+                                      "achieved": ls_ach, "frac": ls_ach / peak}
         prof = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(prof):
             try:

@@ -103,8 +103,8 @@ int kmg_extract(const uint8_t* d_bases, uint64_t n_bases, uint64_t win_begin, ui
  * ~4096-key tile orders all remaining bits (radix_sort.cu: local_sort_kernel).  Tiles the local
  * scheme cannot hold (a prefix bucket above 8192 keys) make the call fall back to the plain LSD
  * passes; the result is identical either way.  The call synchronises the stream in that mode.
- * Keys must have no bits set at or above end_bit in that mode (kmg_extract's keys never do);
- * such bits would come back cleared.
+ * All keys must agree in the bits at and above end_bit in that mode (kmg_extract's keys do: those
+ * bits are zero; after kmg_range_partition they are the rank's common prefix).
  * kmg_set_option("hybrid", 0) switches it off. */
 size_t kmg_radix_sort_workspace_bytes(uint64_t n, int key_bytes, int val_bytes, int begin_bit, int end_bit);
 int kmg_radix_sort(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_alt, uint64_t n, int key_bytes,
@@ -117,6 +117,17 @@ int kmg_radix_sort(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_al
 size_t kmg_rle_workspace_bytes(uint64_t n);
 int kmg_rle_count(const void* d_sorted_keys, uint64_t n, int key_bytes, void* d_uniq_keys_out,
                   uint32_t* d_counts_out, uint64_t* d_n_out, void* d_ws, size_t ws_bytes, void* stream);
+
+/* sort + rle_count in one call (the count path: join.py:63-130 after batch.py:156-168).  Sorts
+ * the n keys on bits [0, end_bit) and leaves the distinct keys ascending in d_keys
+ * (*h_selector_out = 0) or d_keys_alt (1), their multiplicities in d_counts_out and their number
+ * in *d_n_out (device); the other key buffer is scratch.  When the hybrid finish applies (see
+ * kmg_radix_sort) its local sort emits the table directly and the sorted keys are never written
+ * or re-read; otherwise this is kmg_radix_sort followed by kmg_rle_count.  Same result either way. */
+size_t kmg_sort_count_workspace_bytes(uint64_t n, int key_bytes, int end_bit);
+int kmg_sort_count(void* d_keys, void* d_keys_alt, uint64_t n, int key_bytes, int end_bit, const uint64_t* d_hist_in,
+                   uint32_t* d_counts_out, uint64_t* d_n_out, int* h_selector_out, void* d_ws, size_t ws_bytes,
+                   void* stream);
 int kmg_select_singletons(const void* d_sorted_keys, const void* d_vals, uint64_t n, int key_bytes, int val_bytes,
                           void* d_keys_out, void* d_vals_out, uint64_t* d_n_out, void* d_ws, size_t ws_bytes,
                           void* stream);

@@ -18,11 +18,12 @@ extern int g_lb_group;
 extern int g_hybrid;
 extern int g_hybrid_pb;
 extern thread_local int64_t g_stat_hybrid_irregular;
+extern thread_local int64_t g_stat_hybrid_path;
 extern int g_prefetch_tiles;
 extern thread_local int64_t g_stat_sort_passes;
 void timing_collect();
-double timing_total_ms();
-int64_t timing_count();
+double timing_total_ms(int kind);
+int64_t timing_count(int kind);
 void timing_reset();
 
 void set_error(const char* fmt, ...) {
@@ -89,13 +90,22 @@ extern "C" int64_t kmg_get_stat(const char* name) {
     if (!strcmp(name, "launches")) return g_launches;
     if (!strcmp(name, "sort_passes")) return g_stat_sort_passes;
     if (!strcmp(name, "hybrid_irregular")) return g_stat_hybrid_irregular;
+    if (!strcmp(name, "hybrid_path")) return g_stat_hybrid_path;
     if (!strcmp(name, "sort_pass_ns")) {  // total device time of the timed onesweep launches
         timing_collect();
-        return (int64_t)(timing_total_ms() * 1e6);
+        return (int64_t)(timing_total_ms(0) * 1e6);
     }
     if (!strcmp(name, "sort_pass_count")) {
         timing_collect();
-        return timing_count();
+        return timing_count(0);
+    }
+    if (!strcmp(name, "local_sort_ns")) {  // same for the hybrid finish's local sort launches
+        timing_collect();
+        return (int64_t)(timing_total_ms(1) * 1e6);
+    }
+    if (!strcmp(name, "local_sort_count")) {
+        timing_collect();
+        return timing_count(1);
     }
     if (!strcmp(name, "reset_launches")) {
         g_launches = 0;
@@ -232,7 +242,8 @@ static int run_host(kmg_ctx* c, int mode, const uint8_t* h_bases, uint64_t n_bas
     const size_t ws_ex = kmg_extract_workspace_bytes(n_win);
     const size_t ws_sort = kmg_radix_sort_workspace_bytes(n_max, kb, vb, 0, 2 * k);
     const size_t ws_rle = kmg_rle_workspace_bytes(n_max);
-    const size_t ws_bytes = std::max(ws_ex, std::max(ws_sort, ws_rle));
+    const size_t ws_count = mode == 0 ? kmg_sort_count_workspace_bytes(n_max, kb, 2 * k) : 0;
+    const size_t ws_bytes = std::max(std::max(ws_ex, ws_count), std::max(ws_sort, ws_rle));
 
     Carver cv{nullptr, 0};
     for (int round = 0; round < 2; ++round) {
@@ -282,15 +293,21 @@ static int run_host(kmg_ctx* c, int mode, const uint8_t* h_bases, uint64_t n_bas
     const uint64_t n = h_counts[0];
     if (n == 0) return KMG_OK;
     int sel = 0;
-    rcode = kmg_radix_sort(d_keys, d_keys_alt, d_vals, d_vals_alt, n, kb, vb, 0, 2 * k, d_hist, &sel, d_ws, ws_bytes, st);
-    if (rcode != KMG_OK) return rcode;
-    char* sk = sel ? d_keys_alt : d_keys;
-    char* ok = sel ? d_keys : d_keys_alt;  // the other buffer receives the compacted output
-    char* sv = sel ? d_vals_alt : d_vals;
-    char* ov = sel ? d_vals : d_vals_alt;
-    // the sort's look-back words and the RLE state share d_ws: both calls re-zero what they use
-    if (mode == 0) rcode = kmg_rle_count(sk, n, kb, ok, d_counts, c->d_small + 2, d_ws, ws_bytes, st);
-    else rcode = kmg_select_singletons(sk, sv, n, kb, vb, ok, ov, c->d_small + 2, d_ws, ws_bytes, st);
+    char* ok;  // buffer that receives the compacted output
+    char* ov = nullptr;
+    if (mode == 0) {
+        rcode = kmg_sort_count(d_keys, d_keys_alt, n, kb, 2 * k, d_hist, d_counts, c->d_small + 2, &sel, d_ws, ws_bytes, st);
+        ok = sel ? d_keys_alt : d_keys;
+    } else {
+        rcode = kmg_radix_sort(d_keys, d_keys_alt, d_vals, d_vals_alt, n, kb, vb, 0, 2 * k, d_hist, &sel, d_ws, ws_bytes, st);
+        if (rcode != KMG_OK) return rcode;
+        char* sk = sel ? d_keys_alt : d_keys;
+        char* sv = sel ? d_vals_alt : d_vals;
+        ok = sel ? d_keys : d_keys_alt;
+        ov = sel ? d_vals : d_vals_alt;
+        // the sort's look-back words and the RLE state share d_ws: both calls re-zero what they use
+        rcode = kmg_select_singletons(sk, sv, n, kb, vb, ok, ov, c->d_small + 2, d_ws, ws_bytes, st);
+    }
     if (rcode != KMG_OK) return rcode;
     uint64_t n_out = 0;
     KMG_CUDA(cudaMemcpyAsync(&n_out, c->d_small + 2, 8, cudaMemcpyDeviceToHost, st));

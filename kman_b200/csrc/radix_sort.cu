@@ -434,22 +434,29 @@ struct HybridParams {
     const uint64_t* keys_in;
     uint64_t* keys_out;
     uint64_t n;
-    uint64_t key_mask;      // bits [0, key_bits)
     uint64_t* bounds;       // [n_tiles + 1], see tile_bounds_kernel
+    uint32_t* flag;         // [n_tiles] 1 = the local scheme could not hold the tile (zeroed by the host)
+    uint64_t* off;          // [n_tiles + 1] offsets of the flagged tiles' keys in the gather buffer
     uint32_t n_tiles;
     int key_bits, pb;
     unsigned long long* irregular;  // number of tiles the local scheme could not handle
+    // fused run-length count (local_sort_kernel<true>): distinct keys -> keys_out, compacted
+    uint32_t* counts_out;
+    unsigned long long* n_out;      // number of distinct keys
+    uint64_t* tile_state;           // two-level tile prefix over the tiles' distinct-key counts
+    uint32_t* ticket;
+    uint32_t* err;
 };
 
 // First i in [lo, hi) whose prefix differs from `ref`, or hi; the prefixes are non-decreasing.
 // Whole-warp 32-ary search: the common case (buckets of a few keys) ends after one probe round.
 __device__ __forceinline__ uint64_t prefix_run_end(const uint64_t* __restrict__ keys, uint64_t lo, uint64_t hi,
-                                                   uint64_t ref, uint64_t mask, int sh) {
+                                                   uint64_t ref, int sh) {
     const uint32_t lane = threadIdx.x & 31u;
     uint64_t step = 1;  // first round: 32 consecutive keys
     while (lo < hi) {
         const uint64_t i = lo + lane * step;
-        const bool ne = i < hi ? ((keys[i] & mask) >> sh) != ref : true;
+        const bool ne = i < hi ? (keys[i] >> sh) != ref : true;
         const uint32_t bal = __ballot_sync(0xffffffffu, ne);
         const uint32_t first = bal ? __ffs(bal) - 1 : 32u;  // 32: all probes still match
         if (first == 0) return lo;
@@ -477,15 +484,14 @@ __global__ void __launch_bounds__(256) tile_bounds_kernel(const HybridParams p) 
     const uint64_t pos = min((uint64_t)tile * LS_T, p.n);
     uint64_t r = pos;
     if (pos > 0 && pos < p.n) {
-        // a run that reaches past pos + LS_T + LS_CAP makes both this tile and its owner irregular
-        const uint64_t hi = min(p.n, pos + LS_T + LS_CAP + 1);
+        const uint64_t hi = p.n;  // exact even for long runs: irregular tiles are re-sorted range by range
         // one round trip in the common case: keys[pos-1 .. pos+30]
         const uint64_t i = pos - 1 + lane;
-        const uint64_t v = i < hi ? (p.keys_in[i] & p.key_mask) >> sh_pref : ~0ull;
+        const uint64_t v = i < hi ? p.keys_in[i] >> sh_pref : ~0ull;
         const uint64_t ref = __shfl_sync(0xffffffffu, v, 0);
         const uint32_t bal = __ballot_sync(0xffffffffu, v != ref);
         r = bal ? min(pos - 1 + (uint64_t)(__ffs(bal) - 1), hi)
-                : prefix_run_end(p.keys_in, pos + 31, hi, ref, p.key_mask, sh_pref);
+                : prefix_run_end(p.keys_in, pos + 31, hi, ref, sh_pref);
     }
     if (lane == 0) p.bounds[tile] = r;
 }
@@ -497,40 +503,69 @@ struct CellMap {
     int sh;          // x = (key >> sh) - base
     __device__ __forceinline__ uint32_t operator()(uint64_t key) const {
         const uint32_t x = (uint32_t)((key >> sh) - base);
-        return inv ? __umulhi(x, inv) : x;
+        // (the clamp only matters for keys that break the contract: bits >= end_bit not all equal)
+        return min(inv ? __umulhi(x, inv) : x, (uint32_t)LS_CELLS - 1u);
     }
 };
 
+// COUNT: instead of the sorted keys the tile writes its DISTINCT keys and their multiplicities,
+// compacted across tiles with the two-level tile prefix (a run of equal keys never leaves its
+// prefix bucket, hence never its tile): kmg_rle_count's result without writing and re-reading the
+// sorted keys.  Tiles take their ids from a ticket so that waiting for earlier tiles is safe.
+template <bool COUNT>
 __global__ void __launch_bounds__(LS_BLOCK, 2) local_sort_kernel(const HybridParams p) {
     extern __shared__ __align__(16) unsigned char ls_smem[];
     uint64_t* s_stage = reinterpret_cast<uint64_t*>(ls_smem);                             // [LS_CAP]
     uint32_t* s_cell = reinterpret_cast<uint32_t*>(ls_smem + sizeof(uint64_t) * LS_CAP);  // [LS_CELL_WORDS]
     __shared__ uint32_t s_scan[LS_BLOCK / 32 + 1];
     __shared__ int s_bad;
+    __shared__ uint32_t s_tile;
+    __shared__ uint64_t s_base;
     const int t = threadIdx.x;
-    const uint32_t tile = blockIdx.x;
     const int sh_pref = p.key_bits - p.pb;
 
-    if (t == 0) s_bad = 0;
+    if (t == 0) {
+        s_bad = 0;
+        if (COUNT) s_tile = atomicAdd(p.ticket, 1u);
+    }
     {
         uint4* z = reinterpret_cast<uint4*>(s_cell);
         for (uint32_t i = t; i < (uint32_t)LS_CELL_WORDS / 4; i += LS_BLOCK) z[i] = make_uint4(0, 0, 0, 0);
     }
+    if (COUNT) __syncthreads();
+    const uint32_t tile = COUNT ? s_tile : blockIdx.x;
+    // a tile without output still takes part in the tile prefix (and the last one reports the total)
+    auto finish_without_output = [&]() {
+        if constexpr (COUNT) {
+            if (t < 32) {
+                if (t == 0) tile_prefix_publish(p.tile_state, tile, 0);
+                const uint64_t base = tile_prefix_resolve_warp(p.tile_state, p.n_tiles, tile, 0, p.err);
+                if (t == 0 && tile == p.n_tiles - 1) *p.n_out = base;
+            }
+        }
+    };
     const uint64_t s = p.bounds[tile], e = p.bounds[tile + 1];
-    if (s >= min((uint64_t)(tile + 1) * LS_T, p.n) || e <= s) return;  // no bucket starts in this tile
+    if (s >= min((uint64_t)(tile + 1) * LS_T, p.n) || e <= s) {  // no bucket starts in this tile
+        finish_without_output();
+        return;
+    }
     const uint64_t m64 = e - s;
     if (m64 > LS_CAP) {
-        if (t == 0) atomicAdd(p.irregular, 1ull);
+        if (t == 0) {
+            atomicAdd(p.irregular, 1ull);
+            p.flag[tile] = 1;
+        }
+        finish_without_output();
         return;
     }
     const uint32_t m = (uint32_t)m64;
     const uint64_t* kin = p.keys_in + s;
-    const uint64_t k_first = kin[0] & p.key_mask, k_last = kin[m - 1] & p.key_mask;
+    const uint64_t k_first = kin[0], k_last = kin[m - 1];
     uint64_t keys[LS_IPT];
 #pragma unroll
     for (int j = 0; j < LS_IPT; ++j) {
         const uint32_t idx = t + j * LS_BLOCK;
-        keys[j] = idx < m ? kin[idx] & p.key_mask : 0;
+        keys[j] = idx < m ? kin[idx] : 0;
     }
     // Counting sort into <= LS_CELLS cells through a monotone map of the key: the w bits after
     // the prefix, relative to the tile's first bucket, scaled down to the cell range when the
@@ -540,7 +575,7 @@ __global__ void __launch_bounds__(LS_BLOCK, 2) local_sort_kernel(const HybridPar
         const uint64_t b_lo = k_first >> sh_pref;
         const uint64_t R = (k_last >> sh_pref) - b_lo + 1;  // <= 2^24
         int w = min(13, sh_pref);
-        w = min(w, 30 - (63 - __clzll((long long)R)));     // (R << w) < 2^31
+        w = max(0, min(w, 30 - (63 - __clzll((long long)R))));  // (R << w) < 2^31
         cm.sh = sh_pref - w;
         cm.base = b_lo << w;
         const uint64_t range = R << w;
@@ -609,14 +644,116 @@ __global__ void __launch_bounds__(LS_BLOCK, 2) local_sort_kernel(const HybridPar
     }
     __syncthreads();
     if (s_bad) {  // too many distinct keys crowded into one cell: leave the tile to the fallback
-        if (t == 0) atomicAdd(p.irregular, 1ull);
+        if (t == 0) {
+            atomicAdd(p.irregular, 1ull);
+            p.flag[tile] = 1;
+        }
+        finish_without_output();
         return;
     }
-    uint64_t* kout = p.keys_out + s;
+    if constexpr (!COUNT) {
+        uint64_t* kout = p.keys_out + s;
 #pragma unroll
-    for (int j = 0; j < LS_IPT; ++j) {
-        const uint32_t idx = t + j * LS_BLOCK;
-        if (idx < m) kout[idx] = s_stage[idx];
+        for (int j = 0; j < LS_IPT; ++j) {
+            const uint32_t idx = t + j * LS_BLOCK;
+            if (idx < m) kout[idx] = s_stage[idx];
+        }
+    } else {
+        // run heads, striped over the threads (position t + j * LS_BLOCK)
+        const uint32_t lane = t & 31u, warp = t >> 5;
+        constexpr int NW = LS_BLOCK / 32;
+        uint32_t* s_wcnt = s_cell;            // [LS_IPT][NW] heads per (stripe, warp), then their offsets
+        uint32_t* s_pos = s_cell + 512;       // [m] positions of the heads in order
+        static_assert(LS_IPT * NW <= 512 && 512 + LS_CAP <= LS_CELL_WORDS, "head bookkeeping must fit the cell array");
+        uint32_t heads = 0;
+#pragma unroll
+        for (int j = 0; j < LS_IPT; ++j) {
+            const uint32_t idx = t + j * LS_BLOCK;
+            const bool head = idx < m && (idx == 0 || s_stage[idx] != s_stage[idx - 1]);
+            heads |= (head ? 1u : 0u) << j;
+            const uint32_t bal = __ballot_sync(0xffffffffu, head);
+            if (lane == 0) s_wcnt[j * NW + warp] = __popc(bal);
+        }
+        __syncthreads();
+        if (warp == 0) {  // exclusive scan of the LS_IPT * NW = 256 counts, 8 per lane
+            uint32_t v[8], acc = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                v[q] = s_wcnt[lane * 8 + q];
+                acc += v[q];
+            }
+            uint32_t inc = acc;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= (uint32_t)o) inc += y;
+            }
+            uint32_t ex = inc - acc;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                s_wcnt[lane * 8 + q] = ex;
+                ex += v[q];
+            }
+            const uint32_t H = __shfl_sync(0xffffffffu, inc, 31);
+            if (lane == 0) {
+                s_scan[0] = H;
+                tile_prefix_publish(p.tile_state, tile, H);
+            }
+        }
+        __syncthreads();
+        const uint32_t H = s_scan[0];
+#pragma unroll
+        for (int j = 0; j < LS_IPT; ++j) {
+            const bool head = (heads >> j) & 1u;
+            const uint32_t bal = __ballot_sync(0xffffffffu, head);
+            if (head) s_pos[s_wcnt[j * NW + warp] + __popc(bal & ((1u << lane) - 1u))] = t + j * LS_BLOCK;
+        }
+        if (warp == 0) {
+            const uint64_t base = tile_prefix_resolve_warp(p.tile_state, p.n_tiles, tile, H, p.err);
+            if (lane == 0) {
+                s_base = base;
+                if (tile == p.n_tiles - 1) *p.n_out = base + H;
+            }
+        }
+        __syncthreads();
+        const uint64_t base = s_base;
+        for (uint32_t h = t; h < H; h += LS_BLOCK) {
+            const uint32_t i = s_pos[h], nxt = h + 1 < H ? s_pos[h + 1] : m;
+            p.keys_out[base + h] = s_stage[i];
+            p.counts_out[base + h] = nxt - i;
+        }
+    }
+}
+
+// Flagged tiles: off[tile] = exclusive prefix of their key counts (one block), total in off[n_tiles]
+__global__ void __launch_bounds__(1024) irregular_scan_kernel(const HybridParams p) {
+    __shared__ uint64_t s_scan[33];
+    const uint32_t t = threadIdx.x;
+    const uint32_t per = (p.n_tiles + 1023) / 1024;
+    const uint32_t b = min(t * per, p.n_tiles), e = min(b + per, p.n_tiles);
+    uint64_t sum = 0;
+    for (uint32_t i = b; i < e; ++i) sum += p.flag[i] ? p.bounds[i + 1] - p.bounds[i] : 0;
+    uint64_t total;
+    uint64_t run = block_excl_scan<1024, uint64_t>(sum, s_scan, total);
+    for (uint32_t i = b; i < e; ++i) {
+        p.off[i] = run;
+        run += p.flag[i] ? p.bounds[i + 1] - p.bounds[i] : 0;
+    }
+    if (t == 0) p.off[p.n_tiles] = total;
+}
+
+// TO_BUFFER: keys_in[bounds[tile]...] -> buf[off[tile]...] for the flagged tiles; else buf -> keys_out.
+// The ranges are whole prefix buckets in ascending order, so sorting the gathered keys and putting
+// them back range by range leaves keys_out fully sorted.
+template <bool TO_BUFFER>
+__global__ void __launch_bounds__(256) irregular_copy_kernel(const HybridParams p, uint64_t* __restrict__ buf) {
+    for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        if (!p.flag[tile]) continue;
+        const uint64_t s = p.bounds[tile], m = p.bounds[tile + 1] - s, o = p.off[tile];
+        for (uint64_t i = threadIdx.x; i < m; i += 256) {
+            if (TO_BUFFER) buf[o + i] = p.keys_in[s + i];
+            else p.keys_out[s + i] = buf[o + i];
+        }
     }
 }
 
@@ -697,17 +834,19 @@ thread_local int64_t g_stat_hybrid_irregular = -1;
 constexpr int MAX_TIMED = 64;
 thread_local cudaEvent_t g_ev[2 * MAX_TIMED];
 thread_local int g_ev_made = 0, g_ev_used = 0;
-thread_local double g_pass_ms_total = 0;
-thread_local int64_t g_pass_count_total = 0;
+thread_local int g_ev_kind[MAX_TIMED];          // 0: onesweep pass, 1: local sort of the hybrid finish
+thread_local double g_pass_ms_total[2] = {0, 0};
+thread_local int64_t g_pass_count_total[2] = {0, 0};
 
 static void timing_begin(cudaStream_t st) {
     if (!g_time_passes || g_ev_used >= MAX_TIMED) return;
     while (g_ev_made < 2 * MAX_TIMED) cudaEventCreate(&g_ev[g_ev_made++]);
     cudaEventRecord(g_ev[2 * g_ev_used], st);
 }
-static void timing_end(cudaStream_t st) {
+static void timing_end(cudaStream_t st, int kind = 0) {
     if (!g_time_passes || g_ev_used >= MAX_TIMED) return;
     cudaEventRecord(g_ev[2 * g_ev_used + 1], st);
+    g_ev_kind[g_ev_used] = kind;
     ++g_ev_used;
 }
 // folds the recorded pairs into the running totals (synchronises on the last event)
@@ -716,18 +855,18 @@ void timing_collect() {
         float ms = 0;
         if (cudaEventSynchronize(g_ev[2 * i + 1]) == cudaSuccess &&
             cudaEventElapsedTime(&ms, g_ev[2 * i], g_ev[2 * i + 1]) == cudaSuccess) {
-            g_pass_ms_total += ms;
-            ++g_pass_count_total;
+            g_pass_ms_total[g_ev_kind[i]] += ms;
+            ++g_pass_count_total[g_ev_kind[i]];
         }
     }
     g_ev_used = 0;
 }
-double timing_total_ms() { return g_pass_ms_total; }
-int64_t timing_count() { return g_pass_count_total; }
+double timing_total_ms(int kind) { return g_pass_ms_total[kind]; }
+int64_t timing_count(int kind) { return g_pass_count_total[kind]; }
 void timing_reset() {
     g_ev_used = 0;
-    g_pass_ms_total = 0;
-    g_pass_count_total = 0;
+    g_pass_ms_total[0] = g_pass_ms_total[1] = 0;
+    g_pass_count_total[0] = g_pass_count_total[1] = 0;
 }
 
 static int tile_items(int cfg, int key_bytes) {
@@ -745,25 +884,30 @@ struct SortWs {
     uint64_t* bins;            // [MAX_PASSES][2][RADIX]
     uint32_t* lookback;        // [tiles_per_part][RADIX] tile counts, then [groups][RADIX] group prefixes
     size_t lb_words;           // words of the tile-count array
-    int hyb_pb;                // prefix bits of the hybrid finish (0: not applicable)
-    uint64_t* hyb_bounds;      // [n / LS_T + 2] tile bounds of the hybrid finish
+    // hybrid finish (see local_sort_kernel); all null / 0 when the sort cannot take it
+    bool hybrid;
+    uint64_t* hyb_bounds;      // [n / LS_T + 2] tile bounds
+    uint32_t* hyb_flag;        // [n / LS_T + 1] irregular tiles
+    uint64_t* hyb_off;         // [n / LS_T + 2] their offsets in the gather buffer
+    uint64_t* hyb_state;       // tile prefix state of the fused count (sc_state_words(n / LS_T + 2))
+    size_t zero_bytes;         // everything up to here is zeroed at the start of a sort
+    uint64_t irr_cap;          // keys the gather buffers hold
+    uint64_t* irr_buf[2];      // gather buffer + its ping-pong partner
+    void* irr_ws;              // workspace of the sort of the gathered keys
+    size_t irr_ws_bytes;
     size_t total;
 };
 
-// Prefix bits the hybrid finish sorts with ordinary passes before the local sort takes over: the
-// average bucket (n / 2^pb keys) has to stay well under a tile.  0 = do not use the hybrid.
-int g_hybrid = 1;  // kmg_set_option("hybrid", 0/1)
-int g_hybrid_pb = 0;    // kmg_set_option("hybrid_pb", 0 | 16 | 24): force the prefix width (0 = by n)
-static int hybrid_prefix_bits(uint64_t n) {
-    if (!g_hybrid || n < (1ull << 20)) return 0;
-    if (g_hybrid_pb == 16 || g_hybrid_pb == 24) return g_hybrid_pb;
-    if (n <= 112ull << 20) return 16;      // <= ~1790 keys per bucket
-    if (n <= (112ull << 20) * 256) return 24;
-    return 0;
-}
+int g_hybrid = 1;     // kmg_set_option("hybrid", 0/1)
+int g_hybrid_pb = 0;  // kmg_set_option("hybrid_pb", 0 | 16 | 24): force the prefix width (0 = by n and skew)
+constexpr uint64_t HYBRID_MIN_N = 1ull << 20;
 
-static SortWs carve_sort_ws(void* ws, uint64_t n, int key_bytes) {
+// Key-only 8-byte sorts over bits [0, end_bit), end_bit >= 32, of 2^20 .. PART_MAX keys.
+static bool hybrid_applies(uint64_t n, int key_bytes, int val_bytes, int begin_bit, int end_bit);
+
+static SortWs carve_sort_ws(void* ws, uint64_t n, int key_bytes, bool hybrid) {
     SortWs w;
+    memset(&w, 0, sizeof(w));
     char* p = (char*)ws;
     w.hdr = (WsHeader*)p;
     p += sizeof(WsHeader);
@@ -777,42 +921,58 @@ static SortWs carve_sort_ws(void* ws, uint64_t n, int key_bytes) {
     const uint64_t tiles = (part + min_tile - 1) / min_tile + 1;
     w.lb_words = align_up(tiles * SORT_RADIX * sizeof(uint32_t), 256) / sizeof(uint32_t);
     p += w.lb_words * sizeof(uint32_t) + align_up((tiles / LB_GROUP_MIN + 2) * SORT_RADIX * sizeof(uint32_t), 256);
-    w.hyb_pb = key_bytes == 8 ? hybrid_prefix_bits(n) : 0;
-    w.hyb_bounds = (uint64_t*)p;
-    if (w.hyb_pb) p += align_up((n / LS_T + 2) * sizeof(uint64_t), 256);
+    w.hybrid = hybrid;
+    if (hybrid) {
+        const uint64_t lt = n / LS_T + 2;
+        w.hyb_flag = (uint32_t*)p;
+        p += align_up(lt * sizeof(uint32_t), 256);
+        w.hyb_state = (uint64_t*)p;
+        p += align_up(sc_state_words(lt) * sizeof(uint64_t), 256);
+    }
+    w.zero_bytes = p - (char*)ws;
+    if (hybrid) {
+        const uint64_t lt = n / LS_T + 2;
+        w.hyb_bounds = (uint64_t*)p;
+        p += align_up(lt * sizeof(uint64_t), 256);
+        w.hyb_off = (uint64_t*)p;
+        p += align_up(lt * sizeof(uint64_t), 256);
+        // irregular tiles are re-sorted through a side buffer of n / 8 keys (beyond that the whole
+        // sort falls back to the plain passes)
+        w.irr_cap = std::max<uint64_t>(n / 8, 1ull << 16);
+        for (int i = 0; i < 2; ++i) {
+            w.irr_buf[i] = (uint64_t*)p;
+            p += align_up(w.irr_cap * sizeof(uint64_t), 256);
+        }
+        w.irr_ws = p;
+        w.irr_ws_bytes = carve_sort_ws(nullptr, w.irr_cap, 8, false).total;
+        p += align_up(w.irr_ws_bytes, 256);
+    }
     w.total = p - (char*)ws;
     return w;
 }
 
-}  // namespace kmg
-
-using namespace kmg;
-
-extern "C" size_t kmg_radix_sort_workspace_bytes(uint64_t n, int key_bytes, int val_bytes, int begin_bit,
-                                                 int end_bit) {
-    (void)val_bytes; (void)begin_bit; (void)end_bit;
-    return carve_sort_ws(nullptr, n, key_bytes).total;
+static bool hybrid_applies(uint64_t n, int key_bytes, int val_bytes, int begin_bit, int end_bit) {
+    return g_hybrid && key_bytes == 8 && val_bytes == 0 && begin_bit == 0 && end_bit >= 32 && n >= HYBRID_MIN_N &&
+           n <= PART_MAX;
 }
 
-extern "C" int kmg_radix_sort(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_alt, uint64_t n,
-                              int key_bytes, int val_bytes, int begin_bit, int end_bit, const uint64_t* d_hist_in,
-                              int* h_selector_out, void* d_ws, size_t ws_bytes, void* stream) {
-    cudaStream_t st = (cudaStream_t)stream;
-    KMG_REQUIRE(key_bytes == 8 || key_bytes == 16, KMG_ERR_ARG, "key_bytes must be 8 or 16");
-    KMG_REQUIRE(val_bytes == 0 || val_bytes == 4 || val_bytes == 8, KMG_ERR_ARG, "val_bytes must be 0, 4 or 8");
-    KMG_REQUIRE(begin_bit >= 0 && end_bit <= key_bytes * 8 && begin_bit <= end_bit, KMG_ERR_ARG,
-                "bad bit range [%d,%d)", begin_bit, end_bit);
-    KMG_REQUIRE(h_selector_out, KMG_ERR_ARG, "h_selector_out is null");
-    KMG_REQUIRE((val_bytes == 0) == (d_vals == nullptr), KMG_ERR_ARG, "d_vals / val_bytes mismatch");
-    *h_selector_out = 0;
-    g_stat_sort_passes = 0;
-    if (n <= 1 || end_bit == begin_bit) return KMG_OK;
-    KMG_REQUIRE(d_keys && d_keys_alt && d_ws, KMG_ERR_ARG, "null pointer argument");
-    KMG_REQUIRE(val_bytes == 0 || d_vals_alt, KMG_ERR_ARG, "d_vals_alt is null");
-    KMG_REQUIRE(((uintptr_t)d_keys % key_bytes) == 0 && ((uintptr_t)d_keys_alt % key_bytes) == 0, KMG_ERR_ARG,
-                "key buffers misaligned");
-    SortWs w = carve_sort_ws(d_ws, n, key_bytes);
+thread_local int64_t g_stat_hybrid_path = 0;  // 0 plain passes, 1 hybrid, 2 hybrid + re-sorted ranges, 3 fell back
+
+// fused run-length count request (kmg_sort_count): `done` = the hybrid finish produced the table
+struct CountOut {
+    uint32_t* counts;
+    unsigned long long* n_out;
+    bool done;
+};
+
+// `hybrid` = the workspace was carved for (and the call may take) the hybrid finish
+static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_alt, uint64_t n, int key_bytes,
+                     int val_bytes, int begin_bit, int end_bit, const uint64_t* d_hist_in, int* h_selector_out,
+                     void* d_ws, size_t ws_bytes, cudaStream_t st, bool hybrid, bool allow_hybrid,
+                     CountOut* co = nullptr) {
+    SortWs w = carve_sort_ws(d_ws, n, key_bytes, hybrid);
     KMG_REQUIRE(ws_bytes >= w.total, KMG_ERR_WS, "sort workspace too small: %zu < %zu", ws_bytes, w.total);
+    hybrid = hybrid && allow_hybrid;
 
     PassPlan plan = make_plan(begin_bit, end_bit);
     int np = plan.num_passes;
@@ -820,38 +980,55 @@ extern "C" int kmg_radix_sort(void* d_keys, void* d_keys_alt, void* d_vals, void
     const uint64_t n_parts = (n + PART_MAX - 1) / PART_MAX;
 
     // header + hist zero; look-back words zero once per sort -- see OnesweepParams::tag
-    KMG_CUDA(cudaMemsetAsync(d_ws, 0, w.total, st));
-
-    // Hybrid finish (key-only 8-byte sorts over bits [0, end_bit)): ordinary passes over the top
-    // pb bits only, then local_sort_kernel orders everything below them.  d_hist_in rows 14 / 15
-    // are the histograms of the two top bytes when the keys come from kmg_extract.
-    const int pb = (key_bytes == 8 && val_bytes == 0 && begin_bit == 0 && n_parts == 1) ? w.hyb_pb : 0;
-    const bool hybrid = pb != 0 && end_bit >= pb + 8;
-    const uint64_t* hist_in = d_hist_in;
-    if (hybrid) {
-        memset(&plan, 0, sizeof(plan));
-        np = plan.num_passes = pb / 8;
-        for (int i = 0; i < np; ++i) {
-            plan.shift[i] = end_bit - pb + 8 * i;
-            plan.bits[i] = 8;
-        }
-        if (d_hist_in && end_bit >= 24 && (end_bit & 1) == 0) {
-            // kmg_extract's rows 13..15: the three top key bytes (k >= 12)
-            KMG_CUDA(cudaMemcpyAsync(w.hist, d_hist_in + (size_t)(16 - np) * SORT_RADIX,
-                                     (size_t)np * SORT_RADIX * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
-            hist_in = reinterpret_cast<const uint64_t*>(w.hist);
-        } else {
-            hist_in = nullptr;  // histogram sweep over the top bytes
-        }
-    }
+    KMG_CUDA(cudaMemsetAsync(d_ws, 0, w.zero_bytes, st));
 
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+
+    // Hybrid finish: ordinary passes over the top pb = 16 or 24 bits only, then local_sort_kernel
+    // orders everything below them.  The histograms of the three top bytes come from kmg_extract
+    // (d_hist_in rows 13..15) or from one sweep; the top byte's tells how skewed the keys are.
     const unsigned long long* hist = w.hist;
-    if (hist_in) {
+    int pb = 0;
+    if (hybrid) {
+        memset(&plan, 0, sizeof(plan));
+        plan.num_passes = 3;
+        for (int i = 0; i < 3; ++i) {
+            plan.shift[i] = end_bit - 24 + 8 * i;
+            plan.bits[i] = 8;
+        }
+        if (d_hist_in && (end_bit & 1) == 0) {
+            KMG_CUDA(cudaMemcpyAsync(w.hist, d_hist_in + (size_t)13 * SORT_RADIX, (size_t)3 * SORT_RADIX * sizeof(uint64_t),
+                                     cudaMemcpyDeviceToDevice, st));
+        } else {
+            const int grid = (int)std::min<uint64_t>((n + 511) / 512, (uint64_t)sms * 4);
+            radix_hist_kernel<uint64_t, SORT_RADIX_BITS><<<grid, 512, 3 * SORT_RADIX * sizeof(uint32_t), st>>>(
+                (const uint64_t*)d_keys, n, plan, w.hist);
+            KMG_LAUNCH_CHECK();
+        }
+        pb = g_hybrid_pb == 16 || g_hybrid_pb == 24 ? g_hybrid_pb : 0;
+        if (!pb) {
+            // a 16-bit prefix is enough (two passes) while its buckets stay well under a tile: judge
+            // by the fullest top byte -- real genomes are skewed enough to need the third pass early
+            pb = 24;
+            if (n <= (1ull << 27)) {
+                unsigned long long h_top[SORT_RADIX];
+                KMG_CUDA(cudaMemcpyAsync(h_top, w.hist + 2 * SORT_RADIX, sizeof(h_top), cudaMemcpyDeviceToHost, st));
+                KMG_CUDA(cudaStreamSynchronize(st));
+                unsigned long long mx = 0;
+                for (int i = 0; i < SORT_RADIX; ++i) mx = std::max(mx, h_top[i]);
+                if (mx / 256 <= 2048) pb = 16;
+            }
+        }
+        np = pb / 8;
+        // passes run over rows [3 - np, 3) of the three-byte plan
+        for (int i = 0; i < np; ++i) plan.shift[i] = end_bit - pb + 8 * i;
+        plan.num_passes = np;
+        hist = w.hist + (size_t)(3 - np) * SORT_RADIX;
+    } else if (d_hist_in) {
         // digit histograms of exactly these keys and this plan, produced by kmg_extract
-        hist = reinterpret_cast<const unsigned long long*>(hist_in);
+        hist = reinterpret_cast<const unsigned long long*>(d_hist_in);
     } else {
         const int grid = (int)std::min<uint64_t>((n + 511) / 512, (uint64_t)sms * 4);
         const size_t smem = (size_t)np * SORT_RADIX * sizeof(uint32_t);
@@ -891,7 +1068,7 @@ extern "C" int kmg_radix_sort(void* d_keys, void* d_keys_alt, void* d_vals, void
             if (n_parts > 1) {
                 // tile counts differ between parts, so stale words could alias: re-zero
                 if (launch > 0)
-                    KMG_CUDA(cudaMemsetAsync(w.lookback, 0, (char*)d_ws + w.total - (char*)w.lookback, st));
+                    KMG_CUDA(cudaMemsetAsync(w.lookback, 0, (char*)d_ws + w.zero_bytes - (char*)w.lookback, st));
                 p.tag = 1u << 30;
             } else {
                 // every word is rewritten by every launch, so a 3-cycle of tags tells the
@@ -909,48 +1086,169 @@ extern "C" int kmg_radix_sort(void* d_keys, void* d_keys_alt, void* d_vals, void
         std::swap(vin, vout);
         ++g_stat_sort_passes;
     }
-    if (hybrid) {
-        // kin now holds the keys ordered by their top pb bits; finish into kout
-        HybridParams hp;
-        hp.keys_in = reinterpret_cast<const uint64_t*>(kin);
-        hp.keys_out = reinterpret_cast<uint64_t*>(kout);
-        hp.n = n;
-        hp.key_mask = end_bit >= 64 ? ~0ull : (1ull << end_bit) - 1ull;
-        hp.n_tiles = (uint32_t)((n + LS_T - 1) / LS_T);
-        hp.bounds = w.hyb_bounds;
-        hp.key_bits = end_bit;
-        hp.pb = pb;
-        hp.irregular = reinterpret_cast<unsigned long long*>(&w.hdr->pad[0]);  // 8-byte aligned slot of the header
-        tile_bounds_kernel<<<(hp.n_tiles + 1 + 7) / 8, 256, 0, st>>>(hp);
+    if (!hybrid) {
+        *h_selector_out = np & 1;
+        return KMG_OK;
+    }
+
+    // kin now holds the keys ordered by their top pb bits; finish into kout
+    HybridParams hp;
+    hp.keys_in = reinterpret_cast<const uint64_t*>(kin);
+    hp.keys_out = reinterpret_cast<uint64_t*>(kout);
+    hp.n = n;
+    hp.n_tiles = (uint32_t)((n + LS_T - 1) / LS_T);
+    hp.bounds = w.hyb_bounds;
+    hp.flag = w.hyb_flag;
+    hp.off = w.hyb_off;
+    hp.key_bits = end_bit;
+    hp.pb = pb;
+    hp.irregular = reinterpret_cast<unsigned long long*>(&w.hdr->pad[0]);  // 8-byte aligned slot of the header
+    tile_bounds_kernel<<<(hp.n_tiles + 1 + 7) / 8, 256, 0, st>>>(hp);
+    KMG_LAUNCH_CHECK();
+    const size_t smem = sizeof(uint64_t) * LS_CAP + sizeof(uint32_t) * LS_CELL_WORDS;
+    KMG_CUDA(cudaFuncSetAttribute(local_sort_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    KMG_CUDA(cudaFuncSetAttribute(local_sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int sel_done = (np + 1) & 1;  // kout is d_keys_alt when np is even
+    unsigned long long irregular = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        const bool fused = co != nullptr && attempt == 0;
+        if (co == nullptr && attempt == 0) continue;  // plain sort: only the second form
+        if (fused) {
+            hp.counts_out = co->counts;
+            hp.n_out = co->n_out;
+            hp.tile_state = w.hyb_state;
+            hp.ticket = &w.hdr->pad[4];
+            hp.err = &w.hdr->err;
+        } else if (co != nullptr) {
+            // the fused launch met irregular tiles: its table is void, sort the keys instead
+            KMG_CUDA(cudaMemsetAsync(hp.irregular, 0, sizeof(unsigned long long), st));
+            KMG_CUDA(cudaMemsetAsync(hp.flag, 0, (size_t)(hp.n_tiles + 1) * sizeof(uint32_t), st));
+        }
+        if (g_ev_used >= MAX_TIMED) timing_collect();
+        timing_begin(st);
+        if (fused) local_sort_kernel<true><<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);
+        else local_sort_kernel<false><<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);
+        timing_end(st, 1);
         KMG_LAUNCH_CHECK();
-        const size_t smem = sizeof(uint64_t) * LS_CAP + sizeof(uint32_t) * LS_CELL_WORDS;
-        KMG_CUDA(cudaFuncSetAttribute(local_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        local_sort_kernel<<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);
-        KMG_LAUNCH_CHECK();
-        unsigned long long irregular = 0;
         KMG_CUDA(cudaMemcpyAsync(&irregular, hp.irregular, sizeof(irregular), cudaMemcpyDeviceToHost, st));
         KMG_CUDA(cudaStreamSynchronize(st));
         g_stat_hybrid_irregular = (int64_t)irregular;
+        g_stat_hybrid_path = 1;
         if (irregular == 0) {
-            *h_selector_out = (np + 1) & 1;
+            if (fused) co->done = true;
+            *h_selector_out = sel_done;
             return KMG_OK;
         }
-        // some tile did not fit the local scheme: plain LSD over all bits, starting from whichever
-        // buffer holds the (permuted) keys now
-        const int saved = g_hybrid;
-        g_hybrid = 0;
+    }
+    // Some tiles own more keys than the local scheme holds (a huge prefix bucket: repeats).  Their
+    // ranges are gathered, sorted with the plain passes and put back -- unless they are most of the
+    // input, in which case the plain passes sort everything.
+    irregular_scan_kernel<<<1, 1024, 0, st>>>(hp);
+    KMG_LAUNCH_CHECK();
+    unsigned long long m_irr = 0;
+    KMG_CUDA(cudaMemcpyAsync(&m_irr, hp.off + hp.n_tiles, sizeof(m_irr), cudaMemcpyDeviceToHost, st));
+    KMG_CUDA(cudaStreamSynchronize(st));
+    if (m_irr <= w.irr_cap) {
+        g_stat_hybrid_path = 2;
+        const int grid = (int)std::min<uint64_t>(hp.n_tiles, (uint64_t)sms * 8);
+        irregular_copy_kernel<true><<<grid, 256, 0, st>>>(hp, w.irr_buf[0]);
+        KMG_LAUNCH_CHECK();
         int sel2 = 0;
-        const int rcode = kmg_radix_sort(kin, kout, nullptr, nullptr, n, key_bytes, 0, begin_bit, end_bit, nullptr, &sel2,
-                                         d_ws, ws_bytes, stream);
-        g_hybrid = saved;
+        const int64_t passes = g_stat_sort_passes;
+        const int rcode = sort_impl(w.irr_buf[0], w.irr_buf[1], nullptr, nullptr, m_irr, 8, 0, 0, end_bit, nullptr, &sel2,
+                                    w.irr_ws, w.irr_ws_bytes, st, false, false);
+        g_stat_sort_passes = passes;
         if (rcode != KMG_OK) return rcode;
-        // kin is d_keys when np is even
-        const int base = np & 1;  // 0: kin == d_keys
-        *h_selector_out = base ^ sel2;
+        irregular_copy_kernel<false><<<grid, 256, 0, st>>>(hp, w.irr_buf[sel2]);
+        KMG_LAUNCH_CHECK();
+        *h_selector_out = sel_done;
         return KMG_OK;
     }
-    *h_selector_out = np & 1;
+    g_stat_hybrid_path = 3;
+    int sel2 = 0;
+    const int rcode = sort_impl(kin, kout, nullptr, nullptr, n, key_bytes, 0, begin_bit, end_bit, nullptr, &sel2, d_ws,
+                                ws_bytes, st, true, false);
+    if (rcode != KMG_OK) return rcode;
+    *h_selector_out = (np & 1) ^ sel2;  // kin is d_keys when np is even
     return KMG_OK;
+}
+
+}  // namespace kmg
+
+using namespace kmg;
+
+extern "C" size_t kmg_radix_sort_workspace_bytes(uint64_t n, int key_bytes, int val_bytes, int begin_bit,
+                                                 int end_bit) {
+    return carve_sort_ws(nullptr, n, key_bytes, hybrid_applies(n, key_bytes, val_bytes, begin_bit, end_bit)).total;
+}
+
+extern "C" int kmg_radix_sort(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_alt, uint64_t n,
+                              int key_bytes, int val_bytes, int begin_bit, int end_bit, const uint64_t* d_hist_in,
+                              int* h_selector_out, void* d_ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    KMG_REQUIRE(key_bytes == 8 || key_bytes == 16, KMG_ERR_ARG, "key_bytes must be 8 or 16");
+    KMG_REQUIRE(val_bytes == 0 || val_bytes == 4 || val_bytes == 8, KMG_ERR_ARG, "val_bytes must be 0, 4 or 8");
+    KMG_REQUIRE(begin_bit >= 0 && end_bit <= key_bytes * 8 && begin_bit <= end_bit, KMG_ERR_ARG,
+                "bad bit range [%d,%d)", begin_bit, end_bit);
+    KMG_REQUIRE(h_selector_out, KMG_ERR_ARG, "h_selector_out is null");
+    KMG_REQUIRE((val_bytes == 0) == (d_vals == nullptr), KMG_ERR_ARG, "d_vals / val_bytes mismatch");
+    *h_selector_out = 0;
+    g_stat_sort_passes = 0;
+    g_stat_hybrid_path = 0;
+    g_stat_hybrid_irregular = -1;
+    if (n <= 1 || end_bit == begin_bit) return KMG_OK;
+    KMG_REQUIRE(d_keys && d_keys_alt && d_ws, KMG_ERR_ARG, "null pointer argument");
+    KMG_REQUIRE(val_bytes == 0 || d_vals_alt, KMG_ERR_ARG, "d_vals_alt is null");
+    KMG_REQUIRE(((uintptr_t)d_keys % key_bytes) == 0 && ((uintptr_t)d_keys_alt % key_bytes) == 0, KMG_ERR_ARG,
+                "key buffers misaligned");
+    const bool hybrid = hybrid_applies(n, key_bytes, val_bytes, begin_bit, end_bit);
+    return sort_impl(d_keys, d_keys_alt, d_vals, d_vals_alt, n, key_bytes, val_bytes, begin_bit, end_bit, d_hist_in,
+                     h_selector_out, d_ws, ws_bytes, st, hybrid, true);
+}
+
+extern "C" size_t kmg_rle_workspace_bytes(uint64_t n);
+extern "C" int kmg_rle_count(const void* d_sorted_keys, uint64_t n, int key_bytes, void* d_uniq_keys_out,
+                             uint32_t* d_counts_out, uint64_t* d_n_out, void* d_ws, size_t ws_bytes, void* stream);
+
+extern "C" size_t kmg_sort_count_workspace_bytes(uint64_t n, int key_bytes, int end_bit) {
+    return align_up(kmg_radix_sort_workspace_bytes(n, key_bytes, 0, 0, end_bit), 256) + kmg_rle_workspace_bytes(n);
+}
+
+extern "C" int kmg_sort_count(void* d_keys, void* d_keys_alt, uint64_t n, int key_bytes, int end_bit,
+                              const uint64_t* d_hist_in, uint32_t* d_counts_out, uint64_t* d_n_out, int* h_selector_out,
+                              void* d_ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    KMG_REQUIRE(key_bytes == 8 || key_bytes == 16, KMG_ERR_ARG, "key_bytes must be 8 or 16");
+    KMG_REQUIRE(end_bit >= 0 && end_bit <= key_bytes * 8, KMG_ERR_ARG, "bad end_bit %d", end_bit);
+    KMG_REQUIRE(h_selector_out && d_n_out, KMG_ERR_ARG, "null pointer argument");
+    *h_selector_out = 0;
+    g_stat_sort_passes = 0;
+    g_stat_hybrid_path = 0;
+    g_stat_hybrid_irregular = -1;
+    KMG_CUDA(cudaMemsetAsync(d_n_out, 0, sizeof(uint64_t), st));
+    if (n == 0) return KMG_OK;
+    KMG_REQUIRE(d_keys && d_keys_alt && d_counts_out && d_ws, KMG_ERR_ARG, "null pointer argument");
+    KMG_REQUIRE(((uintptr_t)d_keys % key_bytes) == 0 && ((uintptr_t)d_keys_alt % key_bytes) == 0, KMG_ERR_ARG,
+                "key buffers misaligned");
+    const size_t sort_ws = align_up(kmg_radix_sort_workspace_bytes(n, key_bytes, 0, 0, end_bit), 256);
+    KMG_REQUIRE(ws_bytes >= sort_ws + kmg_rle_workspace_bytes(n), KMG_ERR_WS, "sort_count workspace too small");
+    int sel = 0;
+    CountOut co{d_counts_out, reinterpret_cast<unsigned long long*>(d_n_out), false};
+    if (n > 1 && end_bit > 0) {
+        const bool hybrid = hybrid_applies(n, key_bytes, 0, 0, end_bit);
+        const int rcode = sort_impl(d_keys, d_keys_alt, nullptr, nullptr, n, key_bytes, 0, 0, end_bit, d_hist_in, &sel, d_ws,
+                                    sort_ws, st, hybrid, true, &co);
+        if (rcode != KMG_OK) return rcode;
+    }
+    if (co.done) {  // the hybrid finish wrote the table itself
+        *h_selector_out = sel;
+        return KMG_OK;
+    }
+    void* sorted = sel ? d_keys_alt : d_keys;
+    void* other = sel ? d_keys : d_keys_alt;
+    *h_selector_out = sel ^ 1;
+    return kmg_rle_count(sorted, n, key_bytes, other, d_counts_out, d_n_out, (char*)d_ws + sort_ws, ws_bytes - sort_ws,
+                         stream);
 }
 
 extern "C" size_t kmg_partition_workspace_bytes(uint64_t n, int key_bytes, int val_bytes) {
@@ -969,7 +1267,7 @@ extern "C" int kmg_range_partition(const void* d_keys, const void* d_vals, uint6
     KMG_REQUIRE((val_bytes == 0) == (d_vals == nullptr), KMG_ERR_ARG, "d_vals / val_bytes mismatch");
     KMG_CUDA(cudaMemsetAsync(d_part_counts, 0, sizeof(uint64_t) * n_parts, st));
     if (n == 0) return KMG_OK;
-    SortWs w = carve_sort_ws(d_ws, n, key_bytes);
+    SortWs w = carve_sort_ws(d_ws, n, key_bytes, false);
     KMG_REQUIRE(ws_bytes >= w.total, KMG_ERR_WS, "partition workspace too small");
     KMG_CUDA(cudaMemsetAsync(d_ws, 0, w.total, st));
     const RangeDigit op{key_bits - 16, (uint32_t)n_parts};

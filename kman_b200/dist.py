@@ -278,8 +278,7 @@ class DistributedCounter:
             except _PeerUnavailable as exc:
                 self._fall_back(exc)
             else:
-                r = self.eng.sort(r, 0, sort_bits_after_partition(r.key_bits, self.world))
-                return self.eng.rle_count(r, reuse="p2p_")
+                return self.eng.sort_count(r, sort_bits_after_partition(r.key_bits, self.world), reuse="p2p_")
         a = self.eng.extract(d, k, rc, wide=False, val_bytes=0)
         n_other = torch.tensor([a.n_other], dtype=torch.int64, device=a.keys.device)
         dist.all_reduce(n_other, group=self.group)
@@ -287,8 +286,7 @@ class DistributedCounter:
             raise ValueError("distributed path handles the narrow (plain ACGT) stream only in this build; "
                              f"input holds {int(n_other.item())} windows with other alphabet symbols")
         r = self._partition_exchange(a, with_vals=False)
-        r = self.eng.sort(r, 0, sort_bits_after_partition(r.key_bits, self.world))
-        return self.eng.rle_count(r)
+        return self.eng.sort_count(r, sort_bits_after_partition(r.key_bits, self.world))
 
     def _fall_back(self, exc) -> None:
         """Every rank raised together (the failure flag is all-reduced): use the NCCL all-to-all path."""

@@ -281,6 +281,29 @@ class Engine:
         a.is_sorted = True
         return a
 
+    def sort_count(self, a: KeyArray, end_bit: Optional[int] = None, reuse: Optional[str] = None) -> CountTable:
+        """sort() + rle_count() in one native call (kmg_sort_count): when the hybrid finish applies,
+        its local sort emits the (k-mer, count) table directly.  Consumes `a` (both key buffers)."""
+        end_bit = a.key_bits if end_bit is None else end_bit
+        assert a.val_bytes == 0
+        counts = self._buf(reuse + "counts", a.n * 4) if reuse else self._new(a.n * 4)
+        if a.n == 0:
+            return CountTable(a.keys_alt, counts, 0, a.key_bytes, a.k, a.wide)
+        ws_bytes = self.lib.kmg_sort_count_workspace_bytes(a.n, a.key_bytes, end_bit)
+        ws = self._buf("ws_sort", ws_bytes)
+        sel = C.c_int(0)
+        hist = a.hist if end_bit == a.key_bits else None
+        _lib.check(
+            self.lib.kmg_sort_count(a.keys.data_ptr(), a.keys_alt.data_ptr(), a.n, a.key_bytes, end_bit, _ptr(hist),
+                                    counts.data_ptr(), self._small[2:].data_ptr(), C.byref(sel), ws.data_ptr(), ws_bytes,
+                                    self._stream())
+        )
+        a.hist = None
+        self._last_sort_ws = ws
+        self._status(ws)
+        n_out = int(self._small[2:3].cpu().numpy().view(np.uint64)[0])
+        return CountTable(a.keys_alt if sel.value else a.keys, counts, n_out, a.key_bytes, a.k, a.wide)
+
     # ---- K4 -----------------------------------------------------------------------------------
     def rle_count(self, a: KeyArray, reuse: Optional[str] = None) -> CountTable:
         """Distinct keys + counts.  The distinct keys are written into `a.keys_alt`."""
@@ -394,7 +417,17 @@ class Engine:
 
     def count(self, d: DeviceInput, k: int, rc: bool = False) -> List[CountTable]:
         """`kmer count` (SEQ_COUNT) on device: one CountTable per stream."""
-        return [self.rle_count(a) for a in self.sorted_streams(d, k, rc, 0)]
+        narrow = self.extract(d, k, rc, wide=False, val_bytes=0, want_hist=True)
+        n_other = narrow.n_other
+        out = [self.sort_count(narrow)]
+        if n_other:
+            if k > 32:
+                raise ValueError(
+                    f"input holds {n_other} windows with non-ACGT alphabet symbols and k={k} > 32: "
+                    "the wide stream supports k <= 32 in this build (no CPU fallback)"
+                )
+            out.append(self.sort_count(self.extract(d, k, rc, wide=True, val_bytes=0)))
+        return out
 
     def uniq(self, d: DeviceInput, k: int, rc: bool = False) -> List[KeyArray]:
         """`kmer uniq` on device: singleton keys with payload, one KeyArray per stream."""

@@ -519,20 +519,32 @@ def _keyonly_sort(eng, raw, bits):
 
 
 @pytest.mark.parametrize("n", [1 << 20, 1_300_007, 5_000_011])
-@pytest.mark.parametrize("bits", [24, 40, 62, 64])
-def test_hybrid_sort_random(eng, n, bits):
+@pytest.mark.parametrize("bits", [32, 40, 62, 64])
+@pytest.mark.parametrize("pb", [0, 24])
+def test_hybrid_sort_random(eng, n, bits, pb):
     rng = np.random.default_rng(n + bits)
     raw = rng.integers(0, 2**63, size=n, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=n, dtype=np.uint64)
     if bits < 64:
         raw &= np.uint64((1 << bits) - 1)
-    a = _keyonly_sort(eng, raw, bits)
-    assert eng.lib.kmg_get_stat(b"hybrid_irregular") == 0  # the local sort handled every tile
-    assert eng.lib.kmg_get_stat(b"sort_passes") == 2
+    eng.lib.kmg_set_option(b"hybrid_pb", pb)
+    try:
+        a = _keyonly_sort(eng, raw, bits)
+    finally:
+        eng.lib.kmg_set_option(b"hybrid_pb", 0)
+    assert eng.lib.kmg_get_stat(b"hybrid_path") == 1  # the local sort handled every tile
+    assert eng.lib.kmg_get_stat(b"hybrid_irregular") == 0
+    assert eng.lib.kmg_get_stat(b"sort_passes") == (3 if pb == 24 else 2)
     assert first_diff(a.keys_host(), np.sort(raw)) == "equal"
 
 
-@pytest.mark.parametrize("pattern", ["dup50", "dup3", "all_equal", "clustered", "one_big_bucket", "sorted", "ramp"])
+_SKEWED = {"dup50": None, "dup3": 1, "all_equal": 3, "clustered": 3, "one_big_bucket": 2, "few_big_buckets": 2, "sorted": 1,
+           "ramp": 3, "crowded_cells": 2}
+
+
+@pytest.mark.parametrize("pattern", sorted(_SKEWED))
 def test_hybrid_sort_skewed_inputs_fall_back_or_finish(eng, pattern):
+    """hybrid_path: 1 = local sort finished everything, 2 = a few huge prefix buckets were gathered
+    and re-sorted, 3 = most keys sat in such buckets and the plain passes sorted everything."""
     n = 2_000_003
     rng = np.random.default_rng(5)
     rnd = rng.integers(0, 1 << 62, size=n, dtype=np.uint64)
@@ -548,12 +560,21 @@ def test_hybrid_sort_skewed_inputs_fall_back_or_finish(eng, pattern):
     elif pattern == "one_big_bucket":  # 5% of the keys share one 16-bit prefix
         raw = rnd.copy()
         raw[: n // 20] = (raw[: n // 20] & np.uint64((1 << 46) - 1)) | np.uint64(0x1F3 << 46)
+    elif pattern == "few_big_buckets":
+        raw = rnd.copy()
+        for j, pref in enumerate((0x0000, 0x7A31, 0xFFFF)):
+            seg = slice(j * 30_000, (j + 1) * 30_000)
+            raw[seg] = (raw[seg] & np.uint64((1 << 46) - 1)) | np.uint64(pref << 46)
     elif pattern == "sorted":
         raw = np.sort(rnd)
+    elif pattern == "crowded_cells":  # thousands of DISTINCT keys that agree in the 16 + 13 bits the cells see
+        raw = rnd.copy()
+        raw[:6000] = (raw[:6000] & np.uint64((1 << 30) - 1)) | np.uint64(0x2222_0000_0000_000)
     else:
         raw = np.arange(n, dtype=np.uint64) * np.uint64(977)
     a = _keyonly_sort(eng, raw, 62)
-    assert eng.lib.kmg_get_stat(b"hybrid_irregular") >= 0
+    if _SKEWED[pattern] is not None:
+        assert eng.lib.kmg_get_stat(b"hybrid_path") == _SKEWED[pattern], pattern
     assert first_diff(a.keys_host(), np.sort(raw)) == "equal", pattern
 
 
@@ -564,25 +585,101 @@ def test_hybrid_sort_can_be_switched_off(eng):
     try:
         a = _keyonly_sort(eng, raw, 62)
         assert eng.lib.kmg_get_stat(b"sort_passes") == 8
+        assert eng.lib.kmg_get_stat(b"hybrid_path") == 0
     finally:
         eng.lib.kmg_set_option(b"hybrid", 1)
     assert first_diff(a.keys_host(), np.sort(raw)) == "equal"
 
 
-def test_hybrid_sort_24bit_prefix_large(eng):
-    """n above the 16-bit-prefix range: three prefix passes + local sort; torch.sort is the checker."""
+@pytest.mark.parametrize("skew", [False, True])
+def test_hybrid_sort_prefix_width_follows_the_skew_large(eng, skew):
+    """125 M keys: uniform keys take the 16-bit prefix (two passes); keys whose top byte is skewed
+    like a real genome's take 24 bits (three passes).  torch.sort is the checker."""
     import torch
+
+    from kman_b200.engine import KeyArray
 
     n = 125_000_000
     g = torch.Generator(device=eng.device).manual_seed(3)
     keys = torch.randint(0, 1 << 62, (n,), dtype=torch.int64, device=eng.device, generator=g)
+    if skew:  # a third of the keys move into one eighth of the key space
+        keys[: n // 3] >>= 3
     want = torch.sort(keys).values
-    from kman_b200.engine import KeyArray
-
     a = KeyArray(keys.view(torch.uint8), torch.zeros(n * 8, dtype=torch.uint8, device=eng.device), None, None, n, 8, 0, 31, False)
     a = eng.sort(a, 0, 62)
     eng._status(eng._last_sort_ws)
-    assert eng.lib.kmg_get_stat(b"hybrid_irregular") == 0
-    assert eng.lib.kmg_get_stat(b"sort_passes") == 3
+    assert eng.lib.kmg_get_stat(b"hybrid_path") == 1
+    assert eng.lib.kmg_get_stat(b"sort_passes") == (3 if skew else 2)
     got = a.keys.view(torch.int64)[:n]
     assert torch.equal(got, want)
+
+
+# ---- kmg_sort_count: sort + run-length count in one call (fused into the hybrid finish) ---------------
+def _sort_count(eng, raw, bits):
+    import torch
+
+    from kman_b200.engine import KeyArray
+
+    n = len(raw)
+    kb = 8 if raw.ndim == 1 else 16
+    t = lambda x: torch.from_numpy(x.view(np.uint8).reshape(-1)).to(eng.device)  # noqa: E731
+    a = KeyArray(t(raw), torch.zeros(max(n * kb, 16), dtype=torch.uint8, device=eng.device), None, None, n, kb, 0,
+                 bits // 2, False)
+    tab = eng.sort_count(a, bits)
+    keys = tab.keys[: tab.n * kb].cpu().numpy().view(np.uint64)
+    counts = tab.counts[: tab.n * 4].cpu().numpy().view(np.uint32)
+    return (keys if kb == 8 else keys.reshape(-1, 2)), counts
+
+
+@pytest.mark.parametrize("n", [1, 2, 77, 4097, 300_001, 1 << 20, 2_500_003])
+@pytest.mark.parametrize("dup", [1, 3, 40])
+def test_sort_count_u64_matches_numpy_unique(eng, n, dup):
+    rng = np.random.default_rng(n * 7 + dup)
+    pool = rng.integers(0, 1 << 62, size=max(1, n // dup), dtype=np.uint64)
+    raw = pool[rng.integers(0, len(pool), size=n)]
+    keys, counts = _sort_count(eng, raw, 62)
+    wk, wc = np.unique(raw, return_counts=True)
+    assert first_diff(keys, wk) == "equal", (n, dup)
+    assert first_diff(counts.astype(np.uint64), wc.astype(np.uint64)) == "equal", (n, dup)
+    if n >= 1 << 20 and dup < 40:
+        assert eng.lib.kmg_get_stat(b"hybrid_path") == 1  # fused: the local sort wrote the table
+
+
+@pytest.mark.parametrize("pattern", ["one_big_bucket", "all_equal", "crowded_cells", "high_bits_constant"])
+def test_sort_count_skewed_inputs(eng, pattern):
+    n = 2_000_003
+    rng = np.random.default_rng(77)
+    rnd = rng.integers(0, 1 << 62, size=n, dtype=np.uint64)
+    bits = 62
+    if pattern == "one_big_bucket":
+        raw = rnd.copy()
+        raw[: n // 20] = (raw[: n // 20] & np.uint64((1 << 40) - 1)) | np.uint64(0x1F3 << 46)
+    elif pattern == "all_equal":
+        raw = np.full(n, 12345678901234567, np.uint64)
+    elif pattern == "crowded_cells":
+        raw = rnd.copy()
+        raw[:6000] = (raw[:6000] & np.uint64((1 << 30) - 1)) | np.uint64(0x2222_0000_0000_000)
+    else:  # what a rank sorts after the range partition: the top bits are equal in all keys, not zero
+        bits = 59
+        raw = (rnd & np.uint64((1 << 59) - 1)) | np.uint64(0b101 << 59)
+    keys, counts = _sort_count(eng, raw, bits)
+    wk, wc = np.unique(raw, return_counts=True)
+    assert first_diff(keys, wk) == "equal", pattern
+    assert first_diff(counts.astype(np.uint64), wc.astype(np.uint64)) == "equal", pattern
+    assert eng.lib.kmg_get_stat(b"hybrid_path") == {"one_big_bucket": 2, "all_equal": 3, "crowded_cells": 2,
+                                                    "high_bits_constant": 1}[pattern]
+
+
+def test_sort_count_u128(eng):
+    rng = np.random.default_rng(4)
+    n = 400_003
+    pool = rng.integers(0, 1 << 62, size=(n // 3, 2), dtype=np.uint64)
+    raw = pool[rng.integers(0, len(pool), size=n)]
+    keys, counts = _sort_count(eng, raw, 126)
+    order = np.lexsort((raw[:, 0], raw[:, 1]))
+    srt = raw[order]
+    head = np.ones(n, bool)
+    head[1:] = (srt[1:] != srt[:-1]).any(axis=1)
+    idx = np.flatnonzero(head)
+    assert first_diff(keys, srt[idx]) == "equal"
+    assert first_diff(counts.astype(np.uint64), np.diff(np.append(idx, n)).astype(np.uint64)) == "equal"

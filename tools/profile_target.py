@@ -23,10 +23,10 @@ bases = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, size=n, dtype=np.uin
 flat = fasta.FlatInput(np.concatenate([bases, np.array([10], np.uint8)]), np.array([0, n + 1], np.uint64), ["chr1"], ["chr1"])
 d = eng.upload(flat, alphabet="ACGT", with_names=False)
 for it in range(2):
-    a = eng.sort(eng.extract(d, k, False, val_bytes=vb, reuse="p_", want_hist=True))
+    a = eng.extract(d, k, False, val_bytes=vb, reuse="p_", want_hist=True)
     if vb:
-        r = eng.singletons(a)
+        r = eng.singletons(eng.sort(a))
     else:
-        r = eng.rle_count(a, reuse="p_")
+        r = eng.sort_count(a, reuse="p_")
 torch.cuda.synchronize()
 print("profile target done", a.n, r.n)

@@ -113,8 +113,7 @@ def main():
     eng.lib.kmg_set_option(b"prefetch_tiles", 192)
 
     def full():
-        a = eng.sort(eng.extract(d, k, False, val_bytes=0, reuse="b_", want_hist=True))
-        return eng.rle_count(a, reuse="b_")
+        return eng.sort_count(eng.extract(d, k, False, val_bytes=0, reuse="b_", want_hist=True), reuse="b_")
 
     med_full, mn_full = timed(full, flush=flush)
     print(f"full count     : {med_full:8.3f} ms (min {mn_full:.3f})  {N/med_full/1e6:8.2f} G kmers/s")
