@@ -17,6 +17,7 @@ extern int g_time_passes;
 extern int g_lb_group;
 extern int g_hybrid;
 extern int g_hybrid_pb;
+extern int g_count_fused;
 extern thread_local int64_t g_stat_hybrid_irregular;
 extern thread_local int64_t g_stat_hybrid_path;
 extern int g_prefetch_tiles;
@@ -56,6 +57,10 @@ extern "C" int kmg_set_option(const char* name, int64_t value) {
     KMG_REQUIRE(name, KMG_ERR_ARG, "option name is null");
     if (!strcmp(name, "sort_config")) {
         g_sort_config = (int)value;
+        return KMG_OK;
+    }
+    if (!strcmp(name, "count_fused")) {
+        g_count_fused = value != 0;
         return KMG_OK;
     }
     if (!strcmp(name, "hybrid_pb")) {

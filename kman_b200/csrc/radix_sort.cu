@@ -420,7 +420,8 @@ __global__ void __launch_bounds__(BLOCK, min_ctas(BLOCK, IPT)) onesweep_kernel(c
 constexpr int LS_BLOCK = 512;
 constexpr int LS_IPT = 16;
 constexpr int LS_CAP = LS_BLOCK * LS_IPT;  // keys a tile can own
-constexpr int LS_T = 4096;                 // positions per tile (a tile owns the buckets starting in it)
+constexpr int LS_T = 4096;                 // default positions per tile (a tile owns the buckets starting in it)
+constexpr int LS_T_MIN = 2048, LS_T_MAX = 4608;  // range of the run-time tile width (HybridParams::tile_t)
 constexpr int LS_CELLS = 8192;
 constexpr int LS_CPT = LS_CELLS / LS_BLOCK;  // consecutive cells per thread in the prefix / cell-sort phases
 static_assert(LS_CPT == 16, "the cell phases move 4 x uint4 per thread");
@@ -438,6 +439,7 @@ struct HybridParams {
     uint32_t* flag;         // [n_tiles] 1 = the local scheme could not hold the tile (zeroed by the host)
     uint64_t* off;          // [n_tiles + 1] offsets of the flagged tiles' keys in the gather buffer
     uint32_t n_tiles;
+    uint32_t tile_t;        // positions per tile
     int key_bits, pb;
     unsigned long long* irregular;  // number of tiles the local scheme could not handle
     // fused run-length count (local_sort_kernel<true>): distinct keys -> keys_out, compacted
@@ -481,7 +483,7 @@ __global__ void __launch_bounds__(256) tile_bounds_kernel(const HybridParams p) 
     if (tile > p.n_tiles) return;
     const uint32_t lane = threadIdx.x & 31u;
     const int sh_pref = p.key_bits - p.pb;
-    const uint64_t pos = min((uint64_t)tile * LS_T, p.n);
+    const uint64_t pos = min((uint64_t)tile * p.tile_t, p.n);
     uint64_t r = pos;
     if (pos > 0 && pos < p.n) {
         const uint64_t hi = p.n;  // exact even for long runs: irregular tiles are re-sorted range by range
@@ -545,7 +547,7 @@ __global__ void __launch_bounds__(LS_BLOCK, 2) local_sort_kernel(const HybridPar
         }
     };
     const uint64_t s = p.bounds[tile], e = p.bounds[tile + 1];
-    if (s >= min((uint64_t)(tile + 1) * LS_T, p.n) || e <= s) {  // no bucket starts in this tile
+    if (s >= min((uint64_t)(tile + 1) * p.tile_t, p.n) || e <= s) {  // no bucket starts in this tile
         finish_without_output();
         return;
     }
@@ -621,8 +623,8 @@ __global__ void __launch_bounds__(LS_BLOCK, 2) local_sort_kernel(const HybridPar
     // Order every cell in place.  The cells are already in order among themselves, so a thread
     // simply insertion-sorts the contiguous run of its 16 cells (~11 keys): a key moves only
     // inside its own cell, equal keys cost one compare each.
+    const uint32_t lo = s_cell[pc(t * LS_CPT)], hi = s_cell[pc((t + 1) * LS_CPT)];
     {
-        const uint32_t lo = s_cell[pc(t * LS_CPT)], hi = s_cell[pc((t + 1) * LS_CPT)];
         int budget = LS_SORT_BUDGET;
         uint64_t prev = 0;
         for (uint32_t i = lo; i < hi; ++i) {
@@ -659,58 +661,33 @@ __global__ void __launch_bounds__(LS_BLOCK, 2) local_sort_kernel(const HybridPar
             if (idx < m) kout[idx] = s_stage[idx];
         }
     } else {
-        // run heads, striped over the threads (position t + j * LS_BLOCK)
-        const uint32_t lane = t & 31u, warp = t >> 5;
-        constexpr int NW = LS_BLOCK / 32;
-        uint32_t* s_wcnt = s_cell;            // [LS_IPT][NW] heads per (stripe, warp), then their offsets
-        uint32_t* s_pos = s_cell + 512;       // [m] positions of the heads in order
-        static_assert(LS_IPT * NW <= 512 && 512 + LS_CAP <= LS_CELL_WORDS, "head bookkeeping must fit the cell array");
-        uint32_t heads = 0;
-#pragma unroll
-        for (int j = 0; j < LS_IPT; ++j) {
-            const uint32_t idx = t + j * LS_BLOCK;
-            const bool head = idx < m && (idx == 0 || s_stage[idx] != s_stage[idx - 1]);
-            heads |= (head ? 1u : 0u) << j;
-            const uint32_t bal = __ballot_sync(0xffffffffu, head);
-            if (lane == 0) s_wcnt[j * NW + warp] = __popc(bal);
-        }
-        __syncthreads();
-        if (warp == 0) {  // exclusive scan of the LS_IPT * NW = 256 counts, 8 per lane
-            uint32_t v[8], acc = 0;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                v[q] = s_wcnt[lane * 8 + q];
-                acc += v[q];
-            }
-            uint32_t inc = acc;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= (uint32_t)o) inc += y;
-            }
-            uint32_t ex = inc - acc;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                s_wcnt[lane * 8 + q] = ex;
-                ex += v[q];
-            }
-            const uint32_t H = __shfl_sync(0xffffffffu, inc, 31);
-            if (lane == 0) {
-                s_scan[0] = H;
-                tile_prefix_publish(p.tile_state, tile, H);
+        // run heads: every thread walks its own (now sorted) run again; the runs tile [0, m) in
+        // thread order, so a block scan of the per-thread head counts ranks the heads
+        uint32_t* s_pos = s_cell;  // [m] positions of the heads in order (the cell array is dead by now)
+        static_assert(LS_CAP <= LS_CELL_WORDS, "head positions must fit the cell array");
+        uint32_t hc = 0;
+        {
+            uint64_t prev = lo > 0 ? s_stage[lo - 1] : 0;
+            for (uint32_t i = lo; i < hi; ++i) {
+                const uint64_t key = s_stage[i];
+                hc += (i == 0 || key != prev) ? 1u : 0u;
+                prev = key;
             }
         }
-        __syncthreads();
-        const uint32_t H = s_scan[0];
-#pragma unroll
-        for (int j = 0; j < LS_IPT; ++j) {
-            const bool head = (heads >> j) & 1u;
-            const uint32_t bal = __ballot_sync(0xffffffffu, head);
-            if (head) s_pos[s_wcnt[j * NW + warp] + __popc(bal & ((1u << lane) - 1u))] = t + j * LS_BLOCK;
+        uint32_t H;
+        uint32_t hoff = block_excl_scan<LS_BLOCK, uint32_t>(hc, s_scan, H);  // (barriers: everyone is done with s_cell)
+        if (t == 0) tile_prefix_publish(p.tile_state, tile, H);
+        {
+            uint64_t prev = lo > 0 ? s_stage[lo - 1] : 0;
+            for (uint32_t i = lo; i < hi; ++i) {
+                const uint64_t key = s_stage[i];
+                if (i == 0 || key != prev) s_pos[hoff++] = i;
+                prev = key;
+            }
         }
-        if (warp == 0) {
+        if (t < 32) {
             const uint64_t base = tile_prefix_resolve_warp(p.tile_state, p.n_tiles, tile, H, p.err);
-            if (lane == 0) {
+            if (t == 0) {
                 s_base = base;
                 if (tile == p.n_tiles - 1) *p.n_out = base + H;
             }
@@ -899,6 +876,7 @@ struct SortWs {
 };
 
 int g_hybrid = 1;     // kmg_set_option("hybrid", 0/1)
+int g_count_fused = 1;  // kmg_set_option("count_fused", 0/1): let the hybrid finish emit the count table itself
 int g_hybrid_pb = 0;  // kmg_set_option("hybrid_pb", 0 | 16 | 24): force the prefix width (0 = by n and skew)
 constexpr uint64_t HYBRID_MIN_N = 1ull << 20;
 
@@ -923,7 +901,7 @@ static SortWs carve_sort_ws(void* ws, uint64_t n, int key_bytes, bool hybrid) {
     p += w.lb_words * sizeof(uint32_t) + align_up((tiles / LB_GROUP_MIN + 2) * SORT_RADIX * sizeof(uint32_t), 256);
     w.hybrid = hybrid;
     if (hybrid) {
-        const uint64_t lt = n / LS_T + 2;
+        const uint64_t lt = n / LS_T_MIN + 2;
         w.hyb_flag = (uint32_t*)p;
         p += align_up(lt * sizeof(uint32_t), 256);
         w.hyb_state = (uint64_t*)p;
@@ -931,7 +909,7 @@ static SortWs carve_sort_ws(void* ws, uint64_t n, int key_bytes, bool hybrid) {
     }
     w.zero_bytes = p - (char*)ws;
     if (hybrid) {
-        const uint64_t lt = n / LS_T + 2;
+        const uint64_t lt = n / LS_T_MIN + 2;
         w.hyb_bounds = (uint64_t*)p;
         p += align_up(lt * sizeof(uint64_t), 256);
         w.hyb_off = (uint64_t*)p;
@@ -1096,7 +1074,16 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
     hp.keys_in = reinterpret_cast<const uint64_t*>(kin);
     hp.keys_out = reinterpret_cast<uint64_t*>(kout);
     hp.n = n;
-    hp.n_tiles = (uint32_t)((n + LS_T - 1) / LS_T);
+    // Tile width: with a 16-bit prefix the buckets are a sizeable fraction of a tile, and a tile owns
+    // WHOLE buckets; a width of k average buckets gives (for evenly filled buckets) every tile the
+    // same k buckets to sort instead of alternating between k-1 and k
+    hp.tile_t = LS_T;
+    if (pb == 16 && n / 65536 >= 64) {
+        const double avg = (double)n / 65536.0;
+        const int kb = std::max(1, (int)(LS_T_MAX / avg));
+        hp.tile_t = (uint32_t)std::min<double>(LS_T_MAX, std::max<double>(LS_T_MIN, std::ceil(kb * avg)));
+    }
+    hp.n_tiles = (uint32_t)((n + hp.tile_t - 1) / hp.tile_t);
     hp.bounds = w.hyb_bounds;
     hp.flag = w.hyb_flag;
     hp.off = w.hyb_off;
@@ -1111,8 +1098,8 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
     const int sel_done = (np + 1) & 1;  // kout is d_keys_alt when np is even
     unsigned long long irregular = 0;
     for (int attempt = 0; attempt < 2; ++attempt) {
-        const bool fused = co != nullptr && attempt == 0;
-        if (co == nullptr && attempt == 0) continue;  // plain sort: only the second form
+        const bool fused = co != nullptr && g_count_fused && attempt == 0;
+        if (!fused && attempt == 0) continue;  // plain sort: only the second form
         if (fused) {
             hp.counts_out = co->counts;
             hp.n_out = co->n_out;

@@ -115,6 +115,10 @@ def main():
     def full():
         return eng.sort_count(eng.extract(d, k, False, val_bytes=0, reuse="b_", want_hist=True), reuse="b_")
 
+    eng.lib.kmg_set_option(b"count_fused", 0)
+    med_full, mn_full = timed(full, flush=flush)
+    print(f"full count (sort, then rle): {med_full:8.3f} ms (min {mn_full:.3f})  {N/med_full/1e6:8.2f} G kmers/s")
+    eng.lib.kmg_set_option(b"count_fused", 1)
     med_full, mn_full = timed(full, flush=flush)
     print(f"full count     : {med_full:8.3f} ms (min {mn_full:.3f})  {N/med_full/1e6:8.2f} G kmers/s")
     res["full_ms"] = med_full
