@@ -624,22 +624,31 @@ __global__ void __launch_bounds__(LS_BLOCK, 2) local_sort_kernel(const HybridPar
     // simply insertion-sorts the contiguous run of its 16 cells (~11 keys): a key moves only
     // inside its own cell, equal keys cost one compare each.
     const uint32_t lo = s_cell[pc(t * LS_CPT)], hi = s_cell[pc((t + 1) * LS_CPT)];
+    // COUNT: equal keys share a cell, hence a thread's run, so the run heads (distinct keys) can be
+    // counted while inserting: a key is new unless it lands right after an equal one
+    uint32_t hc = 0;
     {
         int budget = LS_SORT_BUDGET;
         uint64_t prev = 0;
         for (uint32_t i = lo; i < hi; ++i) {
             const uint64_t key = s_stage[i];
             if (key >= prev) {
+                if (COUNT) hc += (i == lo || key != prev) ? 1u : 0u;
                 prev = key;
                 continue;
             }
             uint32_t q = i;
+            uint64_t below;
+            bool more;
             do {
                 s_stage[q] = s_stage[q - 1];
                 --q;
                 --budget;
-            } while (q > lo && s_stage[q - 1] > key);
+                more = q > lo;
+                if (more) below = s_stage[q - 1];
+            } while (more && below > key);
             s_stage[q] = key;
+            if (COUNT) hc += (!more || below != key) ? 1u : 0u;
             if (budget < 0) break;
         }
         if (budget < 0) s_bad = 1;
@@ -661,27 +670,18 @@ __global__ void __launch_bounds__(LS_BLOCK, 2) local_sort_kernel(const HybridPar
             if (idx < m) kout[idx] = s_stage[idx];
         }
     } else {
-        // run heads: every thread walks its own (now sorted) run again; the runs tile [0, m) in
-        // thread order, so a block scan of the per-thread head counts ranks the heads
+        // the runs tile [0, m) in thread order, so a block scan of the per-thread head counts ranks
+        // the heads; a second walk over the (now sorted) run records their positions
         uint32_t* s_pos = s_cell;  // [m] positions of the heads in order (the cell array is dead by now)
         static_assert(LS_CAP <= LS_CELL_WORDS, "head positions must fit the cell array");
-        uint32_t hc = 0;
-        {
-            uint64_t prev = lo > 0 ? s_stage[lo - 1] : 0;
-            for (uint32_t i = lo; i < hi; ++i) {
-                const uint64_t key = s_stage[i];
-                hc += (i == 0 || key != prev) ? 1u : 0u;
-                prev = key;
-            }
-        }
         uint32_t H;
         uint32_t hoff = block_excl_scan<LS_BLOCK, uint32_t>(hc, s_scan, H);  // (barriers: everyone is done with s_cell)
         if (t == 0) tile_prefix_publish(p.tile_state, tile, H);
         {
-            uint64_t prev = lo > 0 ? s_stage[lo - 1] : 0;
+            uint64_t prev = 0;
             for (uint32_t i = lo; i < hi; ++i) {
                 const uint64_t key = s_stage[i];
-                if (i == 0 || key != prev) s_pos[hoff++] = i;
+                if (i == lo || key != prev) s_pos[hoff++] = i;  // (a run's first key differs from every other run's keys)
                 prev = key;
             }
         }
