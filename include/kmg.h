@@ -98,7 +98,7 @@ int kmg_extract(const uint8_t* d_bases, uint64_t n_bases, uint64_t win_begin, ui
  * [and (vals, vals_alt)]; *h_selector_out (host, written before return) is 0 if the
  * result is in keys/vals, 1 if in keys_alt/vals_alt.  d_hist_in (optional): the digit histograms
  * kmg_extract produced for exactly these keys (requires begin_bit 0, end_bit 2k).
- * Key-only sorts of 8-byte keys over bits [0, end_bit) with 2^20 <= n <= 2^30 take the "hybrid
+ * Key-only sorts of 8-byte keys over bits [0, end_bit) with 2^20 <= n <= 2^33 take the "hybrid
  * finish": 2-3 ordinary passes over the top 16/24 bits, then ONE shared-memory local sort per
  * ~4096-key tile orders all remaining bits (radix_sort.cu: local_sort_kernel).  Tiles the local
  * scheme cannot hold (a prefix bucket above 8192 keys) make the call fall back to the plain LSD

@@ -879,8 +879,9 @@ int g_hybrid = 1;     // kmg_set_option("hybrid", 0/1)
 int g_count_fused = 1;  // kmg_set_option("count_fused", 0/1): let the hybrid finish emit the count table itself
 int g_hybrid_pb = 0;  // kmg_set_option("hybrid_pb", 0 | 16 | 24): force the prefix width (0 = by n and skew)
 constexpr uint64_t HYBRID_MIN_N = 1ull << 20;
+constexpr uint64_t HYBRID_MAX_N = 1ull << 33;  // 32-bit tile ids at the smallest tile width
 
-// Key-only 8-byte sorts over bits [0, end_bit), end_bit >= 32, of 2^20 .. PART_MAX keys.
+// Key-only 8-byte sorts over bits [0, end_bit), end_bit >= 32, of 2^20 .. 2^33 keys.
 static bool hybrid_applies(uint64_t n, int key_bytes, int val_bytes, int begin_bit, int end_bit);
 
 static SortWs carve_sort_ws(void* ws, uint64_t n, int key_bytes, bool hybrid) {
@@ -931,7 +932,7 @@ static SortWs carve_sort_ws(void* ws, uint64_t n, int key_bytes, bool hybrid) {
 
 static bool hybrid_applies(uint64_t n, int key_bytes, int val_bytes, int begin_bit, int end_bit) {
     return g_hybrid && key_bytes == 8 && val_bytes == 0 && begin_bit == 0 && end_bit >= 32 && n >= HYBRID_MIN_N &&
-           n <= PART_MAX;
+           n <= HYBRID_MAX_N;
 }
 
 thread_local int64_t g_stat_hybrid_path = 0;  // 0 plain passes, 1 hybrid, 2 hybrid + re-sorted ranges, 3 fell back

@@ -54,15 +54,16 @@ assert a.n == n_win, (a.n, n_win)
 kb = a.key_bytes
 words = a.keys[: a.n * kb].view(torch.int64)
 ksum = int(words.sum().item()) & (2**64 - 1) if kb == 8 else None
+n_keys = a.n
 e0.record()
-a = eng.sort(a)
+tab = eng.sort_count(a)
 e1.record(); torch.cuda.synchronize(); t_sort = e0.elapsed_time(e1)
-e0.record()
-tab = eng.rle_count(a)
-e1.record(); torch.cuda.synchronize(); t_rle = e0.elapsed_time(e1)
+t_rle = 0.0
+print("sort passes", eng.lib.kmg_get_stat(b"sort_passes"), "hybrid path", eng.lib.kmg_get_stat(b"hybrid_path"),
+      "irregular tiles", eng.lib.kmg_get_stat(b"hybrid_irregular"), flush=True)
 counts = tab.counts[: tab.n * 4].view(torch.int32)
 total = int(counts.sum(dtype=torch.int64).item())
-print(f"extract {t_ex:.1f} ms, sort {t_sort:.1f} ms ({a.n/t_sort/1e6:.2f} G keys/s), rle {t_rle:.1f} ms; distinct {tab.n}", flush=True)
+print(f"extract {t_ex:.1f} ms, sort+count {t_sort:.1f} ms ({n_keys/t_sort/1e6:.2f} G keys/s); distinct {tab.n}", flush=True)
 assert total == n_win, (total, n_win)
 if kb == 8:
     keys = tab.keys[: tab.n * 8].view(torch.int64)
