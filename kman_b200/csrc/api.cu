@@ -18,6 +18,7 @@ extern int g_lb_group;
 extern int g_hybrid;
 extern int g_hybrid_pb;
 extern int g_count_fused;
+extern int g_local_tile;
 extern thread_local int64_t g_stat_hybrid_irregular;
 extern thread_local int64_t g_stat_hybrid_path;
 extern int g_prefetch_tiles;
@@ -57,6 +58,11 @@ extern "C" int kmg_set_option(const char* name, int64_t value) {
     KMG_REQUIRE(name, KMG_ERR_ARG, "option name is null");
     if (!strcmp(name, "sort_config")) {
         g_sort_config = (int)value;
+        return KMG_OK;
+    }
+    if (!strcmp(name, "local_tile")) {
+        KMG_REQUIRE(value >= 2048 && value <= 7936, KMG_ERR_ARG, "local_tile must be in [2048,7936]");
+        g_local_tile = (int)value;
         return KMG_OK;
     }
     if (!strcmp(name, "count_fused")) {

@@ -421,7 +421,7 @@ constexpr int LS_BLOCK = 512;
 constexpr int LS_IPT = 16;
 constexpr int LS_CAP = LS_BLOCK * LS_IPT;  // keys a tile can own
 constexpr int LS_T = 4096;                 // default positions per tile (a tile owns the buckets starting in it)
-constexpr int LS_T_MIN = 2048, LS_T_MAX = 4608;  // range of the run-time tile width (HybridParams::tile_t)
+constexpr int LS_T_MIN = 2048, LS_T_MAX = LS_CAP - 256;  // range of the run-time tile width (HybridParams::tile_t)
 constexpr int LS_CELLS = 8192;
 constexpr int LS_CPT = LS_CELLS / LS_BLOCK;  // consecutive cells per thread in the prefix / cell-sort phases
 static_assert(LS_CPT == 16, "the cell phases move 4 x uint4 per thread");
@@ -876,6 +876,7 @@ struct SortWs {
 };
 
 int g_hybrid = 1;     // kmg_set_option("hybrid", 0/1)
+int g_local_tile = 7936;  // kmg_set_option("local_tile", positions): target tile width of the local sort
 int g_count_fused = 1;  // kmg_set_option("count_fused", 0/1): let the hybrid finish emit the count table itself
 int g_hybrid_pb = 0;  // kmg_set_option("hybrid_pb", 0 | 16 | 24): force the prefix width (0 = by n and skew)
 constexpr uint64_t HYBRID_MIN_N = 1ull << 20;
@@ -1078,10 +1079,12 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
     // Tile width: with a 16-bit prefix the buckets are a sizeable fraction of a tile, and a tile owns
     // WHOLE buckets; a width of k average buckets gives (for evenly filled buckets) every tile the
     // same k buckets to sort instead of alternating between k-1 and k
-    hp.tile_t = LS_T;
-    if (pb == 16 && n / 65536 >= 64) {
-        const double avg = (double)n / 65536.0;
-        const int kb = std::max(1, (int)(LS_T_MAX / avg));
+    const double avg = (double)n / (double)(1ull << pb);  // average prefix bucket
+    double target = std::min<double>(g_local_tile, LS_CAP - std::max(256.0, 1.35 * avg));  // room for the straddling bucket
+    target = std::max<double>(target, LS_T_MIN);
+    hp.tile_t = (uint32_t)target;
+    if (avg >= 64) {
+        const int kb = std::max(1, (int)(target / avg));
         hp.tile_t = (uint32_t)std::min<double>(LS_T_MAX, std::max<double>(LS_T_MIN, std::ceil(kb * avg)));
     }
     hp.n_tiles = (uint32_t)((n + hp.tile_t - 1) / hp.tile_t);

@@ -41,6 +41,7 @@ def main():
     ap.add_argument("--yardstick", action="store_true")
     ap.add_argument("--lb-groups", default="")
     ap.add_argument("--prefetch", default="")
+    ap.add_argument("--local-tiles", default="")
     args = ap.parse_args()
     eng = get_engine(0)
     rng = np.random.default_rng(1234)
@@ -115,6 +116,14 @@ def main():
     def full():
         return eng.sort_count(eng.extract(d, k, False, val_bytes=0, reuse="b_", want_hist=True), reuse="b_")
 
+    for pbv in (0, 24):
+        eng.lib.kmg_set_option(b"hybrid_pb", pbv)
+        for lt in [int(x) for x in args.local_tiles.split(",") if x]:
+            eng.lib.kmg_set_option(b"local_tile", lt)
+            med_full, mn_full = timed(full, flush=flush)
+            print(f"pb {pbv:2d} local_tile {lt}: full count {med_full:8.3f} ms  {N/med_full/1e6:8.2f} G kmers/s")
+    eng.lib.kmg_set_option(b"hybrid_pb", 0)
+    eng.lib.kmg_set_option(b"local_tile", 7936)
     eng.lib.kmg_set_option(b"count_fused", 0)
     med_full, mn_full = timed(full, flush=flush)
     print(f"full count (sort, then rle): {med_full:8.3f} ms (min {mn_full:.3f})  {N/med_full/1e6:8.2f} G kmers/s")
