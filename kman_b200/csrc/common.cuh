@@ -144,21 +144,29 @@ constexpr uint64_t TP_FLAG_AGG = 1ull << 62;
 constexpr uint64_t TP_FLAG_INCL = 2ull << 62;
 constexpr uint64_t TP_VALUE_MASK = (1ull << 62) - 1;
 
-// ---- two-level tile prefix for single-value scans ------------------------------------------------
-// Tiles form groups of SC_GROUP consecutive tiles.  A tile's exclusive prefix is
-//   (inclusive prefix of the previous GROUP) + (aggregates of the earlier tiles of its own group).
-// Aggregates depend on nothing but the tile's own data, so the only dependency chain is
-// ginc[g-1] -> ginc[g], one link per SC_GROUP tiles and one L2 round trip long; a chained or
-// decoupled look-back over single tiles cannot keep up with B200's tile rate (the walk back to
-// the newest finished prefix grew to 60-90 tiles, see profiles/r01_ncu_summary.md).
-// Layout: state[0 .. n_tiles) = aggregates, state[n_tiles .. ) = group prefixes; zero-initialised;
+// ---- three-level tile prefix for single-value scans ----------------------------------------------
+// Tiles form groups of SC_GROUP consecutive tiles, groups form super-groups of SC_SUPER groups.
+// A tile's exclusive prefix is
+//   (inclusive prefix of the previous SUPER-GROUP)                       sinc[s-1]   1 word
+// + (sums of the earlier groups of its own super-group)                  gsum[..]    <= SC_SUPER-1 words
+// + (aggregates of the earlier tiles of its own group)                   agg[..]     <= SC_GROUP-1 words
+// Aggregates and group sums depend on nothing but their own tiles, so the only dependency CHAIN is
+// sinc[s-1] -> sinc[s]: one link per SC_GROUP * SC_SUPER = 4096 tiles.  (With the chain at group
+// level -- one L2 round trip per 128 tiles -- the 190 links of a 24 k-tile launch took as long as the
+// whole kernel: 38 % of extract's stall samples sat behind it; a chained or decoupled look-back
+// over single tiles is worse still, see profiles/r01_ncu_summary.md.)
+// Layout: state[0 .. n_tiles) aggregates | gsum[n_tiles / SC_GROUP + 1] | sinc[...]; zero-initialised;
 // tile ids handed out in launch order (atomic ticket).  The flag travels in the word (bit 63).
 constexpr uint32_t SC_GROUP = 128;
+constexpr uint32_t SC_SUPER = 32;
 constexpr uint64_t SC_FLAG = 1ull << 63;
 constexpr uint64_t SC_VALUE_MASK = SC_FLAG - 1;
 
+__host__ __device__ __forceinline__ uint64_t sc_groups(uint64_t n_tiles) { return n_tiles / SC_GROUP + 1; }
 // words the state array needs for n_tiles tiles
-static inline size_t sc_state_words(uint64_t n_tiles) { return n_tiles + n_tiles / SC_GROUP + 2; }
+static inline size_t sc_state_words(uint64_t n_tiles) {
+    return n_tiles + sc_groups(n_tiles) + sc_groups(n_tiles) / SC_SUPER + 2;
+}
 
 __device__ __forceinline__ uint64_t sc_wait(const uint64_t* p, uint64_t w, uint32_t& spins, uint32_t* err_flag) {
     while (!(w & SC_FLAG)) {
@@ -181,31 +189,43 @@ __device__ __forceinline__ void tile_prefix_publish(uint64_t* state, uint32_t ti
 // the exclusive prefix (sum of the aggregates of all earlier tiles).
 __device__ __forceinline__ uint64_t tile_prefix_resolve_warp(uint64_t* state, uint32_t n_tiles, uint32_t tile,
                                                              uint64_t aggregate, uint32_t* err_flag) {
+    static_assert(SC_SUPER <= 32, "one group sum per lane");
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t g = tile / SC_GROUP, r = tile % SC_GROUP;
-    uint64_t* ginc = state + n_tiles;
+    const uint32_t s = g / SC_SUPER, q = g % SC_SUPER;
+    uint64_t* gsum = state + n_tiles;
+    uint64_t* sinc = gsum + sc_groups(n_tiles);
     uint32_t spins = 0;
-    uint64_t gv = SC_FLAG;
-    if (lane == 0 && g > 0) gv = ld_relaxed_u64(&ginc[g - 1]);
+    // all loads first, waits afterwards
+    uint64_t sv = SC_FLAG, gv = SC_FLAG;
+    if (lane == 0 && s > 0) sv = ld_relaxed_u64(&sinc[s - 1]);
+    if (lane < q) gv = ld_relaxed_u64(&gsum[g - 1 - lane]);
     uint64_t w[SC_GROUP / 32];
 #pragma unroll
-    for (int q = 0; q < (int)(SC_GROUP / 32); ++q) {
-        const uint32_t j = lane + 1 + 32 * q;
-        w[q] = j <= r ? ld_relaxed_u64(&state[tile - j]) : SC_FLAG;
+    for (int k = 0; k < (int)(SC_GROUP / 32); ++k) {
+        const uint32_t j = lane + 1 + 32 * k;
+        w[k] = j <= r ? ld_relaxed_u64(&state[tile - j]) : SC_FLAG;
     }
-    uint64_t sum = 0;
+    uint64_t own = 0;  // earlier tiles of the own group
 #pragma unroll
-    for (int q = 0; q < (int)(SC_GROUP / 32); ++q) {
-        const uint32_t j = lane + 1 + 32 * q;
-        if (j <= r) w[q] = sc_wait(&state[tile - j], w[q], spins, err_flag);
-        sum += w[q] & SC_VALUE_MASK;
+    for (int k = 0; k < (int)(SC_GROUP / 32); ++k) {
+        const uint32_t j = lane + 1 + 32 * k;
+        if (j <= r) w[k] = sc_wait(&state[tile - j], w[k], spins, err_flag);
+        own += w[k] & SC_VALUE_MASK;
     }
-    if (lane == 0 && g > 0) gv = sc_wait(&ginc[g - 1], gv, spins, err_flag);
-    sum += gv & SC_VALUE_MASK;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    if (r == SC_GROUP - 1 && lane == 0) st_relaxed_u64(&ginc[g], SC_FLAG | (sum + aggregate));
-    return sum;
+    for (int o = 16; o > 0; o >>= 1) own += __shfl_xor_sync(0xffffffffu, own, o);
+    // the group's last tile publishes the group sum -- before it waits for anything outside the group
+    if (r == SC_GROUP - 1 && lane == 0) st_relaxed_u64(&gsum[g], SC_FLAG | (own + aggregate));
+    if (lane < q) gv = sc_wait(&gsum[g - 1 - lane], gv, spins, err_flag);
+    if (lane == 0 && s > 0) sv = sc_wait(&sinc[s - 1], sv, spins, err_flag);
+    uint64_t outer = (gv & SC_VALUE_MASK) + (sv & SC_VALUE_MASK);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) outer += __shfl_xor_sync(0xffffffffu, outer, o);
+    const uint64_t excl = outer + own;
+    // ... and the super-group's last tile the chained inclusive prefix
+    if (r == SC_GROUP - 1 && q == SC_SUPER - 1 && lane == 0) st_relaxed_u64(&sinc[s], SC_FLAG | (excl + aggregate));
+    return excl;
 }
 
 // publish + resolve back to back (kernels without useful work to put in between)
