@@ -683,3 +683,22 @@ def test_sort_count_u128(eng):
     idx = np.flatnonzero(head)
     assert first_diff(keys, srt[idx]) == "equal"
     assert first_diff(counts.astype(np.uint64), np.diff(np.append(idx, n)).astype(np.uint64)) == "equal"
+
+
+@pytest.mark.parametrize("k,rc", [(31, True), (16, False), (33, False)])
+def test_low_complexity_genome_through_the_hybrid_sort(eng, k, rc):
+    """> 2^20 keys with homopolymer / microsatellite runs (huge prefix buckets -> irregular tiles are
+    gathered and re-sorted), soft-masked lower case, N runs and several records: count and uniq text
+    must equal the oracle's byte for byte."""
+    from kman_b200 import fasta
+
+    rnd = ko.synth_bases(1_200_000, 21).decode()
+    s1 = rnd[:400_000] + "A" * 60_000 + rnd[400_000:800_000].lower() + "AC" * 40_000 + "N" * 5_000 + rnd[800_000:] + "T" * 30_000
+    s2 = rnd[100_000:700_000] + "GATTACA" * 9_000 + rnd[:50_000]
+    recs = [("chr1 low complexity", s1), ("chr2", s2), ("tiny", "ACGTACGT")]
+    d = eng.upload(fasta.from_records(recs), alphabet="ACGT")
+    got = eng.count_text(d, k, rc)
+    if k <= 32:
+        assert eng.lib.kmg_get_stat(b"hybrid_path") in (1, 2, 3)
+    assert got == ko.count_text_np(recs, k, rc, "ACGT"), (k, rc)
+    assert eng.uniq_text(d, k, rc) == ko.uniq_text_np(recs, k, rc, "ACGT"), (k, rc)
