@@ -18,6 +18,7 @@ extern int g_lb_group;
 extern int g_hybrid;
 extern int g_hybrid_pb;
 extern int g_count_fused;
+extern int g_hybrid_unstable;
 extern int g_local_tile;
 extern thread_local int64_t g_stat_hybrid_irregular;
 extern thread_local int64_t g_stat_hybrid_path;
@@ -63,6 +64,10 @@ extern "C" int kmg_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "local_tile")) {
         KMG_REQUIRE(value >= 2048 && value <= 7936, KMG_ERR_ARG, "local_tile must be in [2048,7936]");
         g_local_tile = (int)value;
+        return KMG_OK;
+    }
+    if (!strcmp(name, "hybrid_unstable")) {
+        g_hybrid_unstable = value != 0;
         return KMG_OK;
     }
     if (!strcmp(name, "count_fused")) {

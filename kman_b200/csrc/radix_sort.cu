@@ -178,10 +178,13 @@ __device__ __forceinline__ uint32_t lookback_two_level(const uint32_t* __restric
 // MIX: how a warp finds the lanes that hold the same digit
 //   0 = 8 ballots per key (ALU), 1 = shared-memory lane-mask table (LSU), 2 = alternate per item,
 //   3 = table for every 4th item, 4 = table for 3 items out of 4
+//   5 = UNSTABLE: the rank among equal digits is the value the histogram atomic returned -- no
+//       matching at all.  Only for a pass whose order inside a digit does not matter: the first
+//       prefix pass of the hybrid finish (the local sort orders everything below the prefix).
 __host__ __device__ constexpr bool mix_uses_table(int mix, int i) {
     return mix == 1 || (mix == 2 && (i & 1)) || (mix == 3 && (i & 3) == 3) || (mix == 4 && (i & 3) != 0);
 }
-__host__ __device__ constexpr int mix_tables(int mix) { return mix == 0 ? 0 : ((mix == 1 || mix == 4) ? 2 : 1); }
+__host__ __device__ constexpr int mix_tables(int mix) { return (mix == 0 || mix == 5) ? 0 : ((mix == 1 || mix == 4) ? 2 : 1); }
 template <typename KeyT, int VAL_BYTES, int RADIX_BITS, int BLOCK, int IPT, int MIX, typename DigitOp, bool FULL>
 __device__ __forceinline__ void onesweep_tile(const OnesweepParams& p, const DigitOp& digit_of, unsigned char* smem_raw,
                                               uint32_t* s_scan, uint64_t* s_bar, const uint32_t tile,
@@ -190,6 +193,8 @@ __device__ __forceinline__ void onesweep_tile(const OnesweepParams& p, const Dig
     constexpr int WARPS = BLOCK / 32;
     constexpr int TILE = BLOCK * IPT;
     constexpr int NTBL = mix_tables(MIX);
+    // (a partial tile pads with digit RADIX-1 slots that must rank AFTER the real keys: stable path)
+    constexpr bool UNSTABLE = MIX == 5 && FULL;
     static_assert(RADIX <= BLOCK, "one thread per digit in the prefix / look-back phases");
     using ValT = typename ValType<VAL_BYTES>::type;
     constexpr int ITEM_BYTES = sizeof(KeyT) > sizeof(ValT) ? sizeof(KeyT) : sizeof(ValT);
@@ -232,7 +237,8 @@ __device__ __forceinline__ void onesweep_tile(const OnesweepParams& p, const Dig
         const uint32_t idx = wbase + i * 32;
         // slots past the end of a partial tile rank into the last digit, after every real key
         dg[i] = (FULL || idx < n_valid) ? digit_of(keys[i]) : (uint32_t)(RADIX - 1);
-        atomicAdd(&my_hist[dg[i]], 1u);
+        if constexpr (UNSTABLE) dg[i] |= atomicAdd(&my_hist[dg[i]], 1u) << RADIX_BITS;  // digit | rank in the warp
+        else atomicAdd(&my_hist[dg[i]], 1u);
     }
     __syncthreads();
 
@@ -281,6 +287,10 @@ __device__ __forceinline__ void onesweep_tile(const OnesweepParams& p, const Dig
     const uint32_t my_bit = 1u << lane;
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
+        if constexpr (UNSTABLE) {
+            slot[i] = my_hist[dg[i] & (RADIX - 1)] + (dg[i] >> RADIX_BITS);
+            continue;
+        }
         const uint32_t dd = dg[i];
         const bool use_table = mix_uses_table(MIX, i);
         uint32_t m, cur;
@@ -741,7 +751,7 @@ struct SortTile {
 // index = kmg_set_option("sort_config", i)
 static const SortTile kSortTiles[] = {
     {256, 16, 2}, {256, 16, 0}, {256, 16, 1}, {256, 24, 2}, {512, 16, 2}, {256, 16, 3}, {384, 16, 2}, {256, 16, 4},
-    {256, 24, 3}, {256, 20, 2},
+    {256, 24, 3}, {256, 20, 2}, {256, 24, 5},
 };
 constexpr int kNumSortTiles = sizeof(kSortTiles) / sizeof(kSortTiles[0]);
 
@@ -776,6 +786,7 @@ static int dispatch_tile(int cfg, const OnesweepParams& p, const ShiftDigit& op,
         case 7: return launch_onesweep<KeyT, VB, 8, 256, 16, 4>(p, op, st);
         case 8: return launch_onesweep<KeyT, VB, 8, 256, 24, 3>(p, op, st);
         case 9: return launch_onesweep<KeyT, VB, 8, 256, 20, 2>(p, op, st);
+        case 10: return launch_onesweep<KeyT, VB, 8, 256, 24, 5>(p, op, st);
         default: return launch_onesweep<KeyT, VB, 8, 256, 16, 2>(p, op, st);
     }
 }
@@ -876,6 +887,7 @@ struct SortWs {
 };
 
 int g_hybrid = 1;     // kmg_set_option("hybrid", 0/1)
+int g_hybrid_unstable = 1;  // kmg_set_option("hybrid_unstable", 0/1): first prefix pass without stable ranking
 int g_local_tile = 7936;  // kmg_set_option("local_tile", positions): target tile width of the local sort
 int g_count_fused = 1;  // kmg_set_option("count_fused", 0/1): let the hybrid finish emit the count table itself
 int g_hybrid_pb = 0;  // kmg_set_option("hybrid_pb", 0 | 16 | 24): force the prefix width (0 = by n and skew)
@@ -1057,7 +1069,9 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
             }
             if (g_ev_used >= MAX_TIMED) timing_collect();
             timing_begin(st);
-            int rcode = dispatch_onesweep(cfg, key_bytes, val_bytes, p, op, st);
+            // the hybrid finish does not care about the order inside the first pass' digits
+            const int pass_cfg = (hybrid && pass == 0 && g_hybrid_unstable && cfg == 3) ? 10 : cfg;
+            int rcode = dispatch_onesweep(pass_cfg, key_bytes, val_bytes, p, op, st);
             timing_end(st);
             if (rcode != KMG_OK) return rcode;
             ++launch;

@@ -75,6 +75,15 @@ def main():
         print(f"sort cfg {cfg}     : {srt:8.3f} ms  {N/srt/1e6:8.2f} G keys/s  model {alg/srt/1e6:8.1f} GB/s = {alg/srt/1e6/peak:5.3f} of measured peak")
         res[f"sort_cfg{cfg}_ms"] = srt
     eng.lib.kmg_set_option(b"sort_config", 3)
+    for un in (0, 1):
+        eng.lib.kmg_set_option(b"hybrid_unstable", un)
+
+        def run_u():
+            a = eng.extract(d, k, False, val_bytes=args.vb, reuse="b_", want_hist=True)
+            return eng.sort(a)
+
+        med_all, _ = timed(run_u, flush=flush)
+        print(f"hybrid, unstable first pass {un}: sort {med_all - res['extract_ms']:8.3f} ms")
     for hy, pb in ((0, 0), (1, 16), (1, 24), (1, 0)):
         eng.lib.kmg_set_option(b"hybrid", hy)
         eng.lib.kmg_set_option(b"hybrid_pb", pb)
