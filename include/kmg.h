@@ -154,6 +154,17 @@ int kmg_extract_scatter(const uint8_t* d_bases, uint64_t n_bases, uint64_t win_b
                         const uint8_t* d_lut256, int n_parts, void* const* d_dest_keys, void* const* d_dest_vals,
                         int key_bytes, int val_bytes, uint64_t pos_offset, uint64_t* d_cursors, uint64_t* d_counts,
                         int count_only, void* stream);
+/* Single-launch variant: no count-only launch and no count matrix.  Every destination owns ONE
+ * cursor word (d_cursor_ptrs[dst] points to it, peer-mapped, zeroed by its owner before the
+ * exchange) that all sources advance with system-scope atomics over NVLink, so the regions of the
+ * sources interleave tile by tile inside the receive buffer; afterwards the cursor is the number
+ * of keys received.  `capacity` = elements every receive buffer holds: a reservation that would
+ * pass it stores nothing and sets d_status[0] = 1 (the caller then repeats the exchange with exact
+ * region sizes through kmg_extract_scatter); d_status[1] = 1 reports wide-stream windows. */
+int kmg_extract_scatter_shared(const uint8_t* d_bases, uint64_t n_bases, uint64_t win_begin, uint64_t win_end, int k,
+                               int rc, const uint8_t* d_lut256, int n_parts, void* const* d_dest_keys,
+                               void* const* d_dest_vals, int key_bytes, int val_bytes, uint64_t pos_offset,
+                               uint64_t* const* d_cursor_ptrs, uint64_t capacity, uint32_t* d_status, void* stream);
 /* Device memory that other processes of the same box can map (CUDA IPC, 64-byte handle). */
 int kmg_ipc_alloc(size_t bytes, void** d_ptr_out, uint8_t* h_handle64);
 int kmg_ipc_open(const uint8_t* h_handle64, void** d_ptr_out);

@@ -39,6 +39,7 @@ SIGNATURES = {
     "kmg_partition_workspace_bytes": (sz, [u64, i32, i32]),
     "kmg_range_partition": (i32, [vp, vp, u64, i32, i32, i32, i32, vp, vp, vp, vp, sz, vp]),
     "kmg_extract_scatter": (i32, [vp, u64, u64, u64, i32, i32, vp, i32, vp, vp, i32, i32, u64, vp, vp, i32, vp]),
+    "kmg_extract_scatter_shared": (i32, [vp, u64, u64, u64, i32, i32, vp, i32, vp, vp, i32, i32, u64, vp, u64, vp, vp]),
     "kmg_ipc_alloc": (i32, [sz, C.POINTER(vp), u8p]),
     "kmg_ipc_open": (i32, [u8p, C.POINTER(vp)]),
     "kmg_ipc_close": (i32, [vp]),

@@ -36,7 +36,13 @@ struct ScatterParams {
     unsigned long long* cursors;   // [n_parts] next free element in each destination (this source's region)
     unsigned long long* counts;    // COUNT_ONLY: [n_parts] keys per destination, [n_parts] = wide windows
     uint64_t pos_offset;
+    // shared-cursor mode (kmg_extract_scatter_shared): ONE cursor per destination, living in the
+    // destination's memory and advanced by every source with system-scope atomics over NVLink
+    unsigned long long* const* cursor_ptrs;  // device array [n_parts] or null
+    unsigned long long capacity;             // elements every receive buffer holds
+    uint32_t* status;                        // [0] = 1: a reservation passed `capacity`; [1] = 1: wide windows seen
 };
+constexpr unsigned long long DX_NO_STORE = ~0ull;
 
 __device__ __forceinline__ uint64_t dx_rev2_64(uint64_t x) {
     x = __brevll(x);
@@ -222,7 +228,20 @@ __global__ void __launch_bounds__(DX_BLOCK) extract_scatter_kernel(const Scatter
         return;
     } else {
         // reserve the tile's slots in every destination region; group offsets in the staging buffer
-        if (t < p.n_parts && s_cnt[t]) s_base[t] = atomicAdd(&p.cursors[t], (unsigned long long)s_cnt[t]);
+        if (t < p.n_parts && s_cnt[t]) {
+            if (p.cursor_ptrs) {
+                const unsigned long long b = atomicAdd_system(p.cursor_ptrs[t], (unsigned long long)s_cnt[t]);
+                if (b + s_cnt[t] > p.capacity) {  // the caller re-runs the exchange with exact region sizes
+                    atomicExch(&p.status[0], 1u);
+                    s_base[t] = DX_NO_STORE;
+                } else {
+                    s_base[t] = b;
+                }
+            } else {
+                s_base[t] = atomicAdd(&p.cursors[t], (unsigned long long)s_cnt[t]);
+            }
+        }
+        if (t == 0 && s_wide && p.status) atomicExch(&p.status[1], 1u);
         if (t == 0) {
             uint32_t run = 0;
             for (int d = 0; d < p.n_parts; ++d) {
@@ -253,6 +272,7 @@ __global__ void __launch_bounds__(DX_BLOCK) extract_scatter_kernel(const Scatter
         for (uint32_t i = t; i < total; i += DX_BLOCK) {
             const KeyT key = s_keys[i];
             const uint32_t d = part_of(key, key_bits, (uint32_t)p.n_parts);
+            if (s_base[d] == DX_NO_STORE) continue;
             const unsigned long long at = s_base[d] + (i - s_off[d]);
             reinterpret_cast<KeyT*>(p.dest_keys[d])[at] = key;
             if constexpr (VAL_BYTES != 0) reinterpret_cast<ValT*>(p.dest_vals[d])[at] = s_vals[i];
@@ -288,10 +308,11 @@ static int dispatch_scatter(const ScatterParams& p, uint32_t n_tiles, int rc, in
 
 using namespace kmg;
 
-extern "C" int kmg_extract_scatter(const uint8_t* d_bases, uint64_t n_bases, uint64_t win_begin, uint64_t win_end, int k,
-                                   int rc, const uint8_t* d_lut256, int n_parts, void* const* d_dest_keys,
-                                   void* const* d_dest_vals, int key_bytes, int val_bytes, uint64_t pos_offset,
-                                   uint64_t* d_cursors, uint64_t* d_counts, int count_only, void* stream) {
+static int scatter_impl(const uint8_t* d_bases, uint64_t n_bases, uint64_t win_begin, uint64_t win_end, int k, int rc,
+                        const uint8_t* d_lut256, int n_parts, void* const* d_dest_keys, void* const* d_dest_vals,
+                        int key_bytes, int val_bytes, uint64_t pos_offset, uint64_t* d_cursors, uint64_t* d_counts,
+                        int count_only, uint64_t* const* d_cursor_ptrs, uint64_t capacity, uint32_t* d_status,
+                        void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     KMG_REQUIRE(k >= 8, KMG_ERR_RANGE, "the multi-GPU range partition needs k >= 8 (16 key bits), got %d", k);
     KMG_REQUIRE(k <= 64, KMG_ERR_RANGE, "k=%d: this build supports k <= 64", k);
@@ -305,7 +326,7 @@ extern "C" int kmg_extract_scatter(const uint8_t* d_bases, uint64_t n_bases, uin
         KMG_REQUIRE(d_counts, KMG_ERR_ARG, "d_counts is null");
         KMG_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(uint64_t) * (n_parts + 1), st));
     } else {
-        KMG_REQUIRE(d_dest_keys && d_cursors, KMG_ERR_ARG, "null pointer argument");
+        KMG_REQUIRE(d_dest_keys && (d_cursors || d_cursor_ptrs), KMG_ERR_ARG, "null pointer argument");
         KMG_REQUIRE((val_bytes == 0) == (d_dest_vals == nullptr), KMG_ERR_ARG, "d_dest_vals / val_bytes mismatch");
     }
     if (win_end == win_begin) return KMG_OK;
@@ -327,12 +348,33 @@ extern "C" int kmg_extract_scatter(const uint8_t* d_bases, uint64_t n_bases, uin
     p.cursors = reinterpret_cast<unsigned long long*>(d_cursors);
     p.counts = reinterpret_cast<unsigned long long*>(d_counts);
     p.pos_offset = pos_offset;
+    p.cursor_ptrs = reinterpret_cast<unsigned long long* const*>(d_cursor_ptrs);
+    p.capacity = capacity;
+    p.status = d_status;
     if (count_only) {
         if (key_bytes == 8) return dispatch_scatter<uint64_t, 16, true>(p, (uint32_t)n_tiles, rc, 0, st);
         return dispatch_scatter<u128, 8, true>(p, (uint32_t)n_tiles, rc, 0, st);
     }
     if (key_bytes == 8) return dispatch_scatter<uint64_t, 16, false>(p, (uint32_t)n_tiles, rc, val_bytes, st);
     return dispatch_scatter<u128, 8, false>(p, (uint32_t)n_tiles, rc, val_bytes, st);
+}
+
+extern "C" int kmg_extract_scatter(const uint8_t* d_bases, uint64_t n_bases, uint64_t win_begin, uint64_t win_end, int k,
+                                   int rc, const uint8_t* d_lut256, int n_parts, void* const* d_dest_keys,
+                                   void* const* d_dest_vals, int key_bytes, int val_bytes, uint64_t pos_offset,
+                                   uint64_t* d_cursors, uint64_t* d_counts, int count_only, void* stream) {
+    return scatter_impl(d_bases, n_bases, win_begin, win_end, k, rc, d_lut256, n_parts, d_dest_keys, d_dest_vals, key_bytes,
+                        val_bytes, pos_offset, d_cursors, d_counts, count_only, nullptr, 0, nullptr, stream);
+}
+
+extern "C" int kmg_extract_scatter_shared(const uint8_t* d_bases, uint64_t n_bases, uint64_t win_begin, uint64_t win_end,
+                                          int k, int rc, const uint8_t* d_lut256, int n_parts, void* const* d_dest_keys,
+                                          void* const* d_dest_vals, int key_bytes, int val_bytes, uint64_t pos_offset,
+                                          uint64_t* const* d_cursor_ptrs, uint64_t capacity, uint32_t* d_status,
+                                          void* stream) {
+    KMG_REQUIRE(d_cursor_ptrs && d_status && capacity > 0, KMG_ERR_ARG, "null pointer argument");
+    return scatter_impl(d_bases, n_bases, win_begin, win_end, k, rc, d_lut256, n_parts, d_dest_keys, d_dest_vals, key_bytes,
+                        val_bytes, pos_offset, nullptr, nullptr, 0, d_cursor_ptrs, capacity, d_status, stream);
 }
 
 // ---- peer memory through CUDA IPC -----------------------------------------------------------------

@@ -115,7 +115,11 @@ class PeerBuffers:
 
     Every rank allocates its receive buffer through libkmg (kmg_ipc_alloc), the 64-byte handles
     are all-gathered, and each rank maps its peers' buffers (kmg_ipc_open).  `ptr_table` is the
-    device array of per-destination base pointers the scatter kernel indexes."""
+    device array of per-destination base pointers.  Every buffer starts with a HEADER whose first
+    word is the destination's shared cursor (kmg_extract_scatter_shared); the keys / payloads
+    start at `data` / `data_table`."""
+
+    HEADER = 256
 
     def __init__(self, engine, nbytes: int, group=None):
         import ctypes as C
@@ -124,12 +128,14 @@ class PeerBuffers:
 
         self.eng, self.lib, self.group = engine, engine.lib, group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
-        self.nbytes = int(nbytes)
+        self.nbytes = int(nbytes)  # payload bytes (without the header)
         ptr = C.c_void_p()
         handle = (C.c_uint8 * 64)()
-        _lib.check(self.lib.kmg_ipc_alloc(self.nbytes, C.byref(ptr), handle))
+        _lib.check(self.lib.kmg_ipc_alloc(self.nbytes + self.HEADER, C.byref(ptr), handle))
         self.local_ptr = ptr.value
-        self.local = torch.as_tensor(_DevMem(self.local_ptr, self.nbytes), device=engine.device)
+        self.local = torch.as_tensor(_DevMem(self.local_ptr, self.nbytes + self.HEADER), device=engine.device)
+        self.data = self.local[self.HEADER:]
+        self.cursor = self.local[:8].view(torch.int64)
         handles = [None] * self.world
         dist.all_gather_object(handles, bytes(handle), group=group)
         self.peer_ptrs = []
@@ -142,6 +148,7 @@ class PeerBuffers:
             _lib.check(self.lib.kmg_ipc_open(hb, C.byref(q)))
             self.peer_ptrs.append(q.value)
         self.ptr_table = torch.tensor(self.peer_ptrs, dtype=torch.int64, device=engine.device)
+        self.data_table = self.ptr_table + self.HEADER
 
     def close(self):
         torch.cuda.synchronize()
@@ -171,6 +178,24 @@ class DistributedCounter:
         self.p2p = (os.environ.get("KMG_DIST_P2P", "1") != "0") if p2p is None else p2p
         self._peer_keys: Optional[PeerBuffers] = None
         self._peer_vals: Optional[PeerBuffers] = None
+        self.shared = os.environ.get("KMG_DIST_SHARED", "1") != "0"  # single-launch exchange with shared cursors
+        self._cap_key = None
+        self._cap_elems = 0
+        self._timing = {} if os.environ.get("KMG_DIST_TIMING") == "1" else None
+        self._t_last = None
+
+    def _mark(self, name: str) -> None:
+        """KMG_DIST_TIMING=1: wall-clock per stage (synchronising; a development aid, see
+        tools/dist_stage_bench.py)."""
+        if self._timing is None:
+            return
+        import time
+
+        torch.cuda.synchronize()
+        now = time.perf_counter()
+        if self._t_last is not None:
+            self._timing[name] = self._timing.get(name, 0.0) + (now - self._t_last)
+        self._t_last = now
 
     # ---- fused extraction + partition + peer stores ---------------------------------------------
     def _ensure_peer(self, which: str, nbytes: int) -> PeerBuffers:
@@ -206,12 +231,15 @@ class DistributedCounter:
         kb = 8 if k <= 32 else 16
         vb = 8 if with_vals else 0
         n_win = max(0, d.n_bases - k + 1)
+        self._mark("(outside)")
         counts = torch.zeros(G + 1, dtype=torch.int64, device=eng.device)
         _lib.check(lib.kmg_extract_scatter(d.bases.data_ptr(), d.n_bases, 0, n_win, k, int(rc), d.lut.data_ptr(), G, None,
                                            None, kb, 0, d.pos_offset, None, counts.data_ptr(), 1, eng._stream()))
+        self._mark("count-only launch")
         allc = torch.empty(G * (G + 1), dtype=torch.int64, device=eng.device)
         dist.all_gather_into_tensor(allc, counts, group=self.group)
         M = allc.cpu().numpy().reshape(G, G + 1)
+        self._mark("all-gather of the count matrix")
         if int(M[:, G].sum()):
             raise ValueError("distributed path handles the narrow (plain ACGT) stream only in this build; "
                              f"input holds {int(M[:, G].sum())} windows with other alphabet symbols")
@@ -222,14 +250,76 @@ class DistributedCounter:
         pv = self._ensure_peer("_peer_vals", recv_max * vb) if with_vals else None
         # my region inside destination dst starts after the regions of the sources before me
         cursors = torch.from_numpy(np.ascontiguousarray(M[: self.rank, :].sum(axis=0), dtype=np.int64)).to(eng.device)
+        self._mark("host: regions, cursors")
         dist.barrier(group=self.group)  # nobody still reads the receive buffers of the previous step
+        self._mark("barrier 1")
         _lib.check(lib.kmg_extract_scatter(d.bases.data_ptr(), d.n_bases, 0, n_win, k, int(rc), d.lut.data_ptr(), G,
-                                           pk.ptr_table.data_ptr(), pv.ptr_table.data_ptr() if pv else None, kb, vb,
+                                           pk.data_table.data_ptr(), pv.data_table.data_ptr() if pv else None, kb, vb,
                                            d.pos_offset, cursors.data_ptr(), None, 0, eng._stream()))
+        self._mark("extract + scatter kernel")
         dist.barrier(group=self.group)  # every rank's peer stores (stream-ordered before its barrier) have landed
+        self._mark("barrier 2")
         alt = eng._buf("p2p_keys_alt", max(n_recv, 1) * kb)
         valt = eng._buf("p2p_vals_alt", max(n_recv, 1) * vb) if with_vals else None
-        return KeyArray(pk.local, alt, pv.local if pv else None, valt, n_recv, kb, vb, k, False)
+        # what the single-launch exchange should provision next time
+        self._cap_elems = max(self._cap_elems, int(recv_max * 1.1) + 65536)
+        return KeyArray(pk.data, alt, pv.data if pv else None, valt, n_recv, kb, vb, k, False)
+
+    def _extract_exchange_shared(self, d, k: int, rc: bool, with_vals: bool):
+        """Single-launch exchange: no count-only launch, no count matrix.  Every destination owns one
+        cursor (first word of its receive buffer) that all sources advance with system-scope
+        atomics; the buffers are provisioned for 1.25 x the largest per-rank key count (keys that
+        spread evenly over the key ranges).  Returns None when a buffer overflowed (skewed keys): the
+        caller then runs the exact two-launch exchange, which also re-provisions the buffers."""
+        from kman_b200 import _lib
+        from kman_b200.engine import KeyArray
+
+        eng, lib, G = self.eng, self.eng.lib, self.world
+        kb = 8 if k <= 32 else 16
+        vb = 8 if with_vals else 0
+        n_win = max(0, d.n_bases - k + 1)
+        n_mine = n_win * (2 if rc else 1)
+        self._mark("(outside)")
+        if self._cap_key != (n_mine, kb, vb):  # once per input size: agree on the capacity
+            t = torch.tensor([n_mine], dtype=torch.int64, device=eng.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            self._cap_key = (n_mine, kb, vb)
+            scale = float(os.environ.get("KMG_DIST_CAP_SCALE", "1.25"))  # (tests force overflows with a small one)
+            self._cap_elems = max(self._cap_elems, int(int(t.item()) * scale) + 4096)
+        cap = self._cap_elems
+        pk = self._ensure_peer("_peer_keys", cap * kb)
+        pv = self._ensure_peer("_peer_vals", cap * vb) if with_vals else None
+        status = torch.zeros(2, dtype=torch.int32, device=eng.device)
+        pk.cursor.zero_()
+        # device-side barrier (no host sync): every cursor is zero, nobody still reads the last step's keys
+        fence = torch.zeros(1, dtype=torch.int32, device=eng.device)
+        dist.all_reduce(fence, group=self.group)
+        self._mark("fence 1")
+        _lib.check(lib.kmg_extract_scatter_shared(d.bases.data_ptr(), d.n_bases, 0, n_win, k, int(rc), d.lut.data_ptr(), G,
+                                                  pk.data_table.data_ptr(), pv.data_table.data_ptr() if pv else None, kb,
+                                                  vb, d.pos_offset, pk.ptr_table.data_ptr(), cap, status.data_ptr(),
+                                                  eng._stream()))
+        self._mark("extract + scatter kernel")
+        # fence + agreement: every rank's peer stores (stream-ordered before its contribution) have landed
+        dist.all_reduce(status, op=dist.ReduceOp.MAX, group=self.group)
+        st = torch.cat([status.to(torch.int64), pk.cursor]).cpu().numpy()
+        self._mark("fence 2 + read-back")
+        if int(st[1]):
+            raise ValueError("distributed path handles the narrow (plain ACGT) stream only in this build; "
+                             "the input holds windows with other alphabet symbols")
+        if int(st[0]):
+            return None
+        n_recv = int(st[2])
+        alt = eng._buf("p2p_keys_alt", max(n_recv, 1) * kb)
+        valt = eng._buf("p2p_vals_alt", max(n_recv, 1) * vb) if with_vals else None
+        return KeyArray(pk.data, alt, pv.data if pv else None, valt, n_recv, kb, vb, k, False)
+
+    def _exchange(self, d, k: int, rc: bool, with_vals: bool):
+        """Fused extraction + exchange over peer memory: single launch when it fits, exact otherwise."""
+        r = self._extract_exchange_shared(d, k, rc, with_vals) if self.shared else None
+        if r is None:
+            r = self._extract_exchange_p2p(d, k, rc, with_vals)
+        return r
 
     def shard(self, flat, k: int, alphabet: Optional[str] = None, natype=None):
         """Upload this rank's chunk of a host-resident flat input (k-1 overlap)."""
@@ -274,11 +364,13 @@ class DistributedCounter:
         """This rank's slice (key range `rank`) of the global count table, narrow stream."""
         if self.p2p and k >= 8:
             try:
-                r = self._extract_exchange_p2p(d, k, rc, with_vals=False)
+                r = self._exchange(d, k, rc, with_vals=False)
             except _PeerUnavailable as exc:
                 self._fall_back(exc)
             else:
-                return self.eng.sort_count(r, sort_bits_after_partition(r.key_bits, self.world), reuse="p2p_")
+                tab = self.eng.sort_count(r, sort_bits_after_partition(r.key_bits, self.world), reuse="p2p_")
+                self._mark("sort + count")
+                return tab
         a = self.eng.extract(d, k, rc, wide=False, val_bytes=0)
         n_other = torch.tensor([a.n_other], dtype=torch.int64, device=a.keys.device)
         dist.all_reduce(n_other, group=self.group)
@@ -307,7 +399,7 @@ class DistributedCounter:
         """This rank's slice of the global singleton list (keys + (pos<<1|strand) payload)."""
         if self.p2p and k >= 8:
             try:
-                r = self._extract_exchange_p2p(d, k, rc, with_vals=True)
+                r = self._exchange(d, k, rc, with_vals=True)
             except _PeerUnavailable as exc:
                 self._fall_back(exc)
             else:

@@ -702,3 +702,60 @@ def test_low_complexity_genome_through_the_hybrid_sort(eng, k, rc):
         assert eng.lib.kmg_get_stat(b"hybrid_path") in (1, 2, 3)
     assert got == ko.count_text_np(recs, k, rc, "ACGT"), (k, rc)
     assert eng.uniq_text(d, k, rc) == ko.uniq_text_np(recs, k, rc, "ACGT"), (k, rc)
+
+
+@pytest.mark.parametrize("k,rc,n_parts", [(31, True, 4), (45, False, 3)])
+def test_extract_scatter_shared_cursors(eng, k, rc, n_parts):
+    """kmg_extract_scatter_shared on one GPU: one cursor per destination, advanced by every tile;
+    each destination receives exactly its key range (as a multiset); a capacity that is too small
+    is reported through the status word and nothing is stored past it."""
+    import torch
+
+    from kman_b200 import _lib
+
+    rng = np.random.default_rng(900 + k)
+    recs = _rand_records(rng, 3, 30000, p_other=0.0)
+    ex = ko.extract_np(recs, k, rc, "ACGT")
+    d = eng.upload(_flat(recs), alphabet="ACGT")
+    lib = eng.lib
+    kb = 8 if k <= 32 else 16
+    n_win = d.n_bases - k + 1
+    limbs = ex["narrow"]["keys"]
+    sh = 2 * k - 16
+    if len(limbs) == 1:
+        top16 = limbs[0] >> np.uint64(sh)
+    elif sh >= 64:
+        top16 = limbs[0] >> np.uint64(sh - 64)
+    else:
+        top16 = (limbs[1] >> np.uint64(sh)) | (limbs[0] << np.uint64(64 - sh))
+    part = (((top16 & np.uint64(0xFFFF)) * np.uint64(n_parts)) >> np.uint64(16)).astype(np.int64)
+    want_counts = np.bincount(part, minlength=n_parts)
+    cap = int(want_counts.max())
+    rows = limbs_to_rows(limbs)
+    wv = (ex["narrow"]["pos"].astype(np.uint64) << np.uint64(1)) | ex["narrow"]["strand"].astype(np.uint64)
+    for capacity, expect_overflow in ((cap, False), (cap - 1, True)):
+        bufs = [torch.zeros(cap * kb, dtype=torch.uint8, device=eng.device) for _ in range(n_parts)]
+        vbufs = [torch.zeros(cap * 8, dtype=torch.uint8, device=eng.device) for _ in range(n_parts)]
+        cursors = torch.zeros(n_parts * 32, dtype=torch.int64, device=eng.device)  # one cursor per 256-byte line
+        ptrs = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device=eng.device)
+        vptrs = torch.tensor([b.data_ptr() for b in vbufs], dtype=torch.int64, device=eng.device)
+        cptrs = torch.tensor([cursors.data_ptr() + 256 * i for i in range(n_parts)], dtype=torch.int64, device=eng.device)
+        status = torch.zeros(2, dtype=torch.int32, device=eng.device)
+        _lib.check(lib.kmg_extract_scatter_shared(d.bases.data_ptr(), d.n_bases, 0, n_win, k, int(rc), d.lut.data_ptr(),
+                                                  n_parts, ptrs.data_ptr(), vptrs.data_ptr(), kb, 8, 0, cptrs.data_ptr(),
+                                                  capacity, status.data_ptr(), eng._stream()))
+        torch.cuda.synchronize()
+        st = status.cpu().numpy()
+        assert bool(st[0]) == expect_overflow and st[1] == 0
+        if expect_overflow:
+            continue
+        assert list(cursors.cpu().numpy()[::32]) == list(want_counts)
+        for p in range(n_parts):
+            c = int(want_counts[p])
+            got_k = bufs[p][: c * kb].cpu().numpy().view(np.uint64)
+            got_k = got_k if kb == 8 else got_k.reshape(-1, 2)
+            got_v = vbufs[p][: c * 8].cpu().numpy().view(np.uint64)
+            sel = part == p
+            o_got, o_want = np.argsort(got_v), np.argsort(wv[sel])
+            assert first_diff(got_v[o_got], wv[sel][o_want]) == "equal", p
+            assert first_diff(got_k[o_got], rows[sel][o_want]) == "equal", p
