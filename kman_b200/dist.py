@@ -20,6 +20,8 @@ from __future__ import annotations
 from dataclasses import dataclass
 from typing import List, Optional, Tuple
 
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -173,8 +175,6 @@ class DistributedCounter:
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
-        import os
-
         self.p2p = (os.environ.get("KMG_DIST_P2P", "1") != "0") if p2p is None else p2p
         self._peer_keys: Optional[PeerBuffers] = None
         self._peer_vals: Optional[PeerBuffers] = None
