@@ -178,7 +178,11 @@ class DistributedCounter:
         self.p2p = (os.environ.get("KMG_DIST_P2P", "1") != "0") if p2p is None else p2p
         self._peer_keys: Optional[PeerBuffers] = None
         self._peer_vals: Optional[PeerBuffers] = None
-        self.shared = os.environ.get("KMG_DIST_SHARED", "1") != "0"  # single-launch exchange with shared cursors
+        # single-launch exchange with shared cursors: measured faster up to 4 GPUs (N=2 +14 %, N=4 +4.5 %);
+        # at 8 the 8 x 8 sources x destinations contend for the cursor words and the exact two-launch
+        # exchange wins (-4 %).  KMG_DIST_SHARED=0/1 overrides.
+        env = os.environ.get("KMG_DIST_SHARED")
+        self.shared = (self.world <= 4) if env is None else env != "0"
         self._cap_key = None
         self._cap_elems = 0
         self._timing = {} if os.environ.get("KMG_DIST_TIMING") == "1" else None
