@@ -162,7 +162,7 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def workload_config(args, sample_note=None, p2p=None):
+def workload_config(args, sample_note=None, p2p=None, shared=None):
     n = args.gpus
     if p2p is None:
         p2p = os.environ.get("KMG_DIST_P2P", "1") != "0"
@@ -173,7 +173,8 @@ def workload_config(args, sample_note=None, p2p=None):
     else:
         wl = (f"config 2 x {n} (weak): {n}x{CFG2_BASES} bp synthetic random-ACGT genome, one {CFG2_BASES} bp chunk per GPU "
               f"with k-1 overlap, range partition by the top key bits, k={K}, count; exchange: "
-              + ("fused extract+partition kernel storing into the owners' buffers over NVLink (CUDA IPC peer memory)"
+              + (("fused extract+partition kernel storing into the owners' buffers over NVLink (CUDA IPC peer memory), "
+                  + ("one launch, shared per-destination cursors" if shared else "count-only launch + exact regions"))
                  if p2p else "range partition pass + NCCL all-to-all of the partitioned keys"))
     cfg = {"workload": wl, "k": K, "mode": "count", "alphabet": "ACGT",
            "l2": "working set per step (keys 2x0.8 GB + table 1.2 GB per GPU) >> 126 MB L2; no explicit flush"}
@@ -418,7 +419,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "k-mers/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong" if args.workload == "cfg3" else "weak", "vs_baseline": None, "dtype": "u64",
-            "data": "synthetic", "config": workload_config(args, p2p=(dc.p2p if world > 1 else None)), "clocks": clocks,
+            "data": "synthetic", "config": workload_config(args, p2p=(dc.p2p if world > 1 else None), shared=(dc.shared if world > 1 else None)), "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "wall_ms_per_step": t_wall / args.steps * 1e3, "kmers_per_step": n_win_global,

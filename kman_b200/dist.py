@@ -255,14 +255,18 @@ class DistributedCounter:
         # my region inside destination dst starts after the regions of the sources before me
         cursors = torch.from_numpy(np.ascontiguousarray(M[: self.rank, :].sum(axis=0), dtype=np.int64)).to(eng.device)
         self._mark("host: regions, cursors")
-        dist.barrier(group=self.group)  # nobody still reads the receive buffers of the previous step
-        self._mark("barrier 1")
+        # No fence is needed before the stores: the all-gather above completed, so every rank had
+        # entered it, and each rank enters it only after (in stream order) it stopped reading its
+        # receive buffer of the previous step.
         _lib.check(lib.kmg_extract_scatter(d.bases.data_ptr(), d.n_bases, 0, n_win, k, int(rc), d.lut.data_ptr(), G,
                                            pk.data_table.data_ptr(), pv.data_table.data_ptr() if pv else None, kb, vb,
                                            d.pos_offset, cursors.data_ptr(), None, 0, eng._stream()))
         self._mark("extract + scatter kernel")
-        dist.barrier(group=self.group)  # every rank's peer stores (stream-ordered before its barrier) have landed
-        self._mark("barrier 2")
+        # device-side fence (no host sync): every rank's peer stores, stream-ordered before its
+        # contribution, have landed when the all-reduce completes
+        fence = torch.zeros(1, dtype=torch.int32, device=eng.device)
+        dist.all_reduce(fence, group=self.group)
+        self._mark("fence")
         alt = eng._buf("p2p_keys_alt", max(n_recv, 1) * kb)
         valt = eng._buf("p2p_vals_alt", max(n_recv, 1) * vb) if with_vals else None
         # what the single-launch exchange should provision next time
