@@ -99,10 +99,12 @@ int kmg_extract(const uint8_t* d_bases, uint64_t n_bases, uint64_t win_begin, ui
  * result is in keys/vals, 1 if in keys_alt/vals_alt.  d_hist_in (optional): the digit histograms
  * kmg_extract produced for exactly these keys (requires begin_bit 0, end_bit 2k).
  * Key-only sorts of 8-byte keys over bits [0, end_bit) with 2^20 <= n <= 2^33 take the "hybrid
- * finish": 2-3 ordinary passes over the top 16/24 bits, then ONE shared-memory local sort per
- * ~4096-key tile orders all remaining bits (radix_sort.cu: local_sort_kernel).  Tiles the local
- * scheme cannot hold (a prefix bucket above 8192 keys) make the call fall back to the plain LSD
- * passes; the result is identical either way.  The call synchronises the stream in that mode.
+ * finish": 2-3 ordinary passes over the top 16/24 bits (the first of them without stable
+ * ranking), then ONE shared-memory local sort per ~6000-key tile orders all remaining bits
+ * (radix_sort.cu: local_sort_kernel).  Tiles the local scheme cannot hold (prefix buckets above
+ * 8192 keys: repeats) are gathered, sorted by the plain LSD passes and put back; above n/8 such
+ * keys the plain passes sort everything.  The result is identical on every path.  The call
+ * synchronises the stream in that mode (2 KB histogram read-back, irregular-tile count).
  * All keys must agree in the bits at and above end_bit in that mode (kmg_extract's keys do: those
  * bits are zero; after kmg_range_partition they are the rank's common prefix).
  * kmg_set_option("hybrid", 0) switches it off. */
@@ -222,9 +224,20 @@ int kmg_uniq_host(kmg_ctx* ctx, const uint8_t* h_bases, uint64_t n_bases, int k,
                   void* h_keys_out, uint64_t* h_vals_out, uint64_t cap, uint64_t* h_n_out);
 
 /* ---- tuning / introspection -----------------------------------------------------------
- * kmg_set_option("sort_config", i) selects a tile configuration of the sort kernel;
- * kmg_get_stat(name) returns counters of the last call made on this thread
- * ("sort_passes", "sort_launches", "launches"). */
+ * Options (process-wide; defaults in brackets):
+ *   "hybrid" [1]           hybrid finish of key-only 8-byte sorts (0: plain LSD passes only)
+ *   "hybrid_pb" [0]        force its prefix width to 16 or 24 bits (0: by n and key skew)
+ *   "hybrid_unstable" [1]  first prefix pass ranks with the histogram atomics' return values
+ *   "count_fused" [1]      kmg_sort_count: the local sort emits the (k-mer, count) table itself
+ *   "local_tile" [7936]    target tile width of the local sort (positions)
+ *   "sort_config" [3]      tile configuration of the onesweep kernel (radix_sort.cu: kSortTiles)
+ *   "lb_group" [32]        tiles per look-back group of the onesweep kernel
+ *   "prefetch_tiles" [192] L2 prefetch distance of the onesweep kernel, in tiles (0: off)
+ *   "time_passes" [0]      bracket every onesweep / local sort launch with CUDA events
+ * Stats of the calling thread's last call: "launches" (kernel launches since "reset_launches"),
+ * "sort_passes", "hybrid_path" (0 plain passes, 1 hybrid, 2 hybrid + re-sorted ranges, 3 fell
+ * back), "hybrid_irregular" (tiles), and with time_passes: "sort_pass_ns" / "sort_pass_count",
+ * "local_sort_ns" / "local_sort_count" (device time of the timed launches). */
 int kmg_set_option(const char* name, int64_t value);
 int64_t kmg_get_stat(const char* name);
 
