@@ -307,7 +307,8 @@ def main():
         avg_local_ms = ls_ns / 1e6 / ls_cnt if ls_cnt else 0.0
         # plain LSD: P8 passes (a sort of more than 2^30 keys runs every pass in several launches);
         # hybrid finish: 2-3 prefix passes + one local-sort launch, every one a read + write of the keys
-        launches_per_pass = max(1.0, passes_per_sort / P8) if not ls_cnt else 1.0
+        n_passes = int(lib.kmg_get_stat(b"sort_passes")) or P8  # passes of the last sort (2-3 with the hybrid finish)
+        launches_per_pass = max(1.0, passes_per_sort / n_passes)
         alg_bytes = 2 * W * n_keys / launches_per_pass
         achieved = alg_bytes / (avg_pass_ms / 1e3) / 1e9
         sort_ms = avg_pass_ms * passes_per_sort + avg_local_ms * local_per_sort
