@@ -422,28 +422,53 @@ __global__ void __launch_bounds__(BLOCK, min_ctas(BLOCK, IPT)) onesweep_kernel(c
 // ---- hybrid finish: after the keys are sorted by their top PB bits ---------------------------------
 // Every LSD pass pays the full per-key ranking cost again.  For key-only sorts the tail can be
 // cheaper: once the top PB = 16 or 24 bits are in order (2-3 ordinary passes), equal-prefix
-// buckets are contiguous and small, and a tile of ~4096 keys can finish ALL remaining bits at
-// once in shared memory: a counting sort into up to 8192 cells (bucket x next few bits, plain
-// shared atomics -- no stability needed) followed by ranking inside the 1-3 key cells.  Tiles
-// whose buckets do not fit the scheme (long runs of one prefix, huge cells: repeats) are flagged
-// and the caller falls back to the plain LSD sort, so correctness never depends on the data.
+// buckets are contiguous and small, and a tile of a few thousand keys can finish ALL remaining
+// bits at once in shared memory: a counting sort into as many cells as the tile can hold keys
+// (monotone key -> cell map, plain shared atomics -- no stability needed) followed by an insertion
+// sort of each thread's consecutive cells.  Tiles whose buckets do not fit the scheme (long runs
+// of one prefix, crowded cells: repeats) are flagged; the caller re-sorts their ranges with the
+// plain LSD passes, so correctness never depends on the data.
+template <typename KeyT>
+struct LS;
+template <>
+struct LS<uint64_t> {
+    static constexpr int IPT = 16;  // keys per thread
+    static constexpr int CPT = 16;  // consecutive cells per thread in the prefix / cell-sort phases
+};
+template <>
+struct LS<u128> {
+    static constexpr int IPT = 8;
+    static constexpr int CPT = 8;
+};
 constexpr int LS_BLOCK = 512;
-constexpr int LS_IPT = 16;
-constexpr int LS_CAP = LS_BLOCK * LS_IPT;  // keys a tile can own
-constexpr int LS_T = 4096;                 // default positions per tile (a tile owns the buckets starting in it)
-constexpr int LS_T_MIN = 2048, LS_T_MAX = LS_CAP - 256;  // range of the run-time tile width (HybridParams::tile_t)
-constexpr int LS_CELLS = 8192;
-constexpr int LS_CPT = LS_CELLS / LS_BLOCK;  // consecutive cells per thread in the prefix / cell-sort phases
-static_assert(LS_CPT == 16, "the cell phases move 4 x uint4 per thread");
+template <typename KeyT>
+__host__ __device__ constexpr int ls_cap() { return LS_BLOCK * LS<KeyT>::IPT; }  // keys a tile can own: 8192 / 4096
+template <typename KeyT>
+__host__ __device__ constexpr int ls_cells() { return LS_BLOCK * LS<KeyT>::CPT; }
+// cell counters are padded (4 words per CPT) so that one thread's consecutive cells are
+// conflict-free 128-bit accesses: thread stride 20 / 12 words
+template <typename KeyT>
+__device__ __forceinline__ uint32_t pc(uint32_t c) {
+    return LS<KeyT>::CPT == 16 ? c + ((c >> 4) << 2) : c + ((c >> 3) << 2);
+}
+template <typename KeyT>
+__host__ __device__ constexpr int ls_cell_words() { return ls_cells<KeyT>() + ls_cells<KeyT>() / LS<KeyT>::CPT * 4 + 4; }
+template <typename KeyT>
+__host__ __device__ constexpr size_t ls_smem_bytes() { return sizeof(KeyT) * ls_cap<KeyT>() + sizeof(uint32_t) * ls_cell_words<KeyT>(); }
+constexpr int LS_T_MIN = 1024;             // smallest run-time tile width (workspace sizing)
 constexpr int LS_SORT_BUDGET = 4096;       // insertion-sort moves one thread may spend before the tile gives up
-// cell counters are padded (4 words per 16) so that one thread's 16 consecutive cells are four
-// conflict-free 128-bit accesses: thread stride 20 words
-__device__ __forceinline__ uint32_t pc(uint32_t c) { return c + ((c >> 4) << 2); }
-constexpr int LS_CELL_WORDS = LS_CELLS + LS_CELLS / 4 + 4;
+
+// low 64 bits of (key >> s): prefix / cell arithmetic works modulo 2^64 (keys agree above end_bit)
+__device__ __forceinline__ uint64_t shr64(uint64_t k, int s) { return k >> s; }
+__device__ __forceinline__ uint64_t shr64(const u128& k, int s) {
+    if (s >= 64) return k.hi >> (s - 64);
+    if (s == 0) return k.lo;
+    return (k.lo >> s) | (k.hi << (64 - s));
+}
 
 struct HybridParams {
-    const uint64_t* keys_in;
-    uint64_t* keys_out;
+    const void* keys_in;
+    void* keys_out;
     uint64_t n;
     uint64_t* bounds;       // [n_tiles + 1], see tile_bounds_kernel
     uint32_t* flag;         // [n_tiles] 1 = the local scheme could not hold the tile (zeroed by the host)
@@ -452,23 +477,24 @@ struct HybridParams {
     uint32_t tile_t;        // positions per tile
     int key_bits, pb;
     unsigned long long* irregular;  // number of tiles the local scheme could not handle
-    // fused run-length count (local_sort_kernel<true>): distinct keys -> keys_out, compacted
+    // fused run-length count (local_sort_kernel<.., true>): distinct keys -> keys_out, compacted
     uint32_t* counts_out;
     unsigned long long* n_out;      // number of distinct keys
-    uint64_t* tile_state;           // two-level tile prefix over the tiles' distinct-key counts
+    uint64_t* tile_state;           // tile prefix over the tiles' distinct-key counts
     uint32_t* ticket;
     uint32_t* err;
 };
 
 // First i in [lo, hi) whose prefix differs from `ref`, or hi; the prefixes are non-decreasing.
 // Whole-warp 32-ary search: the common case (buckets of a few keys) ends after one probe round.
-__device__ __forceinline__ uint64_t prefix_run_end(const uint64_t* __restrict__ keys, uint64_t lo, uint64_t hi,
+template <typename KeyT>
+__device__ __forceinline__ uint64_t prefix_run_end(const KeyT* __restrict__ keys, uint64_t lo, uint64_t hi,
                                                    uint64_t ref, int sh) {
     const uint32_t lane = threadIdx.x & 31u;
     uint64_t step = 1;  // first round: 32 consecutive keys
     while (lo < hi) {
         const uint64_t i = lo + lane * step;
-        const bool ne = i < hi ? (keys[i] >> sh) != ref : true;
+        const bool ne = i < hi ? shr64(keys[i], sh) != ref : true;
         const uint32_t bal = __ballot_sync(0xffffffffu, ne);
         const uint32_t first = bal ? __ffs(bal) - 1 : 32u;  // 32: all probes still match
         if (first == 0) return lo;
@@ -486,11 +512,13 @@ __device__ __forceinline__ uint64_t prefix_run_end(const uint64_t* __restrict__ 
     return hi;
 }
 
-// bounds[tile] = first position >= tile * LS_T where a new prefix bucket starts (one warp per tile);
+// bounds[tile] = first position >= tile * tile_t where a new prefix bucket starts (one warp per tile);
 // tile owns [bounds[tile], bounds[tile + 1])
+template <typename KeyT>
 __global__ void __launch_bounds__(256) tile_bounds_kernel(const HybridParams p) {
     const uint32_t tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (tile > p.n_tiles) return;
+    const KeyT* keys_in = reinterpret_cast<const KeyT*>(p.keys_in);
     const uint32_t lane = threadIdx.x & 31u;
     const int sh_pref = p.key_bits - p.pb;
     const uint64_t pos = min((uint64_t)tile * p.tile_t, p.n);
@@ -499,36 +527,40 @@ __global__ void __launch_bounds__(256) tile_bounds_kernel(const HybridParams p) 
         const uint64_t hi = p.n;  // exact even for long runs: irregular tiles are re-sorted range by range
         // one round trip in the common case: keys[pos-1 .. pos+30]
         const uint64_t i = pos - 1 + lane;
-        const uint64_t v = i < hi ? p.keys_in[i] >> sh_pref : ~0ull;
+        const uint64_t v = i < hi ? shr64(keys_in[i], sh_pref) : ~0ull;
         const uint64_t ref = __shfl_sync(0xffffffffu, v, 0);
         const uint32_t bal = __ballot_sync(0xffffffffu, v != ref);
-        r = bal ? min(pos - 1 + (uint64_t)(__ffs(bal) - 1), hi)
-                : prefix_run_end(p.keys_in, pos + 31, hi, ref, sh_pref);
+        r = bal ? min(pos - 1 + (uint64_t)(__ffs(bal) - 1), hi) : prefix_run_end(keys_in, pos + 31, hi, ref, sh_pref);
     }
     if (lane == 0) p.bounds[tile] = r;
 }
 
 // monotone map key -> cell of the tile's counting sort (see local_sort_kernel)
+template <typename KeyT>
 struct CellMap {
     uint64_t base;   // b_lo << w
     uint32_t inv;    // 0: cell = x, else cell = umulhi(x, inv)
     int sh;          // x = (key >> sh) - base
-    __device__ __forceinline__ uint32_t operator()(uint64_t key) const {
-        const uint32_t x = (uint32_t)((key >> sh) - base);
+    __device__ __forceinline__ uint32_t operator()(const KeyT& key) const {
+        const uint32_t x = (uint32_t)(shr64(key, sh) - base);
         // (the clamp only matters for keys that break the contract: bits >= end_bit not all equal)
-        return min(inv ? __umulhi(x, inv) : x, (uint32_t)LS_CELLS - 1u);
+        return min(inv ? __umulhi(x, inv) : x, (uint32_t)ls_cells<KeyT>() - 1u);
     }
 };
 
 // COUNT: instead of the sorted keys the tile writes its DISTINCT keys and their multiplicities,
-// compacted across tiles with the two-level tile prefix (a run of equal keys never leaves its
-// prefix bucket, hence never its tile): kmg_rle_count's result without writing and re-reading the
-// sorted keys.  Tiles take their ids from a ticket so that waiting for earlier tiles is safe.
-template <bool COUNT>
+// compacted across tiles with the tile prefix (a run of equal keys never leaves its prefix bucket,
+// hence never its tile): kmg_rle_count's result without writing and re-reading the sorted keys.
+// Tiles take their ids from a ticket so that waiting for earlier tiles is safe.
+template <typename KeyT, bool COUNT>
 __global__ void __launch_bounds__(LS_BLOCK, 2) local_sort_kernel(const HybridParams p) {
+    constexpr int IPT = LS<KeyT>::IPT, CPT = LS<KeyT>::CPT;
+    constexpr int CAP = ls_cap<KeyT>(), CELLS = ls_cells<KeyT>(), CELL_WORDS = ls_cell_words<KeyT>();
+    constexpr int CELL_BITS = CELLS == 8192 ? 13 : 12;
+    static_assert((1 << CELL_BITS) == CELLS, "cell index width");
     extern __shared__ __align__(16) unsigned char ls_smem[];
-    uint64_t* s_stage = reinterpret_cast<uint64_t*>(ls_smem);                             // [LS_CAP]
-    uint32_t* s_cell = reinterpret_cast<uint32_t*>(ls_smem + sizeof(uint64_t) * LS_CAP);  // [LS_CELL_WORDS]
+    KeyT* s_stage = reinterpret_cast<KeyT*>(ls_smem);                                 // [CAP]
+    uint32_t* s_cell = reinterpret_cast<uint32_t*>(ls_smem + sizeof(KeyT) * CAP);     // [CELL_WORDS]
     __shared__ uint32_t s_scan[LS_BLOCK / 32 + 1];
     __shared__ int s_bad;
     __shared__ uint32_t s_tile;
@@ -542,7 +574,7 @@ __global__ void __launch_bounds__(LS_BLOCK, 2) local_sort_kernel(const HybridPar
     }
     {
         uint4* z = reinterpret_cast<uint4*>(s_cell);
-        for (uint32_t i = t; i < (uint32_t)LS_CELL_WORDS / 4; i += LS_BLOCK) z[i] = make_uint4(0, 0, 0, 0);
+        for (uint32_t i = t; i < (uint32_t)CELL_WORDS / 4; i += LS_BLOCK) z[i] = make_uint4(0, 0, 0, 0);
     }
     if (COUNT) __syncthreads();
     const uint32_t tile = COUNT ? s_tile : blockIdx.x;
@@ -562,7 +594,7 @@ __global__ void __launch_bounds__(LS_BLOCK, 2) local_sort_kernel(const HybridPar
         return;
     }
     const uint64_t m64 = e - s;
-    if (m64 > LS_CAP) {
+    if (m64 > (uint64_t)CAP) {
         if (t == 0) {
             atomicAdd(p.irregular, 1ull);
             p.flag[tile] = 1;
@@ -571,93 +603,94 @@ __global__ void __launch_bounds__(LS_BLOCK, 2) local_sort_kernel(const HybridPar
         return;
     }
     const uint32_t m = (uint32_t)m64;
-    const uint64_t* kin = p.keys_in + s;
-    const uint64_t k_first = kin[0], k_last = kin[m - 1];
-    uint64_t keys[LS_IPT];
+    const KeyT* kin = reinterpret_cast<const KeyT*>(p.keys_in) + s;
+    const uint64_t p_first = shr64(kin[0], sh_pref), p_last = shr64(kin[m - 1], sh_pref);
+    KeyT keys[IPT];
 #pragma unroll
-    for (int j = 0; j < LS_IPT; ++j) {
+    for (int j = 0; j < IPT; ++j) {
         const uint32_t idx = t + j * LS_BLOCK;
-        keys[j] = idx < m ? kin[idx] : 0;
+        keys[j] = idx < m ? kin[idx] : KeyT{};
     }
-    // Counting sort into <= LS_CELLS cells through a monotone map of the key: the w bits after
-    // the prefix, relative to the tile's first bucket, scaled down to the cell range when the
-    // tile spans more than LS_CELLS such values.  Monotone, so sorting inside cells finishes it.
-    CellMap cm;
+    // Counting sort into <= CELLS cells through a monotone map of the key: the w bits after the
+    // prefix, relative to the tile's first bucket, scaled down to the cell range when the tile
+    // spans more than CELLS such values.  Monotone, so sorting inside cells finishes it.
+    CellMap<KeyT> cm;
     {
-        const uint64_t b_lo = k_first >> sh_pref;
-        const uint64_t R = (k_last >> sh_pref) - b_lo + 1;  // <= 2^24
-        int w = min(13, sh_pref);
+        const uint64_t R = p_last - p_first + 1;  // <= 2^24
+        int w = min(CELL_BITS, sh_pref);
         w = max(0, min(w, 30 - (63 - __clzll((long long)R))));  // (R << w) < 2^31
         cm.sh = sh_pref - w;
-        cm.base = b_lo << w;
+        cm.base = p_first << w;
         const uint64_t range = R << w;
-        cm.inv = range <= (uint64_t)LS_CELLS ? 0u : (uint32_t)((((uint64_t)LS_CELLS) << 32) / range);
+        cm.inv = range <= (uint64_t)CELLS ? 0u : (uint32_t)((((uint64_t)CELLS) << 32) / range);
     }
-    __syncthreads();        // cells are zero
-    uint32_t meta[LS_IPT];  // cell | slot inside the cell << 13
+    __syncthreads();     // cells are zero
+    uint32_t meta[IPT];  // cell | slot inside the cell << CELL_BITS
 #pragma unroll
-    for (int j = 0; j < LS_IPT; ++j) {
+    for (int j = 0; j < IPT; ++j) {
         const uint32_t idx = t + j * LS_BLOCK;
         if (idx < m) {
             const uint32_t c = cm(keys[j]);
-            meta[j] = c | (atomicAdd(&s_cell[pc(c)], 1u) << 13);
+            meta[j] = c | (atomicAdd(&s_cell[pc<KeyT>(c)], 1u) << CELL_BITS);
         }
     }
     __syncthreads();
-    // exclusive prefix over the cells: 16 consecutive cells per thread
-    uint4* cv = reinterpret_cast<uint4*>(s_cell + pc(t * LS_CPT));
-    uint4 q0 = cv[0], q1 = cv[1], q2 = cv[2], q3 = cv[3];
-    const uint32_t sum = q0.x + q0.y + q0.z + q0.w + q1.x + q1.y + q1.z + q1.w + q2.x + q2.y + q2.z + q2.w + q3.x + q3.y +
-                         q3.z + q3.w;
+    // exclusive prefix over the cells: CPT consecutive cells per thread, 128 bits at a time
+    uint4* cv = reinterpret_cast<uint4*>(s_cell + pc<KeyT>(t * CPT));
+    uint4 q[CPT / 4];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int i = 0; i < CPT / 4; ++i) {
+        q[i] = cv[i];
+        sum += q[i].x + q[i].y + q[i].z + q[i].w;
+    }
     uint32_t total;
     uint32_t run = block_excl_scan<LS_BLOCK, uint32_t>(sum, s_scan, total);
-    {
+#pragma unroll
+    for (int i = 0; i < CPT / 4; ++i) {
         uint32_t v;
 #define KMG_LS_STEP(f) v = f; f = run; run += v;
-        KMG_LS_STEP(q0.x) KMG_LS_STEP(q0.y) KMG_LS_STEP(q0.z) KMG_LS_STEP(q0.w)
-        KMG_LS_STEP(q1.x) KMG_LS_STEP(q1.y) KMG_LS_STEP(q1.z) KMG_LS_STEP(q1.w)
-        KMG_LS_STEP(q2.x) KMG_LS_STEP(q2.y) KMG_LS_STEP(q2.z) KMG_LS_STEP(q2.w)
-        KMG_LS_STEP(q3.x) KMG_LS_STEP(q3.y) KMG_LS_STEP(q3.z) KMG_LS_STEP(q3.w)
+        KMG_LS_STEP(q[i].x) KMG_LS_STEP(q[i].y) KMG_LS_STEP(q[i].z) KMG_LS_STEP(q[i].w)
 #undef KMG_LS_STEP
+        cv[i] = q[i];
     }
-    cv[0] = q0; cv[1] = q1; cv[2] = q2; cv[3] = q3;
     asm volatile("" ::: "memory");
-    if (t == LS_BLOCK - 1) s_cell[pc(LS_CELLS)] = run;  // sentinel: end of the last cell
+    if (t == LS_BLOCK - 1) s_cell[pc<KeyT>(CELLS)] = run;  // sentinel: end of the last cell
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < LS_IPT; ++j) {
+    for (int j = 0; j < IPT; ++j) {
         const uint32_t idx = t + j * LS_BLOCK;
-        if (idx < m) s_stage[s_cell[pc(meta[j] & 8191u)] + (meta[j] >> 13)] = keys[j];
+        if (idx < m) s_stage[s_cell[pc<KeyT>(meta[j] & (CELLS - 1))] + (meta[j] >> CELL_BITS)] = keys[j];
     }
     __syncthreads();
     // Order every cell in place.  The cells are already in order among themselves, so a thread
-    // simply insertion-sorts the contiguous run of its 16 cells (~11 keys): a key moves only
+    // simply insertion-sorts the contiguous run of its CPT cells (~11 / ~6 keys): a key moves only
     // inside its own cell, equal keys cost one compare each.
-    const uint32_t lo = s_cell[pc(t * LS_CPT)], hi = s_cell[pc((t + 1) * LS_CPT)];
+    const uint32_t lo = s_cell[pc<KeyT>(t * CPT)], hi = s_cell[pc<KeyT>((t + 1) * CPT)];
     // COUNT: equal keys share a cell, hence a thread's run, so the run heads (distinct keys) can be
     // counted while inserting: a key is new unless it lands right after an equal one
     uint32_t hc = 0;
     {
         int budget = LS_SORT_BUDGET;
-        uint64_t prev = 0;
+        KeyT prev{};
         for (uint32_t i = lo; i < hi; ++i) {
-            const uint64_t key = s_stage[i];
-            if (key >= prev) {
+            const KeyT key = s_stage[i];
+            if (!(key < prev)) {
                 if (COUNT) hc += (i == lo || key != prev) ? 1u : 0u;
                 prev = key;
                 continue;
             }
-            uint32_t q = i;
-            uint64_t below;
+            uint32_t qi = i;
+            KeyT below{};
             bool more;
             do {
-                s_stage[q] = s_stage[q - 1];
-                --q;
+                s_stage[qi] = s_stage[qi - 1];
+                --qi;
                 --budget;
-                more = q > lo;
-                if (more) below = s_stage[q - 1];
-            } while (more && below > key);
-            s_stage[q] = key;
+                more = qi > lo;
+                if (more) below = s_stage[qi - 1];
+            } while (more && key < below);
+            s_stage[qi] = key;
             if (COUNT) hc += (!more || below != key) ? 1u : 0u;
             if (budget < 0) break;
         }
@@ -673,9 +706,9 @@ __global__ void __launch_bounds__(LS_BLOCK, 2) local_sort_kernel(const HybridPar
         return;
     }
     if constexpr (!COUNT) {
-        uint64_t* kout = p.keys_out + s;
+        KeyT* kout = reinterpret_cast<KeyT*>(p.keys_out) + s;
 #pragma unroll
-        for (int j = 0; j < LS_IPT; ++j) {
+        for (int j = 0; j < IPT; ++j) {
             const uint32_t idx = t + j * LS_BLOCK;
             if (idx < m) kout[idx] = s_stage[idx];
         }
@@ -683,14 +716,14 @@ __global__ void __launch_bounds__(LS_BLOCK, 2) local_sort_kernel(const HybridPar
         // the runs tile [0, m) in thread order, so a block scan of the per-thread head counts ranks
         // the heads; a second walk over the (now sorted) run records their positions
         uint32_t* s_pos = s_cell;  // [m] positions of the heads in order (the cell array is dead by now)
-        static_assert(LS_CAP <= LS_CELL_WORDS, "head positions must fit the cell array");
+        static_assert(CAP <= CELL_WORDS, "head positions must fit the cell array");
         uint32_t H;
         uint32_t hoff = block_excl_scan<LS_BLOCK, uint32_t>(hc, s_scan, H);  // (barriers: everyone is done with s_cell)
         if (t == 0) tile_prefix_publish(p.tile_state, tile, H);
         {
-            uint64_t prev = 0;
+            KeyT prev{};
             for (uint32_t i = lo; i < hi; ++i) {
-                const uint64_t key = s_stage[i];
+                const KeyT key = s_stage[i];
                 if (i == lo || key != prev) s_pos[hoff++] = i;  // (a run's first key differs from every other run's keys)
                 prev = key;
             }
@@ -704,9 +737,10 @@ __global__ void __launch_bounds__(LS_BLOCK, 2) local_sort_kernel(const HybridPar
         }
         __syncthreads();
         const uint64_t base = s_base;
+        KeyT* kout = reinterpret_cast<KeyT*>(p.keys_out);
         for (uint32_t h = t; h < H; h += LS_BLOCK) {
             const uint32_t i = s_pos[h], nxt = h + 1 < H ? s_pos[h + 1] : m;
-            p.keys_out[base + h] = s_stage[i];
+            kout[base + h] = s_stage[i];
             p.counts_out[base + h] = nxt - i;
         }
     }
@@ -732,14 +766,16 @@ __global__ void __launch_bounds__(1024) irregular_scan_kernel(const HybridParams
 // TO_BUFFER: keys_in[bounds[tile]...] -> buf[off[tile]...] for the flagged tiles; else buf -> keys_out.
 // The ranges are whole prefix buckets in ascending order, so sorting the gathered keys and putting
 // them back range by range leaves keys_out fully sorted.
-template <bool TO_BUFFER>
-__global__ void __launch_bounds__(256) irregular_copy_kernel(const HybridParams p, uint64_t* __restrict__ buf) {
+template <typename KeyT, bool TO_BUFFER>
+__global__ void __launch_bounds__(256) irregular_copy_kernel(const HybridParams p, KeyT* __restrict__ buf) {
+    const KeyT* keys_in = reinterpret_cast<const KeyT*>(p.keys_in);
+    KeyT* keys_out = reinterpret_cast<KeyT*>(p.keys_out);
     for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         if (!p.flag[tile]) continue;
         const uint64_t s = p.bounds[tile], m = p.bounds[tile + 1] - s, o = p.off[tile];
         for (uint64_t i = threadIdx.x; i < m; i += 256) {
-            if (TO_BUFFER) buf[o + i] = p.keys_in[s + i];
-            else p.keys_out[s + i] = buf[o + i];
+            if (TO_BUFFER) buf[o + i] = keys_in[s + i];
+            else keys_out[s + i] = buf[o + i];
         }
     }
 }
@@ -874,13 +910,13 @@ struct SortWs {
     size_t lb_words;           // words of the tile-count array
     // hybrid finish (see local_sort_kernel); all null / 0 when the sort cannot take it
     bool hybrid;
-    uint64_t* hyb_bounds;      // [n / LS_T + 2] tile bounds
-    uint32_t* hyb_flag;        // [n / LS_T + 1] irregular tiles
-    uint64_t* hyb_off;         // [n / LS_T + 2] their offsets in the gather buffer
-    uint64_t* hyb_state;       // tile prefix state of the fused count (sc_state_words(n / LS_T + 2))
+    uint64_t* hyb_bounds;      // [n / LS_T_MIN + 2] tile bounds
+    uint32_t* hyb_flag;        // [n / LS_T_MIN + 2] irregular tiles
+    uint64_t* hyb_off;         // [n / LS_T_MIN + 2] their offsets in the gather buffer
+    uint64_t* hyb_state;       // tile prefix state of the fused count (sc_state_words(n / LS_T_MIN + 2))
     size_t zero_bytes;         // everything up to here is zeroed at the start of a sort
     uint64_t irr_cap;          // keys the gather buffers hold
-    uint64_t* irr_buf[2];      // gather buffer + its ping-pong partner
+    void* irr_buf[2];          // gather buffer + its ping-pong partner (irr_cap keys each)
     void* irr_ws;              // workspace of the sort of the gathered keys
     size_t irr_ws_bytes;
     size_t total;
@@ -894,7 +930,7 @@ int g_hybrid_pb = 0;  // kmg_set_option("hybrid_pb", 0 | 16 | 24): force the pre
 constexpr uint64_t HYBRID_MIN_N = 1ull << 20;
 constexpr uint64_t HYBRID_MAX_N = 1ull << 33;  // 32-bit tile ids at the smallest tile width
 
-// Key-only 8-byte sorts over bits [0, end_bit), end_bit >= 32, of 2^20 .. 2^33 keys.
+// Key-only sorts (8- or 16-byte keys) over bits [0, end_bit), end_bit >= 32, of 2^20 .. 2^33 keys.
 static bool hybrid_applies(uint64_t n, int key_bytes, int val_bytes, int begin_bit, int end_bit);
 
 static SortWs carve_sort_ws(void* ws, uint64_t n, int key_bytes, bool hybrid) {
@@ -932,11 +968,11 @@ static SortWs carve_sort_ws(void* ws, uint64_t n, int key_bytes, bool hybrid) {
         // sort falls back to the plain passes)
         w.irr_cap = std::max<uint64_t>(n / 8, 1ull << 16);
         for (int i = 0; i < 2; ++i) {
-            w.irr_buf[i] = (uint64_t*)p;
-            p += align_up(w.irr_cap * sizeof(uint64_t), 256);
+            w.irr_buf[i] = p;
+            p += align_up(w.irr_cap * (size_t)key_bytes, 256);
         }
         w.irr_ws = p;
-        w.irr_ws_bytes = carve_sort_ws(nullptr, w.irr_cap, 8, false).total;
+        w.irr_ws_bytes = carve_sort_ws(nullptr, w.irr_cap, key_bytes, false).total;
         p += align_up(w.irr_ws_bytes, 256);
     }
     w.total = p - (char*)ws;
@@ -944,8 +980,7 @@ static SortWs carve_sort_ws(void* ws, uint64_t n, int key_bytes, bool hybrid) {
 }
 
 static bool hybrid_applies(uint64_t n, int key_bytes, int val_bytes, int begin_bit, int end_bit) {
-    return g_hybrid && key_bytes == 8 && val_bytes == 0 && begin_bit == 0 && end_bit >= 32 && n >= HYBRID_MIN_N &&
-           n <= HYBRID_MAX_N;
+    return g_hybrid && val_bytes == 0 && begin_bit == 0 && end_bit >= 32 && n >= HYBRID_MIN_N && n <= HYBRID_MAX_N;
 }
 
 thread_local int64_t g_stat_hybrid_path = 0;  // 0 plain passes, 1 hybrid, 2 hybrid + re-sorted ranges, 3 fell back
@@ -990,13 +1025,17 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
             plan.shift[i] = end_bit - 24 + 8 * i;
             plan.bits[i] = 8;
         }
-        if (d_hist_in && (end_bit & 1) == 0) {
+        if (d_hist_in && key_bytes == 8 && (end_bit & 1) == 0) {
             KMG_CUDA(cudaMemcpyAsync(w.hist, d_hist_in + (size_t)13 * SORT_RADIX, (size_t)3 * SORT_RADIX * sizeof(uint64_t),
                                      cudaMemcpyDeviceToDevice, st));
         } else {
             const int grid = (int)std::min<uint64_t>((n + 511) / 512, (uint64_t)sms * 4);
-            radix_hist_kernel<uint64_t, SORT_RADIX_BITS><<<grid, 512, 3 * SORT_RADIX * sizeof(uint32_t), st>>>(
-                (const uint64_t*)d_keys, n, plan, w.hist);
+            if (key_bytes == 8)
+                radix_hist_kernel<uint64_t, SORT_RADIX_BITS><<<grid, 512, 3 * SORT_RADIX * sizeof(uint32_t), st>>>(
+                    (const uint64_t*)d_keys, n, plan, w.hist);
+            else
+                radix_hist_kernel<u128, SORT_RADIX_BITS><<<grid, 512, 3 * SORT_RADIX * sizeof(uint32_t), st>>>(
+                    (const u128*)d_keys, n, plan, w.hist);
             KMG_LAUNCH_CHECK();
         }
         pb = g_hybrid_pb == 16 || g_hybrid_pb == 24 ? g_hybrid_pb : 0;
@@ -1010,7 +1049,7 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
                 KMG_CUDA(cudaStreamSynchronize(st));
                 unsigned long long mx = 0;
                 for (int i = 0; i < SORT_RADIX; ++i) mx = std::max(mx, h_top[i]);
-                if (mx / 256 <= 2048) pb = 16;
+                if (mx / 256 <= (uint64_t)(key_bytes == 8 ? 2048 : 1024)) pb = 16;  // a quarter of a tile's capacity
             }
         }
         np = pb / 8;
@@ -1086,20 +1125,22 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
     }
 
     // kin now holds the keys ordered by their top pb bits; finish into kout
+    const bool wide_key = key_bytes == 16;
+    const int cap = wide_key ? ls_cap<u128>() : ls_cap<uint64_t>();
     HybridParams hp;
-    hp.keys_in = reinterpret_cast<const uint64_t*>(kin);
-    hp.keys_out = reinterpret_cast<uint64_t*>(kout);
+    hp.keys_in = kin;
+    hp.keys_out = kout;
     hp.n = n;
-    // Tile width: with a 16-bit prefix the buckets are a sizeable fraction of a tile, and a tile owns
-    // WHOLE buckets; a width of k average buckets gives (for evenly filled buckets) every tile the
-    // same k buckets to sort instead of alternating between k-1 and k
+    // Tile width: a tile owns WHOLE prefix buckets, so leave room for the straddling one; with a
+    // 16-bit prefix the buckets are a sizeable fraction of a tile and a width of k average buckets
+    // gives (for evenly filled buckets) every tile the same k buckets instead of k-1 or k
     const double avg = (double)n / (double)(1ull << pb);  // average prefix bucket
-    double target = std::min<double>(g_local_tile, LS_CAP - std::max(256.0, 1.35 * avg));  // room for the straddling bucket
+    double target = std::min<double>(g_local_tile, cap - std::max(256.0, 1.35 * avg));
     target = std::max<double>(target, LS_T_MIN);
     hp.tile_t = (uint32_t)target;
     if (avg >= 64) {
-        const int kb = std::max(1, (int)(target / avg));
-        hp.tile_t = (uint32_t)std::min<double>(LS_T_MAX, std::max<double>(LS_T_MIN, std::ceil(kb * avg)));
+        const int kbk = std::max(1, (int)(target / avg));
+        hp.tile_t = (uint32_t)std::min<double>(cap - 256, std::max<double>(LS_T_MIN, std::ceil(kbk * avg)));
     }
     hp.n_tiles = (uint32_t)((n + hp.tile_t - 1) / hp.tile_t);
     hp.bounds = w.hyb_bounds;
@@ -1108,11 +1149,18 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
     hp.key_bits = end_bit;
     hp.pb = pb;
     hp.irregular = reinterpret_cast<unsigned long long*>(&w.hdr->pad[0]);  // 8-byte aligned slot of the header
-    tile_bounds_kernel<<<(hp.n_tiles + 1 + 7) / 8, 256, 0, st>>>(hp);
+    if (wide_key) tile_bounds_kernel<u128><<<(hp.n_tiles + 1 + 7) / 8, 256, 0, st>>>(hp);
+    else tile_bounds_kernel<uint64_t><<<(hp.n_tiles + 1 + 7) / 8, 256, 0, st>>>(hp);
     KMG_LAUNCH_CHECK();
-    const size_t smem = sizeof(uint64_t) * LS_CAP + sizeof(uint32_t) * LS_CELL_WORDS;
-    KMG_CUDA(cudaFuncSetAttribute(local_sort_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    KMG_CUDA(cudaFuncSetAttribute(local_sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = wide_key ? ls_smem_bytes<u128>() : ls_smem_bytes<uint64_t>();
+    KMG_CUDA(cudaFuncSetAttribute(local_sort_kernel<uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)ls_smem_bytes<uint64_t>()));
+    KMG_CUDA(cudaFuncSetAttribute(local_sort_kernel<uint64_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)ls_smem_bytes<uint64_t>()));
+    KMG_CUDA(cudaFuncSetAttribute(local_sort_kernel<u128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)ls_smem_bytes<u128>()));
+    KMG_CUDA(cudaFuncSetAttribute(local_sort_kernel<u128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)ls_smem_bytes<u128>()));
     const int sel_done = (np + 1) & 1;  // kout is d_keys_alt when np is even
     unsigned long long irregular = 0;
     for (int attempt = 0; attempt < 2; ++attempt) {
@@ -1131,8 +1179,13 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
         }
         if (g_ev_used >= MAX_TIMED) timing_collect();
         timing_begin(st);
-        if (fused) local_sort_kernel<true><<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);
-        else local_sort_kernel<false><<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);
+        if (fused) {
+            if (wide_key) local_sort_kernel<u128, true><<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);
+            else local_sort_kernel<uint64_t, true><<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);
+        } else {
+            if (wide_key) local_sort_kernel<u128, false><<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);
+            else local_sort_kernel<uint64_t, false><<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);
+        }
         timing_end(st, 1);
         KMG_LAUNCH_CHECK();
         KMG_CUDA(cudaMemcpyAsync(&irregular, hp.irregular, sizeof(irregular), cudaMemcpyDeviceToHost, st));
@@ -1156,15 +1209,17 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
     if (m_irr <= w.irr_cap) {
         g_stat_hybrid_path = 2;
         const int grid = (int)std::min<uint64_t>(hp.n_tiles, (uint64_t)sms * 8);
-        irregular_copy_kernel<true><<<grid, 256, 0, st>>>(hp, w.irr_buf[0]);
+        if (wide_key) irregular_copy_kernel<u128, true><<<grid, 256, 0, st>>>(hp, (u128*)w.irr_buf[0]);
+        else irregular_copy_kernel<uint64_t, true><<<grid, 256, 0, st>>>(hp, (uint64_t*)w.irr_buf[0]);
         KMG_LAUNCH_CHECK();
         int sel2 = 0;
         const int64_t passes = g_stat_sort_passes;
-        const int rcode = sort_impl(w.irr_buf[0], w.irr_buf[1], nullptr, nullptr, m_irr, 8, 0, 0, end_bit, nullptr, &sel2,
+        const int rcode = sort_impl(w.irr_buf[0], w.irr_buf[1], nullptr, nullptr, m_irr, key_bytes, 0, 0, end_bit, nullptr, &sel2,
                                     w.irr_ws, w.irr_ws_bytes, st, false, false);
         g_stat_sort_passes = passes;
         if (rcode != KMG_OK) return rcode;
-        irregular_copy_kernel<false><<<grid, 256, 0, st>>>(hp, w.irr_buf[sel2]);
+        if (wide_key) irregular_copy_kernel<u128, false><<<grid, 256, 0, st>>>(hp, (u128*)w.irr_buf[sel2]);
+        else irregular_copy_kernel<uint64_t, false><<<grid, 256, 0, st>>>(hp, (uint64_t*)w.irr_buf[sel2]);
         KMG_LAUNCH_CHECK();
         *h_selector_out = sel_done;
         return KMG_OK;

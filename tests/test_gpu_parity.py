@@ -759,3 +759,67 @@ def test_extract_scatter_shared_cursors(eng, k, rc, n_parts):
             o_got, o_want = np.argsort(got_v), np.argsort(wv[sel])
             assert first_diff(got_v[o_got], wv[sel][o_want]) == "equal", p
             assert first_diff(got_k[o_got], rows[sel][o_want]) == "equal", p
+
+
+# ---- the hybrid finish on 16-byte keys (k > 32) ---------------------------------------------------------
+def _u128_sorted(raw):
+    order = np.lexsort((raw[:, 0], raw[:, 1]))
+    return raw[order]
+
+
+def _u128_keys(rng, n, bits, dup=1):
+    pool = rng.integers(0, 2**63, size=(max(1, n // dup), 2), dtype=np.uint64) * np.uint64(2) + \
+        rng.integers(0, 2, size=(max(1, n // dup), 2), dtype=np.uint64)
+    hb = bits - 64
+    if hb < 64:
+        pool[:, 1] &= np.uint64((1 << hb) - 1)
+    return pool if dup == 1 else pool[rng.integers(0, len(pool), size=n)]
+
+
+def _keyonly_sort_u128(eng, raw, bits):
+    import torch
+
+    from kman_b200.engine import KeyArray
+
+    n = len(raw)
+    t = lambda x: torch.from_numpy(np.ascontiguousarray(x).view(np.uint8).reshape(-1)).to(eng.device)  # noqa: E731
+    a = KeyArray(t(raw), torch.zeros(n * 16, dtype=torch.uint8, device=eng.device), None, None, n, 16, 0, bits // 2, False)
+    a = eng.sort(a, 0, bits)
+    eng._status(eng._last_sort_ws)
+    return a
+
+
+@pytest.mark.parametrize("bits", [66, 90, 126, 128])
+@pytest.mark.parametrize("pb", [0, 24])
+def test_hybrid_sort_u128_random(eng, bits, pb):
+    rng = np.random.default_rng(bits * 3 + pb)
+    raw = _u128_keys(rng, 1_400_003, bits)
+    eng.lib.kmg_set_option(b"hybrid_pb", pb)
+    try:
+        a = _keyonly_sort_u128(eng, raw, bits)
+    finally:
+        eng.lib.kmg_set_option(b"hybrid_pb", 0)
+    assert eng.lib.kmg_get_stat(b"hybrid_path") == 1
+    assert eng.lib.kmg_get_stat(b"sort_passes") == (3 if pb == 24 else 2)
+    assert first_diff(a.keys_host(), _u128_sorted(raw)) == "equal"
+
+
+@pytest.mark.parametrize("pattern", ["dup7", "one_big_bucket", "all_equal", "low_limb_only"])
+def test_hybrid_sort_count_u128_skewed(eng, pattern):
+    rng = np.random.default_rng(31)
+    n, bits = 1_600_001, 126
+    raw = _u128_keys(rng, n, bits, dup=7 if pattern == "dup7" else 1)
+    if pattern == "one_big_bucket":  # 6 % of the keys share their top 16 bits (and differ below)
+        raw[: n // 16, 1] = (raw[: n // 16, 1] & np.uint64((1 << 46) - 1)) | np.uint64(0x2A5B << 46)
+    elif pattern == "all_equal":
+        raw[:] = raw[0]
+    elif pattern == "low_limb_only":  # everything above bit 64 equal: one huge prefix bucket
+        raw[:, 1] = np.uint64(0x1234567)
+    keys, counts = _sort_count(eng, raw, bits)
+    srt = _u128_sorted(raw)
+    head = np.ones(n, bool)
+    head[1:] = (srt[1:] != srt[:-1]).any(axis=1)
+    idx = np.flatnonzero(head)
+    assert first_diff(keys, srt[idx]) == "equal", pattern
+    assert first_diff(counts.astype(np.uint64), np.diff(np.append(idx, n)).astype(np.uint64)) == "equal", pattern
+    assert eng.lib.kmg_get_stat(b"hybrid_path") == {"dup7": 1, "one_big_bucket": 2, "all_equal": 3, "low_limb_only": 3}[pattern]
