@@ -98,11 +98,11 @@ int kmg_extract(const uint8_t* d_bases, uint64_t n_bases, uint64_t win_begin, ui
  * [and (vals, vals_alt)]; *h_selector_out (host, written before return) is 0 if the
  * result is in keys/vals, 1 if in keys_alt/vals_alt.  d_hist_in (optional): the digit histograms
  * kmg_extract produced for exactly these keys (requires begin_bit 0, end_bit 2k).
- * Key-only sorts of 8-byte keys over bits [0, end_bit) with 2^20 <= n <= 2^33 take the "hybrid
+ * Key-only sorts over bits [0, end_bit), end_bit >= 32, with 2^20 <= n <= 2^33 take the "hybrid
  * finish": 2-3 ordinary passes over the top 16/24 bits (the first of them without stable
  * ranking), then ONE shared-memory local sort per ~6000-key tile orders all remaining bits
  * (radix_sort.cu: local_sort_kernel).  Tiles the local scheme cannot hold (prefix buckets above
- * 8192 keys: repeats) are gathered, sorted by the plain LSD passes and put back; above n/8 such
+ * 8192 keys, 4096 for 16-byte keys: repeats) are gathered, sorted by the plain LSD passes and put back; above n/8 such
  * keys the plain passes sort everything.  The result is identical on every path.  The call
  * synchronises the stream in that mode (2 KB histogram read-back, irregular-tile count).
  * All keys must agree in the bits at and above end_bit in that mode (kmg_extract's keys do: those

@@ -1049,7 +1049,8 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
                 KMG_CUDA(cudaStreamSynchronize(st));
                 unsigned long long mx = 0;
                 for (int i = 0; i < SORT_RADIX; ++i) mx = std::max(mx, h_top[i]);
-                if (mx / 256 <= (uint64_t)(key_bytes == 8 ? 2048 : 1024)) pb = 16;  // a quarter of a tile's capacity
+                // (a tile must hold one bucket-wide window plus the straddling bucket: capacity / 2.4)
+                if (mx / 256 <= (uint64_t)(key_bytes == 8 ? 3400 : 1700)) pb = 16;
             }
         }
         np = pb / 8;
