@@ -31,8 +31,6 @@ struct Seg {
 };
 __device__ __forceinline__ uint32_t seg_apply(uint32_t f, uint32_t s) { return (f >> (2 * s)) & 3u; }
 constexpr uint32_t F_ID = ST_PRE | (ST_HDR << 2) | (ST_SEQ << 4);
-constexpr uint32_t F_N = ST_PRE | (ST_SEQ << 2) | (ST_SEQ << 4);     // a normal line starts
-constexpr uint32_t F_H = ST_HDR | (ST_HDR << 2) | (ST_HDR << 4);     // a header line starts
 __device__ __forceinline__ Seg seg_identity() { return Seg{F_ID, {0, 0, 0}, 0}; }
 // a then b
 __device__ __forceinline__ Seg seg_compose(const Seg& a, const Seg& b) {

@@ -781,15 +781,10 @@ __global__ void __launch_bounds__(256) irregular_copy_kernel(const HybridParams 
 }
 
 // ---- tile configurations ----------------------------------------------------------------------
-struct SortTile {
-    int block, ipt, mix;
-};
-// index = kmg_set_option("sort_config", i)
-static const SortTile kSortTiles[] = {
-    {256, 16, 2}, {256, 16, 0}, {256, 16, 1}, {256, 24, 2}, {512, 16, 2}, {256, 16, 3}, {384, 16, 2}, {256, 16, 4},
-    {256, 24, 3}, {256, 20, 2}, {256, 24, 5},
-};
-constexpr int kNumSortTiles = sizeof(kSortTiles) / sizeof(kSortTiles[0]);
+// kmg_set_option("sort_config", i) -> (threads, keys per thread, ranking mix), see dispatch_tile():
+//   0: 256x16 mix2   1: 256x16 mix0   2: 256x16 mix1   3: 256x24 mix2 (default)   4: 512x16 mix2
+//   5: 256x16 mix3   6: 384x16 mix2   7: 256x16 mix4   8: 256x24 mix3   9: 256x20 mix2
+//  10: 256x24 mix5 (unstable ranking; the hybrid finish uses it for its first prefix pass)
 
 template <typename KeyT, int VB, int RB, int BLOCK, int IPT, int MIX>
 static size_t onesweep_smem() {
@@ -891,12 +886,6 @@ void timing_reset() {
     g_ev_used = 0;
     g_pass_ms_total[0] = g_pass_ms_total[1] = 0;
     g_pass_count_total[0] = g_pass_count_total[1] = 0;
-}
-
-static int tile_items(int cfg, int key_bytes) {
-    if (key_bytes == 16) return 256 * 8;
-    if (cfg < 0 || cfg >= kNumSortTiles) cfg = 0;
-    return kSortTiles[cfg].block * kSortTiles[cfg].ipt;
 }
 
 // keys per look-back part: 30-bit counts, multiple of every tile size (lcm of tiles | 2^k*3)
