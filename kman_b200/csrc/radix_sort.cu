@@ -535,6 +535,16 @@ __global__ void __launch_bounds__(256) tile_bounds_kernel(const HybridParams p) 
     if (lane == 0) p.bounds[tile] = r;
 }
 
+// Tiles that own more keys than the local sort holds are known from the bounds alone: count them
+// before the launch so that a fused count is not attempted in vain (repeats: real genomes always
+// have some).  The local sort flags them again, together with the rare crowded-cell tiles.
+__global__ void __launch_bounds__(256) oversize_tiles_kernel(const HybridParams p, uint32_t cap, unsigned long long* n_oversize) {
+    const uint32_t tile = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tile >= p.n_tiles) return;
+    const uint64_t s = p.bounds[tile], e = p.bounds[tile + 1];
+    if (s < min((uint64_t)(tile + 1) * p.tile_t, p.n) && e > s && e - s > cap) atomicAdd(n_oversize, 1ull);
+}
+
 // monotone map key -> cell of the tile's counting sort (see local_sort_kernel)
 template <typename KeyT>
 struct CellMap {
@@ -1153,8 +1163,22 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
                                   (int)ls_smem_bytes<u128>()));
     const int sel_done = (np + 1) & 1;  // kout is d_keys_alt when np is even
     unsigned long long irregular = 0;
+    bool try_fused = co != nullptr && g_count_fused;
+    // (adaptive: the check costs a stream synchronisation, so it runs only after a fused attempt of
+    // this thread was void; it switches itself off again when it finds nothing)
+    static thread_local bool expect_oversize = false;
+    if (try_fused && expect_oversize) {
+        unsigned long long* d_over = reinterpret_cast<unsigned long long*>(&w.hdr->pad[2]);
+        unsigned long long n_over = 0;
+        oversize_tiles_kernel<<<(hp.n_tiles + 255) / 256, 256, 0, st>>>(hp, (uint32_t)cap, d_over);
+        KMG_LAUNCH_CHECK();
+        KMG_CUDA(cudaMemcpyAsync(&n_over, d_over, sizeof(n_over), cudaMemcpyDeviceToHost, st));
+        KMG_CUDA(cudaStreamSynchronize(st));
+        if (n_over) try_fused = false;  // the table would be void: sort, re-sort those ranges, then count
+        else expect_oversize = false;
+    }
     for (int attempt = 0; attempt < 2; ++attempt) {
-        const bool fused = co != nullptr && g_count_fused && attempt == 0;
+        const bool fused = try_fused && attempt == 0;
         if (!fused && attempt == 0) continue;  // plain sort: only the second form
         if (fused) {
             hp.counts_out = co->counts;
@@ -1187,6 +1211,7 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
             *h_selector_out = sel_done;
             return KMG_OK;
         }
+        if (fused) expect_oversize = true;
     }
     // Some tiles own more keys than the local scheme holds (a huge prefix bucket: repeats).  Their
     // ranges are gathered, sorted with the plain passes and put back -- unless they are most of the

@@ -140,6 +140,14 @@ def main():
     med_full, mn_full = timed(full, flush=flush)
     print(f"full count     : {med_full:8.3f} ms (min {mn_full:.3f})  {N/med_full/1e6:8.2f} G kmers/s")
     res["full_ms"] = med_full
+
+    def full_uniq():
+        a = eng.sort(eng.extract(d, k, False, val_bytes=4, reuse="u_", want_hist=True))
+        return eng.singletons(a)
+
+    med_u, mn_u = timed(full_uniq, flush=flush)
+    print(f"full uniq (u32 payload): {med_u:8.3f} ms (min {mn_u:.3f})  {N/med_u/1e6:8.2f} G kmers/s")
+    res["full_uniq_ms"] = med_u
     if args.yardstick:
         a = eng.extract(d, k, False, val_bytes=0, reuse="b_", want_hist=True)
         keys = a.keys[: a.n * 8].view(torch.int64)
