@@ -130,6 +130,15 @@ size_t kmg_sort_count_workspace_bytes(uint64_t n, int key_bytes, int end_bit);
 int kmg_sort_count(void* d_keys, void* d_keys_alt, uint64_t n, int key_bytes, int end_bit, const uint64_t* d_hist_in,
                    uint32_t* d_counts_out, uint64_t* d_n_out, int* h_selector_out, void* d_ws, size_t ws_bytes,
                    void* stream);
+/* sort + select_singletons in one call (the uniq path: join.py:63-130 + join_unique :243-263).
+ * Leaves the keys that occur exactly once, ascending, with their payload in (d_keys, d_vals)
+ * (*h_selector_out = 0) or (d_keys_alt, d_vals_alt) (1); *d_n_out (device) = their number.  Because
+ * repeated keys are dropped, their relative order does not matter and 8-byte keys take the
+ * hybrid finish with the payload following through a 16-bit index (6144-key tiles). */
+size_t kmg_sort_uniq_workspace_bytes(uint64_t n, int key_bytes, int val_bytes, int end_bit);
+int kmg_sort_uniq(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_alt, uint64_t n, int key_bytes,
+                  int val_bytes, int end_bit, const uint64_t* d_hist_in, uint64_t* d_n_out, int* h_selector_out,
+                  void* d_ws, size_t ws_bytes, void* stream);
 int kmg_select_singletons(const void* d_sorted_keys, const void* d_vals, uint64_t n, int key_bytes, int val_bytes,
                           void* d_keys_out, void* d_vals_out, uint64_t* d_n_out, void* d_ws, size_t ws_bytes,
                           void* stream);

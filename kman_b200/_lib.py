@@ -33,6 +33,8 @@ SIGNATURES = {
     "kmg_radix_sort": (i32, [vp, vp, vp, vp, u64, i32, i32, i32, i32, vp, C.POINTER(i32), vp, sz, vp]),
     "kmg_rle_workspace_bytes": (sz, [u64]),
     "kmg_rle_count": (i32, [vp, u64, i32, vp, vp, vp, vp, sz, vp]),
+    "kmg_sort_uniq_workspace_bytes": (sz, [u64, i32, i32, i32]),
+    "kmg_sort_uniq": (i32, [vp, vp, vp, vp, u64, i32, i32, i32, vp, vp, C.POINTER(C.c_int), vp, sz, vp]),
     "kmg_sort_count_workspace_bytes": (sz, [u64, i32, i32]),
     "kmg_sort_count": (i32, [vp, vp, u64, i32, i32, vp, vp, vp, C.POINTER(C.c_int), vp, sz, vp]),
     "kmg_select_singletons": (i32, [vp, vp, u64, i32, i32, vp, vp, vp, vp, sz, vp]),

@@ -258,7 +258,8 @@ static int run_host(kmg_ctx* c, int mode, const uint8_t* h_bases, uint64_t n_bas
     const size_t ws_ex = kmg_extract_workspace_bytes(n_win);
     const size_t ws_sort = kmg_radix_sort_workspace_bytes(n_max, kb, vb, 0, 2 * k);
     const size_t ws_rle = kmg_rle_workspace_bytes(n_max);
-    const size_t ws_count = mode == 0 ? kmg_sort_count_workspace_bytes(n_max, kb, 2 * k) : 0;
+    const size_t ws_count = mode == 0 ? kmg_sort_count_workspace_bytes(n_max, kb, 2 * k)
+                                      : kmg_sort_uniq_workspace_bytes(n_max, kb, vb, 2 * k);
     const size_t ws_bytes = std::max(std::max(ws_ex, ws_count), std::max(ws_sort, ws_rle));
 
     Carver cv{nullptr, 0};
@@ -315,14 +316,10 @@ static int run_host(kmg_ctx* c, int mode, const uint8_t* h_bases, uint64_t n_bas
         rcode = kmg_sort_count(d_keys, d_keys_alt, n, kb, 2 * k, d_hist, d_counts, c->d_small + 2, &sel, d_ws, ws_bytes, st);
         ok = sel ? d_keys_alt : d_keys;
     } else {
-        rcode = kmg_radix_sort(d_keys, d_keys_alt, d_vals, d_vals_alt, n, kb, vb, 0, 2 * k, d_hist, &sel, d_ws, ws_bytes, st);
-        if (rcode != KMG_OK) return rcode;
-        char* sk = sel ? d_keys_alt : d_keys;
-        char* sv = sel ? d_vals_alt : d_vals;
-        ok = sel ? d_keys : d_keys_alt;
-        ov = sel ? d_vals : d_vals_alt;
-        // the sort's look-back words and the RLE state share d_ws: both calls re-zero what they use
-        rcode = kmg_select_singletons(sk, sv, n, kb, vb, ok, ov, c->d_small + 2, d_ws, ws_bytes, st);
+        rcode = kmg_sort_uniq(d_keys, d_keys_alt, d_vals, d_vals_alt, n, kb, vb, 2 * k, d_hist, c->d_small + 2, &sel, d_ws,
+                              ws_bytes, st);
+        ok = sel ? d_keys_alt : d_keys;
+        ov = sel ? d_vals_alt : d_vals;
     }
     if (rcode != KMG_OK) return rcode;
     uint64_t n_out = 0;

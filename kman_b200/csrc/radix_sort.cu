@@ -428,33 +428,46 @@ __global__ void __launch_bounds__(BLOCK, min_ctas(BLOCK, IPT)) onesweep_kernel(c
 // sort of each thread's consecutive cells.  Tiles whose buckets do not fit the scheme (long runs
 // of one prefix, crowded cells: repeats) are flagged; the caller re-sorts their ranges with the
 // plain LSD passes, so correctness never depends on the data.
-template <typename KeyT>
+// Tile geometry.  PAIRS: a 4- or 8-byte payload follows its key through a 16-bit index array
+// (kmg_sort_uniq), which costs shared memory: smaller tiles.
+template <typename KeyT, bool PAIRS>
 struct LS;
 template <>
-struct LS<uint64_t> {
+struct LS<uint64_t, false> {
     static constexpr int IPT = 16;  // keys per thread
     static constexpr int CPT = 16;  // consecutive cells per thread in the prefix / cell-sort phases
 };
 template <>
-struct LS<u128> {
+struct LS<u128, false> {
     static constexpr int IPT = 8;
     static constexpr int CPT = 8;
 };
+template <>
+struct LS<uint64_t, true> {
+    static constexpr int IPT = 12;
+    static constexpr int CPT = 12;
+};
 constexpr int LS_BLOCK = 512;
-template <typename KeyT>
-__host__ __device__ constexpr int ls_cap() { return LS_BLOCK * LS<KeyT>::IPT; }  // keys a tile can own: 8192 / 4096
-template <typename KeyT>
-__host__ __device__ constexpr int ls_cells() { return LS_BLOCK * LS<KeyT>::CPT; }
-// cell counters are padded (4 words per CPT) so that one thread's consecutive cells are
-// conflict-free 128-bit accesses: thread stride 20 / 12 words
-template <typename KeyT>
+template <typename KeyT, bool PAIRS>
+__host__ __device__ constexpr int ls_cap() { return LS_BLOCK * LS<KeyT, PAIRS>::IPT; }  // keys a tile can own
+template <typename KeyT, bool PAIRS>
+__host__ __device__ constexpr int ls_cells() { return LS_BLOCK * LS<KeyT, PAIRS>::CPT; }
+// cell counters are padded so that one thread's consecutive cells are conflict-free 128-bit
+// accesses: thread stride 16 + 4 = 20 words, 8 + 4 = 12 words, 12 words (no padding needed)
+template <typename KeyT, bool PAIRS>
 __device__ __forceinline__ uint32_t pc(uint32_t c) {
-    return LS<KeyT>::CPT == 16 ? c + ((c >> 4) << 2) : c + ((c >> 3) << 2);
+    constexpr int CPT = LS<KeyT, PAIRS>::CPT;
+    return CPT == 16 ? c + ((c >> 4) << 2) : (CPT == 8 ? c + ((c >> 3) << 2) : c);
 }
-template <typename KeyT>
-__host__ __device__ constexpr int ls_cell_words() { return ls_cells<KeyT>() + ls_cells<KeyT>() / LS<KeyT>::CPT * 4 + 4; }
-template <typename KeyT>
-__host__ __device__ constexpr size_t ls_smem_bytes() { return sizeof(KeyT) * ls_cap<KeyT>() + sizeof(uint32_t) * ls_cell_words<KeyT>(); }
+template <typename KeyT, bool PAIRS>
+__host__ __device__ constexpr int ls_cell_words() {
+    return ls_cells<KeyT, PAIRS>() + (LS<KeyT, PAIRS>::CPT == 12 ? 0 : ls_cells<KeyT, PAIRS>() / LS<KeyT, PAIRS>::CPT * 4) + 4;
+}
+template <typename KeyT, bool PAIRS>
+__host__ __device__ constexpr size_t ls_smem_bytes() {
+    return sizeof(KeyT) * ls_cap<KeyT, PAIRS>() + sizeof(uint32_t) * ls_cell_words<KeyT, PAIRS>() +
+           (PAIRS ? sizeof(uint16_t) * ls_cap<KeyT, PAIRS>() : 0);
+}
 constexpr int LS_T_MIN = 1024;             // smallest run-time tile width (workspace sizing)
 constexpr int LS_SORT_BUDGET = 4096;       // insertion-sort moves one thread may spend before the tile gives up
 
@@ -469,6 +482,8 @@ __device__ __forceinline__ uint64_t shr64(const u128& k, int s) {
 struct HybridParams {
     const void* keys_in;
     void* keys_out;
+    const void* vals_in;    // payload sorts (local_sort_kernel<.., VB != 0>)
+    void* vals_out;
     uint64_t n;
     uint64_t* bounds;       // [n_tiles + 1], see tile_bounds_kernel
     uint32_t* flag;         // [n_tiles] 1 = the local scheme could not hold the tile (zeroed by the host)
@@ -546,7 +561,7 @@ __global__ void __launch_bounds__(256) oversize_tiles_kernel(const HybridParams 
 }
 
 // monotone map key -> cell of the tile's counting sort (see local_sort_kernel)
-template <typename KeyT>
+template <typename KeyT, int CELLS>
 struct CellMap {
     uint64_t base;   // b_lo << w
     uint32_t inv;    // 0: cell = x, else cell = umulhi(x, inv)
@@ -554,7 +569,7 @@ struct CellMap {
     __device__ __forceinline__ uint32_t operator()(const KeyT& key) const {
         const uint32_t x = (uint32_t)(shr64(key, sh) - base);
         // (the clamp only matters for keys that break the contract: bits >= end_bit not all equal)
-        return min(inv ? __umulhi(x, inv) : x, (uint32_t)ls_cells<KeyT>() - 1u);
+        return min(inv ? __umulhi(x, inv) : x, (uint32_t)CELLS - 1u);
     }
 };
 
@@ -562,15 +577,22 @@ struct CellMap {
 // compacted across tiles with the tile prefix (a run of equal keys never leaves its prefix bucket,
 // hence never its tile): kmg_rle_count's result without writing and re-reading the sorted keys.
 // Tiles take their ids from a ticket so that waiting for earlier tiles is safe.
-template <typename KeyT, bool COUNT>
+// VB != 0: the payload (4 or 8 bytes) follows its key: a 16-bit index array travels with the
+// staged keys and the payload is gathered from the tile's (L2-resident) input range at the end.
+// Equal keys come out in no particular order (kmg_sort_uniq only keeps keys that occur once).
+template <typename KeyT, bool COUNT, int VB>
 __global__ void __launch_bounds__(LS_BLOCK, 2) local_sort_kernel(const HybridParams p) {
-    constexpr int IPT = LS<KeyT>::IPT, CPT = LS<KeyT>::CPT;
-    constexpr int CAP = ls_cap<KeyT>(), CELLS = ls_cells<KeyT>(), CELL_WORDS = ls_cell_words<KeyT>();
-    constexpr int CELL_BITS = CELLS == 8192 ? 13 : 12;
-    static_assert((1 << CELL_BITS) == CELLS, "cell index width");
+    constexpr bool PAIRS = VB != 0;
+    static_assert(!(PAIRS && COUNT), "the fused count is key-only");
+    constexpr int IPT = LS<KeyT, PAIRS>::IPT, CPT = LS<KeyT, PAIRS>::CPT;
+    constexpr int CAP = ls_cap<KeyT, PAIRS>(), CELLS = ls_cells<KeyT, PAIRS>(), CELL_WORDS = ls_cell_words<KeyT, PAIRS>();
+    constexpr int CELL_BITS = CELLS > 4096 ? 13 : 12;
+    static_assert((1 << CELL_BITS) >= CELLS && CAP <= (1 << 16), "cell / index widths");
+    using ValT = typename ValType<VB == 0 ? 8 : VB>::type;
     extern __shared__ __align__(16) unsigned char ls_smem[];
     KeyT* s_stage = reinterpret_cast<KeyT*>(ls_smem);                                 // [CAP]
     uint32_t* s_cell = reinterpret_cast<uint32_t*>(ls_smem + sizeof(KeyT) * CAP);     // [CELL_WORDS]
+    uint16_t* s_idx = reinterpret_cast<uint16_t*>(s_cell + CELL_WORDS);               // [CAP] (PAIRS)
     __shared__ uint32_t s_scan[LS_BLOCK / 32 + 1];
     __shared__ int s_bad;
     __shared__ uint32_t s_tile;
@@ -624,7 +646,7 @@ __global__ void __launch_bounds__(LS_BLOCK, 2) local_sort_kernel(const HybridPar
     // Counting sort into <= CELLS cells through a monotone map of the key: the w bits after the
     // prefix, relative to the tile's first bucket, scaled down to the cell range when the tile
     // spans more than CELLS such values.  Monotone, so sorting inside cells finishes it.
-    CellMap<KeyT> cm;
+    CellMap<KeyT, CELLS> cm;
     {
         const uint64_t R = p_last - p_first + 1;  // <= 2^24
         int w = min(CELL_BITS, sh_pref);
@@ -641,12 +663,12 @@ __global__ void __launch_bounds__(LS_BLOCK, 2) local_sort_kernel(const HybridPar
         const uint32_t idx = t + j * LS_BLOCK;
         if (idx < m) {
             const uint32_t c = cm(keys[j]);
-            meta[j] = c | (atomicAdd(&s_cell[pc<KeyT>(c)], 1u) << CELL_BITS);
+            meta[j] = c | (atomicAdd(&s_cell[pc<KeyT, PAIRS>(c)], 1u) << CELL_BITS);
         }
     }
     __syncthreads();
     // exclusive prefix over the cells: CPT consecutive cells per thread, 128 bits at a time
-    uint4* cv = reinterpret_cast<uint4*>(s_cell + pc<KeyT>(t * CPT));
+    uint4* cv = reinterpret_cast<uint4*>(s_cell + pc<KeyT, PAIRS>(t * CPT));
     uint4 q[CPT / 4];
     uint32_t sum = 0;
 #pragma unroll
@@ -665,18 +687,22 @@ __global__ void __launch_bounds__(LS_BLOCK, 2) local_sort_kernel(const HybridPar
         cv[i] = q[i];
     }
     asm volatile("" ::: "memory");
-    if (t == LS_BLOCK - 1) s_cell[pc<KeyT>(CELLS)] = run;  // sentinel: end of the last cell
+    if (t == LS_BLOCK - 1) s_cell[pc<KeyT, PAIRS>(CELLS)] = run;  // sentinel: end of the last cell
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < IPT; ++j) {
         const uint32_t idx = t + j * LS_BLOCK;
-        if (idx < m) s_stage[s_cell[pc<KeyT>(meta[j] & (CELLS - 1))] + (meta[j] >> CELL_BITS)] = keys[j];
+        if (idx < m) {
+            const uint32_t at = s_cell[pc<KeyT, PAIRS>(meta[j] & ((1u << CELL_BITS) - 1u))] + (meta[j] >> CELL_BITS);
+            s_stage[at] = keys[j];
+            if constexpr (PAIRS) s_idx[at] = (uint16_t)idx;
+        }
     }
     __syncthreads();
     // Order every cell in place.  The cells are already in order among themselves, so a thread
     // simply insertion-sorts the contiguous run of its CPT cells (~11 / ~6 keys): a key moves only
     // inside its own cell, equal keys cost one compare each.
-    const uint32_t lo = s_cell[pc<KeyT>(t * CPT)], hi = s_cell[pc<KeyT>((t + 1) * CPT)];
+    const uint32_t lo = s_cell[pc<KeyT, PAIRS>(t * CPT)], hi = s_cell[pc<KeyT, PAIRS>((t + 1) * CPT)];
     // COUNT: equal keys share a cell, hence a thread's run, so the run heads (distinct keys) can be
     // counted while inserting: a key is new unless it lands right after an equal one
     uint32_t hc = 0;
@@ -693,14 +719,18 @@ __global__ void __launch_bounds__(LS_BLOCK, 2) local_sort_kernel(const HybridPar
             uint32_t qi = i;
             KeyT below{};
             bool more;
+            uint16_t my_idx = 0;
+            if constexpr (PAIRS) my_idx = s_idx[i];
             do {
                 s_stage[qi] = s_stage[qi - 1];
+                if constexpr (PAIRS) s_idx[qi] = s_idx[qi - 1];
                 --qi;
                 --budget;
                 more = qi > lo;
                 if (more) below = s_stage[qi - 1];
             } while (more && key < below);
             s_stage[qi] = key;
+            if constexpr (PAIRS) s_idx[qi] = my_idx;
             if (COUNT) hc += (!more || below != key) ? 1u : 0u;
             if (budget < 0) break;
         }
@@ -721,6 +751,15 @@ __global__ void __launch_bounds__(LS_BLOCK, 2) local_sort_kernel(const HybridPar
         for (int j = 0; j < IPT; ++j) {
             const uint32_t idx = t + j * LS_BLOCK;
             if (idx < m) kout[idx] = s_stage[idx];
+        }
+        if constexpr (PAIRS) {
+            const ValT* vin = reinterpret_cast<const ValT*>(p.vals_in) + s;
+            ValT* vout = reinterpret_cast<ValT*>(p.vals_out) + s;
+#pragma unroll
+            for (int j = 0; j < IPT; ++j) {
+                const uint32_t idx = t + j * LS_BLOCK;
+                if (idx < m) vout[idx] = vin[s_idx[idx]];
+            }
         }
     } else {
         // the runs tile [0, m) in thread order, so a block scan of the per-thread head counts ranks
@@ -773,24 +812,35 @@ __global__ void __launch_bounds__(1024) irregular_scan_kernel(const HybridParams
     if (t == 0) p.off[p.n_tiles] = total;
 }
 
-// TO_BUFFER: keys_in[bounds[tile]...] -> buf[off[tile]...] for the flagged tiles; else buf -> keys_out.
-// The ranges are whole prefix buckets in ascending order, so sorting the gathered keys and putting
-// them back range by range leaves keys_out fully sorted.
-template <typename KeyT, bool TO_BUFFER>
-__global__ void __launch_bounds__(256) irregular_copy_kernel(const HybridParams p, KeyT* __restrict__ buf) {
-    const KeyT* keys_in = reinterpret_cast<const KeyT*>(p.keys_in);
-    KeyT* keys_out = reinterpret_cast<KeyT*>(p.keys_out);
+// TO_BUFFER: in[bounds[tile]...] -> buf[off[tile]...] for the flagged tiles; else buf -> out (keys, and
+// again for the payload).  The ranges are whole prefix buckets in ascending order, so sorting the
+// gathered items and putting them back range by range leaves the output fully sorted.
+template <typename T, bool TO_BUFFER>
+__global__ void __launch_bounds__(256) irregular_copy_kernel(const HybridParams p, const T* __restrict__ in,
+                                                             T* __restrict__ out, T* __restrict__ buf) {
     for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         if (!p.flag[tile]) continue;
         const uint64_t s = p.bounds[tile], m = p.bounds[tile + 1] - s, o = p.off[tile];
         for (uint64_t i = threadIdx.x; i < m; i += 256) {
-            if (TO_BUFFER) buf[o + i] = keys_in[s + i];
-            else keys_out[s + i] = buf[o + i];
+            if (TO_BUFFER) buf[o + i] = in[s + i];
+            else out[s + i] = buf[o + i];
         }
     }
 }
 
-// ---- tile configurations ----------------------------------------------------------------------
+template <bool TO_BUFFER>
+static int irregular_copy(const HybridParams& hp, int item_bytes, const void* in, void* out, void* buf, int grid,
+                          cudaStream_t st) {
+    if (item_bytes == 16)
+        irregular_copy_kernel<u128, TO_BUFFER><<<grid, 256, 0, st>>>(hp, (const u128*)in, (u128*)out, (u128*)buf);
+    else if (item_bytes == 8)
+        irregular_copy_kernel<uint64_t, TO_BUFFER><<<grid, 256, 0, st>>>(hp, (const uint64_t*)in, (uint64_t*)out, (uint64_t*)buf);
+    else
+        irregular_copy_kernel<uint32_t, TO_BUFFER><<<grid, 256, 0, st>>>(hp, (const uint32_t*)in, (uint32_t*)out, (uint32_t*)buf);
+    KMG_LAUNCH_CHECK();
+    return KMG_OK;
+}
+
 // kmg_set_option("sort_config", i) -> (threads, keys per thread, ranking mix), see dispatch_tile():
 //   0: 256x16 mix2   1: 256x16 mix0   2: 256x16 mix1   3: 256x24 mix2 (default)   4: 512x16 mix2
 //   5: 256x16 mix3   6: 384x16 mix2   7: 256x16 mix4   8: 256x24 mix3   9: 256x20 mix2
@@ -916,6 +966,7 @@ struct SortWs {
     size_t zero_bytes;         // everything up to here is zeroed at the start of a sort
     uint64_t irr_cap;          // keys the gather buffers hold
     void* irr_buf[2];          // gather buffer + its ping-pong partner (irr_cap keys each)
+    void* irr_vbuf[2];         // the same for the payload (payload sorts)
     void* irr_ws;              // workspace of the sort of the gathered keys
     size_t irr_ws_bytes;
     size_t total;
@@ -930,9 +981,9 @@ constexpr uint64_t HYBRID_MIN_N = 1ull << 20;
 constexpr uint64_t HYBRID_MAX_N = 1ull << 33;  // 32-bit tile ids at the smallest tile width
 
 // Key-only sorts (8- or 16-byte keys) over bits [0, end_bit), end_bit >= 32, of 2^20 .. 2^33 keys.
-static bool hybrid_applies(uint64_t n, int key_bytes, int val_bytes, int begin_bit, int end_bit);
+static bool hybrid_applies(uint64_t n, int key_bytes, int val_bytes, int begin_bit, int end_bit, bool pairs_ok = false);
 
-static SortWs carve_sort_ws(void* ws, uint64_t n, int key_bytes, bool hybrid) {
+static SortWs carve_sort_ws(void* ws, uint64_t n, int key_bytes, bool hybrid, int val_bytes = 0) {
     SortWs w;
     memset(&w, 0, sizeof(w));
     char* p = (char*)ws;
@@ -970,6 +1021,10 @@ static SortWs carve_sort_ws(void* ws, uint64_t n, int key_bytes, bool hybrid) {
             w.irr_buf[i] = p;
             p += align_up(w.irr_cap * (size_t)key_bytes, 256);
         }
+        for (int i = 0; i < 2 && val_bytes; ++i) {
+            w.irr_vbuf[i] = p;
+            p += align_up(w.irr_cap * (size_t)val_bytes, 256);
+        }
         w.irr_ws = p;
         w.irr_ws_bytes = carve_sort_ws(nullptr, w.irr_cap, key_bytes, false).total;
         p += align_up(w.irr_ws_bytes, 256);
@@ -978,8 +1033,11 @@ static SortWs carve_sort_ws(void* ws, uint64_t n, int key_bytes, bool hybrid) {
     return w;
 }
 
-static bool hybrid_applies(uint64_t n, int key_bytes, int val_bytes, int begin_bit, int end_bit) {
-    return g_hybrid && val_bytes == 0 && begin_bit == 0 && end_bit >= 32 && n >= HYBRID_MIN_N && n <= HYBRID_MAX_N;
+// Payload sorts take it only when the caller does not need equal keys in input order (`pairs_ok`:
+// kmg_sort_uniq), and only with 8-byte keys.
+static bool hybrid_applies(uint64_t n, int key_bytes, int val_bytes, int begin_bit, int end_bit, bool pairs_ok) {
+    if (val_bytes != 0 && !(pairs_ok && key_bytes == 8)) return false;
+    return g_hybrid && begin_bit == 0 && end_bit >= 32 && n >= HYBRID_MIN_N && n <= HYBRID_MAX_N;
 }
 
 thread_local int64_t g_stat_hybrid_path = 0;  // 0 plain passes, 1 hybrid, 2 hybrid + re-sorted ranges, 3 fell back
@@ -996,7 +1054,7 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
                      int val_bytes, int begin_bit, int end_bit, const uint64_t* d_hist_in, int* h_selector_out,
                      void* d_ws, size_t ws_bytes, cudaStream_t st, bool hybrid, bool allow_hybrid,
                      CountOut* co = nullptr) {
-    SortWs w = carve_sort_ws(d_ws, n, key_bytes, hybrid);
+    SortWs w = carve_sort_ws(d_ws, n, key_bytes, hybrid, val_bytes);
     KMG_REQUIRE(ws_bytes >= w.total, KMG_ERR_WS, "sort workspace too small: %zu < %zu", ws_bytes, w.total);
     hybrid = hybrid && allow_hybrid;
 
@@ -1049,7 +1107,7 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
                 unsigned long long mx = 0;
                 for (int i = 0; i < SORT_RADIX; ++i) mx = std::max(mx, h_top[i]);
                 // (a tile must hold one bucket-wide window plus the straddling bucket: capacity / 2.4)
-                if (mx / 256 <= (uint64_t)(key_bytes == 8 ? 3400 : 1700)) pb = 16;
+                if (mx / 256 <= (uint64_t)(key_bytes == 16 ? 1700 : (val_bytes ? 2500 : 3400))) pb = 16;
             }
         }
         np = pb / 8;
@@ -1126,10 +1184,13 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
 
     // kin now holds the keys ordered by their top pb bits; finish into kout
     const bool wide_key = key_bytes == 16;
-    const int cap = wide_key ? ls_cap<u128>() : ls_cap<uint64_t>();
+    const bool pairs = val_bytes != 0;
+    const int cap = wide_key ? ls_cap<u128, false>() : (pairs ? ls_cap<uint64_t, true>() : ls_cap<uint64_t, false>());
     HybridParams hp;
     hp.keys_in = kin;
     hp.keys_out = kout;
+    hp.vals_in = vin;
+    hp.vals_out = vout;
     hp.n = n;
     // Tile width: a tile owns WHOLE prefix buckets, so leave room for the straddling one; with a
     // 16-bit prefix the buckets are a sizeable fraction of a tile and a width of k average buckets
@@ -1152,15 +1213,22 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
     if (wide_key) tile_bounds_kernel<u128><<<(hp.n_tiles + 1 + 7) / 8, 256, 0, st>>>(hp);
     else tile_bounds_kernel<uint64_t><<<(hp.n_tiles + 1 + 7) / 8, 256, 0, st>>>(hp);
     KMG_LAUNCH_CHECK();
-    const size_t smem = wide_key ? ls_smem_bytes<u128>() : ls_smem_bytes<uint64_t>();
-    KMG_CUDA(cudaFuncSetAttribute(local_sort_kernel<uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)ls_smem_bytes<uint64_t>()));
-    KMG_CUDA(cudaFuncSetAttribute(local_sort_kernel<uint64_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)ls_smem_bytes<uint64_t>()));
-    KMG_CUDA(cudaFuncSetAttribute(local_sort_kernel<u128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)ls_smem_bytes<u128>()));
-    KMG_CUDA(cudaFuncSetAttribute(local_sort_kernel<u128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)ls_smem_bytes<u128>()));
+    const size_t smem = wide_key ? ls_smem_bytes<u128, false>()
+                                 : (pairs ? ls_smem_bytes<uint64_t, true>() : ls_smem_bytes<uint64_t, false>());
+    {
+        static bool attrs_set = false;  // (idempotent; racing threads set the same values)
+        if (!attrs_set) {
+            const int s64 = (int)ls_smem_bytes<uint64_t, false>(), s128 = (int)ls_smem_bytes<u128, false>(),
+                      sp = (int)ls_smem_bytes<uint64_t, true>();
+            KMG_CUDA(cudaFuncSetAttribute(local_sort_kernel<uint64_t, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, s64));
+            KMG_CUDA(cudaFuncSetAttribute(local_sort_kernel<uint64_t, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, s64));
+            KMG_CUDA(cudaFuncSetAttribute(local_sort_kernel<u128, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, s128));
+            KMG_CUDA(cudaFuncSetAttribute(local_sort_kernel<u128, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, s128));
+            KMG_CUDA(cudaFuncSetAttribute(local_sort_kernel<uint64_t, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp));
+            KMG_CUDA(cudaFuncSetAttribute(local_sort_kernel<uint64_t, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp));
+            attrs_set = true;
+        }
+    }
     const int sel_done = (np + 1) & 1;  // kout is d_keys_alt when np is even
     unsigned long long irregular = 0;
     bool try_fused = co != nullptr && g_count_fused;
@@ -1194,11 +1262,14 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
         if (g_ev_used >= MAX_TIMED) timing_collect();
         timing_begin(st);
         if (fused) {
-            if (wide_key) local_sort_kernel<u128, true><<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);
-            else local_sort_kernel<uint64_t, true><<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);
+            if (wide_key) local_sort_kernel<u128, true, 0><<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);
+            else local_sort_kernel<uint64_t, true, 0><<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);
+        } else if (pairs) {
+            if (val_bytes == 4) local_sort_kernel<uint64_t, false, 4><<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);
+            else local_sort_kernel<uint64_t, false, 8><<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);
         } else {
-            if (wide_key) local_sort_kernel<u128, false><<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);
-            else local_sort_kernel<uint64_t, false><<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);
+            if (wide_key) local_sort_kernel<u128, false, 0><<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);
+            else local_sort_kernel<uint64_t, false, 0><<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);
         }
         timing_end(st, 1);
         KMG_LAUNCH_CHECK();
@@ -1224,24 +1295,25 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
     if (m_irr <= w.irr_cap) {
         g_stat_hybrid_path = 2;
         const int grid = (int)std::min<uint64_t>(hp.n_tiles, (uint64_t)sms * 8);
-        if (wide_key) irregular_copy_kernel<u128, true><<<grid, 256, 0, st>>>(hp, (u128*)w.irr_buf[0]);
-        else irregular_copy_kernel<uint64_t, true><<<grid, 256, 0, st>>>(hp, (uint64_t*)w.irr_buf[0]);
-        KMG_LAUNCH_CHECK();
+        int rc2 = irregular_copy<true>(hp, key_bytes, kin, nullptr, w.irr_buf[0], grid, st);
+        if (rc2 == KMG_OK && pairs) rc2 = irregular_copy<true>(hp, val_bytes, vin, nullptr, w.irr_vbuf[0], grid, st);
+        if (rc2 != KMG_OK) return rc2;
         int sel2 = 0;
         const int64_t passes = g_stat_sort_passes;
-        const int rcode = sort_impl(w.irr_buf[0], w.irr_buf[1], nullptr, nullptr, m_irr, key_bytes, 0, 0, end_bit, nullptr, &sel2,
-                                    w.irr_ws, w.irr_ws_bytes, st, false, false);
+        const int rcode = sort_impl(w.irr_buf[0], w.irr_buf[1], pairs ? w.irr_vbuf[0] : nullptr, pairs ? w.irr_vbuf[1] : nullptr,
+                                    m_irr, key_bytes, val_bytes, 0, end_bit, nullptr, &sel2, w.irr_ws, w.irr_ws_bytes, st, false,
+                                    false);
         g_stat_sort_passes = passes;
         if (rcode != KMG_OK) return rcode;
-        if (wide_key) irregular_copy_kernel<u128, false><<<grid, 256, 0, st>>>(hp, (u128*)w.irr_buf[sel2]);
-        else irregular_copy_kernel<uint64_t, false><<<grid, 256, 0, st>>>(hp, (uint64_t*)w.irr_buf[sel2]);
-        KMG_LAUNCH_CHECK();
+        rc2 = irregular_copy<false>(hp, key_bytes, nullptr, kout, w.irr_buf[sel2], grid, st);
+        if (rc2 == KMG_OK && pairs) rc2 = irregular_copy<false>(hp, val_bytes, nullptr, vout, w.irr_vbuf[sel2], grid, st);
+        if (rc2 != KMG_OK) return rc2;
         *h_selector_out = sel_done;
         return KMG_OK;
     }
     g_stat_hybrid_path = 3;
     int sel2 = 0;
-    const int rcode = sort_impl(kin, kout, nullptr, nullptr, n, key_bytes, 0, begin_bit, end_bit, nullptr, &sel2, d_ws,
+    const int rcode = sort_impl(kin, kout, vin, vout, n, key_bytes, val_bytes, begin_bit, end_bit, nullptr, &sel2, d_ws,
                                 ws_bytes, st, true, false);
     if (rcode != KMG_OK) return rcode;
     *h_selector_out = (np & 1) ^ sel2;  // kin is d_keys when np is even
@@ -1324,6 +1396,52 @@ extern "C" int kmg_sort_count(void* d_keys, void* d_keys_alt, uint64_t n, int ke
     *h_selector_out = sel ^ 1;
     return kmg_rle_count(sorted, n, key_bytes, other, d_counts_out, d_n_out, (char*)d_ws + sort_ws, ws_bytes - sort_ws,
                          stream);
+}
+
+extern "C" int kmg_select_singletons(const void* d_sorted_keys, const void* d_vals, uint64_t n, int key_bytes, int val_bytes,
+                                     void* d_keys_out, void* d_vals_out, uint64_t* d_n_out, void* d_ws, size_t ws_bytes,
+                                     void* stream);
+
+static size_t sort_uniq_sort_ws(uint64_t n, int key_bytes, int val_bytes, int end_bit) {
+    return align_up(carve_sort_ws(nullptr, n, key_bytes, hybrid_applies(n, key_bytes, val_bytes, 0, end_bit, true), val_bytes).total,
+                    256);
+}
+
+extern "C" size_t kmg_sort_uniq_workspace_bytes(uint64_t n, int key_bytes, int val_bytes, int end_bit) {
+    return sort_uniq_sort_ws(n, key_bytes, val_bytes, end_bit) + kmg_rle_workspace_bytes(n);
+}
+
+extern "C" int kmg_sort_uniq(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_alt, uint64_t n, int key_bytes,
+                             int val_bytes, int end_bit, const uint64_t* d_hist_in, uint64_t* d_n_out, int* h_selector_out,
+                             void* d_ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    KMG_REQUIRE(key_bytes == 8 || key_bytes == 16, KMG_ERR_ARG, "key_bytes must be 8 or 16");
+    KMG_REQUIRE(val_bytes == 4 || val_bytes == 8, KMG_ERR_ARG, "val_bytes must be 4 or 8");
+    KMG_REQUIRE(end_bit >= 0 && end_bit <= key_bytes * 8, KMG_ERR_ARG, "bad end_bit %d", end_bit);
+    KMG_REQUIRE(h_selector_out && d_n_out, KMG_ERR_ARG, "null pointer argument");
+    *h_selector_out = 0;
+    g_stat_sort_passes = 0;
+    g_stat_hybrid_path = 0;
+    g_stat_hybrid_irregular = -1;
+    KMG_CUDA(cudaMemsetAsync(d_n_out, 0, sizeof(uint64_t), st));
+    if (n == 0) return KMG_OK;
+    KMG_REQUIRE(d_keys && d_keys_alt && d_vals && d_vals_alt && d_ws, KMG_ERR_ARG, "null pointer argument");
+    KMG_REQUIRE(((uintptr_t)d_keys % key_bytes) == 0 && ((uintptr_t)d_keys_alt % key_bytes) == 0, KMG_ERR_ARG,
+                "key buffers misaligned");
+    const size_t sort_ws = sort_uniq_sort_ws(n, key_bytes, val_bytes, end_bit);
+    KMG_REQUIRE(ws_bytes >= sort_ws + kmg_rle_workspace_bytes(n), KMG_ERR_WS, "sort_uniq workspace too small");
+    int sel = 0;
+    if (n > 1 && end_bit > 0) {
+        // equal keys may come out in any order: only keys that occur once are kept
+        const bool hybrid = hybrid_applies(n, key_bytes, val_bytes, 0, end_bit, true);
+        const int rcode = sort_impl(d_keys, d_keys_alt, d_vals, d_vals_alt, n, key_bytes, val_bytes, 0, end_bit, d_hist_in, &sel,
+                                    d_ws, sort_ws, st, hybrid, true);
+        if (rcode != KMG_OK) return rcode;
+    }
+    *h_selector_out = sel ^ 1;
+    return kmg_select_singletons(sel ? d_keys_alt : d_keys, sel ? d_vals_alt : d_vals, n, key_bytes, val_bytes,
+                                 sel ? d_keys : d_keys_alt, sel ? d_vals : d_vals_alt, d_n_out, (char*)d_ws + sort_ws,
+                                 ws_bytes - sort_ws, stream);
 }
 
 extern "C" size_t kmg_partition_workspace_bytes(uint64_t n, int key_bytes, int val_bytes) {

@@ -411,13 +411,11 @@ class DistributedCounter:
             except _PeerUnavailable as exc:
                 self._fall_back(exc)
             else:
-                r = self.eng.sort(r, 0, sort_bits_after_partition(r.key_bits, self.world))
-                return self.eng.singletons(r)
+                return self.eng.sort_uniq(r, sort_bits_after_partition(r.key_bits, self.world))
         a = self.eng.extract(d, k, rc, wide=False, val_bytes=8)
         n_other = torch.tensor([a.n_other], dtype=torch.int64, device=a.keys.device)
         dist.all_reduce(n_other, group=self.group)
         if int(n_other.item()):
             raise ValueError("distributed path handles the narrow (plain ACGT) stream only in this build")
         r = self._partition_exchange(a, with_vals=True)
-        r = self.eng.sort(r, 0, sort_bits_after_partition(r.key_bits, self.world))
-        return self.eng.singletons(r)
+        return self.eng.sort_uniq(r, sort_bits_after_partition(r.key_bits, self.world))

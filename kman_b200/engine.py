@@ -321,6 +321,29 @@ class Engine:
         n_out = int(self._small[2:3].cpu().numpy().view(np.uint64)[0])
         return CountTable(a.keys_alt, counts, n_out, a.key_bytes, a.k, a.wide)
 
+    def sort_uniq(self, a: KeyArray, end_bit: Optional[int] = None) -> KeyArray:
+        """sort() + singletons() in one native call (kmg_sort_uniq).  Repeated keys are dropped, so
+        their order is irrelevant and 8-byte keys take the hybrid finish with the payload.  Consumes `a`."""
+        end_bit = a.key_bits if end_bit is None else end_bit
+        assert a.val_bytes in (4, 8)
+        if a.n == 0:
+            return KeyArray(a.keys_alt, None, a.vals_alt, None, 0, a.key_bytes, a.val_bytes, a.k, a.wide, is_sorted=True)
+        ws_bytes = self.lib.kmg_sort_uniq_workspace_bytes(a.n, a.key_bytes, a.val_bytes, end_bit)
+        ws = self._buf("ws_sort", ws_bytes)
+        sel = C.c_int(0)
+        hist = a.hist if end_bit == a.key_bits else None
+        _lib.check(
+            self.lib.kmg_sort_uniq(a.keys.data_ptr(), a.keys_alt.data_ptr(), a.vals.data_ptr(), a.vals_alt.data_ptr(), a.n,
+                                   a.key_bytes, a.val_bytes, end_bit, _ptr(hist), self._small[2:].data_ptr(), C.byref(sel),
+                                   ws.data_ptr(), ws_bytes, self._stream())
+        )
+        a.hist = None
+        self._last_sort_ws = ws
+        self._status(ws)
+        n_out = int(self._small[2:3].cpu().numpy().view(np.uint64)[0])
+        k_, v_ = (a.keys_alt, a.vals_alt) if sel.value else (a.keys, a.vals)
+        return KeyArray(k_, None, v_, None, n_out, a.key_bytes, a.val_bytes, a.k, a.wide, is_sorted=True)
+
     def singletons(self, a: KeyArray) -> KeyArray:
         """Keys (+payload) that occur exactly once, ascending (written into the alt buffers)."""
         assert a.is_sorted
@@ -432,7 +455,17 @@ class Engine:
     def uniq(self, d: DeviceInput, k: int, rc: bool = False) -> List[KeyArray]:
         """`kmer uniq` on device: singleton keys with payload, one KeyArray per stream."""
         vb = 4 if ((d.pos_offset + d.n_bases) << 1) < (1 << 32) else 8
-        return [self.singletons(a) for a in self.sorted_streams(d, k, rc, vb)]
+        narrow = self.extract(d, k, rc, wide=False, val_bytes=vb, want_hist=True)
+        n_other = narrow.n_other
+        out = [self.sort_uniq(narrow)]
+        if n_other:
+            if k > 32:
+                raise ValueError(
+                    f"input holds {n_other} windows with non-ACGT alphabet symbols and k={k} > 32: "
+                    "the wide stream supports k <= 32 in this build (no CPU fallback)"
+                )
+            out.append(self.sort_uniq(self.extract(d, k, rc, wide=True, val_bytes=vb)))
+        return out
 
     # ---- text (interleaves the narrow and the wide stream in ASCII order) -----------------------
     def _interleave(self, texts: List[torch.Tensor], keys: List[torch.Tensor], ns: List[int], k: int, rna: int,

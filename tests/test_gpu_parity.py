@@ -823,3 +823,74 @@ def test_hybrid_sort_count_u128_skewed(eng, pattern):
     assert first_diff(keys, srt[idx]) == "equal", pattern
     assert first_diff(counts.astype(np.uint64), np.diff(np.append(idx, n)).astype(np.uint64)) == "equal", pattern
     assert eng.lib.kmg_get_stat(b"hybrid_path") == {"dup7": 1, "one_big_bucket": 2, "all_equal": 3, "low_limb_only": 3}[pattern]
+
+
+# ---- kmg_sort_uniq: sort (hybrid finish with payload) + singletons in one call --------------------------
+def _sort_uniq(eng, raw, vals, bits):
+    import torch
+
+    from kman_b200.engine import KeyArray
+
+    n = len(raw)
+    kb = 8 if raw.ndim == 1 else 16
+    vb = vals.dtype.itemsize
+    t = lambda x: torch.from_numpy(np.ascontiguousarray(x).view(np.uint8).reshape(-1)).to(eng.device)  # noqa: E731
+    z = lambda b: torch.zeros(max(b, 16), dtype=torch.uint8, device=eng.device)  # noqa: E731
+    a = KeyArray(t(raw), z(n * kb), t(vals), z(n * vb), n, kb, vb, bits // 2, False)
+    r = eng.sort_uniq(a, bits)
+    keys = r.keys[: r.n * kb].cpu().numpy().view(np.uint64)
+    got_v = r.vals[: r.n * vb].cpu().numpy().view(vals.dtype)
+    return (keys if kb == 8 else keys.reshape(-1, 2)), got_v
+
+
+def _want_singletons(raw, vals):
+    order = np.argsort(raw, kind="stable")
+    sk, sv = raw[order], vals[order]
+    head = np.ones(len(raw), bool)
+    head[1:] = sk[1:] != sk[:-1]
+    tail = np.ones(len(raw), bool)
+    tail[:-1] = sk[1:] != sk[:-1]
+    one = head & tail
+    return sk[one], sv[one]
+
+
+@pytest.mark.parametrize("n", [1, 2, 4097, 300_001, 1 << 20, 3_000_017])
+@pytest.mark.parametrize("vdt", [np.uint32, np.uint64])
+@pytest.mark.parametrize("dup", [1, 2, 30])
+def test_sort_uniq_u64_matches_numpy(eng, n, vdt, dup):
+    rng = np.random.default_rng(n + dup)
+    pool = rng.integers(0, 1 << 62, size=max(1, n // dup), dtype=np.uint64)
+    raw = pool[rng.integers(0, len(pool), size=n)] if dup > 1 else pool[:n]
+    vals = np.arange(n, dtype=vdt) * vdt(3) + vdt(1)
+    keys, got_v = _sort_uniq(eng, raw, vals, 62)
+    wk, wv = _want_singletons(raw, vals)
+    assert first_diff(keys, wk) == "equal", (n, dup)
+    assert first_diff(got_v.astype(np.uint64), wv.astype(np.uint64)) == "equal", (n, dup)
+    if n >= 1 << 20 and dup < 30:
+        assert eng.lib.kmg_get_stat(b"hybrid_path") == 1 and eng.lib.kmg_get_stat(b"sort_passes") == 2
+
+
+@pytest.mark.parametrize("pattern", ["one_big_bucket", "all_equal", "crowded_cells", "high_bits_constant"])
+def test_sort_uniq_skewed_inputs(eng, pattern):
+    n = 2_000_003
+    rng = np.random.default_rng(78)
+    rnd = rng.integers(0, 1 << 62, size=n, dtype=np.uint64)
+    bits = 62
+    if pattern == "one_big_bucket":
+        raw = rnd.copy()
+        raw[: n // 20] = (raw[: n // 20] & np.uint64((1 << 40) - 1)) | np.uint64(0x1F3 << 46)
+    elif pattern == "all_equal":
+        raw = np.full(n, 12345678901234567, np.uint64)
+    elif pattern == "crowded_cells":
+        raw = rnd.copy()
+        raw[:6000] = (raw[:6000] & np.uint64((1 << 30) - 1)) | np.uint64(0x2222_0000_0000_000)
+    else:
+        bits = 59
+        raw = (rnd & np.uint64((1 << 59) - 1)) | np.uint64(0b101 << 59)
+    vals = np.arange(n, dtype=np.uint64)
+    keys, got_v = _sort_uniq(eng, raw, vals, bits)
+    wk, wv = _want_singletons(raw, vals)
+    assert first_diff(keys, wk) == "equal", pattern
+    assert first_diff(got_v, wv) == "equal", pattern
+    assert eng.lib.kmg_get_stat(b"hybrid_path") == {"one_big_bucket": 2, "all_equal": 3, "crowded_cells": 2,
+                                                    "high_bits_constant": 1}[pattern]

@@ -142,11 +142,14 @@ def main():
     res["full_ms"] = med_full
 
     def full_uniq():
-        a = eng.sort(eng.extract(d, k, False, val_bytes=4, reuse="u_", want_hist=True))
-        return eng.singletons(a)
+        return eng.sort_uniq(eng.extract(d, k, False, val_bytes=4, reuse="u_", want_hist=True))
 
+    eng.lib.kmg_set_option(b"hybrid", 0)
     med_u, mn_u = timed(full_uniq, flush=flush)
-    print(f"full uniq (u32 payload): {med_u:8.3f} ms (min {mn_u:.3f})  {N/med_u/1e6:8.2f} G kmers/s")
+    print(f"full uniq (u32 payload, plain LSD passes): {med_u:8.3f} ms (min {mn_u:.3f})  {N/med_u/1e6:8.2f} G kmers/s")
+    eng.lib.kmg_set_option(b"hybrid", 1)
+    med_u, mn_u = timed(full_uniq, flush=flush)
+    print(f"full uniq (u32 payload): {med_u:8.3f} ms (min {mn_u:.3f})  {N/med_u/1e6:8.2f} G kmers/s  passes {eng.lib.kmg_get_stat(b'sort_passes')} path {eng.lib.kmg_get_stat(b'hybrid_path')}")
     res["full_uniq_ms"] = med_u
     if args.yardstick:
         a = eng.extract(d, k, False, val_bytes=0, reuse="b_", want_hist=True)
