@@ -580,10 +580,14 @@ struct CellMap {
 // VB != 0: the payload (4 or 8 bytes) follows its key: a 16-bit index array travels with the
 // staged keys and the payload is gathered from the tile's (L2-resident) input range at the end.
 // Equal keys come out in no particular order (kmg_sort_uniq only keeps keys that occur once).
-template <typename KeyT, bool COUNT, int VB>
+// EMIT: 0 = the sorted keys (and payload), 1 = the count table (COUNT above), 2 = the keys that
+// occur exactly once with their payload, compacted across tiles like the count table (kmg_sort_uniq).
+template <typename KeyT, int EMIT, int VB>
 __global__ void __launch_bounds__(LS_BLOCK, 2) local_sort_kernel(const HybridParams p) {
     constexpr bool PAIRS = VB != 0;
+    constexpr bool COUNT = EMIT == 1, UNIQ = EMIT == 2, FUSED = EMIT != 0;
     static_assert(!(PAIRS && COUNT), "the fused count is key-only");
+    static_assert(!UNIQ || PAIRS, "singletons carry their payload");
     constexpr int IPT = LS<KeyT, PAIRS>::IPT, CPT = LS<KeyT, PAIRS>::CPT;
     constexpr int CAP = ls_cap<KeyT, PAIRS>(), CELLS = ls_cells<KeyT, PAIRS>(), CELL_WORDS = ls_cell_words<KeyT, PAIRS>();
     constexpr int CELL_BITS = CELLS > 4096 ? 13 : 12;
@@ -602,17 +606,17 @@ __global__ void __launch_bounds__(LS_BLOCK, 2) local_sort_kernel(const HybridPar
 
     if (t == 0) {
         s_bad = 0;
-        if (COUNT) s_tile = atomicAdd(p.ticket, 1u);
+        if (FUSED) s_tile = atomicAdd(p.ticket, 1u);
     }
     {
         uint4* z = reinterpret_cast<uint4*>(s_cell);
         for (uint32_t i = t; i < (uint32_t)CELL_WORDS / 4; i += LS_BLOCK) z[i] = make_uint4(0, 0, 0, 0);
     }
-    if (COUNT) __syncthreads();
-    const uint32_t tile = COUNT ? s_tile : blockIdx.x;
+    if (FUSED) __syncthreads();
+    const uint32_t tile = FUSED ? s_tile : blockIdx.x;
     // a tile without output still takes part in the tile prefix (and the last one reports the total)
     auto finish_without_output = [&]() {
-        if constexpr (COUNT) {
+        if constexpr (FUSED) {
             if (t < 32) {
                 if (t == 0) tile_prefix_publish(p.tile_state, tile, 0);
                 const uint64_t base = tile_prefix_resolve_warp(p.tile_state, p.n_tiles, tile, 0, p.err);
@@ -745,7 +749,7 @@ __global__ void __launch_bounds__(LS_BLOCK, 2) local_sort_kernel(const HybridPar
         finish_without_output();
         return;
     }
-    if constexpr (!COUNT) {
+    if constexpr (!FUSED) {
         KeyT* kout = reinterpret_cast<KeyT*>(p.keys_out) + s;
 #pragma unroll
         for (int j = 0; j < IPT; ++j) {
@@ -760,6 +764,45 @@ __global__ void __launch_bounds__(LS_BLOCK, 2) local_sort_kernel(const HybridPar
                 const uint32_t idx = t + j * LS_BLOCK;
                 if (idx < m) vout[idx] = vin[s_idx[idx]];
             }
+        }
+    } else if constexpr (UNIQ) {
+        // keys that occur once: a run of equal keys lies inside one thread's run, so every thread
+        // finds the singletons of its own run; a block scan ranks them, the tile prefix places them
+        uint32_t* s_pos = s_cell;  // [m] positions of the singletons in order (the cell array is dead by now)
+        static_assert(CAP <= CELL_WORDS, "singleton positions must fit the cell array");
+        auto walk = [&](auto&& emit) {
+            KeyT prev{}, key{}, next{};
+            if (lo < hi) next = s_stage[lo];
+            for (uint32_t i = lo; i < hi; ++i) {
+                key = next;
+                const bool last = i + 1 == hi;
+                if (!last) next = s_stage[i + 1];
+                if ((i == lo || key != prev) && (last || key != next)) emit(i);
+                prev = key;
+            }
+        };
+        uint32_t hs = 0;
+        walk([&](uint32_t) { ++hs; });
+        uint32_t S;
+        uint32_t soff = block_excl_scan<LS_BLOCK, uint32_t>(hs, s_scan, S);  // (barriers: everyone is done with s_cell)
+        if (t == 0) tile_prefix_publish(p.tile_state, tile, S);
+        walk([&](uint32_t i) { s_pos[soff++] = i; });
+        if (t < 32) {
+            const uint64_t base = tile_prefix_resolve_warp(p.tile_state, p.n_tiles, tile, S, p.err);
+            if (t == 0) {
+                s_base = base;
+                if (tile == p.n_tiles - 1) *p.n_out = base + S;
+            }
+        }
+        __syncthreads();
+        const uint64_t base = s_base;
+        KeyT* kout = reinterpret_cast<KeyT*>(p.keys_out);
+        const ValT* vin = reinterpret_cast<const ValT*>(p.vals_in) + s;
+        ValT* vout = reinterpret_cast<ValT*>(p.vals_out);
+        for (uint32_t h = t; h < S; h += LS_BLOCK) {
+            const uint32_t i = s_pos[h];
+            kout[base + h] = s_stage[i];
+            vout[base + h] = vin[s_idx[i]];
         }
     } else {
         // the runs tile [0, m) in thread order, so a block scan of the per-thread head counts ranks
@@ -1044,7 +1087,7 @@ thread_local int64_t g_stat_hybrid_path = 0;  // 0 plain passes, 1 hybrid, 2 hyb
 
 // fused run-length count request (kmg_sort_count): `done` = the hybrid finish produced the table
 struct CountOut {
-    uint32_t* counts;
+    uint32_t* counts;  // null: the request is for singletons with payload (kmg_sort_uniq)
     unsigned long long* n_out;
     bool done;
 };
@@ -1220,12 +1263,14 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
         if (!attrs_set) {
             const int s64 = (int)ls_smem_bytes<uint64_t, false>(), s128 = (int)ls_smem_bytes<u128, false>(),
                       sp = (int)ls_smem_bytes<uint64_t, true>();
-            KMG_CUDA(cudaFuncSetAttribute(local_sort_kernel<uint64_t, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, s64));
-            KMG_CUDA(cudaFuncSetAttribute(local_sort_kernel<uint64_t, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, s64));
-            KMG_CUDA(cudaFuncSetAttribute(local_sort_kernel<u128, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, s128));
-            KMG_CUDA(cudaFuncSetAttribute(local_sort_kernel<u128, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, s128));
-            KMG_CUDA(cudaFuncSetAttribute(local_sort_kernel<uint64_t, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp));
-            KMG_CUDA(cudaFuncSetAttribute(local_sort_kernel<uint64_t, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp));
+            KMG_CUDA(cudaFuncSetAttribute(local_sort_kernel<uint64_t, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, s64));
+            KMG_CUDA(cudaFuncSetAttribute(local_sort_kernel<uint64_t, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, s64));
+            KMG_CUDA(cudaFuncSetAttribute(local_sort_kernel<u128, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, s128));
+            KMG_CUDA(cudaFuncSetAttribute(local_sort_kernel<u128, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, s128));
+            KMG_CUDA(cudaFuncSetAttribute(local_sort_kernel<uint64_t, 0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp));
+            KMG_CUDA(cudaFuncSetAttribute(local_sort_kernel<uint64_t, 0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp));
+            KMG_CUDA(cudaFuncSetAttribute(local_sort_kernel<uint64_t, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp));
+            KMG_CUDA(cudaFuncSetAttribute(local_sort_kernel<uint64_t, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp));
             attrs_set = true;
         }
     }
@@ -1261,15 +1306,18 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
         }
         if (g_ev_used >= MAX_TIMED) timing_collect();
         timing_begin(st);
-        if (fused) {
-            if (wide_key) local_sort_kernel<u128, true, 0><<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);
-            else local_sort_kernel<uint64_t, true, 0><<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);
+        if (fused && pairs) {
+            if (val_bytes == 4) local_sort_kernel<uint64_t, 2, 4><<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);
+            else local_sort_kernel<uint64_t, 2, 8><<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);
+        } else if (fused) {
+            if (wide_key) local_sort_kernel<u128, 1, 0><<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);
+            else local_sort_kernel<uint64_t, 1, 0><<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);
         } else if (pairs) {
-            if (val_bytes == 4) local_sort_kernel<uint64_t, false, 4><<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);
-            else local_sort_kernel<uint64_t, false, 8><<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);
+            if (val_bytes == 4) local_sort_kernel<uint64_t, 0, 4><<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);
+            else local_sort_kernel<uint64_t, 0, 8><<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);
         } else {
-            if (wide_key) local_sort_kernel<u128, false, 0><<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);
-            else local_sort_kernel<uint64_t, false, 0><<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);
+            if (wide_key) local_sort_kernel<u128, 0, 0><<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);
+            else local_sort_kernel<uint64_t, 0, 0><<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);
         }
         timing_end(st, 1);
         KMG_LAUNCH_CHECK();
@@ -1431,12 +1479,17 @@ extern "C" int kmg_sort_uniq(void* d_keys, void* d_keys_alt, void* d_vals, void*
     const size_t sort_ws = sort_uniq_sort_ws(n, key_bytes, val_bytes, end_bit);
     KMG_REQUIRE(ws_bytes >= sort_ws + kmg_rle_workspace_bytes(n), KMG_ERR_WS, "sort_uniq workspace too small");
     int sel = 0;
+    CountOut uo{nullptr, reinterpret_cast<unsigned long long*>(d_n_out), false};
     if (n > 1 && end_bit > 0) {
         // equal keys may come out in any order: only keys that occur once are kept
         const bool hybrid = hybrid_applies(n, key_bytes, val_bytes, 0, end_bit, true);
         const int rcode = sort_impl(d_keys, d_keys_alt, d_vals, d_vals_alt, n, key_bytes, val_bytes, 0, end_bit, d_hist_in, &sel,
-                                    d_ws, sort_ws, st, hybrid, true);
+                                    d_ws, sort_ws, st, hybrid, true, &uo);
         if (rcode != KMG_OK) return rcode;
+    }
+    if (uo.done) {  // the hybrid finish emitted the singletons itself
+        *h_selector_out = sel;
+        return KMG_OK;
     }
     *h_selector_out = sel ^ 1;
     return kmg_select_singletons(sel ? d_keys_alt : d_keys, sel ? d_vals_alt : d_vals, n, key_bytes, val_bytes,
