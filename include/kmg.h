@@ -134,7 +134,8 @@ int kmg_sort_count(void* d_keys, void* d_keys_alt, uint64_t n, int key_bytes, in
  * Leaves the keys that occur exactly once, ascending, with their payload in (d_keys, d_vals)
  * (*h_selector_out = 0) or (d_keys_alt, d_vals_alt) (1); *d_n_out (device) = their number.  Because
  * repeated keys are dropped, their relative order does not matter and 8-byte keys take the
- * hybrid finish with the payload following through a 16-bit index (6144-key tiles). */
+ * hybrid finish with the payload following through a 16-bit index (6144-key tiles); its local
+ * sort emits the singletons itself unless irregular tiles force sort + kmg_select_singletons. */
 size_t kmg_sort_uniq_workspace_bytes(uint64_t n, int key_bytes, int val_bytes, int end_bit);
 int kmg_sort_uniq(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_alt, uint64_t n, int key_bytes,
                   int val_bytes, int end_bit, const uint64_t* d_hist_in, uint64_t* d_n_out, int* h_selector_out,
