@@ -469,7 +469,8 @@ __host__ __device__ constexpr size_t ls_smem_bytes() {
            (PAIRS ? sizeof(uint16_t) * ls_cap<KeyT, PAIRS>() : 0);
 }
 constexpr int LS_T_MIN = 1024;             // smallest run-time tile width (workspace sizing)
-constexpr int LS_SORT_BUDGET = 4096;       // insertion-sort moves one thread may spend before the tile gives up
+constexpr int LS_SORT_BUDGET = 128;        // insertion-sort moves one thread may spend before its run is sorted by the whole block
+constexpr int LS_MAX_BIG = 48;             // such runs per tile (more: the tile gives up)
 
 // low 64 bits of (key >> s): prefix / cell arithmetic works modulo 2^64 (keys agree above end_bit)
 __device__ __forceinline__ uint64_t shr64(uint64_t k, int s) { return k >> s; }
@@ -553,11 +554,14 @@ __global__ void __launch_bounds__(256) tile_bounds_kernel(const HybridParams p) 
 // Tiles that own more keys than the local sort holds are known from the bounds alone: count them
 // before the launch so that a fused count is not attempted in vain (repeats: real genomes always
 // have some).  The local sort flags them again, together with the rare crowded-cell tiles.
-__global__ void __launch_bounds__(256) oversize_tiles_kernel(const HybridParams p, uint32_t cap, unsigned long long* n_oversize) {
+__global__ void __launch_bounds__(256) oversize_tiles_kernel(const HybridParams p, uint32_t cap, unsigned long long* over) {
     const uint32_t tile = blockIdx.x * blockDim.x + threadIdx.x;
     if (tile >= p.n_tiles) return;
     const uint64_t s = p.bounds[tile], e = p.bounds[tile + 1];
-    if (s < min((uint64_t)(tile + 1) * p.tile_t, p.n) && e > s && e - s > cap) atomicAdd(n_oversize, 1ull);
+    if (s < min((uint64_t)(tile + 1) * p.tile_t, p.n) && e > s && e - s > cap) {
+        atomicAdd(&over[0], 1ull);              // tiles
+        atomicAdd(&over[1], (unsigned long long)(e - s));  // keys
+    }
 }
 
 // monotone map key -> cell of the tile's counting sort (see local_sort_kernel)
@@ -601,11 +605,14 @@ __global__ void __launch_bounds__(LS_BLOCK, 2) local_sort_kernel(const HybridPar
     __shared__ int s_bad;
     __shared__ uint32_t s_tile;
     __shared__ uint64_t s_base;
+    __shared__ uint32_t s_big_n;
+    __shared__ uint32_t s_big[LS_MAX_BIG][2];
     const int t = threadIdx.x;
     const int sh_pref = p.key_bits - p.pb;
 
     if (t == 0) {
         s_bad = 0;
+        s_big_n = 0;
         if (FUSED) s_tile = atomicAdd(p.ticket, 1u);
     }
     {
@@ -710,6 +717,7 @@ __global__ void __launch_bounds__(LS_BLOCK, 2) local_sort_kernel(const HybridPar
     // COUNT: equal keys share a cell, hence a thread's run, so the run heads (distinct keys) can be
     // counted while inserting: a key is new unless it lands right after an equal one
     uint32_t hc = 0;
+    bool my_run_is_big = false;
     {
         int budget = LS_SORT_BUDGET;
         KeyT prev{};
@@ -738,7 +746,83 @@ __global__ void __launch_bounds__(LS_BLOCK, 2) local_sort_kernel(const HybridPar
             if (COUNT) hc += (!more || below != key) ? 1u : 0u;
             if (budget < 0) break;
         }
-        if (budget < 0) s_bad = 1;
+        if (budget < 0) {
+            // many DISTINCT keys that agree in all the bits the cells see (diverged copies of a repeat):
+            // the run (still a permutation of itself) is left to the whole block, below
+            my_run_is_big = true;
+            const uint32_t slot = atomicAdd(&s_big_n, 1u);
+            if (slot < (uint32_t)LS_MAX_BIG) {
+                s_big[slot][0] = lo;
+                s_big[slot][1] = hi;
+            } else {
+                s_bad = 1;
+            }
+        }
+    }
+    __syncthreads();
+    if (s_big_n != 0 && !s_bad) {
+        // bitonic sort of every big run by the whole block, in the (now dead) cell array, padded to a
+        // power of two with all-ones keys (O(s log^2 s): a repeat family puts hundreds of distinct
+        // keys into one cell, and there are thousands of such cells in a genome)
+        constexpr uint32_t TEMP_CAP = (uint32_t)(CELL_WORDS * sizeof(uint32_t) / (sizeof(KeyT) + (PAIRS ? 2 : 0)));
+        constexpr uint32_t TEMP_POW2 = TEMP_CAP >= 4096 ? 4096 : (TEMP_CAP >= 2048 ? 2048 : 1024);
+        static_assert(TEMP_POW2 <= TEMP_CAP, "bitonic buffer");
+        KeyT* tmp_k = reinterpret_cast<KeyT*>(s_cell);
+        uint16_t* tmp_i = reinterpret_cast<uint16_t*>(tmp_k + TEMP_POW2);
+        const uint32_t nb = s_big_n;
+        for (uint32_t b = 0; b < nb; ++b) {
+            const uint32_t blo = s_big[b][0], sz = s_big[b][1] - blo;
+            if (sz > TEMP_POW2) {
+                s_bad = 1;  // (every thread takes the same branch)
+                break;
+            }
+            uint32_t N = 64;
+            while (N < sz) N <<= 1;
+            for (uint32_t e = t; e < N; e += LS_BLOCK) {
+                tmp_k[e] = e < sz ? s_stage[blo + e] : key_all_ones(KeyT{});
+                if constexpr (PAIRS) tmp_i[e] = e < sz ? s_idx[blo + e] : (uint16_t)0xFFFF;  // padding sorts last
+            }
+            __syncthreads();
+            for (uint32_t kk = 2; kk <= N; kk <<= 1) {
+                for (uint32_t jj = kk >> 1; jj > 0; jj >>= 1) {
+                    for (uint32_t e = t; e < N / 2; e += LS_BLOCK) {
+                        // e-th compare-exchange of this stage: partner indices i < l = i ^ jj
+                        const uint32_t i = ((e & ~(jj - 1)) << 1) | (e & (jj - 1));
+                        const uint32_t l = i | jj;
+                        const bool up = (i & kk) == 0;
+                        const KeyT a0 = tmp_k[i], a1 = tmp_k[l];
+                        bool less = a1 < a0;
+                        if constexpr (PAIRS) {  // total order (key, index): the padding can never displace a real pair
+                            const uint16_t i0 = tmp_i[i], i1 = tmp_i[l];
+                            less = less || (a1 == a0 && i1 < i0);
+                            if (less == up) {
+                                tmp_i[i] = i1;
+                                tmp_i[l] = i0;
+                            }
+                        }
+                        if (less == up) {
+                            tmp_k[i] = a1;
+                            tmp_k[l] = a0;
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+            for (uint32_t e = t; e < sz; e += LS_BLOCK) {
+                s_stage[blo + e] = tmp_k[e];
+                if constexpr (PAIRS) s_idx[blo + e] = tmp_i[e];
+            }
+            __syncthreads();
+        }
+        if (COUNT && my_run_is_big && !s_bad) {  // heads of my run, now that it is sorted
+            hc = 0;
+            KeyT prev{};
+            for (uint32_t i = lo; i < hi; ++i) {
+                const KeyT key = s_stage[i];
+                hc += (i == lo || key != prev) ? 1u : 0u;
+                prev = key;
+            }
+        }
     }
     __syncthreads();
     if (s_bad) {  // too many distinct keys crowded into one cell: leave the tile to the fallback
@@ -1239,23 +1323,19 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
     // 16-bit prefix the buckets are a sizeable fraction of a tile and a width of k average buckets
     // gives (for evenly filled buckets) every tile the same k buckets instead of k-1 or k
     const double avg = (double)n / (double)(1ull << pb);  // average prefix bucket
-    double target = std::min<double>(g_local_tile, cap - std::max(256.0, 1.35 * avg));
-    target = std::max<double>(target, LS_T_MIN);
-    hp.tile_t = (uint32_t)target;
-    if (avg >= 64) {
+    auto tile_width = [&](double want) {
+        double target = std::min<double>(want, cap - std::max(256.0, 1.35 * avg));
+        target = std::max<double>(target, LS_T_MIN);
+        if (avg < 64) return (uint32_t)target;
         const int kbk = std::max(1, (int)(target / avg));
-        hp.tile_t = (uint32_t)std::min<double>(cap - 256, std::max<double>(LS_T_MIN, std::ceil(kbk * avg)));
-    }
-    hp.n_tiles = (uint32_t)((n + hp.tile_t - 1) / hp.tile_t);
+        return (uint32_t)std::min<double>(cap - 256, std::max<double>(LS_T_MIN, std::ceil(kbk * avg)));
+    };
     hp.bounds = w.hyb_bounds;
     hp.flag = w.hyb_flag;
     hp.off = w.hyb_off;
     hp.key_bits = end_bit;
     hp.pb = pb;
     hp.irregular = reinterpret_cast<unsigned long long*>(&w.hdr->pad[0]);  // 8-byte aligned slot of the header
-    if (wide_key) tile_bounds_kernel<u128><<<(hp.n_tiles + 1 + 7) / 8, 256, 0, st>>>(hp);
-    else tile_bounds_kernel<uint64_t><<<(hp.n_tiles + 1 + 7) / 8, 256, 0, st>>>(hp);
-    KMG_LAUNCH_CHECK();
     const size_t smem = wide_key ? ls_smem_bytes<u128, false>()
                                  : (pairs ? ls_smem_bytes<uint64_t, true>() : ls_smem_bytes<uint64_t, false>());
     {
@@ -1277,18 +1357,42 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
     const int sel_done = (np + 1) & 1;  // kout is d_keys_alt when np is even
     unsigned long long irregular = 0;
     bool try_fused = co != nullptr && g_count_fused;
-    // (adaptive: the check costs a stream synchronisation, so it runs only after a fused attempt of
-    // this thread was void; it switches itself off again when it finds nothing)
+    // Tile width.  The widest tiles are the fastest, but a tile owns WHOLE buckets: with big buckets
+    // around (repeat families: thousands of keys per 12-mer prefix) wide tiles overflow.  After a
+    // call of this thread met irregular tiles, the next ones first count the oversize tiles for the
+    // candidate widths (tile bounds + one tiny kernel + a stream synchronisation each) and take the
+    // widest one that leaves at most n/32 keys in oversize tiles; the check switches itself off
+    // again when the widest width has none.  A fused count / uniq is attempted only without them.
     static thread_local bool expect_oversize = false;
-    if (try_fused && expect_oversize) {
-        unsigned long long* d_over = reinterpret_cast<unsigned long long*>(&w.hdr->pad[2]);
-        unsigned long long n_over = 0;
-        oversize_tiles_kernel<<<(hp.n_tiles + 255) / 256, 256, 0, st>>>(hp, (uint32_t)cap, d_over);
+    auto launch_bounds = [&](uint32_t T) -> int {
+        hp.tile_t = T;
+        hp.n_tiles = (uint32_t)((n + T - 1) / T);
+        if (wide_key) tile_bounds_kernel<u128><<<(hp.n_tiles + 1 + 7) / 8, 256, 0, st>>>(hp);
+        else tile_bounds_kernel<uint64_t><<<(hp.n_tiles + 1 + 7) / 8, 256, 0, st>>>(hp);
         KMG_LAUNCH_CHECK();
-        KMG_CUDA(cudaMemcpyAsync(&n_over, d_over, sizeof(n_over), cudaMemcpyDeviceToHost, st));
-        KMG_CUDA(cudaStreamSynchronize(st));
-        if (n_over) try_fused = false;  // the table would be void: sort, re-sort those ranges, then count
-        else expect_oversize = false;
+        return KMG_OK;
+    };
+    const uint32_t t_wide = tile_width(g_local_tile);
+    if (!expect_oversize) {
+        const int rc0 = launch_bounds(t_wide);
+        if (rc0 != KMG_OK) return rc0;
+    } else {
+        unsigned long long* d_over = reinterpret_cast<unsigned long long*>(&w.hdr->pad[6]);  // 2 words
+        unsigned long long over[2] = {0, 0};
+        const uint32_t cand[3] = {t_wide, tile_width(cap / 2), tile_width(cap / 4)};
+        for (int c = 0; c < 3; ++c) {
+            if (c > 0 && cand[c] >= cand[c - 1]) continue;
+            const int rc0 = launch_bounds(cand[c]);
+            if (rc0 != KMG_OK) return rc0;
+            KMG_CUDA(cudaMemsetAsync(d_over, 0, 2 * sizeof(unsigned long long), st));
+            oversize_tiles_kernel<<<(hp.n_tiles + 255) / 256, 256, 0, st>>>(hp, (uint32_t)cap, d_over);
+            KMG_LAUNCH_CHECK();
+            KMG_CUDA(cudaMemcpyAsync(over, d_over, sizeof(over), cudaMemcpyDeviceToHost, st));
+            KMG_CUDA(cudaStreamSynchronize(st));
+            if (over[1] <= n / 32) break;
+        }
+        if (over[0]) try_fused = false;  // the table would be void: sort, re-sort those ranges, then count
+        else if (hp.tile_t == t_wide) expect_oversize = false;
     }
     for (int attempt = 0; attempt < 2; ++attempt) {
         const bool fused = try_fused && attempt == 0;
@@ -1330,7 +1434,7 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
             *h_selector_out = sel_done;
             return KMG_OK;
         }
-        if (fused) expect_oversize = true;
+        expect_oversize = true;
     }
     // Some tiles own more keys than the local scheme holds (a huge prefix bucket: repeats).  Their
     // ranges are gathered, sorted with the plain passes and put back -- unless they are most of the

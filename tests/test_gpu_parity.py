@@ -894,3 +894,35 @@ def test_sort_uniq_skewed_inputs(eng, pattern):
     assert first_diff(got_v, wv) == "equal", pattern
     assert eng.lib.kmg_get_stat(b"hybrid_path") == {"one_big_bucket": 2, "all_equal": 3, "crowded_cells": 2,
                                                     "high_bits_constant": 1}[pattern]
+
+
+@pytest.mark.parametrize("mode", ["sort", "count", "uniq"])
+def test_hybrid_crowded_runs_are_sorted_by_the_block(eng, mode):
+    """Hundreds of DISTINCT keys that agree in every bit the cells look at (diverged copies of a
+    repeat family): the thread that owns them hands the run to the whole block (rank sort) instead
+    of giving the tile up -- the local sort still finishes everything (hybrid_path 1)."""
+    n = 1_500_007
+    rng = np.random.default_rng(2024)
+    raw = rng.integers(0, 1 << 62, size=n, dtype=np.uint64)
+    for j in range(300):  # 300 groups of 500 keys sharing their top 40 bits; a few exact duplicates inside
+        seg = slice(j * 500, (j + 1) * 500)
+        top = rng.integers(0, 1 << 40, dtype=np.uint64) << np.uint64(22)
+        raw[seg] = top | (raw[seg] & np.uint64((1 << 22) - 1))
+        raw[j * 500 + 7] = raw[j * 500 + 3]
+    if mode == "sort":
+        a = _keyonly_sort(eng, raw, 62)
+        assert first_diff(a.keys_host(), np.sort(raw)) == "equal"
+    elif mode == "count":
+        keys, counts = _sort_count(eng, raw, 62)
+        wk, wc = np.unique(raw, return_counts=True)
+        assert first_diff(keys, wk) == "equal"
+        assert first_diff(counts.astype(np.uint64), wc.astype(np.uint64)) == "equal"
+    else:
+        vals = np.arange(n, dtype=np.uint32)
+        keys, got_v = _sort_uniq(eng, raw, vals, 62)
+        wk, wv = _want_singletons(raw, vals)
+        assert first_diff(keys, wk) == "equal"
+        assert first_diff(got_v.astype(np.uint64), wv.astype(np.uint64)) == "equal"
+    # (a 500-key bucket that straddles the end of a full-width tile can still overflow it: path 2)
+    assert eng.lib.kmg_get_stat(b"hybrid_path") in (1, 2)
+    assert eng.lib.kmg_get_stat(b"hybrid_irregular") <= 40
