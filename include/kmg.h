@@ -246,7 +246,9 @@ int kmg_uniq_host(kmg_ctx* ctx, const uint8_t* h_bases, uint64_t n_bases, int k,
  *   "time_passes" [0]      bracket every onesweep / local sort launch with CUDA events
  * Stats of the calling thread's last call: "launches" (kernel launches since "reset_launches"),
  * "sort_passes", "hybrid_path" (0 plain passes, 1 hybrid, 2 hybrid + re-sorted ranges, 3 fell
- * back), "hybrid_irregular" (tiles), and with time_passes: "sort_pass_ns" / "sort_pass_count",
+ * back), "hybrid_irregular" (tiles), "hybrid_big_runs" (runs a whole block had to sort),
+ * "hybrid_backoff" (sorts of this thread that will still skip the hybrid finish after crowded
+ * data; setting the "hybrid" option resets it), and with time_passes: "sort_pass_ns" / "sort_pass_count",
  * "local_sort_ns" / "local_sort_count" (device time of the timed launches). */
 int kmg_set_option(const char* name, int64_t value);
 int64_t kmg_get_stat(const char* name);

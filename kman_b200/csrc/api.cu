@@ -22,6 +22,8 @@ extern int g_hybrid_unstable;
 extern int g_local_tile;
 extern thread_local int64_t g_stat_hybrid_irregular;
 extern thread_local int64_t g_stat_hybrid_path;
+extern thread_local int64_t g_stat_hybrid_big_runs;
+extern thread_local int g_hybrid_backoff;
 extern int g_prefetch_tiles;
 extern thread_local int64_t g_stat_sort_passes;
 void timing_collect();
@@ -79,6 +81,7 @@ extern "C" int kmg_set_option(const char* name, int64_t value) {
         return KMG_OK;
     }
     if (!strcmp(name, "hybrid")) {
+        g_hybrid_backoff = 0;
         g_hybrid = value != 0;
         return KMG_OK;
     }
@@ -107,6 +110,8 @@ extern "C" int64_t kmg_get_stat(const char* name) {
     if (!strcmp(name, "sort_passes")) return g_stat_sort_passes;
     if (!strcmp(name, "hybrid_irregular")) return g_stat_hybrid_irregular;
     if (!strcmp(name, "hybrid_path")) return g_stat_hybrid_path;
+    if (!strcmp(name, "hybrid_big_runs")) return g_stat_hybrid_big_runs;
+    if (!strcmp(name, "hybrid_backoff")) return g_hybrid_backoff;
     if (!strcmp(name, "sort_pass_ns")) {  // total device time of the timed onesweep launches
         timing_collect();
         return (int64_t)(timing_total_ms(0) * 1e6);

@@ -492,7 +492,7 @@ struct HybridParams {
     uint32_t n_tiles;
     uint32_t tile_t;        // positions per tile
     int key_bits, pb;
-    unsigned long long* irregular;  // number of tiles the local scheme could not handle
+    unsigned long long* irregular;  // [0] tiles the local scheme could not handle, [1] runs the block had to sort
     // fused run-length count (local_sort_kernel<.., true>): distinct keys -> keys_out, compacted
     uint32_t* counts_out;
     unsigned long long* n_out;      // number of distinct keys
@@ -770,6 +770,7 @@ __global__ void __launch_bounds__(LS_BLOCK, 2) local_sort_kernel(const HybridPar
         KeyT* tmp_k = reinterpret_cast<KeyT*>(s_cell);
         uint16_t* tmp_i = reinterpret_cast<uint16_t*>(tmp_k + TEMP_POW2);
         const uint32_t nb = s_big_n;
+        if (t == 0) atomicAdd(&p.irregular[1], (unsigned long long)nb);
         for (uint32_t b = 0; b < nb; ++b) {
             const uint32_t blo = s_big[b][0], sz = s_big[b][1] - blo;
             if (sz > TEMP_POW2) {
@@ -1168,6 +1169,8 @@ static bool hybrid_applies(uint64_t n, int key_bytes, int val_bytes, int begin_b
 }
 
 thread_local int64_t g_stat_hybrid_path = 0;  // 0 plain passes, 1 hybrid, 2 hybrid + re-sorted ranges, 3 fell back
+thread_local int64_t g_stat_hybrid_big_runs = -1;
+thread_local int g_hybrid_backoff = 0;        // sorts of this thread that skip the hybrid finish (see sort_impl)
 
 // fused run-length count request (kmg_sort_count): `done` = the hybrid finish produced the table
 struct CountOut {
@@ -1184,6 +1187,10 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
     SortWs w = carve_sort_ws(d_ws, n, key_bytes, hybrid, val_bytes);
     KMG_REQUIRE(ws_bytes >= w.total, KMG_ERR_WS, "sort workspace too small: %zu < %zu", ws_bytes, w.total);
     hybrid = hybrid && allow_hybrid;
+    if (hybrid && g_hybrid_backoff > 0 && g_hybrid_pb == 0) {
+        --g_hybrid_backoff;
+        hybrid = false;
+    }
 
     PassPlan plan = make_plan(begin_bit, end_bit);
     int np = plan.num_passes;
@@ -1405,7 +1412,7 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
             hp.err = &w.hdr->err;
         } else if (co != nullptr) {
             // the fused launch met irregular tiles: its table is void, sort the keys instead
-            KMG_CUDA(cudaMemsetAsync(hp.irregular, 0, sizeof(unsigned long long), st));
+            KMG_CUDA(cudaMemsetAsync(hp.irregular, 0, 2 * sizeof(unsigned long long), st));
             KMG_CUDA(cudaMemsetAsync(hp.flag, 0, (size_t)(hp.n_tiles + 1) * sizeof(uint32_t), st));
         }
         if (g_ev_used >= MAX_TIMED) timing_collect();
@@ -1425,9 +1432,16 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
         }
         timing_end(st, 1);
         KMG_LAUNCH_CHECK();
-        KMG_CUDA(cudaMemcpyAsync(&irregular, hp.irregular, sizeof(irregular), cudaMemcpyDeviceToHost, st));
+        unsigned long long fb[2] = {0, 0};
+        KMG_CUDA(cudaMemcpyAsync(fb, hp.irregular, sizeof(fb), cudaMemcpyDeviceToHost, st));
         KMG_CUDA(cudaStreamSynchronize(st));
+        irregular = fb[0];
         g_stat_hybrid_irregular = (int64_t)irregular;
+        g_stat_hybrid_big_runs = (int64_t)fb[1];
+        // Keys crowded into cells by the thousand (diverged copies of repeat families) make the local
+        // sort slower than the passes it replaces: leave the next sorts of this thread to the plain
+        // passes, then probe again.
+        if (fb[1] > hp.n_tiles / 8) g_hybrid_backoff = 16;
         g_stat_hybrid_path = 1;
         if (irregular == 0) {
             if (fused) co->done = true;

@@ -19,6 +19,14 @@ def eng():
     return get_engine()
 
 
+@pytest.fixture(autouse=True)
+def _fresh_sort_heuristics(eng):
+    """The hybrid sort adapts to what the calling thread saw before (tile width search, back-off
+    after crowded data); every test starts from the default state."""
+    eng.lib.kmg_set_option(b"hybrid", 1)
+    yield
+
+
 def _flat(recs):
     from kman_b200 import fasta
 
@@ -926,3 +934,23 @@ def test_hybrid_crowded_runs_are_sorted_by_the_block(eng, mode):
     # (a 500-key bucket that straddles the end of a full-width tile can still overflow it: path 2)
     assert eng.lib.kmg_get_stat(b"hybrid_path") in (1, 2)
     assert eng.lib.kmg_get_stat(b"hybrid_irregular") <= 40
+
+
+def test_hybrid_backs_off_after_crowded_data(eng):
+    """Thousands of crowded cells: the sort is still exact, and the thread leaves its next sorts to
+    the plain passes (hybrid_backoff > 0) until it probes again."""
+    n = 1_200_011
+    rng = np.random.default_rng(5150)
+    raw = rng.integers(0, 1 << 62, size=n, dtype=np.uint64)
+    g = 1000  # 1000 groups of 300 distinct keys sharing their top 40 bits
+    tops = rng.integers(0, 1 << 40, size=g, dtype=np.uint64) << np.uint64(22)
+    raw[: g * 300] = np.repeat(tops, 300) | (raw[: g * 300] & np.uint64((1 << 22) - 1))
+    a = _keyonly_sort(eng, raw, 62)
+    assert first_diff(a.keys_host(), np.sort(raw)) == "equal"
+    assert eng.lib.kmg_get_stat(b"hybrid_big_runs") >= 500
+    assert eng.lib.kmg_get_stat(b"hybrid_backoff") > 0
+    a = _keyonly_sort(eng, raw, 62)
+    assert eng.lib.kmg_get_stat(b"hybrid_path") == 0 and eng.lib.kmg_get_stat(b"sort_passes") == 8
+    assert first_diff(a.keys_host(), np.sort(raw)) == "equal"
+    eng.lib.kmg_set_option(b"hybrid", 1)  # (resets the back-off)
+    assert eng.lib.kmg_get_stat(b"hybrid_backoff") == 0
