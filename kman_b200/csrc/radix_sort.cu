@@ -469,7 +469,8 @@ __host__ __device__ constexpr size_t ls_smem_bytes() {
            (PAIRS ? sizeof(uint16_t) * ls_cap<KeyT, PAIRS>() : 0);
 }
 constexpr int LS_T_MIN = 1024;             // smallest run-time tile width (workspace sizing)
-constexpr int LS_SORT_BUDGET = 128;        // insertion-sort moves one thread may spend before its run is sorted by the whole block
+constexpr int LS_THREAD_RUN_MAX = 24;      // keys a thread insertion-sorts itself
+constexpr int LS_WARP_RUN_MAX = 128;       // keys a warp rank-sorts; longer runs go to the whole block
 constexpr int LS_MAX_BIG = 48;             // such runs per tile (more: the tile gives up)
 
 // low 64 bits of (key >> s): prefix / cell arithmetic works modulo 2^64 (keys agree above end_bit)
@@ -717,9 +718,26 @@ __global__ void __launch_bounds__(LS_BLOCK, 2) local_sort_kernel(const HybridPar
     // COUNT: equal keys share a cell, hence a thread's run, so the run heads (distinct keys) can be
     // counted while inserting: a key is new unless it lands right after an equal one
     uint32_t hc = 0;
-    bool my_run_is_big = false;
-    {
-        int budget = LS_SORT_BUDGET;
+    bool my_run_is_big = false;   // sorted by the warp or by the block: heads are recounted afterwards
+    const uint32_t run_len = hi - lo;
+    // Who sorts a run: its thread by insertion (the normal ~11 keys), its WARP by rank sort when it
+    // holds 25..128 keys (a crowded cell: near-copies of a repeat; one thread would spend hundreds of
+    // serial moves while the block waits), the whole BLOCK (bitonic, below) beyond that.
+    const bool by_block = run_len > (uint32_t)LS_WARP_RUN_MAX;
+    const bool by_warp = !by_block && run_len > (uint32_t)LS_THREAD_RUN_MAX;
+    uint32_t warp_runs = __ballot_sync(0xffffffffu, by_warp);
+    if (by_block) {
+        my_run_is_big = true;
+        const uint32_t slot = atomicAdd(&s_big_n, 1u);
+        if (slot < (uint32_t)LS_MAX_BIG) {
+            s_big[slot][0] = lo;
+            s_big[slot][1] = hi;
+        } else {
+            s_bad = 1;
+        }
+    } else if (by_warp) {
+        my_run_is_big = true;
+    } else {
         KeyT prev{};
         for (uint32_t i = lo; i < hi; ++i) {
             const KeyT key = s_stage[i];
@@ -737,27 +755,44 @@ __global__ void __launch_bounds__(LS_BLOCK, 2) local_sort_kernel(const HybridPar
                 s_stage[qi] = s_stage[qi - 1];
                 if constexpr (PAIRS) s_idx[qi] = s_idx[qi - 1];
                 --qi;
-                --budget;
                 more = qi > lo;
                 if (more) below = s_stage[qi - 1];
             } while (more && key < below);
             s_stage[qi] = key;
             if constexpr (PAIRS) s_idx[qi] = my_idx;
             if (COUNT) hc += (!more || below != key) ? 1u : 0u;
-            if (budget < 0) break;
         }
-        if (budget < 0) {
-            // many DISTINCT keys that agree in all the bits the cells see (diverged copies of a repeat):
-            // the run (still a permutation of itself) is left to the whole block, below
-            my_run_is_big = true;
-            const uint32_t slot = atomicAdd(&s_big_n, 1u);
-            if (slot < (uint32_t)LS_MAX_BIG) {
-                s_big[slot][0] = lo;
-                s_big[slot][1] = hi;
-            } else {
-                s_bad = 1;
+    }
+    while (warp_runs) {  // (warp-uniform)
+        const int src = __ffs(warp_runs) - 1;
+        warp_runs &= warp_runs - 1;
+        const uint32_t rlo = __shfl_sync(0xffffffffu, lo, src), rlen = __shfl_sync(0xffffffffu, run_len, src);
+        constexpr int Q = LS_WARP_RUN_MAX / 32;
+        const uint32_t lane = t & 31u;
+        KeyT kq[Q];
+        uint32_t rk[Q];
+        uint16_t iq[Q];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const uint32_t e = lane + 32u * q;
+            kq[q] = e < rlen ? s_stage[rlo + e] : KeyT{};
+            if constexpr (PAIRS) iq[q] = e < rlen ? s_idx[rlo + e] : (uint16_t)0;
+            rk[q] = 0;
+        }
+        for (uint32_t j = 0; j < rlen; ++j) {
+            const KeyT o = s_stage[rlo + j];  // one address for the whole warp: a broadcast
+#pragma unroll
+            for (int q = 0; q < Q; ++q) rk[q] += (o < kq[q] || (o == kq[q] && j < lane + 32u * q)) ? 1u : 0u;
+        }
+        __syncwarp();  // every lane has read the run
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            if (lane + 32u * q < rlen) {
+                s_stage[rlo + rk[q]] = kq[q];
+                if constexpr (PAIRS) s_idx[rlo + rk[q]] = iq[q];
             }
         }
+        __syncwarp();
     }
     __syncthreads();
     if (s_big_n != 0 && !s_bad) {
@@ -815,14 +850,14 @@ __global__ void __launch_bounds__(LS_BLOCK, 2) local_sort_kernel(const HybridPar
             }
             __syncthreads();
         }
-        if (COUNT && my_run_is_big && !s_bad) {  // heads of my run, now that it is sorted
-            hc = 0;
-            KeyT prev{};
-            for (uint32_t i = lo; i < hi; ++i) {
-                const KeyT key = s_stage[i];
-                hc += (i == lo || key != prev) ? 1u : 0u;
-                prev = key;
-            }
+    }
+    if (COUNT && my_run_is_big && !s_bad) {  // heads of my run, now that the warp / the block has sorted it
+        hc = 0;
+        KeyT prev{};
+        for (uint32_t i = lo; i < hi; ++i) {
+            const KeyT key = s_stage[i];
+            hc += (i == lo || key != prev) ? 1u : 0u;
+            prev = key;
         }
     }
     __syncthreads();
@@ -1438,10 +1473,10 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
         irregular = fb[0];
         g_stat_hybrid_irregular = (int64_t)irregular;
         g_stat_hybrid_big_runs = (int64_t)fb[1];
-        // Keys crowded into cells by the thousand (diverged copies of repeat families) make the local
-        // sort slower than the passes it replaces: leave the next sorts of this thread to the plain
-        // passes, then probe again.
-        if (fb[1] > hp.n_tiles / 8) g_hybrid_backoff = 16;
+        // More block-sorted runs than tiles (keys crowded into cells by the hundred, everywhere) make the
+        // local sort slower than the passes it replaces: leave the next sorts of this thread to the
+        // plain passes, then probe again.
+        if (fb[1] > hp.n_tiles) g_hybrid_backoff = 16;
         g_stat_hybrid_path = 1;
         if (irregular == 0) {
             if (fused) co->done = true;
