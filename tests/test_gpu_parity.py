@@ -2,6 +2,8 @@
 vectors produced by the unmodified reference.  Bit-exact everywhere (integer/byte work)."""
 import ctypes as C
 import hashlib
+import os
+import sys
 
 import numpy as np
 import pytest
@@ -954,3 +956,15 @@ def test_hybrid_backs_off_after_crowded_data(eng):
     assert first_diff(a.keys_host(), np.sort(raw)) == "equal"
     eng.lib.kmg_set_option(b"hybrid", 1)  # (resets the back-off)
     assert eng.lib.kmg_get_stat(b"hybrid_backoff") == 0
+
+
+@pytest.mark.parametrize("seed", [7, 8])
+def test_hybrid_sort_family_fuzz(eng, seed, monkeypatch, capsys):
+    """A dozen randomised trials of tools/fuzz_sort.py (sort / count / uniq, 8- and 16-byte keys,
+    clustered + duplicated + skewed keys, forced prefix and tile widths) against numpy."""
+    import runpy
+
+    monkeypatch.setattr(sys, "argv", ["fuzz_sort.py", "--trials", "12", "--seconds", "120", "--seed", str(seed)])
+    runpy.run_path(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "fuzz_sort.py"),
+                   run_name="__main__")
+    assert "FUZZ_OK 12 trials" in capsys.readouterr().out
