@@ -101,7 +101,7 @@ int kmg_extract(const uint8_t* d_bases, uint64_t n_bases, uint64_t win_begin, ui
  * Key-only sorts over bits [0, end_bit), end_bit >= 32, with 2^20 <= n <= 2^33 take the "hybrid
  * finish": 2-3 ordinary passes over the top 16/24 bits (the first of them without stable
  * ranking), then ONE shared-memory local sort per ~6000-key tile orders all remaining bits
- * (radix_sort.cu: local_sort_kernel).  Tiles the local scheme cannot hold (prefix buckets above
+ * (local_sort.cuh: local_sort_kernel).  Tiles the local scheme cannot hold (prefix buckets above
  * 8192 keys, 4096 for 16-byte keys: repeats) are gathered, sorted by the plain LSD passes and put back; above n/8 such
  * keys the plain passes sort everything.  The result is identical on every path.  The call
  * synchronises the stream in that mode (2 KB histogram read-back, irregular-tile count).
@@ -240,7 +240,7 @@ int kmg_uniq_host(kmg_ctx* ctx, const uint8_t* h_bases, uint64_t n_bases, int k,
  *   "hybrid_unstable" [1]  first prefix pass ranks with the histogram atomics' return values
  *   "count_fused" [1]      kmg_sort_count: the local sort emits the (k-mer, count) table itself
  *   "local_tile" [7936]    target tile width of the local sort (positions)
- *   "sort_config" [3]      tile configuration of the onesweep kernel (radix_sort.cu: kSortTiles)
+ *   "sort_config" [3]      tile configuration of the onesweep kernel (radix_sort.cu: dispatch_tile)
  *   "lb_group" [32]        tiles per look-back group of the onesweep kernel
  *   "prefetch_tiles" [192] L2 prefetch distance of the onesweep kernel, in tiles (0: off)
  *   "time_passes" [0]      bracket every onesweep / local sort launch with CUDA events
