@@ -185,3 +185,24 @@ def test_bench_reference_arm_contract():
 
     rate, sec = bench.cpu_port_rate(200_000, 1, 0)
     assert rate > 0 and sec > 0
+
+
+def test_every_option_and_stat_is_documented_in_the_header():
+    """kmg_set_option / kmg_get_stat names handled in api.cu must appear in include/kmg.h's
+    tuning section (and nothing documented may be unknown to the library)."""
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    api = open(os.path.join(root, "kman_b200", "csrc", "api.cu")).read()
+    hdr = open(os.path.join(root, "include", "kmg.h")).read()
+    doc = hdr[hdr.index("tuning / introspection"):]
+    set_body = api[api.index('extern "C" int kmg_set_option'):api.index('extern "C" int64_t kmg_get_stat')]
+    get_body = api[api.index('extern "C" int64_t kmg_get_stat'):]
+    get_body = get_body[: get_body.index("\n}\n")]
+    options = set(re.findall(r'strcmp\(name, "([a-z_]+)"\)', set_body))
+    stats = set(re.findall(r'strcmp\(name, "([a-z_]+)"\)', get_body))
+    assert options and stats
+    documented = set(re.findall(r'"([a-z_]+)"', doc))
+    assert options <= documented, sorted(options - documented)
+    assert stats <= documented, sorted(stats - documented)
+    assert documented <= options | stats, sorted(documented - options - stats)
