@@ -238,6 +238,7 @@ int kmg_uniq_host(kmg_ctx* ctx, const uint8_t* h_bases, uint64_t n_bases, int k,
  *   "hybrid" [1]           hybrid finish of key-only 8-byte sorts (0: plain LSD passes only)
  *   "hybrid_pb" [0]        force its prefix width to 16 or 24 bits (0: by n and key skew)
  *   "hybrid_unstable" [1]  first prefix pass ranks with the histogram atomics' return values
+ *   "unstable_config" [10] tile shape of that pass (10: 256x24, 11: 256x16, 12: 384x16)
  *   "count_fused" [1]      kmg_sort_count: the local sort emits the (k-mer, count) table itself
  *   "local_tile" [7936]    target tile width of the local sort (positions)
  *   "sort_config" [3]      tile configuration of the onesweep kernel (radix_sort.cu: dispatch_tile)

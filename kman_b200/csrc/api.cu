@@ -19,6 +19,7 @@ extern int g_hybrid;
 extern int g_hybrid_pb;
 extern int g_count_fused;
 extern int g_hybrid_unstable;
+extern int g_unstable_config;
 extern int g_local_tile;
 extern thread_local int64_t g_stat_hybrid_irregular;
 extern thread_local int64_t g_stat_hybrid_path;
@@ -66,6 +67,11 @@ extern "C" int kmg_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "local_tile")) {
         KMG_REQUIRE(value >= 2048 && value <= 7936, KMG_ERR_ARG, "local_tile must be in [2048,7936]");
         g_local_tile = (int)value;
+        return KMG_OK;
+    }
+    if (!strcmp(name, "unstable_config")) {
+        KMG_REQUIRE(value >= 10 && value <= 12, KMG_ERR_ARG, "unstable_config must be 10, 11 or 12");
+        g_unstable_config = (int)value;
         return KMG_OK;
     }
     if (!strcmp(name, "hybrid_unstable")) {

@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(BLOCK, min_ctas(BLOCK, IPT)) onesweep_kernel(c
 // kmg_set_option("sort_config", i) -> (threads, keys per thread, ranking mix), see dispatch_tile():
 //   0: 256x16 mix2   1: 256x16 mix0   2: 256x16 mix1   3: 256x24 mix2 (default)   4: 512x16 mix2
 //   5: 256x16 mix3   6: 384x16 mix2   7: 256x16 mix4   8: 256x24 mix3   9: 256x20 mix2
-//  10: 256x24 mix5 (unstable ranking; the hybrid finish uses it for its first prefix pass)
+//  10: 256x24 mix5 (unstable ranking; the hybrid finish uses it for its first prefix pass)   11: 256x16 mix5   12: 384x16 mix5
 
 template <typename KeyT, int VB, int RB, int BLOCK, int IPT, int MIX>
 static size_t onesweep_smem() {
@@ -458,6 +458,8 @@ static int dispatch_tile(int cfg, const OnesweepParams& p, const ShiftDigit& op,
         case 8: return launch_onesweep<KeyT, VB, 8, 256, 24, 3>(p, op, st);
         case 9: return launch_onesweep<KeyT, VB, 8, 256, 20, 2>(p, op, st);
         case 10: return launch_onesweep<KeyT, VB, 8, 256, 24, 5>(p, op, st);
+        case 11: return launch_onesweep<KeyT, VB, 8, 256, 16, 5>(p, op, st);
+        case 12: return launch_onesweep<KeyT, VB, 8, 384, 16, 5>(p, op, st);
         default: return launch_onesweep<KeyT, VB, 8, 256, 16, 2>(p, op, st);
     }
 }
@@ -553,6 +555,7 @@ struct SortWs {
 };
 
 int g_hybrid = 1;     // kmg_set_option("hybrid", 0/1)
+int g_unstable_config = 10;  // kmg_set_option("unstable_config", 10 | 11 | 12): tile shape of that pass
 int g_hybrid_unstable = 1;  // kmg_set_option("hybrid_unstable", 0/1): first prefix pass without stable ranking
 int g_local_tile = 7936;  // kmg_set_option("local_tile", positions): target tile width of the local sort
 int g_count_fused = 1;  // kmg_set_option("count_fused", 0/1): let the hybrid finish emit the count table itself
@@ -753,7 +756,7 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
             if (g_ev_used >= MAX_TIMED) timing_collect();
             timing_begin(st);
             // the hybrid finish does not care about the order inside the first pass' digits
-            const int pass_cfg = (hybrid && pass == 0 && g_hybrid_unstable && cfg == 3) ? 10 : cfg;
+            const int pass_cfg = (hybrid && pass == 0 && g_hybrid_unstable && cfg == 3) ? g_unstable_config : cfg;
             int rcode = dispatch_onesweep(pass_cfg, key_bytes, val_bytes, p, op, st);
             timing_end(st);
             if (rcode != KMG_OK) return rcode;

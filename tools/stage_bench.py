@@ -84,6 +84,16 @@ def main():
 
         med_all, _ = timed(run_u, flush=flush)
         print(f"hybrid, unstable first pass {un}: sort {med_all - res['extract_ms']:8.3f} ms")
+    for uc in (10, 11, 12):
+        eng.lib.kmg_set_option(b"unstable_config", uc)
+
+        def run_uc():
+            a = eng.extract(d, k, False, val_bytes=args.vb, reuse="b_", want_hist=True)
+            return eng.sort(a)
+
+        med_all, _ = timed(run_uc, flush=flush)
+        print(f"unstable_config {uc}: sort {med_all - res['extract_ms']:8.3f} ms")
+    eng.lib.kmg_set_option(b"unstable_config", 10)
     for hy, pb in ((0, 0), (1, 16), (1, 24), (1, 0)):
         eng.lib.kmg_set_option(b"hybrid", hy)
         eng.lib.kmg_set_option(b"hybrid_pb", pb)
