@@ -83,9 +83,10 @@ def main():
         return eng.sort_uniq(eng.extract(d, k, False, val_bytes=4, reuse="gu_", want_hist=True))
 
     res = {}
-    for hy in (0, 1, 2):
+    for hy in (0, 1, 2, 3):
         eng.lib.kmg_set_option(b"hybrid", min(hy, 1))  # (also resets the back-off)
-        eng.lib.kmg_set_option(b"hybrid_pb", 24 if hy == 2 else 0)  # 2: forced (a forced prefix width disables the back-off)
+        # 2 / 3: prefix width forced to 24 / 16 bits (a forced width also disables the back-off)
+        eng.lib.kmg_set_option(b"hybrid_pb", {2: 24, 3: 16}.get(hy, 0))
         eng.lib.kmg_set_option(b"time_passes", 1)
         tab = count()
         torch.cuda.synchronize()
@@ -104,7 +105,7 @@ def main():
         print(f"   uniq  {t_u:7.3f} ms = {nk/t_u/1e6:6.2f} G k-mers/s  (passes {st_u[0]}, path {st_u[1]}, irregular tiles {st_u[2]})")
         print(f"   back-off now {eng.lib.kmg_get_stat(b'hybrid_backoff')}, runs sorted by the block in the last hybrid sort {eng.lib.kmg_get_stat(b'hybrid_big_runs')}")
     eng.lib.kmg_set_option(b"hybrid_pb", 0)
-    assert res[0] == res[1] == res[2], "hybrid and plain sorts disagree"
+    assert res[0] == res[1] == res[2] == res[3], "hybrid and plain sorts disagree"
     print("GENOME_LIKE_OK")
 
 
