@@ -252,7 +252,9 @@ def main():
             return dc.count(d, K, False)
     else:
         def step():
-            return eng.sort_count(eng.extract(d, K, False, val_bytes=0, reuse="bench_", want_hist=True), reuse="bench_")
+            # ONE native call: histogram pre-pass over the bases, extraction fused with the first prefix
+            # pass, remaining prefix pass(es), local sort emitting the (k-mer, count) table
+            return eng.count_narrow(d, K, False, reuse="bench_")[0]
 
     def barrier():
         if world > 1:

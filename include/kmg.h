@@ -104,7 +104,8 @@ int kmg_extract(const uint8_t* d_bases, uint64_t n_bases, uint64_t win_begin, ui
  * (local_sort.cuh: local_sort_kernel).  Tiles the local scheme cannot hold (prefix buckets above
  * 8192 keys, 4096 for 16-byte keys: repeats) are gathered, sorted by the plain LSD passes and put back; above n/8 such
  * keys the plain passes sort everything.  The result is identical on every path.  The call
- * synchronises the stream in that mode (2 KB histogram read-back, irregular-tile count).
+ * synchronises the stream in that mode (2 KB histogram read-back unless d_hist_in is given; one
+ * 56-byte read-back of the status words after the local sort).
  * All keys must agree in the bits at and above end_bit in that mode (kmg_extract's keys do: those
  * bits are zero; after kmg_range_partition they are the rank's common prefix).
  * kmg_set_option("hybrid", 0) switches it off. */
@@ -144,6 +145,27 @@ int kmg_select_singletons(const void* d_sorted_keys, const void* d_vals, uint64_
                           void* d_keys_out, void* d_vals_out, uint64_t* d_n_out, void* d_ws, size_t ws_bytes,
                           void* stream);
 
+/* ---- K1-K4 in one call: the device path of `kmer count` / `kmer uniq` for the narrow stream -------
+ * (FastaBatcher.do batcher.py:454-487 + KJoiner.join join.py:337-391 on one flat base buffer.)
+ * Same results as kmg_extract followed by kmg_sort_count / kmg_sort_uniq, but when the hybrid sort
+ * applies (>= 2^20 keys, k >= 16; with payload: k <= 32) the extraction kernel itself is the sort's
+ * first prefix pass: a pre-pass over the BASES yields the histograms of the top key bytes (4-mer
+ * histogram), then every key is written once, straight into the region of its digit -- the keys are
+ * never stored in extraction order.  Two host synchronisations per call (32 + 56 bytes read back).
+ * d_keys / d_keys_alt (and d_vals / d_vals_alt): capacity (win_end-win_begin)*(1+rc) items each.
+ * h_result[4] (host): [0] rows of the result ((k-mer, count) pairs / singletons), [1] keys that were
+ * sorted, [2] windows that belong to the WIDE stream (the caller runs those through the stage
+ * API), [3] selector: 0 = result keys in d_keys (payload in d_vals), 1 = in the alt buffers.
+ * count: multiplicities in d_counts_out[0 .. h_result[0]). */
+size_t kmg_pipeline_workspace_bytes(uint64_t n_windows, int k, int rc, int val_bytes);
+int kmg_extract_sort_count(const uint8_t* d_bases, uint64_t n_bases, uint64_t win_begin, uint64_t win_end, int k, int rc,
+                           const uint8_t* d_lut256, void* d_keys, void* d_keys_alt, uint32_t* d_counts_out,
+                           uint64_t* h_result, void* d_ws, size_t ws_bytes, void* stream);
+int kmg_extract_sort_uniq(const uint8_t* d_bases, uint64_t n_bases, uint64_t win_begin, uint64_t win_end, int k, int rc,
+                          const uint8_t* d_lut256, void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_alt,
+                          int val_bytes, uint64_t pos_offset, uint64_t* h_result, void* d_ws, size_t ws_bytes,
+                          void* stream);
+
 /* ---- K5: range partition for the multi-GPU exchange (no reference counterpart) --------
  * Stable split of keys into n_parts contiguous regions of the output by
  *   part = ((key >> (key_bits-16)) * n_parts) >> 16      (key_bits >= 16)
@@ -177,6 +199,21 @@ int kmg_extract_scatter_shared(const uint8_t* d_bases, uint64_t n_bases, uint64_
                                int rc, const uint8_t* d_lut256, int n_parts, void* const* d_dest_keys,
                                void* const* d_dest_vals, int key_bytes, int val_bytes, uint64_t pos_offset,
                                uint64_t* const* d_cursor_ptrs, uint64_t capacity, uint32_t* d_status, void* stream);
+/* kmg_extract_scatter with a guard for callers that launch before they know whether the receive
+ * buffers still fit: a reservation that would pass `capacity` elements stores nothing and sets
+ * d_status[0] = 1 (re-provision, repeat). */
+int kmg_extract_scatter_checked(const uint8_t* d_bases, uint64_t n_bases, uint64_t win_begin, uint64_t win_end, int k,
+                                int rc, const uint8_t* d_lut256, int n_parts, void* const* d_dest_keys,
+                                void* const* d_dest_vals, int key_bytes, int val_bytes, uint64_t pos_offset,
+                                uint64_t* d_cursors, uint64_t capacity, uint32_t* d_status, void* stream);
+/* What kmg_extract_scatter's count-only launch computes, from the 4-mer histogram of the BASES instead
+ * of a second key-building pass (power-of-two n_parts <= 256, k >= 12): the top log2(n_parts) bits of a
+ * key are its first bases.  d_counts[0..n_parts) keys per destination, d_counts[n_parts] windows of
+ * the wide stream. */
+size_t kmg_dest_counts_workspace_bytes(void);
+int kmg_extract_dest_counts(const uint8_t* d_bases, uint64_t n_bases, uint64_t win_begin, uint64_t win_end, int k, int rc,
+                            const uint8_t* d_lut256, int n_parts, uint64_t* d_counts, void* d_ws, size_t ws_bytes,
+                            void* stream);
 /* Device memory that other processes of the same box can map (CUDA IPC, 64-byte handle). */
 int kmg_ipc_alloc(size_t bytes, void** d_ptr_out, uint8_t* h_handle64);
 int kmg_ipc_open(const uint8_t* h_handle64, void** d_ptr_out);
@@ -245,12 +282,17 @@ int kmg_uniq_host(kmg_ctx* ctx, const uint8_t* h_bases, uint64_t n_bases, int k,
  *   "lb_group" [32]        tiles per look-back group of the onesweep kernel
  *   "prefetch_tiles" [192] L2 prefetch distance of the onesweep kernel, in tiles (0: off)
  *   "time_passes" [0]      bracket every onesweep / local sort launch with CUDA events
+ *   "count_limit" [0]      test hook: run lengths above it raise KMG_ERR_RANGE in the run-length stage
+ *                          (0 = the real limit 2^32-1)
  * Stats of the calling thread's last call: "launches" (kernel launches since "reset_launches"),
  * "sort_passes", "hybrid_path" (0 plain passes, 1 hybrid, 2 hybrid + re-sorted ranges, 3 fell
  * back), "hybrid_irregular" (tiles), "hybrid_big_runs" (runs a whole block had to sort),
- * "hybrid_backoff" (sorts of this thread that will still skip the hybrid finish after crowded
- * data; setting the "hybrid" option resets it), and with time_passes: "sort_pass_ns" / "sort_pass_count",
- * "local_sort_ns" / "local_sort_count" (device time of the timed launches). */
+ * "n_out" / "ws_err" (result rows and status word the last kmg_sort_count / kmg_sort_uniq already
+ * read back when its hybrid finish synchronised, -1 otherwise: a caller can then skip its own
+ * read-back of *d_n_out and kmg_ws_status), and with time_passes: "sort_pass_ns" /
+ * "sort_pass_count", "local_sort_ns" / "local_sort_count", "prepass_ns" / "prepass_count",
+ * "scatter_ns" / "scatter_count" (device time of the timed launches: onesweep passes, the local
+ * sort, and the fused pipeline's histogram pre-pass and extraction pass). */
 int kmg_set_option(const char* name, int64_t value);
 int64_t kmg_get_stat(const char* name);
 

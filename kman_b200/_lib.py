@@ -37,10 +37,16 @@ SIGNATURES = {
     "kmg_sort_uniq": (i32, [vp, vp, vp, vp, u64, i32, i32, i32, vp, vp, C.POINTER(C.c_int), vp, sz, vp]),
     "kmg_sort_count_workspace_bytes": (sz, [u64, i32, i32]),
     "kmg_sort_count": (i32, [vp, vp, u64, i32, i32, vp, vp, vp, C.POINTER(C.c_int), vp, sz, vp]),
+    "kmg_pipeline_workspace_bytes": (sz, [u64, i32, i32, i32]),
+    "kmg_extract_sort_count": (i32, [vp, u64, u64, u64, i32, i32, vp, vp, vp, vp, u64p, vp, sz, vp]),
+    "kmg_extract_sort_uniq": (i32, [vp, u64, u64, u64, i32, i32, vp, vp, vp, vp, vp, i32, u64, u64p, vp, sz, vp]),
     "kmg_select_singletons": (i32, [vp, vp, u64, i32, i32, vp, vp, vp, vp, sz, vp]),
     "kmg_partition_workspace_bytes": (sz, [u64, i32, i32]),
     "kmg_range_partition": (i32, [vp, vp, u64, i32, i32, i32, i32, vp, vp, vp, vp, sz, vp]),
     "kmg_extract_scatter": (i32, [vp, u64, u64, u64, i32, i32, vp, i32, vp, vp, i32, i32, u64, vp, vp, i32, vp]),
+    "kmg_extract_scatter_checked": (i32, [vp, u64, u64, u64, i32, i32, vp, i32, vp, vp, i32, i32, u64, vp, u64, vp, vp]),
+    "kmg_dest_counts_workspace_bytes": (sz, []),
+    "kmg_extract_dest_counts": (i32, [vp, u64, u64, u64, i32, i32, vp, i32, vp, vp, sz, vp]),
     "kmg_extract_scatter_shared": (i32, [vp, u64, u64, u64, i32, i32, vp, i32, vp, vp, i32, i32, u64, vp, u64, vp, vp]),
     "kmg_ipc_alloc": (i32, [sz, C.POINTER(vp), u8p]),
     "kmg_ipc_open": (i32, [u8p, C.POINTER(vp)]),

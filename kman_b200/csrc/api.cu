@@ -24,8 +24,8 @@ extern int g_local_tile;
 extern thread_local int64_t g_stat_hybrid_irregular;
 extern thread_local int64_t g_stat_hybrid_path;
 extern thread_local int64_t g_stat_hybrid_big_runs;
-extern thread_local int g_hybrid_backoff;
 extern int g_prefetch_tiles;
+extern int64_t g_count_limit;
 extern thread_local int64_t g_stat_sort_passes;
 void timing_collect();
 double timing_total_ms(int kind);
@@ -87,7 +87,6 @@ extern "C" int kmg_set_option(const char* name, int64_t value) {
         return KMG_OK;
     }
     if (!strcmp(name, "hybrid")) {
-        g_hybrid_backoff = 0;
         g_hybrid = value != 0;
         return KMG_OK;
     }
@@ -99,6 +98,11 @@ extern "C" int kmg_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "lb_group")) {
         KMG_REQUIRE(value >= 8 && value <= 4096, KMG_ERR_ARG, "lb_group must be in [8,4096]");
         g_lb_group = (int)value;
+        return KMG_OK;
+    }
+    if (!strcmp(name, "count_limit")) {
+        KMG_REQUIRE(value >= 0 && value <= 0xffffffffll, KMG_ERR_ARG, "count_limit must be in [0, 2^32-1]");
+        g_count_limit = value;
         return KMG_OK;
     }
     if (!strcmp(name, "time_passes")) {
@@ -117,7 +121,8 @@ extern "C" int64_t kmg_get_stat(const char* name) {
     if (!strcmp(name, "hybrid_irregular")) return g_stat_hybrid_irregular;
     if (!strcmp(name, "hybrid_path")) return g_stat_hybrid_path;
     if (!strcmp(name, "hybrid_big_runs")) return g_stat_hybrid_big_runs;
-    if (!strcmp(name, "hybrid_backoff")) return g_hybrid_backoff;
+    if (!strcmp(name, "n_out")) return g_stat_last_n_out;
+    if (!strcmp(name, "ws_err")) return g_stat_last_err;
     if (!strcmp(name, "sort_pass_ns")) {  // total device time of the timed onesweep launches
         timing_collect();
         return (int64_t)(timing_total_ms(0) * 1e6);
@@ -133,6 +138,14 @@ extern "C" int64_t kmg_get_stat(const char* name) {
     if (!strcmp(name, "local_sort_count")) {
         timing_collect();
         return timing_count(1);
+    }
+    if (!strcmp(name, "prepass_ns") || !strcmp(name, "scatter_ns")) {  // pipeline.cu's two extraction launches
+        timing_collect();
+        return (int64_t)(timing_total_ms(name[0] == 'p' ? 2 : 3) * 1e6);
+    }
+    if (!strcmp(name, "prepass_count") || !strcmp(name, "scatter_count")) {
+        timing_collect();
+        return timing_count(name[0] == 'p' ? 2 : 3);
     }
     if (!strcmp(name, "reset_launches")) {
         g_launches = 0;
@@ -266,12 +279,7 @@ static int run_host(kmg_ctx* c, int mode, const uint8_t* h_bases, uint64_t n_bas
     const uint64_t n_win = n_bases >= (uint64_t)k ? n_bases - k + 1 : 0;
     if (n_win == 0) return KMG_OK;
     const uint64_t n_max = n_win * (rc ? 2 : 1);
-    const size_t ws_ex = kmg_extract_workspace_bytes(n_win);
-    const size_t ws_sort = kmg_radix_sort_workspace_bytes(n_max, kb, vb, 0, 2 * k);
-    const size_t ws_rle = kmg_rle_workspace_bytes(n_max);
-    const size_t ws_count = mode == 0 ? kmg_sort_count_workspace_bytes(n_max, kb, 2 * k)
-                                      : kmg_sort_uniq_workspace_bytes(n_max, kb, vb, 2 * k);
-    const size_t ws_bytes = std::max(std::max(ws_ex, ws_count), std::max(ws_sort, ws_rle));
+    const size_t ws_bytes = kmg_pipeline_workspace_bytes(n_win, k, rc, vb);
 
     Carver cv{nullptr, 0};
     for (int round = 0; round < 2; ++round) {
@@ -307,36 +315,22 @@ static int run_host(kmg_ctx* c, int mode, const uint8_t* h_bases, uint64_t n_bas
 
     KMG_CUDA(cudaMemcpyAsync(c->d_lut, h_lut256, 256, cudaMemcpyHostToDevice, st));
     KMG_CUDA(cudaMemcpyAsync(d_bases, h_bases, n_bases, cudaMemcpyHostToDevice, st));
-    uint64_t* d_hist = k >= 4 ? c->d_hist : nullptr;
-    int rcode = kmg_extract(d_bases, n_bases, 0, n_win, k, rc, 0, c->d_lut, nullptr, d_keys, kb, d_vals, vb, 0,
-                            c->d_small, d_hist, d_ws, ws_bytes, st);
+    // the fused device path: pre-pass, extraction = first prefix pass, remaining passes, local sort
+    uint64_t res[4] = {0, 0, 0, 0};
+    int rcode;
+    if (mode == 0)
+        rcode = kmg_extract_sort_count(d_bases, n_bases, 0, n_win, k, rc, c->d_lut, d_keys, d_keys_alt, d_counts, res, d_ws,
+                                       ws_bytes, st);
+    else
+        rcode = kmg_extract_sort_uniq(d_bases, n_bases, 0, n_win, k, rc, c->d_lut, d_keys, d_keys_alt, d_vals, d_vals_alt, vb,
+                                      0, res, d_ws, ws_bytes, st);
     if (rcode != KMG_OK) return rcode;
-    uint64_t h_counts[2] = {0, 0};
-    KMG_CUDA(cudaMemcpyAsync(h_counts, c->d_small, 16, cudaMemcpyDeviceToHost, st));
-    rcode = kmg_ws_status(d_ws, st);  // synchronises
-    if (rcode != KMG_OK) return rcode;
-    KMG_REQUIRE(h_counts[1] == 0, KMG_ERR_STATE,
+    KMG_REQUIRE(res[2] == 0, KMG_ERR_STATE,
                 "input holds %llu windows with non-ACGT alphabet symbols: use the stage API (wide stream)",
-                (unsigned long long)h_counts[1]);
-    const uint64_t n = h_counts[0];
-    if (n == 0) return KMG_OK;
-    int sel = 0;
-    char* ok;  // buffer that receives the compacted output
-    char* ov = nullptr;
-    if (mode == 0) {
-        rcode = kmg_sort_count(d_keys, d_keys_alt, n, kb, 2 * k, d_hist, d_counts, c->d_small + 2, &sel, d_ws, ws_bytes, st);
-        ok = sel ? d_keys_alt : d_keys;
-    } else {
-        rcode = kmg_sort_uniq(d_keys, d_keys_alt, d_vals, d_vals_alt, n, kb, vb, 2 * k, d_hist, c->d_small + 2, &sel, d_ws,
-                              ws_bytes, st);
-        ok = sel ? d_keys_alt : d_keys;
-        ov = sel ? d_vals_alt : d_vals;
-    }
-    if (rcode != KMG_OK) return rcode;
-    uint64_t n_out = 0;
-    KMG_CUDA(cudaMemcpyAsync(&n_out, c->d_small + 2, 8, cudaMemcpyDeviceToHost, st));
-    rcode = kmg_ws_status(d_ws, st);
-    if (rcode != KMG_OK) return rcode;
+                (unsigned long long)res[2]);
+    const uint64_t n_out = res[0];
+    char* ok = res[3] ? d_keys_alt : d_keys;  // buffer that holds the compacted output
+    char* ov = res[3] ? d_vals_alt : d_vals;
     *h_n_out = n_out;
     KMG_REQUIRE(n_out <= cap, KMG_ERR_RANGE, "output capacity %llu < %llu results", (unsigned long long)cap,
                 (unsigned long long)n_out);

@@ -71,6 +71,43 @@ static inline PassPlan make_plan(int begin_bit, int end_bit) {
     return plan;
 }
 
+// ---- cross-file plumbing of the fused pipeline (pipeline.cu) -----------------------------------------
+// fused run-length count / singleton request of a hybrid sort: `done` = the local sort produced the
+// result itself (counts == null: singletons with payload, kmg_sort_uniq)
+struct CountOut {
+    uint32_t* counts;
+    unsigned long long* n_out;
+    bool done;
+};
+// keys already grouped by the lowest prefix byte + the histograms of the three top key bytes
+struct PrePartitioned {
+    int pb;                         // prefix width, 16 or 24
+    const unsigned long long* top;  // device [3][256]: bits [2k-24,2k-16), [2k-16,2k-8), [2k-8,2k)
+};
+// extract.cu
+size_t top_hist_workspace_bytes();
+int extract_top_hist(const uint8_t* d_bases, uint64_t n_bases, uint64_t win_begin, uint64_t win_end, int k, int rc,
+                     const uint8_t* d_lut256, uint64_t* d_counts, unsigned long long* d_top, unsigned long long* d_plan,
+                     void* d_ws, size_t ws_bytes, cudaStream_t st);
+int extract_digit_scatter(const uint8_t* d_bases, uint64_t n_bases, uint64_t win_begin, uint64_t win_end, int k, int rc,
+                          const uint8_t* d_lut256, void* d_keys_out, int key_bytes, void* d_vals_out, int val_bytes,
+                          uint64_t pos_offset, unsigned long long* d_cursors, int digit_shift, cudaStream_t st);
+// radix_sort.cu
+bool hybrid_sort_applies(uint64_t n, int key_bytes, int val_bytes, int end_bit, bool pairs_ok);
+int hybrid_choose_pb(uint64_t n, unsigned long long max_top_byte_count, int key_bytes, int val_bytes);
+int sort_count_core(void* d_keys, void* d_keys_alt, uint64_t n, int key_bytes, int end_bit, const uint64_t* d_hist_in,
+                    uint32_t* d_counts_out, uint64_t* d_n_out, int* h_selector_out, void* d_ws, size_t ws_bytes, void* stream,
+                    const PrePartitioned* pre);
+int sort_uniq_core(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_alt, uint64_t n, int key_bytes, int val_bytes,
+                   int end_bit, const uint64_t* d_hist_in, uint64_t* d_n_out, int* h_selector_out, void* d_ws,
+                   size_t ws_bytes, void* stream, const PrePartitioned* pre);
+void exclusive_scan_256(const unsigned long long* d_hist_row, unsigned long long* d_out, cudaStream_t st);
+extern thread_local int64_t g_stat_last_n_out, g_stat_last_err;
+// kmg_set_option("time_passes", 1): event pairs around a launch (kind 0 onesweep pass, 1 local sort,
+// 2 histogram pre-pass, 3 fused extraction pass)
+void timing_begin(cudaStream_t st);
+void timing_end(cudaStream_t st, int kind);
+
 // ---- 128-bit key ------------------------------------------------------------------------
 struct __align__(16) u128 {
     uint64_t lo, hi;

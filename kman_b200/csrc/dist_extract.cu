@@ -238,7 +238,15 @@ __global__ void __launch_bounds__(DX_BLOCK) extract_scatter_kernel(const Scatter
                     s_base[t] = b;
                 }
             } else {
-                s_base[t] = atomicAdd(&p.cursors[t], (unsigned long long)s_cnt[t]);
+                const unsigned long long b = atomicAdd(&p.cursors[t], (unsigned long long)s_cnt[t]);
+                // (kmg_extract_scatter_checked: the caller launched before it knew whether the receive
+                // buffers still fit; nothing is stored past their end)
+                if (p.capacity && b + s_cnt[t] > p.capacity) {
+                    atomicExch(&p.status[0], 1u);
+                    s_base[t] = DX_NO_STORE;
+                } else {
+                    s_base[t] = b;
+                }
             }
         }
         if (t == 0 && s_wide && p.status) atomicExch(&p.status[1], 1u);
@@ -365,6 +373,15 @@ extern "C" int kmg_extract_scatter(const uint8_t* d_bases, uint64_t n_bases, uin
                                    uint64_t* d_cursors, uint64_t* d_counts, int count_only, void* stream) {
     return scatter_impl(d_bases, n_bases, win_begin, win_end, k, rc, d_lut256, n_parts, d_dest_keys, d_dest_vals, key_bytes,
                         val_bytes, pos_offset, d_cursors, d_counts, count_only, nullptr, 0, nullptr, stream);
+}
+
+extern "C" int kmg_extract_scatter_checked(const uint8_t* d_bases, uint64_t n_bases, uint64_t win_begin, uint64_t win_end,
+                                           int k, int rc, const uint8_t* d_lut256, int n_parts, void* const* d_dest_keys,
+                                           void* const* d_dest_vals, int key_bytes, int val_bytes, uint64_t pos_offset,
+                                           uint64_t* d_cursors, uint64_t capacity, uint32_t* d_status, void* stream) {
+    KMG_REQUIRE(d_cursors && d_status && capacity > 0, KMG_ERR_ARG, "null pointer argument");
+    return scatter_impl(d_bases, n_bases, win_begin, win_end, k, rc, d_lut256, n_parts, d_dest_keys, d_dest_vals, key_bytes,
+                        val_bytes, pos_offset, d_cursors, nullptr, 0, nullptr, capacity, d_status, stream);
 }
 
 extern "C" int kmg_extract_scatter_shared(const uint8_t* d_bases, uint64_t n_bases, uint64_t win_begin, uint64_t win_end,

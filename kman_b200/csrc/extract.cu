@@ -13,7 +13,7 @@
 
 namespace kmg {
 
-constexpr int EX_BLOCK = 256;
+constexpr int EX_BLOCK_DEFAULT = 256;  // threads of the position-ordered extraction (MODE 0)
 constexpr int EX_HALO_WORDS = 8;  // 16-base words past the tile that masks/codes may touch
 
 struct ExtractParams {
@@ -36,6 +36,10 @@ struct ExtractParams {
     unsigned long long* hs;
     int n_off;
     int hist_off[2 * MAX_PASSES];
+    // MODE 2 (fused first prefix pass): every key goes straight to the region of its digit
+    // (key >> digit_shift) & 255; cursors[256] hold the next free element of every region
+    unsigned long long* cursors;
+    int digit_shift;
 };
 
 constexpr int EX_MAX_OFF = 2 * MAX_PASSES;
@@ -82,8 +86,20 @@ __device__ __forceinline__ ValT make_val(uint64_t pos, uint32_t strand) {
 }
 
 // KeyT: uint64_t (k<=32) or u128 (33<=k<=64).  PPT: window starts per thread (8 or 16).
-template <typename KeyT, int PPT, bool RC, int VAL_BYTES, bool HIST>
+// MODE 0: keys (and payload) of the valid windows in position order (kmg_extract).
+// MODE 1: nothing is emitted -- only the 4-mer histograms (HIST) and the window counts: the
+//         pre-pass of the fused pipeline (pipeline.cu), which needs every prefix pass' histogram
+//         before the first key is placed.
+// MODE 2: extraction fused with the FIRST prefix pass of the hybrid sort: that pass may place the
+//         keys of one digit in any order (the local sort orders everything below the prefix), so
+//         a tile ranks its keys with the return values of shared-memory atomics, reserves its
+//         slots in the 256 digit regions with one global atomic per digit and writes digit runs
+//         -- no compaction in position order, no tile prefix, no waiting for other tiles, and the
+//         keys never make the extra round trip through HBM in extraction order.
+template <typename KeyT, int PPT, bool RC, int VAL_BYTES, bool HIST, int MODE, int EX_BLOCK>
 __global__ void __launch_bounds__(EX_BLOCK) extract_narrow_kernel(const ExtractParams p) {
+    static_assert(MODE != 1 || HIST, "the pre-pass exists for its histograms");
+    static_assert(MODE != 2 || !HIST, "the fused pass takes its histograms from the pre-pass");
     constexpr int TILE = EX_BLOCK * PPT;
     constexpr int WORDS = TILE / 16 + EX_HALO_WORDS;
     constexpr int OUT_PER_WIN = RC ? 2 : 1;
@@ -108,15 +124,22 @@ __global__ void __launch_bounds__(EX_BLOCK) extract_narrow_kernel(const ExtractP
     uint32_t* s_c = reinterpret_cast<uint32_t*>(smem_raw);  // [n_off][256] corrections for skipped windows;
                                                             // aliases the key staging buffer, used before it
     __shared__ uint32_t s_any_skipped;
+    __shared__ uint32_t s_cnt[MODE == 2 ? 256 : 1];            // keys per digit in this tile
+    __shared__ uint32_t s_off[MODE == 2 ? 256 : 1];            // first staging slot of every digit
+    __shared__ unsigned long long s_gb[MODE == 2 ? 256 : 1];   // global slot of staging slot i = s_gb[digit] + i
 
     const int t = threadIdx.x;
     if (t == 0) {
-        s_tile = atomicAdd(p.ticket, 1u);
+        // (only the position-ordered mode waits for earlier tiles: it needs launch-ordered ids)
+        s_tile = MODE == 0 ? atomicAdd(p.ticket, 1u) : blockIdx.x;
         s_wide = 0;
         s_any_skipped = 0;
     }
-    if (HIST) s_g[t] = 0;
-    s_lut[t] = p.lut[t];
+    if (t < 256) {
+        if (HIST) s_g[t] = 0;
+        if (MODE == 2) s_cnt[t] = 0;
+        s_lut[t] = p.lut[t];
+    }
     __syncthreads();
     const uint32_t tile = s_tile;
     const uint64_t tile_pos = (p.first_tile + tile) * (uint64_t)TILE;
@@ -209,10 +232,12 @@ __global__ void __launch_bounds__(EX_BLOCK) extract_narrow_kernel(const ExtractP
         }
     }
     const uint32_t cnt = __popc(vf);
-    uint32_t total;
-    const uint32_t excl = block_excl_scan<EX_BLOCK, uint32_t>(cnt, s_scan, total);
-    if (t == 0) tile_prefix_publish(p.tile_state, tile, (uint64_t)total * OUT_PER_WIN);
-    if (nwide) atomicAdd(&s_wide, nwide);
+    uint32_t total = 0, excl = 0;
+    if constexpr (MODE != 2) excl = block_excl_scan<EX_BLOCK, uint32_t>(cnt, s_scan, total);
+    if constexpr (MODE == 0) {
+        if (t == 0) tile_prefix_publish(p.tile_state, tile, (uint64_t)total * OUT_PER_WIN);
+    }
+    if (MODE != 2 && nwide) atomicAdd(&s_wide, nwide);
 
     if constexpr (HIST) {
         // G: one count per window start whose first 4 bases are plain.  Digit p of a valid
@@ -246,17 +271,22 @@ __global__ void __launch_bounds__(EX_BLOCK) extract_narrow_kernel(const ExtractP
             }
             __syncthreads();  // the staging buffer is about to be reused for the keys
         }
-        {
+        if (t < 256) {
             const uint32_t c = s_g[t];
             if (c) atomicAdd(&p.hs[p.n_off * 256 + t], (unsigned long long)c);
         }
     }
+    if constexpr (MODE == 1) {  // the pre-pass stops here: window counts only
+        __syncthreads();
+        if (t == 0) {
+            if (total) atomicAdd(&p.counts[0], (unsigned long long)total * OUT_PER_WIN);
+            if (s_wide) atomicAdd(&p.counts[1], (unsigned long long)s_wide);
+        }
+        return;
+    }
 
-    // ---- keys of the valid windows, compacted in position order into the staging buffer -----
-    uint32_t r = excl;
-#pragma unroll
-    for (int j = 0; j < PPT; ++j) {
-        if (!(vf & (1u << j))) continue;
+    // key of my j-th window start
+    auto build_key = [&](int j) -> KeyT {
         const int je = joff + j;
         const int s2 = 2 * je;
         const uint64_t hi = je == 0 ? X0 : ((X0 << s2) | (X1 >> (64 - s2)));
@@ -274,6 +304,71 @@ __global__ void __launch_bounds__(EX_BLOCK) extract_narrow_kernel(const ExtractP
                 key.hi = hi >> s;
             }
         }
+        return key;
+    };
+
+    if constexpr (MODE == 2) {
+        // ---- fused first prefix pass: rank inside the tile = what the digit counter returned ----------
+        const int dsh = p.digit_shift;
+        uint32_t wh[PPT * OUT_PER_WIN];  // digit | rank << 8
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+            if (!(vf & (1u << j))) continue;
+            const KeyT key = build_key(j);
+            const uint32_t d0 = key_digit(key, dsh, 255u);
+            wh[j * OUT_PER_WIN] = d0 | (atomicAdd(&s_cnt[d0], 1u) << 8);
+            if constexpr (RC) {
+                const uint32_t d1 = key_digit(rc_key(key, k), dsh, 255u);
+                wh[j * 2 + 1] = d1 | (atomicAdd(&s_cnt[d1], 1u) << 8);
+            }
+        }
+        __syncthreads();
+        // one thread per digit: reserve the tile's slots in the digit's region (any order is fine,
+        // so a plain atomic cursor does it -- no tile waits for another one)
+        const uint32_t c = t < 256 ? s_cnt[t] : 0u;
+        unsigned long long g = 0;
+        if (c) g = atomicAdd(&p.cursors[t], (unsigned long long)c);
+        uint32_t n_tile;
+        const uint32_t off = block_excl_scan<EX_BLOCK, uint32_t>(c, s_scan, n_tile);
+        if (t < 256) {
+            s_off[t] = off;
+            s_gb[t] = g - off;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+            if (!(vf & (1u << j))) continue;
+            const KeyT key = build_key(j);
+            const uint64_t pos = tile_pos + (uint64_t)t * PPT + j + p.pos_offset;
+            const uint32_t w0 = wh[j * OUT_PER_WIN];
+            const uint32_t i0 = s_off[w0 & 255u] + (w0 >> 8);
+            s_keys[i0] = key;
+            if constexpr (VAL_BYTES != 0) s_vals[i0] = make_val<ValT>(pos, 0);
+            if constexpr (RC) {
+                const uint32_t w1 = wh[j * 2 + 1];
+                const uint32_t i1 = s_off[w1 & 255u] + (w1 >> 8);
+                s_keys[i1] = rc_key(key, k);
+                if constexpr (VAL_BYTES != 0) s_vals[i1] = make_val<ValT>(pos, 1);
+            }
+        }
+        __syncthreads();
+        KeyT* keys_out = reinterpret_cast<KeyT*>(p.keys_out);
+        ValT* vals_out = reinterpret_cast<ValT*>(p.vals_out);
+        for (uint32_t i = t; i < n_tile; i += EX_BLOCK) {
+            const KeyT key = s_keys[i];
+            const unsigned long long at = s_gb[key_digit(key, dsh, 255u)] + i;
+            keys_out[at] = key;
+            if constexpr (VAL_BYTES != 0) vals_out[at] = s_vals[i];
+        }
+        return;
+    }
+
+    // ---- keys of the valid windows, compacted in position order into the staging buffer -----
+    uint32_t r = excl;
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+        if (!(vf & (1u << j))) continue;
+        const KeyT key = build_key(j);
         const uint64_t pos = tile_pos + (uint64_t)t * PPT + j + p.pos_offset;
         s_keys[pad_idx<KB>(r * OUT_PER_WIN)] = key;
         if constexpr (VAL_BYTES != 0) s_vals[pad_idx<VB>(r * OUT_PER_WIN)] = make_val<ValT>(pos, 0);
@@ -392,15 +487,17 @@ __global__ void __launch_bounds__(EXW_BLOCK) extract_wide_kernel(const ExtractPa
     if (t == 0 && tile == gridDim.x - 1) p.counts[0] = base + (uint64_t)total * OUT_PER_WIN;
 }
 
-template <typename KeyT, int PPT, bool RC, int VB, bool HIST>
+template <typename KeyT, int PPT, bool RC, int VB, bool HIST, int MODE = 0, int BLOCK = EX_BLOCK_DEFAULT>
 static int launch_narrow(const ExtractParams& p, uint32_t n_tiles, cudaStream_t st) {
-    constexpr int TILE = EX_BLOCK * PPT;
+    constexpr int TILE = BLOCK * PPT;
     constexpr uint32_t STAGE = TILE * (RC ? 2 : 1);
     constexpr uint32_t STAGE_PAD = STAGE + STAGE / 8 + 8;
-    const size_t smem = (sizeof(KeyT) + (VB == 4 ? 4 : (VB == 8 ? 8 : 0))) * (size_t)STAGE_PAD;
-    auto kern = extract_narrow_kernel<KeyT, PPT, RC, VB, HIST>;
+    // (the pre-pass stages no keys: its dynamic shared memory only holds the correction tables)
+    const size_t smem = MODE == 1 ? (size_t)8 * 256 * sizeof(uint32_t)
+                                  : (sizeof(KeyT) + (VB == 4 ? 4 : (VB == 8 ? 8 : 0))) * (size_t)STAGE_PAD;
+    auto kern = extract_narrow_kernel<KeyT, PPT, RC, VB, HIST, MODE, BLOCK>;
     KMG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<n_tiles, EX_BLOCK, smem, st>>>(p);
+    kern<<<n_tiles, BLOCK, smem, st>>>(p);
     KMG_LAUNCH_CHECK();
     return KMG_OK;
 }
@@ -420,6 +517,22 @@ template <typename KeyT, int PPT>
 static int dispatch_narrow(const ExtractParams& p, uint32_t n_tiles, int rc, int vb, bool hist, cudaStream_t st) {
     return hist ? dispatch_narrow2<KeyT, PPT, true>(p, n_tiles, rc, vb, st)
                 : dispatch_narrow2<KeyT, PPT, false>(p, n_tiles, rc, vb, st);
+}
+
+// fused first prefix pass (MODE 2).  Key-only forward extraction stages 8192 keys per tile in 512
+// threads (digit runs of ~32 keys = 256 bytes); with payload or reverse complements 256 threads
+// keep the staging buffer at 64 KB.
+template <typename KeyT, int PPT>
+static int dispatch_scatter_digit(const ExtractParams& p, uint64_t n_win_tiles_256, int rc, int vb, cudaStream_t st) {
+    const uint32_t t256 = (uint32_t)n_win_tiles_256;
+    if (rc) {
+        if (vb == 0) return launch_narrow<KeyT, PPT, true, 0, false, 2, 256>(p, t256, st);
+        if (vb == 4) return launch_narrow<KeyT, PPT, true, 4, false, 2, 256>(p, t256, st);
+        return launch_narrow<KeyT, PPT, true, 8, false, 2, 256>(p, t256, st);
+    }
+    if (vb == 4) return launch_narrow<KeyT, PPT, false, 4, false, 2, 256>(p, t256, st);
+    if (vb == 8) return launch_narrow<KeyT, PPT, false, 8, false, 2, 256>(p, t256, st);
+    return KMG_ERR_ARG;  // (key-only forward: 512 threads, see extract_digit_scatter)
 }
 
 // ---- fused digit histograms: edges and final assembly -----------------------------------------------
@@ -499,6 +612,46 @@ __global__ void hist_finalize_kernel(const unsigned long long* __restrict__ hs, 
     }
 }
 
+// Pre-pass of the fused pipeline: histograms of the three TOP key bytes only (rows 0..2 = bits
+// [2k-24,2k-16), [2k-16,2k-8), [2k-8,2k)), i.e. of the 4-mers at window offsets 8, 4, 0 (rc keys:
+// rc4 of those at k-12, k-8, k-4) -- valid for 8- and 16-byte keys alike.  hs rows as laid out by
+// extract_top_hist: [0..2] forward offsets 8, 4, 0, then (rc) [3..5] offsets k-12, k-8, k-4.
+// plan[0] = number of keys, plan[1] = largest top-byte count (how skewed the keys are).
+__global__ void hist_top_finalize_kernel(const unsigned long long* __restrict__ hs, int n_off, int rc,
+                                         unsigned long long* __restrict__ top, unsigned long long* __restrict__ plan) {
+    __shared__ unsigned long long s_sum[8], s_max[8];
+    const unsigned long long* G = hs + (size_t)n_off * 256;
+    const int x = threadIdx.x;  // 256 threads
+    unsigned long long v_top = 0;
+    for (int j = 0; j < 3; ++j) {
+        unsigned long long v = G[x] + hs[(size_t)j * 256 + x];
+        if (rc) v += G[rc4(x)] + hs[(size_t)(3 + j) * 256 + rc4(x)];
+        top[j * 256 + x] = v;
+        v_top = v;
+    }
+    unsigned long long sum = v_top, mx = v_top;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((x & 31) == 0) {
+        s_sum[x >> 5] = sum;
+        s_max[x >> 5] = mx;
+    }
+    __syncthreads();
+    if (x == 0) {
+        sum = 0;
+        mx = 0;
+        for (int i = 0; i < 8; ++i) {
+            sum += s_sum[i];
+            mx = max(mx, s_max[i]);
+        }
+        plan[0] = sum;
+        plan[1] = mx;
+    }
+}
+
 template <bool RC>
 static int dispatch_wide(const ExtractParams& p, uint32_t n_tiles, int vb, cudaStream_t st) {
     if (vb == 0) extract_wide_kernel<RC, 0><<<n_tiles, EXW_BLOCK, 0, st>>>(p);
@@ -506,6 +659,82 @@ static int dispatch_wide(const ExtractParams& p, uint32_t n_tiles, int vb, cudaS
     else extract_wide_kernel<RC, 8><<<n_tiles, EXW_BLOCK, 0, st>>>(p);
     KMG_LAUNCH_CHECK();
     return KMG_OK;
+}
+
+static void fill_common(ExtractParams& p, const uint8_t* d_bases, uint64_t n_bases, uint64_t win_begin, uint64_t win_end,
+                        uint64_t tile, int k, const uint8_t* d_lut256) {
+    memset(&p, 0, sizeof(p));
+    p.bases = d_bases;
+    p.n_bases = n_bases;
+    p.win_begin = win_begin;
+    p.win_end = win_end;
+    p.first_tile = win_begin / tile;
+    p.k = k;
+    p.lut = d_lut256;
+}
+
+size_t top_hist_workspace_bytes() { return sizeof(WsHeader) + (size_t)(6 + 1) * 256 * sizeof(uint64_t); }
+
+// see common.cuh
+int extract_top_hist(const uint8_t* d_bases, uint64_t n_bases, uint64_t win_begin, uint64_t win_end, int k, int rc,
+                     const uint8_t* d_lut256, uint64_t* d_counts, unsigned long long* d_top, unsigned long long* d_plan,
+                     void* d_ws, size_t ws_bytes, cudaStream_t st) {
+    KMG_REQUIRE(k >= 12 && k <= 64, KMG_ERR_ARG, "the top-byte histograms need 12 <= k <= 64");
+    KMG_REQUIRE(ws_bytes >= top_hist_workspace_bytes(), KMG_ERR_WS, "top-hist workspace too small");
+    KMG_CUDA(cudaMemsetAsync(d_counts, 0, 2 * sizeof(uint64_t), st));
+    KMG_CUDA(cudaMemsetAsync(d_ws, 0, top_hist_workspace_bytes(), st));
+    constexpr uint64_t TILE = (uint64_t)EX_BLOCK_DEFAULT * 16;
+    ExtractParams p;
+    fill_common(p, d_bases, n_bases, win_begin, win_end, TILE, k, d_lut256);
+    p.counts = reinterpret_cast<unsigned long long*>(d_counts);
+    p.hs = reinterpret_cast<unsigned long long*>((char*)d_ws + sizeof(WsHeader));
+    p.hist_off[0] = 8;
+    p.hist_off[1] = 4;
+    p.hist_off[2] = 0;
+    p.n_off = 3;
+    if (rc) {
+        p.hist_off[3] = k - 12;
+        p.hist_off[4] = k - 8;
+        p.hist_off[5] = k - 4;
+        p.n_off = 6;
+    }
+    if (win_end > win_begin) {
+        const uint64_t n_tiles = (win_end + TILE - 1) / TILE - p.first_tile;
+        KMG_REQUIRE(n_tiles < (1ull << 31), KMG_ERR_RANGE, "too many tiles");
+        // (the histograms do not depend on the key width; one window per lane and 16 per thread
+        // span at most 79 bases, which the 96-base code words cover for every k <= 64)
+        const int rcode = launch_narrow<uint64_t, 16, false, 0, true, 1, EX_BLOCK_DEFAULT>(p, (uint32_t)n_tiles, st);
+        if (rcode != KMG_OK) return rcode;
+        hist_edges_kernel<<<1, 256, 0, st>>>(p);
+        KMG_LAUNCH_CHECK();
+    }
+    hist_top_finalize_kernel<<<1, 256, 0, st>>>(p.hs, p.n_off, rc, d_top, d_plan);
+    KMG_LAUNCH_CHECK();
+    return KMG_OK;
+}
+
+int extract_digit_scatter(const uint8_t* d_bases, uint64_t n_bases, uint64_t win_begin, uint64_t win_end, int k, int rc,
+                          const uint8_t* d_lut256, void* d_keys_out, int key_bytes, void* d_vals_out, int val_bytes,
+                          uint64_t pos_offset, unsigned long long* d_cursors, int digit_shift, cudaStream_t st) {
+    if (win_end == win_begin) return KMG_OK;
+    const int ppt = key_bytes == 8 ? 16 : 8;
+    const bool big = !rc && val_bytes == 0;  // 512-thread tiles
+    const uint64_t tile = (uint64_t)(big ? 512 : 256) * ppt;
+    ExtractParams p;
+    fill_common(p, d_bases, n_bases, win_begin, win_end, tile, k, d_lut256);
+    p.keys_out = d_keys_out;
+    p.vals_out = d_vals_out;
+    p.pos_offset = pos_offset;
+    p.cursors = d_cursors;
+    p.digit_shift = digit_shift;
+    const uint64_t n_tiles = (win_end + tile - 1) / tile - p.first_tile;
+    KMG_REQUIRE(n_tiles < (1ull << 31), KMG_ERR_RANGE, "too many tiles");
+    if (big) {
+        if (key_bytes == 8) return launch_narrow<uint64_t, 16, false, 0, false, 2, 512>(p, (uint32_t)n_tiles, st);
+        return launch_narrow<u128, 8, false, 0, false, 2, 512>(p, (uint32_t)n_tiles, st);
+    }
+    if (key_bytes == 8) return dispatch_scatter_digit<uint64_t, 16>(p, n_tiles, rc, val_bytes, st);
+    return dispatch_scatter_digit<u128, 8>(p, n_tiles, rc, val_bytes, st);
 }
 
 }  // namespace kmg
@@ -548,7 +777,7 @@ extern "C" int kmg_extract(const uint8_t* d_bases, uint64_t n_bases, uint64_t wi
     if (d_hist_out) KMG_CUDA(cudaMemsetAsync(d_hist_out, 0, sizeof(uint64_t) * MAX_PASSES * 256, st));
     if (win_end == win_begin) return KMG_OK;
 
-    const uint64_t tile = wide ? (uint64_t)EXW_TILE : (uint64_t)(EX_BLOCK * (key_bytes == 8 ? 16 : 8));
+    const uint64_t tile = wide ? (uint64_t)EXW_TILE : (uint64_t)(EX_BLOCK_DEFAULT * (key_bytes == 8 ? 16 : 8));
     const uint64_t first_tile = win_begin / tile;
     const uint64_t n_tiles = (win_end + tile - 1) / tile - first_tile;
     KMG_REQUIRE(n_tiles < (1ull << 31), KMG_ERR_RANGE, "too many tiles");

@@ -78,6 +78,9 @@ struct HybridParams {
     uint32_t tile_t;        // positions per tile
     int key_bits, pb;
     unsigned long long* irregular;  // [0] tiles the local scheme could not handle, [1] runs the block had to sort
+    unsigned long long* over;       // [0] tiles that own more keys than the local sort holds, [1] their keys
+                                    // (oversize_tiles_kernel); a fused launch stands down when there are any
+    unsigned long long* n_out_copy; // second home of *n_out, next to the status words the host reads back
     // fused run-length count (local_sort_kernel<.., true>): distinct keys -> keys_out, compacted
     uint32_t* counts_out;
     unsigned long long* n_out;      // number of distinct keys
@@ -194,6 +197,9 @@ __global__ void __launch_bounds__(LS_BLOCK, 2) local_sort_kernel(const HybridPar
     __shared__ uint32_t s_big[LS_MAX_BIG][2];
     const int t = threadIdx.x;
     const int sh_pref = p.key_bits - p.pb;
+    // a fused table cannot be patched up afterwards: with oversize tiles around the host falls back to
+    // sort + run-length stage, and this launch has nothing to do (every CTA takes the same exit)
+    if (FUSED && p.over[0] != 0) return;
 
     if (t == 0) {
         s_bad = 0;
@@ -212,7 +218,7 @@ __global__ void __launch_bounds__(LS_BLOCK, 2) local_sort_kernel(const HybridPar
             if (t < 32) {
                 if (t == 0) tile_prefix_publish(p.tile_state, tile, 0);
                 const uint64_t base = tile_prefix_resolve_warp(p.tile_state, p.n_tiles, tile, 0, p.err);
-                if (t == 0 && tile == p.n_tiles - 1) *p.n_out = base;
+                if (t == 0 && tile == p.n_tiles - 1) *p.n_out = *p.n_out_copy = base;
             }
         }
     };
@@ -495,7 +501,7 @@ __global__ void __launch_bounds__(LS_BLOCK, 2) local_sort_kernel(const HybridPar
             const uint64_t base = tile_prefix_resolve_warp(p.tile_state, p.n_tiles, tile, S, p.err);
             if (t == 0) {
                 s_base = base;
-                if (tile == p.n_tiles - 1) *p.n_out = base + S;
+                if (tile == p.n_tiles - 1) *p.n_out = *p.n_out_copy = base + S;
             }
         }
         __syncthreads();
@@ -528,7 +534,7 @@ __global__ void __launch_bounds__(LS_BLOCK, 2) local_sort_kernel(const HybridPar
             const uint64_t base = tile_prefix_resolve_warp(p.tile_state, p.n_tiles, tile, H, p.err);
             if (t == 0) {
                 s_base = base;
-                if (tile == p.n_tiles - 1) *p.n_out = base + H;
+                if (tile == p.n_tiles - 1) *p.n_out = *p.n_out_copy = base + H;
             }
         }
         __syncthreads();

@@ -495,16 +495,18 @@ thread_local int64_t g_stat_hybrid_irregular = -1;
 constexpr int MAX_TIMED = 64;
 thread_local cudaEvent_t g_ev[2 * MAX_TIMED];
 thread_local int g_ev_made = 0, g_ev_used = 0;
-thread_local int g_ev_kind[MAX_TIMED];          // 0: onesweep pass, 1: local sort of the hybrid finish
-thread_local double g_pass_ms_total[2] = {0, 0};
-thread_local int64_t g_pass_count_total[2] = {0, 0};
+thread_local int g_ev_kind[MAX_TIMED];          // 0: onesweep pass, 1: local sort, 2: histogram pre-pass, 3: fused extraction pass
+thread_local double g_pass_ms_total[4] = {0, 0, 0, 0};
+thread_local int64_t g_pass_count_total[4] = {0, 0, 0, 0};
 
-static void timing_begin(cudaStream_t st) {
+void timing_collect();
+void timing_begin(cudaStream_t st) {
+    if (g_time_passes && g_ev_used >= MAX_TIMED) timing_collect();
     if (!g_time_passes || g_ev_used >= MAX_TIMED) return;
     while (g_ev_made < 2 * MAX_TIMED) cudaEventCreate(&g_ev[g_ev_made++]);
     cudaEventRecord(g_ev[2 * g_ev_used], st);
 }
-static void timing_end(cudaStream_t st, int kind = 0) {
+void timing_end(cudaStream_t st, int kind) {
     if (!g_time_passes || g_ev_used >= MAX_TIMED) return;
     cudaEventRecord(g_ev[2 * g_ev_used + 1], st);
     g_ev_kind[g_ev_used] = kind;
@@ -526,8 +528,10 @@ double timing_total_ms(int kind) { return g_pass_ms_total[kind]; }
 int64_t timing_count(int kind) { return g_pass_count_total[kind]; }
 void timing_reset() {
     g_ev_used = 0;
-    g_pass_ms_total[0] = g_pass_ms_total[1] = 0;
-    g_pass_count_total[0] = g_pass_count_total[1] = 0;
+    for (int i = 0; i < 4; ++i) {
+        g_pass_ms_total[i] = 0;
+        g_pass_count_total[i] = 0;
+    }
 }
 
 // keys per look-back part: 30-bit counts, multiple of every tile size (lcm of tiles | 2^k*3)
@@ -625,27 +629,45 @@ static bool hybrid_applies(uint64_t n, int key_bytes, int val_bytes, int begin_b
 
 thread_local int64_t g_stat_hybrid_path = 0;  // 0 plain passes, 1 hybrid, 2 hybrid + re-sorted ranges, 3 fell back
 thread_local int64_t g_stat_hybrid_big_runs = -1;
-thread_local int g_hybrid_backoff = 0;        // sorts of this thread that skip the hybrid finish (see sort_impl)
+// what the last hybrid sort of this thread already read back when it synchronised (-1: nothing):
+// callers that would otherwise read the status word / the result count again can skip their own sync
+thread_local int64_t g_stat_last_n_out = -1;
+thread_local int64_t g_stat_last_err = -1;
 
-// fused run-length count request (kmg_sort_count): `done` = the hybrid finish produced the table
-struct CountOut {
-    uint32_t* counts;  // null: the request is for singletons with payload (kmg_sort_uniq)
-    unsigned long long* n_out;
-    bool done;
+// header words of a sort workspace used by the hybrid finish (all inside WsHeader::pad, zeroed with it)
+//   pad[0..1] irregular tiles   pad[2..3] runs the block had to sort   pad[4] tile ticket of the fused launch
+//   pad[6..7] oversize tiles    pad[8..9] keys in oversize tiles       pad[10..11] copy of the fused result count
+struct HybridHeaderView {
+    uint32_t ticket, err;
+    unsigned long long irregular, big_runs;
+    uint32_t ls_ticket, pad5;
+    unsigned long long over_tiles, over_keys, n_out;
 };
+static_assert(sizeof(HybridHeaderView) == 56, "layout of the header words");
 
 // `hybrid` = the workspace was carved for (and the call may take) the hybrid finish
+// a 16-bit prefix is enough (two passes) while its buckets stay well under a tile: judged by the
+// fullest top byte -- real genomes are skewed enough to need the third pass early
+// (a tile must hold one bucket-wide window plus the straddling bucket: capacity / 2.4)
+static bool hybrid_pb16_ok(unsigned long long max_top_byte_count, int key_bytes, int val_bytes) {
+    return max_top_byte_count / 256 <= (unsigned long long)(key_bytes == 16 ? 1700 : (val_bytes ? 2500 : 3400));
+}
+int hybrid_choose_pb(uint64_t n, unsigned long long max_top_byte_count, int key_bytes, int val_bytes) {
+    if (g_hybrid_pb == 16 || g_hybrid_pb == 24) return g_hybrid_pb;
+    return n <= (1ull << 27) && hybrid_pb16_ok(max_top_byte_count, key_bytes, val_bytes) ? 16 : 24;
+}
+
+// `pre` (fused pipeline): the keys in d_keys are ALREADY grouped by the lowest prefix byte (the first,
+// order-free prefix pass ran inside the extraction kernel); pre->top holds the histograms of the
+// three top key bytes and pre->pb the prefix width the caller chose.
 static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_alt, uint64_t n, int key_bytes,
                      int val_bytes, int begin_bit, int end_bit, const uint64_t* d_hist_in, int* h_selector_out,
                      void* d_ws, size_t ws_bytes, cudaStream_t st, bool hybrid, bool allow_hybrid,
-                     CountOut* co = nullptr) {
+                     CountOut* co = nullptr, const PrePartitioned* pre = nullptr) {
     SortWs w = carve_sort_ws(d_ws, n, key_bytes, hybrid, val_bytes);
     KMG_REQUIRE(ws_bytes >= w.total, KMG_ERR_WS, "sort workspace too small: %zu < %zu", ws_bytes, w.total);
     hybrid = hybrid && allow_hybrid;
-    if (hybrid && g_hybrid_backoff > 0 && g_hybrid_pb == 0) {
-        --g_hybrid_backoff;
-        hybrid = false;
-    }
+    KMG_REQUIRE(!pre || hybrid, KMG_ERR_ARG, "pre-partitioned keys need the hybrid finish");
 
     PassPlan plan = make_plan(begin_bit, end_bit);
     int np = plan.num_passes;
@@ -671,7 +693,9 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
             plan.shift[i] = end_bit - 24 + 8 * i;
             plan.bits[i] = 8;
         }
-        if (d_hist_in && key_bytes == 8 && (end_bit & 1) == 0) {
+        if (pre) {
+            KMG_CUDA(cudaMemcpyAsync(w.hist, pre->top, (size_t)3 * SORT_RADIX * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+        } else if (d_hist_in && key_bytes == 8 && (end_bit & 1) == 0) {
             KMG_CUDA(cudaMemcpyAsync(w.hist, d_hist_in + (size_t)13 * SORT_RADIX, (size_t)3 * SORT_RADIX * sizeof(uint64_t),
                                      cudaMemcpyDeviceToDevice, st));
         } else {
@@ -684,7 +708,7 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
                     (const u128*)d_keys, n, plan, w.hist);
             KMG_LAUNCH_CHECK();
         }
-        pb = g_hybrid_pb == 16 || g_hybrid_pb == 24 ? g_hybrid_pb : 0;
+        pb = pre ? pre->pb : (g_hybrid_pb == 16 || g_hybrid_pb == 24 ? g_hybrid_pb : 0);
         if (!pb) {
             // a 16-bit prefix is enough (two passes) while its buckets stay well under a tile: judge
             // by the fullest top byte -- real genomes are skewed enough to need the third pass early
@@ -696,7 +720,7 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
                 unsigned long long mx = 0;
                 for (int i = 0; i < SORT_RADIX; ++i) mx = std::max(mx, h_top[i]);
                 // (a tile must hold one bucket-wide window plus the straddling bucket: capacity / 2.4)
-                if (mx / 256 <= (uint64_t)(key_bytes == 16 ? 1700 : (val_bytes ? 2500 : 3400))) pb = 16;
+                if (hybrid_pb16_ok(mx, key_bytes, val_bytes)) pb = 16;
             }
         }
         np = pb / 8;
@@ -724,7 +748,7 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
     char* vin = (char*)d_vals;
     char* vout = (char*)d_vals_alt;
     uint32_t launch = 0;
-    for (int pass = 0; pass < np; ++pass) {
+    for (int pass = pre ? 1 : 0; pass < np; ++pass) {
         const ShiftDigit op{plan.shift[pass], (1u << plan.bits[pass]) - 1u};
         for (uint64_t part = 0; part < n_parts; ++part) {
             const uint64_t off = part * PART_MAX;
@@ -758,7 +782,7 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
             // the hybrid finish does not care about the order inside the first pass' digits
             const int pass_cfg = (hybrid && pass == 0 && g_hybrid_unstable && cfg == 3) ? g_unstable_config : cfg;
             int rcode = dispatch_onesweep(pass_cfg, key_bytes, val_bytes, p, op, st);
-            timing_end(st);
+            timing_end(st, 0);
             if (rcode != KMG_OK) return rcode;
             ++launch;
         }
@@ -776,6 +800,7 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
     const bool pairs = val_bytes != 0;
     const int cap = wide_key ? ls_cap<u128, false>() : (pairs ? ls_cap<uint64_t, true>() : ls_cap<uint64_t, false>());
     HybridParams hp;
+    memset(&hp, 0, sizeof(hp));
     hp.keys_in = kin;
     hp.keys_out = kout;
     hp.vals_in = vin;
@@ -797,117 +822,118 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
     hp.off = w.hyb_off;
     hp.key_bits = end_bit;
     hp.pb = pb;
-    hp.irregular = reinterpret_cast<unsigned long long*>(&w.hdr->pad[0]);  // 8-byte aligned slot of the header
+    HybridHeaderView* hv = reinterpret_cast<HybridHeaderView*>(w.hdr);
+    hp.irregular = &hv->irregular;  // [0] irregular tiles, [1] runs sorted by the block
+    hp.over = &hv->over_tiles;      // [0] oversize tiles, [1] their keys
+    hp.n_out_copy = &hv->n_out;
+    hp.tile_state = w.hyb_state;
+    hp.ticket = &hv->ls_ticket;
+    hp.err = &w.hdr->err;
     const size_t smem = wide_key ? ls_smem_bytes<u128, false>()
                                  : (pairs ? ls_smem_bytes<uint64_t, true>() : ls_smem_bytes<uint64_t, false>());
-    {
-        static bool attrs_set = false;  // (idempotent; racing threads set the same values)
-        if (!attrs_set) {
-            const int s64 = (int)ls_smem_bytes<uint64_t, false>(), s128 = (int)ls_smem_bytes<u128, false>(),
-                      sp = (int)ls_smem_bytes<uint64_t, true>();
-            KMG_CUDA(cudaFuncSetAttribute(local_sort_kernel<uint64_t, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, s64));
-            KMG_CUDA(cudaFuncSetAttribute(local_sort_kernel<uint64_t, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, s64));
-            KMG_CUDA(cudaFuncSetAttribute(local_sort_kernel<u128, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, s128));
-            KMG_CUDA(cudaFuncSetAttribute(local_sort_kernel<u128, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, s128));
-            KMG_CUDA(cudaFuncSetAttribute(local_sort_kernel<uint64_t, 0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp));
-            KMG_CUDA(cudaFuncSetAttribute(local_sort_kernel<uint64_t, 0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp));
-            KMG_CUDA(cudaFuncSetAttribute(local_sort_kernel<uint64_t, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp));
-            KMG_CUDA(cudaFuncSetAttribute(local_sort_kernel<uint64_t, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp));
-            attrs_set = true;
-        }
-    }
-    const int sel_done = (np + 1) & 1;  // kout is d_keys_alt when np is even
-    unsigned long long irregular = 0;
-    bool try_fused = co != nullptr && g_count_fused;
-    // Tile width.  The widest tiles are the fastest, but a tile owns WHOLE buckets: with big buckets
-    // around (repeat families: thousands of keys per 12-mer prefix) wide tiles overflow.  After a
-    // call of this thread met irregular tiles, the next ones first count the oversize tiles for the
-    // candidate widths (tile bounds + one tiny kernel + a stream synchronisation each) and take the
-    // widest one that leaves at most n/32 keys in oversize tiles; the check switches itself off
-    // again when the widest width has none.  A fused count / uniq is attempted only without them.
-    static thread_local bool expect_oversize = false;
+    const int sel_in = kin == (char*)d_keys ? 0 : 1;  // where the prefix-ordered keys are
+    const int sel_done = sel_in ^ 1;                   // ... and where the finish puts its result
+    const bool want_fused = co != nullptr && g_count_fused;
+
     auto launch_bounds = [&](uint32_t T) -> int {
         hp.tile_t = T;
         hp.n_tiles = (uint32_t)((n + T - 1) / T);
         if (wide_key) tile_bounds_kernel<u128><<<(hp.n_tiles + 1 + 7) / 8, 256, 0, st>>>(hp);
         else tile_bounds_kernel<uint64_t><<<(hp.n_tiles + 1 + 7) / 8, 256, 0, st>>>(hp);
         KMG_LAUNCH_CHECK();
+        // tiles that own more keys than the local sort holds (huge prefix buckets: repeats) are known
+        // from the bounds alone; the fused launch reads the count from device memory and stands
+        // down when there are any (its table would be void), so no host round trip sits between
+        KMG_CUDA(cudaMemsetAsync(hp.over, 0, 2 * sizeof(unsigned long long), st));
+        oversize_tiles_kernel<<<(hp.n_tiles + 255) / 256, 256, 0, st>>>(hp, (uint32_t)cap, hp.over);
+        KMG_LAUNCH_CHECK();
         return KMG_OK;
     };
-    const uint32_t t_wide = tile_width(g_local_tile);
-    if (!expect_oversize) {
-        const int rc0 = launch_bounds(t_wide);
-        if (rc0 != KMG_OK) return rc0;
-    } else {
-        unsigned long long* d_over = reinterpret_cast<unsigned long long*>(&w.hdr->pad[6]);  // 2 words
-        unsigned long long over[2] = {0, 0};
-        const uint32_t cand[3] = {t_wide, tile_width(cap / 2), tile_width(cap / 4)};
-        for (int c = 0; c < 3; ++c) {
-            if (c > 0 && cand[c] >= cand[c - 1]) continue;
-            const int rc0 = launch_bounds(cand[c]);
-            if (rc0 != KMG_OK) return rc0;
-            KMG_CUDA(cudaMemsetAsync(d_over, 0, 2 * sizeof(unsigned long long), st));
-            oversize_tiles_kernel<<<(hp.n_tiles + 255) / 256, 256, 0, st>>>(hp, (uint32_t)cap, d_over);
-            KMG_LAUNCH_CHECK();
-            KMG_CUDA(cudaMemcpyAsync(over, d_over, sizeof(over), cudaMemcpyDeviceToHost, st));
-            KMG_CUDA(cudaStreamSynchronize(st));
-            if (over[1] <= n / 32) break;
-        }
-        if (over[0]) try_fused = false;  // the table would be void: sort, re-sort those ranges, then count
-        else if (hp.tile_t == t_wide) expect_oversize = false;
-    }
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        const bool fused = try_fused && attempt == 0;
-        if (!fused && attempt == 0) continue;  // plain sort: only the second form
-        if (fused) {
-            hp.counts_out = co->counts;
-            hp.n_out = co->n_out;
-            hp.tile_state = w.hyb_state;
-            hp.ticket = &w.hdr->pad[4];
-            hp.err = &w.hdr->err;
-        } else if (co != nullptr) {
-            // the fused launch met irregular tiles: its table is void, sort the keys instead
-            KMG_CUDA(cudaMemsetAsync(hp.irregular, 0, 2 * sizeof(unsigned long long), st));
-            KMG_CUDA(cudaMemsetAsync(hp.flag, 0, (size_t)(hp.n_tiles + 1) * sizeof(uint32_t), st));
-        }
+    auto launch_local = [&](bool fused) -> int {
+        hp.counts_out = fused ? co->counts : nullptr;
+        hp.n_out = fused ? co->n_out : nullptr;
         if (g_ev_used >= MAX_TIMED) timing_collect();
         timing_begin(st);
+#define KMG_LS_LAUNCH(K, E, V)                                                                                   \
+    do {                                                                                                         \
+        KMG_CUDA(cudaFuncSetAttribute(local_sort_kernel<K, E, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        local_sort_kernel<K, E, V><<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);                                       \
+    } while (0)
         if (fused && pairs) {
-            if (val_bytes == 4) local_sort_kernel<uint64_t, 2, 4><<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);
-            else local_sort_kernel<uint64_t, 2, 8><<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);
+            if (val_bytes == 4) KMG_LS_LAUNCH(uint64_t, 2, 4);
+            else KMG_LS_LAUNCH(uint64_t, 2, 8);
         } else if (fused) {
-            if (wide_key) local_sort_kernel<u128, 1, 0><<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);
-            else local_sort_kernel<uint64_t, 1, 0><<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);
+            if (wide_key) KMG_LS_LAUNCH(u128, 1, 0);
+            else KMG_LS_LAUNCH(uint64_t, 1, 0);
         } else if (pairs) {
-            if (val_bytes == 4) local_sort_kernel<uint64_t, 0, 4><<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);
-            else local_sort_kernel<uint64_t, 0, 8><<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);
+            if (val_bytes == 4) KMG_LS_LAUNCH(uint64_t, 0, 4);
+            else KMG_LS_LAUNCH(uint64_t, 0, 8);
         } else {
-            if (wide_key) local_sort_kernel<u128, 0, 0><<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);
-            else local_sort_kernel<uint64_t, 0, 0><<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);
+            if (wide_key) KMG_LS_LAUNCH(u128, 0, 0);
+            else KMG_LS_LAUNCH(uint64_t, 0, 0);
         }
+#undef KMG_LS_LAUNCH
         timing_end(st, 1);
         KMG_LAUNCH_CHECK();
-        unsigned long long fb[2] = {0, 0};
-        KMG_CUDA(cudaMemcpyAsync(fb, hp.irregular, sizeof(fb), cudaMemcpyDeviceToHost, st));
+        return KMG_OK;
+    };
+    // ONE read-back per attempt: everything the host needs to know about it
+    HybridHeaderView hh;
+    auto read_header = [&]() -> int {
+        KMG_CUDA(cudaMemcpyAsync(&hh, w.hdr, sizeof(hh), cudaMemcpyDeviceToHost, st));
         KMG_CUDA(cudaStreamSynchronize(st));
-        irregular = fb[0];
-        g_stat_hybrid_irregular = (int64_t)irregular;
-        g_stat_hybrid_big_runs = (int64_t)fb[1];
-        // More block-sorted runs than tiles (keys crowded into cells by the hundred, everywhere) make the
-        // local sort slower than the passes it replaces: leave the next sorts of this thread to the
-        // plain passes, then probe again.
-        if (fb[1] > hp.n_tiles) g_hybrid_backoff = 16;
-        g_stat_hybrid_path = 1;
-        if (irregular == 0) {
-            if (fused) co->done = true;
+        g_stat_hybrid_irregular = (int64_t)hh.irregular;
+        g_stat_hybrid_big_runs = (int64_t)hh.big_runs;
+        g_stat_last_err = (int64_t)hh.err;
+        return KMG_OK;
+    };
+
+    // First attempt at the widest tiles: the fused emission when the caller asked for one, else the sort.
+    int rcode = launch_bounds(tile_width(g_local_tile));
+    if (rcode != KMG_OK) return rcode;
+    rcode = launch_local(want_fused);
+    if (rcode != KMG_OK) return rcode;
+    rcode = read_header();
+    if (rcode != KMG_OK) return rcode;
+    g_stat_hybrid_path = 1;
+    if (hh.irregular == 0 && (!want_fused || hh.over_tiles == 0)) {
+        if (want_fused) {
+            co->done = true;
+            g_stat_last_n_out = (int64_t)hh.n_out;
+        }
+        *h_selector_out = sel_done;
+        return KMG_OK;
+    }
+    // Some tiles own more keys than the local scheme holds (a huge prefix bucket: repeats) or crowd
+    // too many distinct keys into one cell.  The keys get sorted (no fused emission: the caller
+    // follows up with kmg_rle_count / kmg_select_singletons), the irregular tiles' ranges are
+    // gathered, sorted with the plain passes and put back.
+    if (want_fused || hh.over_keys > n / 32) {
+        // The widest tiles are the fastest, but a tile owns WHOLE buckets: with big buckets around
+        // (repeat families: thousands of keys per 12-mer prefix) wide tiles overflow.  Take the widest
+        // candidate width that leaves at most n/32 keys in oversize tiles.
+        const uint32_t cand[3] = {tile_width(g_local_tile), tile_width(cap / 2), tile_width(cap / 4)};
+        if (hh.over_keys > n / 32) {
+            for (int c = 1; c < 3; ++c) {
+                if (cand[c] >= cand[c - 1]) continue;
+                rcode = launch_bounds(cand[c]);
+                if (rcode != KMG_OK) return rcode;
+                rcode = read_header();
+                if (rcode != KMG_OK) return rcode;
+                if (hh.over_keys <= n / 32) break;
+            }
+        }
+        KMG_CUDA(cudaMemsetAsync(hp.irregular, 0, 2 * sizeof(unsigned long long), st));
+        KMG_CUDA(cudaMemsetAsync(hp.flag, 0, (size_t)(n / LS_T_MIN + 2) * sizeof(uint32_t), st));
+        rcode = launch_local(false);
+        if (rcode != KMG_OK) return rcode;
+        rcode = read_header();
+        if (rcode != KMG_OK) return rcode;
+        if (hh.irregular == 0) {
             *h_selector_out = sel_done;
             return KMG_OK;
         }
-        expect_oversize = true;
     }
-    // Some tiles own more keys than the local scheme holds (a huge prefix bucket: repeats).  Their
-    // ranges are gathered, sorted with the plain passes and put back -- unless they are most of the
-    // input, in which case the plain passes sort everything.
     irregular_scan_kernel<<<1, 1024, 0, st>>>(hp);
     KMG_LAUNCH_CHECK();
     unsigned long long m_irr = 0;
@@ -921,9 +947,9 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
         if (rc2 != KMG_OK) return rc2;
         int sel2 = 0;
         const int64_t passes = g_stat_sort_passes;
-        const int rcode = sort_impl(w.irr_buf[0], w.irr_buf[1], pairs ? w.irr_vbuf[0] : nullptr, pairs ? w.irr_vbuf[1] : nullptr,
-                                    m_irr, key_bytes, val_bytes, 0, end_bit, nullptr, &sel2, w.irr_ws, w.irr_ws_bytes, st, false,
-                                    false);
+        rcode = sort_impl(w.irr_buf[0], w.irr_buf[1], pairs ? w.irr_vbuf[0] : nullptr, pairs ? w.irr_vbuf[1] : nullptr,
+                          m_irr, key_bytes, val_bytes, 0, end_bit, nullptr, &sel2, w.irr_ws, w.irr_ws_bytes, st, false,
+                          false);
         g_stat_sort_passes = passes;
         if (rcode != KMG_OK) return rcode;
         rc2 = irregular_copy<false>(hp, key_bytes, nullptr, kout, w.irr_buf[sel2], grid, st);
@@ -934,13 +960,22 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
     }
     g_stat_hybrid_path = 3;
     int sel2 = 0;
-    const int rcode = sort_impl(kin, kout, vin, vout, n, key_bytes, val_bytes, begin_bit, end_bit, nullptr, &sel2, d_ws,
-                                ws_bytes, st, true, false);
+    rcode = sort_impl(kin, kout, vin, vout, n, key_bytes, val_bytes, begin_bit, end_bit, nullptr, &sel2, d_ws, ws_bytes, st,
+                      true, false);
     if (rcode != KMG_OK) return rcode;
-    *h_selector_out = (np & 1) ^ sel2;  // kin is d_keys when np is even
+    *h_selector_out = sel_in ^ sel2;
     return KMG_OK;
 }
 
+// exclusive scan of one 256-bin histogram row (the cursors of the fused first prefix pass)
+void exclusive_scan_256(const unsigned long long* d_hist_row, unsigned long long* d_out, cudaStream_t st) {
+    radix_scan_kernel<<<1, 32, 0, st>>>(d_hist_row, reinterpret_cast<uint64_t*>(d_out), SORT_RADIX, SORT_RADIX, nullptr);
+    bump_launches();
+}
+
+bool hybrid_sort_applies(uint64_t n, int key_bytes, int val_bytes, int end_bit, bool pairs_ok) {
+    return hybrid_applies(n, key_bytes, val_bytes, 0, end_bit, pairs_ok);
+}
 }  // namespace kmg
 
 using namespace kmg;
@@ -964,6 +999,7 @@ extern "C" int kmg_radix_sort(void* d_keys, void* d_keys_alt, void* d_vals, void
     g_stat_sort_passes = 0;
     g_stat_hybrid_path = 0;
     g_stat_hybrid_irregular = -1;
+    g_stat_last_n_out = g_stat_last_err = -1;
     if (n <= 1 || end_bit == begin_bit) return KMG_OK;
     KMG_REQUIRE(d_keys && d_keys_alt && d_ws, KMG_ERR_ARG, "null pointer argument");
     KMG_REQUIRE(val_bytes == 0 || d_vals_alt, KMG_ERR_ARG, "d_vals_alt is null");
@@ -982,9 +1018,15 @@ extern "C" size_t kmg_sort_count_workspace_bytes(uint64_t n, int key_bytes, int 
     return align_up(kmg_radix_sort_workspace_bytes(n, key_bytes, 0, 0, end_bit), 256) + kmg_rle_workspace_bytes(n);
 }
 
-extern "C" int kmg_sort_count(void* d_keys, void* d_keys_alt, uint64_t n, int key_bytes, int end_bit,
-                              const uint64_t* d_hist_in, uint32_t* d_counts_out, uint64_t* d_n_out, int* h_selector_out,
-                              void* d_ws, size_t ws_bytes, void* stream) {
+// the run-length / singleton stage keeps its status word in its own workspace header: fold it into the
+// sort's, which is the one callers check (kmg_ws_status(d_ws))
+__global__ void merge_err_kernel(uint32_t* dst, const uint32_t* src) {
+    if (*src) atomicMax(dst, *src);
+}
+
+int kmg::sort_count_core(void* d_keys, void* d_keys_alt, uint64_t n, int key_bytes, int end_bit, const uint64_t* d_hist_in,
+                         uint32_t* d_counts_out, uint64_t* d_n_out, int* h_selector_out, void* d_ws, size_t ws_bytes,
+                         void* stream, const PrePartitioned* pre) {
     cudaStream_t st = (cudaStream_t)stream;
     KMG_REQUIRE(key_bytes == 8 || key_bytes == 16, KMG_ERR_ARG, "key_bytes must be 8 or 16");
     KMG_REQUIRE(end_bit >= 0 && end_bit <= key_bytes * 8, KMG_ERR_ARG, "bad end_bit %d", end_bit);
@@ -993,6 +1035,7 @@ extern "C" int kmg_sort_count(void* d_keys, void* d_keys_alt, uint64_t n, int ke
     g_stat_sort_passes = 0;
     g_stat_hybrid_path = 0;
     g_stat_hybrid_irregular = -1;
+    g_stat_last_n_out = g_stat_last_err = -1;
     KMG_CUDA(cudaMemsetAsync(d_n_out, 0, sizeof(uint64_t), st));
     if (n == 0) return KMG_OK;
     KMG_REQUIRE(d_keys && d_keys_alt && d_counts_out && d_ws, KMG_ERR_ARG, "null pointer argument");
@@ -1005,18 +1048,31 @@ extern "C" int kmg_sort_count(void* d_keys, void* d_keys_alt, uint64_t n, int ke
     if (n > 1 && end_bit > 0) {
         const bool hybrid = hybrid_applies(n, key_bytes, 0, 0, end_bit);
         const int rcode = sort_impl(d_keys, d_keys_alt, nullptr, nullptr, n, key_bytes, 0, 0, end_bit, d_hist_in, &sel, d_ws,
-                                    sort_ws, st, hybrid, true, &co);
+                                    sort_ws, st, hybrid, true, &co, pre);
         if (rcode != KMG_OK) return rcode;
     }
     if (co.done) {  // the hybrid finish wrote the table itself
         *h_selector_out = sel;
         return KMG_OK;
     }
+    g_stat_last_n_out = g_stat_last_err = -1;  // (whatever the sort read back is not the final word)
     void* sorted = sel ? d_keys_alt : d_keys;
     void* other = sel ? d_keys : d_keys_alt;
     *h_selector_out = sel ^ 1;
-    return kmg_rle_count(sorted, n, key_bytes, other, d_counts_out, d_n_out, (char*)d_ws + sort_ws, ws_bytes - sort_ws,
-                         stream);
+    const int rcode = kmg_rle_count(sorted, n, key_bytes, other, d_counts_out, d_n_out, (char*)d_ws + sort_ws,
+                                    ws_bytes - sort_ws, stream);
+    if (rcode != KMG_OK) return rcode;
+    merge_err_kernel<<<1, 1, 0, st>>>(&reinterpret_cast<WsHeader*>(d_ws)->err,
+                                      &reinterpret_cast<WsHeader*>((char*)d_ws + sort_ws)->err);
+    KMG_LAUNCH_CHECK();
+    return KMG_OK;
+}
+
+extern "C" int kmg_sort_count(void* d_keys, void* d_keys_alt, uint64_t n, int key_bytes, int end_bit,
+                              const uint64_t* d_hist_in, uint32_t* d_counts_out, uint64_t* d_n_out, int* h_selector_out,
+                              void* d_ws, size_t ws_bytes, void* stream) {
+    return sort_count_core(d_keys, d_keys_alt, n, key_bytes, end_bit, d_hist_in, d_counts_out, d_n_out, h_selector_out, d_ws,
+                           ws_bytes, stream, nullptr);
 }
 
 extern "C" int kmg_select_singletons(const void* d_sorted_keys, const void* d_vals, uint64_t n, int key_bytes, int val_bytes,
@@ -1032,9 +1088,9 @@ extern "C" size_t kmg_sort_uniq_workspace_bytes(uint64_t n, int key_bytes, int v
     return sort_uniq_sort_ws(n, key_bytes, val_bytes, end_bit) + kmg_rle_workspace_bytes(n);
 }
 
-extern "C" int kmg_sort_uniq(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_alt, uint64_t n, int key_bytes,
-                             int val_bytes, int end_bit, const uint64_t* d_hist_in, uint64_t* d_n_out, int* h_selector_out,
-                             void* d_ws, size_t ws_bytes, void* stream) {
+int kmg::sort_uniq_core(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_alt, uint64_t n, int key_bytes,
+                        int val_bytes, int end_bit, const uint64_t* d_hist_in, uint64_t* d_n_out, int* h_selector_out,
+                        void* d_ws, size_t ws_bytes, void* stream, const PrePartitioned* pre) {
     cudaStream_t st = (cudaStream_t)stream;
     KMG_REQUIRE(key_bytes == 8 || key_bytes == 16, KMG_ERR_ARG, "key_bytes must be 8 or 16");
     KMG_REQUIRE(val_bytes == 4 || val_bytes == 8, KMG_ERR_ARG, "val_bytes must be 4 or 8");
@@ -1044,6 +1100,7 @@ extern "C" int kmg_sort_uniq(void* d_keys, void* d_keys_alt, void* d_vals, void*
     g_stat_sort_passes = 0;
     g_stat_hybrid_path = 0;
     g_stat_hybrid_irregular = -1;
+    g_stat_last_n_out = g_stat_last_err = -1;
     KMG_CUDA(cudaMemsetAsync(d_n_out, 0, sizeof(uint64_t), st));
     if (n == 0) return KMG_OK;
     KMG_REQUIRE(d_keys && d_keys_alt && d_vals && d_vals_alt && d_ws, KMG_ERR_ARG, "null pointer argument");
@@ -1057,17 +1114,30 @@ extern "C" int kmg_sort_uniq(void* d_keys, void* d_keys_alt, void* d_vals, void*
         // equal keys may come out in any order: only keys that occur once are kept
         const bool hybrid = hybrid_applies(n, key_bytes, val_bytes, 0, end_bit, true);
         const int rcode = sort_impl(d_keys, d_keys_alt, d_vals, d_vals_alt, n, key_bytes, val_bytes, 0, end_bit, d_hist_in, &sel,
-                                    d_ws, sort_ws, st, hybrid, true, &uo);
+                                    d_ws, sort_ws, st, hybrid, true, &uo, pre);
         if (rcode != KMG_OK) return rcode;
     }
     if (uo.done) {  // the hybrid finish emitted the singletons itself
         *h_selector_out = sel;
         return KMG_OK;
     }
+    g_stat_last_n_out = g_stat_last_err = -1;
     *h_selector_out = sel ^ 1;
-    return kmg_select_singletons(sel ? d_keys_alt : d_keys, sel ? d_vals_alt : d_vals, n, key_bytes, val_bytes,
-                                 sel ? d_keys : d_keys_alt, sel ? d_vals : d_vals_alt, d_n_out, (char*)d_ws + sort_ws,
-                                 ws_bytes - sort_ws, stream);
+    const int rcode = kmg_select_singletons(sel ? d_keys_alt : d_keys, sel ? d_vals_alt : d_vals, n, key_bytes, val_bytes,
+                                            sel ? d_keys : d_keys_alt, sel ? d_vals : d_vals_alt, d_n_out,
+                                            (char*)d_ws + sort_ws, ws_bytes - sort_ws, stream);
+    if (rcode != KMG_OK) return rcode;
+    merge_err_kernel<<<1, 1, 0, st>>>(&reinterpret_cast<WsHeader*>(d_ws)->err,
+                                      &reinterpret_cast<WsHeader*>((char*)d_ws + sort_ws)->err);
+    KMG_LAUNCH_CHECK();
+    return KMG_OK;
+}
+
+extern "C" int kmg_sort_uniq(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_alt, uint64_t n, int key_bytes,
+                             int val_bytes, int end_bit, const uint64_t* d_hist_in, uint64_t* d_n_out, int* h_selector_out,
+                             void* d_ws, size_t ws_bytes, void* stream) {
+    return sort_uniq_core(d_keys, d_keys_alt, d_vals, d_vals_alt, n, key_bytes, val_bytes, end_bit, d_hist_in, d_n_out,
+                          h_selector_out, d_ws, ws_bytes, stream, nullptr);
 }
 
 extern "C" size_t kmg_partition_workspace_bytes(uint64_t n, int key_bytes, int val_bytes) {

@@ -23,6 +23,8 @@
 
 namespace kmg {
 
+int64_t g_count_limit = 0;  // kmg_set_option("count_limit", n): test hook, 0 = the real limit 2^32-1
+
 constexpr int RLE_BLOCK = 256;
 constexpr int RLE_WARPS = RLE_BLOCK / 32;
 
@@ -53,6 +55,7 @@ struct RleParams {
     uint64_t* t_spre;     // [tiles] singletons before the tile
     uint64_t* t_carry;    // [tiles] position + 1 of the last head before the tile (0 = none)
     uint32_t* err;
+    unsigned long long count_limit;  // run lengths above it raise err = 2 (2^32-1; lower only in tests)
 };
 
 // lanes of step j whose element exists (tile-local index < n_local)
@@ -281,7 +284,7 @@ __device__ __forceinline__ void rle_count_tile(const RleParams& p, const uint32_
                 uint64_t len;
                 if (h_incl) len = (uint64_t)(li - s_hpos[h_incl - 1]) + 1;
                 else len = tile_base + li - (carry - 1) + 1;
-                if (len > 0xffffffffull) atomicExch(p.err, 2u);
+                if (len > p.count_limit) atomicExch(p.err, 2u);
                 *(counts_out + (int64_t)h_incl - 1) = (uint32_t)len;
             }
         }
@@ -394,6 +397,7 @@ static int rle_setup(RleParams& p, uint64_t n, int key_bytes, void* d_ws, size_t
     p.t_spre = (uint64_t*)at; at += a64;
     p.t_carry = (uint64_t*)at; at += a64;
     p.err = &hdr->err;
+    p.count_limit = g_count_limit > 0 ? (unsigned long long)g_count_limit : 0xffffffffull;
     return KMG_OK;
 }
 

@@ -119,7 +119,12 @@ class PeerBuffers:
     are all-gathered, and each rank maps its peers' buffers (kmg_ipc_open).  `ptr_table` is the
     device array of per-destination base pointers.  Every buffer starts with a HEADER whose first
     word is the destination's shared cursor (kmg_extract_scatter_shared); the keys / payloads
-    start at `data` / `data_table`."""
+    start at `data` / `data_table`.
+
+    The constructor never raises between collectives: a rank whose allocation or mapping fails still
+    takes part in the handle all-gather (with None) and ends up with `ok = False`; the caller
+    all-reduces `ok` and every rank then releases what it holds WITHOUT further collectives
+    (`release_local`)."""
 
     HEADER = 256
 
@@ -131,36 +136,62 @@ class PeerBuffers:
         self.eng, self.lib, self.group = engine, engine.lib, group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.nbytes = int(nbytes)  # payload bytes (without the header)
-        ptr = C.c_void_p()
+        self.ok, self.error = True, ""
+        self.local_ptr, self.local, self.peer_ptrs = None, None, []
         handle = (C.c_uint8 * 64)()
-        _lib.check(self.lib.kmg_ipc_alloc(self.nbytes + self.HEADER, C.byref(ptr), handle))
-        self.local_ptr = ptr.value
+        try:
+            ptr = C.c_void_p()
+            _lib.check(self.lib.kmg_ipc_alloc(self.nbytes + self.HEADER, C.byref(ptr), handle))
+            self.local_ptr = ptr.value
+        except Exception as exc:  # CUDA IPC unavailable (container policy, out of memory, ...)
+            self.ok, self.error = False, repr(exc)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle) if self.ok else None, group=group)
+        if self.ok and any(h is None for h in handles):
+            self.ok, self.error = False, "a peer could not allocate its receive buffer"
+        if self.ok:
+            try:
+                for r, h in enumerate(handles):
+                    if r == self.rank:
+                        self.peer_ptrs.append(self.local_ptr)
+                        continue
+                    q = C.c_void_p()
+                    hb = (C.c_uint8 * 64).from_buffer_copy(h)
+                    _lib.check(self.lib.kmg_ipc_open(hb, C.byref(q)))
+                    self.peer_ptrs.append(q.value)
+            except Exception as exc:
+                self.ok, self.error = False, repr(exc)
+        if not self.ok:
+            return
         self.local = torch.as_tensor(_DevMem(self.local_ptr, self.nbytes + self.HEADER), device=engine.device)
         self.data = self.local[self.HEADER:]
         self.cursor = self.local[:8].view(torch.int64)
-        handles = [None] * self.world
-        dist.all_gather_object(handles, bytes(handle), group=group)
-        self.peer_ptrs = []
-        for r, h in enumerate(handles):
-            if r == self.rank:
-                self.peer_ptrs.append(self.local_ptr)
-                continue
-            q = C.c_void_p()
-            hb = (C.c_uint8 * 64).from_buffer_copy(h)
-            _lib.check(self.lib.kmg_ipc_open(hb, C.byref(q)))
-            self.peer_ptrs.append(q.value)
         self.ptr_table = torch.tensor(self.peer_ptrs, dtype=torch.int64, device=engine.device)
         self.data_table = self.ptr_table + self.HEADER
 
+    def owns(self, t: Optional[torch.Tensor]) -> bool:
+        """Does `t` live inside this rank's receive buffer?"""
+        if t is None or self.local_ptr is None:
+            return False
+        return self.local_ptr <= t.data_ptr() < self.local_ptr + self.nbytes + self.HEADER
+
+    def release_local(self):
+        """Unmap the peers and free the own buffer; no collective (safe when only some ranks fail)."""
+        torch.cuda.synchronize()
+        for r, q in enumerate(self.peer_ptrs):
+            if r != self.rank and q is not None:
+                self.lib.kmg_ipc_close(q)
+        self.peer_ptrs = []
+        self.local = None
+        if self.local_ptr is not None:
+            self.lib.kmg_ipc_free(self.local_ptr)
+            self.local_ptr = None
+
     def close(self):
+        """Collective release: nobody may still be storing into a buffer that is about to be freed."""
         torch.cuda.synchronize()
         dist.barrier(group=self.group)
-        for r, q in enumerate(self.peer_ptrs):
-            if r != self.rank:
-                self.lib.kmg_ipc_close(q)
-        self.local = None
-        self.lib.kmg_ipc_free(self.local_ptr)
-        self.peer_ptrs = []
+        self.release_local()
 
 
 class DistributedCounter:
@@ -168,7 +199,12 @@ class DistributedCounter:
 
     Two exchange paths: `p2p=True` (default when CUDA IPC works) fuses extraction, range partition
     and the transfer into ONE kernel that stores keys into the owners' receive buffers over NVLink;
-    `p2p=False` is the plain path: extract -> range partition pass -> NCCL all-to-all."""
+    `p2p=False` is the plain path: extract -> range partition pass -> NCCL all-to-all.
+
+    Results (CountTable / KeyArray) live in torch-owned memory: a table that the sort left inside the
+    peer-mapped receive buffer is copied out before it is returned, so it stays valid while peers
+    store the next step's keys.  With `reuse` scratch (the benchmark loop) a result is valid until
+    the next call on this counter."""
 
     def __init__(self, engine, group=None, p2p: Optional[bool] = None):
         self.eng = engine
@@ -179,14 +215,14 @@ class DistributedCounter:
         self._peer_keys: Optional[PeerBuffers] = None
         self._peer_vals: Optional[PeerBuffers] = None
         # single-launch exchange with shared cursors: measured faster up to 4 GPUs (N=2 +14 %, N=4 +4.5 %);
-        # at 8 the 8 x 8 sources x destinations contend for the cursor words and the exact two-launch
-        # exchange wins (-4 %).  KMG_DIST_SHARED=0/1 overrides.
+        # at 8 the 8 x 8 sources x destinations contend for the cursor words and the exact exchange
+        # wins (-4 %).  KMG_DIST_SHARED=0/1 overrides.
         env = os.environ.get("KMG_DIST_SHARED")
         self.shared = (self.world <= 4) if env is None else env != "0"
-        self._cap_key = None
-        self._cap_elems = 0
+        self._cap_elems = 0  # elements the receive buffers are provisioned for; identical on every rank
         self._timing = {} if os.environ.get("KMG_DIST_TIMING") == "1" else None
         self._t_last = None
+        self._info_host = torch.zeros(8, dtype=torch.int64).pin_memory() if torch.cuda.is_available() else None
 
     def _mark(self, name: str) -> None:
         """KMG_DIST_TIMING=1: wall-clock per stage (synchronising; a development aid, see
@@ -203,31 +239,50 @@ class DistributedCounter:
 
     # ---- fused extraction + partition + peer stores ---------------------------------------------
     def _ensure_peer(self, which: str, nbytes: int) -> PeerBuffers:
-        """(Re)allocate the mapped receive buffers.  `nbytes` comes from the all-gathered count
-        matrix, so every rank takes the same decision without further communication."""
+        """(Re)allocate the mapped receive buffers.  `nbytes` derives from values every rank agrees on
+        (all-gathered counts / all-reduced maxima), so all ranks take the same decision here and
+        issue the same collectives, whether or not the mapping succeeds on every one of them."""
         cur = getattr(self, which)
         if cur is not None and cur.nbytes >= nbytes:
             return cur
         if cur is not None:
             cur.close()
             setattr(self, which, None)
-        try:
-            cur = PeerBuffers(self.eng, int(nbytes * 1.1) + 4096, self.group)
-            ok = 1
-        except Exception as exc:  # CUDA IPC unavailable (container policy, no peer access, ...)
-            cur, ok, self._p2p_error = None, 0, repr(exc)
-        flag = torch.tensor([ok], dtype=torch.int64, device=self.eng.device)
+        cur = PeerBuffers(self.eng, int(nbytes * 1.1) + 4096, self.group)
+        flag = torch.tensor([1 if cur.ok else 0], dtype=torch.int64, device=self.eng.device)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
         if int(flag.item()) == 0:
-            if cur is not None:
-                cur.close()
-            raise _PeerUnavailable(getattr(self, "_p2p_error", "a peer could not map the receive buffers"))
+            err = cur.error or "a peer could not map the receive buffers"
+            cur.release_local()  # no collective: ranks that failed early hold nothing to fence
+            raise _PeerUnavailable(err)
         setattr(self, which, cur)
         return cur
 
+    def _dest_counts(self, d, k: int, rc: bool, kb: int) -> torch.Tensor:
+        """Per-destination key counts of this rank's windows (+ wide-stream windows in [G])."""
+        from kman_b200 import _lib
+
+        eng, lib, G = self.eng, self.eng.lib, self.world
+        n_win = max(0, d.n_bases - k + 1)
+        counts = torch.zeros(G + 1, dtype=torch.int64, device=eng.device)
+        if k >= 12 and G & (G - 1) == 0:
+            # from the 4-mer histogram of the bases: no second key-building pass
+            ws_bytes = lib.kmg_dest_counts_workspace_bytes()
+            ws = eng._buf("ws_dest_counts", ws_bytes)
+            _lib.check(lib.kmg_extract_dest_counts(d.bases.data_ptr(), d.n_bases, 0, n_win, k, int(rc), d.lut.data_ptr(), G,
+                                                   counts.data_ptr(), ws.data_ptr(), ws_bytes, eng._stream()))
+        else:
+            _lib.check(lib.kmg_extract_scatter(d.bases.data_ptr(), d.n_bases, 0, n_win, k, int(rc), d.lut.data_ptr(), G, None,
+                                               None, kb, 0, d.pos_offset, None, counts.data_ptr(), 1, eng._stream()))
+        return counts
+
     def _extract_exchange_p2p(self, d, k: int, rc: bool, with_vals: bool):
-        """extract_scatter: size the regions (count-only launch), agree on offsets, then one kernel
-        extracts the keys and stores them into the owning GPUs' receive buffers."""
+        """Exact regions: per-destination counts (from the 4-mer histogram), ONE all-gather of the
+        G x G matrix, region offsets computed on the device, then one kernel extracts the keys and
+        stores them into the owning GPUs' receive buffers.  In steady state (buffers provisioned) the
+        host does not look at the matrix before the scatter launch: the kernel itself refuses to store
+        past the buffers' capacity, and ONE read-back after the fence brings the received count, the
+        overflow flag and the wide-window total."""
         from kman_b200 import _lib
         from kman_b200.engine import KeyArray
 
@@ -236,49 +291,62 @@ class DistributedCounter:
         vb = 8 if with_vals else 0
         n_win = max(0, d.n_bases - k + 1)
         self._mark("(outside)")
-        counts = torch.zeros(G + 1, dtype=torch.int64, device=eng.device)
-        _lib.check(lib.kmg_extract_scatter(d.bases.data_ptr(), d.n_bases, 0, n_win, k, int(rc), d.lut.data_ptr(), G, None,
-                                           None, kb, 0, d.pos_offset, None, counts.data_ptr(), 1, eng._stream()))
-        self._mark("count-only launch")
+        counts = self._dest_counts(d, k, rc, kb)
+        self._mark("per-destination counts")
         allc = torch.empty(G * (G + 1), dtype=torch.int64, device=eng.device)
         dist.all_gather_into_tensor(allc, counts, group=self.group)
-        M = allc.cpu().numpy().reshape(G, G + 1)
-        self._mark("all-gather of the count matrix")
-        if int(M[:, G].sum()):
-            raise ValueError("distributed path handles the narrow (plain ACGT) stream only in this build; "
-                             f"input holds {int(M[:, G].sum())} windows with other alphabet symbols")
-        M = M[:, :G]
-        n_recv = int(M[:, self.rank].sum())
-        recv_max = int(M.sum(axis=0).max())
-        pk = self._ensure_peer("_peer_keys", recv_max * kb)
-        pv = self._ensure_peer("_peer_vals", recv_max * vb) if with_vals else None
+        M = allc.view(G, G + 1)
         # my region inside destination dst starts after the regions of the sources before me
-        cursors = torch.from_numpy(np.ascontiguousarray(M[: self.rank, :].sum(axis=0), dtype=np.int64)).to(eng.device)
-        self._mark("host: regions, cursors")
-        # No fence is needed before the stores: the all-gather above completed, so every rank had
-        # entered it, and each rank enters it only after (in stream order) it stopped reading its
-        # receive buffer of the previous step.
-        _lib.check(lib.kmg_extract_scatter(d.bases.data_ptr(), d.n_bases, 0, n_win, k, int(rc), d.lut.data_ptr(), G,
-                                           pk.data_table.data_ptr(), pv.data_table.data_ptr() if pv else None, kb, vb,
-                                           d.pos_offset, cursors.data_ptr(), None, 0, eng._stream()))
-        self._mark("extract + scatter kernel")
-        # device-side fence (no host sync): every rank's peer stores, stream-ordered before its
-        # contribution, have landed when the all-reduce completes
-        fence = torch.zeros(1, dtype=torch.int32, device=eng.device)
-        dist.all_reduce(fence, group=self.group)
-        self._mark("fence")
+        cursors = M[: self.rank, :G].sum(dim=0) if self.rank else torch.zeros(G, dtype=torch.int64, device=eng.device)
+        per_dst = M[:, :G].sum(dim=0)
+        info = torch.stack([per_dst[self.rank], per_dst.max(), M[:, G].sum()])
+        self._mark("all-gather of the count matrix + device-side offsets")
+        for attempt in range(2):
+            have = self._peer_keys is not None and (not with_vals or self._peer_vals is not None)
+            if not have or attempt == 1:
+                # (first use, or the guarded launch overflowed: size the buffers from the matrix)
+                n_recv, recv_max, n_wide = (int(x) for x in info.cpu())
+                self._cap_elems = max(self._cap_elems, int(recv_max * 1.1) + 65536)
+            cap = self._cap_elems
+            pk = self._ensure_peer("_peer_keys", cap * kb)
+            pv = self._ensure_peer("_peer_vals", cap * vb) if with_vals else None
+            cap_fit = min(pk.nbytes // kb, pv.nbytes // vb) if pv else pk.nbytes // kb
+            status = torch.zeros(2, dtype=torch.int32, device=eng.device)
+            cur = cursors.clone()
+            # No fence is needed before the stores: the all-gather above completed, so every rank had
+            # entered it, and each rank enters it only after (in stream order) it stopped reading its
+            # receive buffer of the previous step.
+            _lib.check(lib.kmg_extract_scatter_checked(d.bases.data_ptr(), d.n_bases, 0, n_win, k, int(rc), d.lut.data_ptr(),
+                                                       G, pk.data_table.data_ptr(), pv.data_table.data_ptr() if pv else None,
+                                                       kb, vb, d.pos_offset, cur.data_ptr(), cap_fit, status.data_ptr(),
+                                                       eng._stream()))
+            self._mark("extract + scatter kernel")
+            # device-side fence (no host sync): every rank's peer stores, stream-ordered before its
+            # contribution, have landed when the all-reduce completes; it also carries the overflow flag
+            dist.all_reduce(status, op=dist.ReduceOp.MAX, group=self.group)
+            self._info_host[:5].copy_(torch.cat([info, status.to(torch.int64)]), non_blocking=True)
+            torch.cuda.current_stream(eng.device).synchronize()
+            n_recv, recv_max, n_wide, overflow = (int(self._info_host[i]) for i in (0, 1, 2, 3))
+            self._mark("fence + read-back")
+            if not overflow:
+                break
+        assert not overflow, "receive buffers sized from the exact count matrix overflowed"
+        self._cap_elems = max(self._cap_elems, int(recv_max * 1.1) + 65536)
         alt = eng._buf("p2p_keys_alt", max(n_recv, 1) * kb)
         valt = eng._buf("p2p_vals_alt", max(n_recv, 1) * vb) if with_vals else None
-        # what the single-launch exchange should provision next time
-        self._cap_elems = max(self._cap_elems, int(recv_max * 1.1) + 65536)
-        return KeyArray(pk.data, alt, pv.data if pv else None, valt, n_recv, kb, vb, k, False)
+        return KeyArray(pk.data, alt, pv.data if pv else None, valt, n_recv, kb, vb, k, False), n_wide
 
     def _extract_exchange_shared(self, d, k: int, rc: bool, with_vals: bool):
-        """Single-launch exchange: no count-only launch, no count matrix.  Every destination owns one
+        """Single-launch exchange: no count launch, no count matrix.  Every destination owns one
         cursor (first word of its receive buffer) that all sources advance with system-scope
-        atomics; the buffers are provisioned for 1.25 x the largest per-rank key count (keys that
-        spread evenly over the key ranges).  Returns None when a buffer overflowed (skewed keys): the
-        caller then runs the exact two-launch exchange, which also re-provisions the buffers."""
+        atomics; the buffers are provisioned for 1.25 x the largest per-rank key count seen so far
+        (keys that spread evenly over the key ranges).  Returns None when a buffer overflowed (skewed
+        keys, or an input larger than any before): the caller then runs the exact exchange, which
+        also re-provisions the buffers.
+
+        Every rank issues the same collectives in the same order whatever its own chunk size is: the
+        capacity only ever changes through all-reduced values (the MAX of the per-rank key counts
+        rides on the second fence, which every step runs anyway)."""
         from kman_b200 import _lib
         from kman_b200.engine import KeyArray
 
@@ -287,17 +355,18 @@ class DistributedCounter:
         vb = 8 if with_vals else 0
         n_win = max(0, d.n_bases - k + 1)
         n_mine = n_win * (2 if rc else 1)
+        scale = float(os.environ.get("KMG_DIST_CAP_SCALE", "1.25"))  # (tests force overflows with a small one)
         self._mark("(outside)")
-        if self._cap_key != (n_mine, kb, vb):  # once per input size: agree on the capacity
+        if self._cap_elems == 0:  # first exchange of this counter -- on every rank
             t = torch.tensor([n_mine], dtype=torch.int64, device=eng.device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
-            self._cap_key = (n_mine, kb, vb)
-            scale = float(os.environ.get("KMG_DIST_CAP_SCALE", "1.25"))  # (tests force overflows with a small one)
-            self._cap_elems = max(self._cap_elems, int(int(t.item()) * scale) + 4096)
+            self._cap_elems = int(int(t.item()) * scale) + 4096
         cap = self._cap_elems
         pk = self._ensure_peer("_peer_keys", cap * kb)
         pv = self._ensure_peer("_peer_vals", cap * vb) if with_vals else None
-        status = torch.zeros(2, dtype=torch.int32, device=eng.device)
+        cap_fit = min(pk.nbytes // kb, pv.nbytes // vb) if pv else pk.nbytes // kb
+        status = torch.zeros(3, dtype=torch.int64, device=eng.device)  # overflow, wide windows seen, keys of this rank
+        status32 = torch.zeros(2, dtype=torch.int32, device=eng.device)
         pk.cursor.zero_()
         # device-side barrier (no host sync): every cursor is zero, nobody still reads the last step's keys
         fence = torch.zeros(1, dtype=torch.int32, device=eng.device)
@@ -305,25 +374,28 @@ class DistributedCounter:
         self._mark("fence 1")
         _lib.check(lib.kmg_extract_scatter_shared(d.bases.data_ptr(), d.n_bases, 0, n_win, k, int(rc), d.lut.data_ptr(), G,
                                                   pk.data_table.data_ptr(), pv.data_table.data_ptr() if pv else None, kb,
-                                                  vb, d.pos_offset, pk.ptr_table.data_ptr(), cap, status.data_ptr(),
+                                                  vb, d.pos_offset, pk.ptr_table.data_ptr(), cap_fit, status32.data_ptr(),
                                                   eng._stream()))
         self._mark("extract + scatter kernel")
         # fence + agreement: every rank's peer stores (stream-ordered before its contribution) have landed
+        status[:2] = status32
+        status[2] = n_mine
         dist.all_reduce(status, op=dist.ReduceOp.MAX, group=self.group)
-        st = torch.cat([status.to(torch.int64), pk.cursor]).cpu().numpy()
+        self._info_host[:4].copy_(torch.cat([status, pk.cursor]), non_blocking=True)
+        torch.cuda.current_stream(eng.device).synchronize()
+        overflow, wide_seen, n_max, n_recv = (int(self._info_host[i]) for i in range(4))
         self._mark("fence 2 + read-back")
-        if int(st[1]):
-            raise ValueError("distributed path handles the narrow (plain ACGT) stream only in this build; "
-                             "the input holds windows with other alphabet symbols")
-        if int(st[0]):
+        # the same value on every rank: inputs that grew are provisioned for from the next step on
+        self._cap_elems = max(self._cap_elems, int(n_max * scale) + 4096)
+        if overflow:
             return None
-        n_recv = int(st[2])
         alt = eng._buf("p2p_keys_alt", max(n_recv, 1) * kb)
         valt = eng._buf("p2p_vals_alt", max(n_recv, 1) * vb) if with_vals else None
-        return KeyArray(pk.data, alt, pv.data if pv else None, valt, n_recv, kb, vb, k, False)
+        return KeyArray(pk.data, alt, pv.data if pv else None, valt, n_recv, kb, vb, k, False), wide_seen
 
     def _exchange(self, d, k: int, rc: bool, with_vals: bool):
-        """Fused extraction + exchange over peer memory: single launch when it fits, exact otherwise."""
+        """Fused extraction + exchange over peer memory: single launch when it fits, exact otherwise.
+        Returns (received KeyArray, wide-stream indicator: > 0 if ANY rank saw wide windows)."""
         r = self._extract_exchange_shared(d, k, rc, with_vals) if self.shared else None
         if r is None:
             r = self._extract_exchange_p2p(d, k, rc, with_vals)
@@ -366,27 +438,73 @@ class DistributedCounter:
         valt = torch.empty(max(rvals.numel(), 16), dtype=torch.uint8, device=kbuf.device) if with_vals else None
         if kbuf.numel() == 0:
             kbuf = torch.empty(16, dtype=torch.uint8, device=alt.device)
+        if with_vals and rvals.numel() == 0:
+            rvals = torch.empty(16, dtype=torch.uint8, device=alt.device)
         return KeyArray(kbuf, alt, rvals, valt, n, a.key_bytes, 8 if with_vals else 0, a.k, a.wide)
 
-    def count(self, d, k: int, rc: bool = False):
-        """This rank's slice (key range `rank`) of the global count table, narrow stream."""
+    def _own(self, t: Optional[torch.Tensor], nbytes: int) -> Optional[torch.Tensor]:
+        """A result tensor the sort left inside a peer-mapped receive buffer is copied into torch-owned
+        memory (peers overwrite the buffer in the next exchange; it may even be freed and re-mapped)."""
+        if t is None:
+            return None
+        for pb in (self._peer_keys, self._peer_vals):
+            if pb is not None and pb.owns(t):
+                return t[: max(nbytes, 16)].clone()
+        return t
+
+    def _narrow(self, d, k: int, rc: bool, with_vals: bool):
+        """(received narrow keys of this rank's key range, does ANY rank hold wide-stream windows)"""
         if self.p2p and k >= 8:
             try:
-                r = self._exchange(d, k, rc, with_vals=False)
+                return self._exchange(d, k, rc, with_vals)
             except _PeerUnavailable as exc:
                 self._fall_back(exc)
-            else:
-                tab = self.eng.sort_count(r, sort_bits_after_partition(r.key_bits, self.world), reuse="p2p_")
-                self._mark("sort + count")
-                return tab
-        a = self.eng.extract(d, k, rc, wide=False, val_bytes=0)
+        a = self.eng.extract(d, k, rc, wide=False, val_bytes=8 if with_vals else 0)
         n_other = torch.tensor([a.n_other], dtype=torch.int64, device=a.keys.device)
         dist.all_reduce(n_other, group=self.group)
-        if int(n_other.item()):
-            raise ValueError("distributed path handles the narrow (plain ACGT) stream only in this build; "
-                             f"input holds {int(n_other.item())} windows with other alphabet symbols")
-        r = self._partition_exchange(a, with_vals=False)
-        return self.eng.sort_count(r, sort_bits_after_partition(r.key_bits, self.world))
+        return self._partition_exchange(a, with_vals), int(n_other.item())
+
+    def _wide(self, d, k: int, rc: bool, with_vals: bool):
+        """The wide (non-ACGT alphabet symbols) stream across ranks: windows are rare, so the plain
+        path does it -- local extraction, range partition on the 4-bit keys, NCCL all-to-all.
+        Collective: every rank calls it once any rank saw a wide window."""
+        if k > 32:
+            raise ValueError(f"input holds windows with non-ACGT alphabet symbols and k={k} > 32: the wide stream "
+                             "supports k <= 32 in this build (no CPU fallback)")
+        a = self.eng.extract(d, k, rc, wide=True, val_bytes=8 if with_vals else 0)
+        return self._partition_exchange(a, with_vals)
+
+    def count_streams(self, d, k: int, rc: bool = False, reuse: Optional[str] = "p2p_"):
+        """This rank's slice (key range `rank`) of the global count table: [narrow] or [narrow, wide]
+        CountTables; rank-order concatenation per stream is globally sorted, counts are final."""
+        r, any_wide = self._narrow(d, k, rc, with_vals=False)
+        tab = self.eng.sort_count(r, sort_bits_after_partition(r.key_bits, self.world), reuse=reuse)
+        tab.keys = self._own(tab.keys, tab.n * tab.key_bytes)
+        self._mark("sort + count")
+        out = [tab]
+        if any_wide:
+            w = self._wide(d, k, rc, with_vals=False)
+            out.append(self.eng.sort_count(w, sort_bits_after_partition(w.key_bits, self.world)))
+        return out
+
+    def count(self, d, k: int, rc: bool = False):
+        """Narrow-stream slice of the count table (see count_streams for inputs with N / IUPAC symbols:
+        with the ACGT-only alphabet every valid window is narrow)."""
+        return self.count_streams(d, k, rc)[0]
+
+    def uniq_streams(self, d, k: int, rc: bool = False):
+        """This rank's slice of the global singleton list (keys + (pos<<1|strand) payload) per stream."""
+        r, any_wide = self._narrow(d, k, rc, with_vals=True)
+        s = self.eng.sort_uniq(r, sort_bits_after_partition(r.key_bits, self.world))
+        s.keys, s.vals = self._own(s.keys, s.n * s.key_bytes), self._own(s.vals, s.n * s.val_bytes)
+        out = [s]
+        if any_wide:
+            w = self._wide(d, k, rc, with_vals=True)
+            out.append(self.eng.sort_uniq(w, sort_bits_after_partition(w.key_bits, self.world)))
+        return out
+
+    def uniq(self, d, k: int, rc: bool = False):
+        return self.uniq_streams(d, k, rc)[0]
 
     def _fall_back(self, exc) -> None:
         """Every rank raised together (the failure flag is all-reduced): use the NCCL all-to-all path."""
@@ -402,20 +520,3 @@ class DistributedCounter:
             if cur is not None:
                 cur.close()
                 setattr(self, which, None)
-
-    def uniq(self, d, k: int, rc: bool = False):
-        """This rank's slice of the global singleton list (keys + (pos<<1|strand) payload)."""
-        if self.p2p and k >= 8:
-            try:
-                r = self._exchange(d, k, rc, with_vals=True)
-            except _PeerUnavailable as exc:
-                self._fall_back(exc)
-            else:
-                return self.eng.sort_uniq(r, sort_bits_after_partition(r.key_bits, self.world))
-        a = self.eng.extract(d, k, rc, wide=False, val_bytes=8)
-        n_other = torch.tensor([a.n_other], dtype=torch.int64, device=a.keys.device)
-        dist.all_reduce(n_other, group=self.group)
-        if int(n_other.item()):
-            raise ValueError("distributed path handles the narrow (plain ACGT) stream only in this build")
-        r = self._partition_exchange(a, with_vals=True)
-        return self.eng.sort_uniq(r, sort_bits_after_partition(r.key_bits, self.world))

@@ -28,6 +28,22 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+def _on_device(fn):
+    """Run an Engine method with the engine's GPU current: libkmg launches on the current device
+    (kernel attributes, workspaces and streams are per device), and one process may own several
+    engines (get_engine(device))."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        if torch.cuda.current_device() == self.device.index:
+            return fn(self, *args, **kwargs)
+        with torch.cuda.device(self.device):
+            return fn(self, *args, **kwargs)
+
+    return wrapper
+
+
 @dataclass
 class DeviceInput:
     """Flat base buffer resident in HBM."""
@@ -140,6 +156,7 @@ class Engine:
         return self._luts[key]
 
     # ---- upload -----------------------------------------------------------------------------
+    @_on_device
     def upload(self, flat: FlatInput, alphabet: Optional[str] = None, natype: ab.NATYPES = ab.NATYPES.DNA,
                with_names: bool = True) -> DeviceInput:
         alphabet = alphabet or ab.default_alphabet()
@@ -154,6 +171,7 @@ class Engine:
             self._upload_names(d)
         return d
 
+    @_on_device
     def load_fasta(self, path: str, alphabet: Optional[str] = None, natype: ab.NATYPES = ab.NATYPES.DNA,
                    with_names: bool = True) -> DeviceInput:
         """Read a FASTA file and flatten it ON THE GPU (kmg_fasta_flatten): the raw bytes go to
@@ -219,6 +237,7 @@ class Engine:
         d.names_buf = torch.from_numpy(np.frombuffer(b"".join(nb) + b"\0", np.uint8).copy()).to(self.device)
 
     # ---- K1+K2 ------------------------------------------------------------------------------
+    @_on_device
     def extract(self, d: DeviceInput, k: int, rc: bool = False, wide: bool = False, val_bytes: int = 0,
                 win_begin: int = 0, win_end: Optional[int] = None, reuse: Optional[str] = None,
                 want_hist: bool = False) -> KeyArray:
@@ -260,6 +279,7 @@ class Engine:
                         hist=hist)
 
     # ---- K3 -----------------------------------------------------------------------------------
+    @_on_device
     def sort(self, a: KeyArray, begin_bit: int = 0, end_bit: Optional[int] = None) -> KeyArray:
         end_bit = a.key_bits if end_bit is None else end_bit
         if a.n > 1 and end_bit > begin_bit:
@@ -281,6 +301,7 @@ class Engine:
         a.is_sorted = True
         return a
 
+    @_on_device
     def sort_count(self, a: KeyArray, end_bit: Optional[int] = None, reuse: Optional[str] = None) -> CountTable:
         """sort() + rle_count() in one native call (kmg_sort_count): when the hybrid finish applies,
         its local sort emits the (k-mer, count) table directly.  Consumes `a` (both key buffers)."""
@@ -300,11 +321,21 @@ class Engine:
         )
         a.hist = None
         self._last_sort_ws = ws
-        self._status(ws)
-        n_out = int(self._small[2:3].cpu().numpy().view(np.uint64)[0])
+        n_out = self._sort_result_rows(ws)
         return CountTable(a.keys_alt if sel.value else a.keys, counts, n_out, a.key_bytes, a.k, a.wide)
 
+    def _sort_result_rows(self, ws: torch.Tensor) -> int:
+        """Rows of the table kmg_sort_count / kmg_sort_uniq just produced.  When the hybrid finish ran,
+        the call already synchronised and read the count and the status word back together
+        (kmg_get_stat "n_out" / "ws_err"): no second round trip."""
+        n_out, err = int(self.lib.kmg_get_stat(b"n_out")), int(self.lib.kmg_get_stat(b"ws_err"))
+        if n_out >= 0 and err == 0:
+            return n_out
+        self._status(ws)
+        return int(self._small[2:3].cpu().numpy().view(np.uint64)[0])
+
     # ---- K4 -----------------------------------------------------------------------------------
+    @_on_device
     def rle_count(self, a: KeyArray, reuse: Optional[str] = None) -> CountTable:
         """Distinct keys + counts.  The distinct keys are written into `a.keys_alt`."""
         assert a.is_sorted
@@ -321,6 +352,7 @@ class Engine:
         n_out = int(self._small[2:3].cpu().numpy().view(np.uint64)[0])
         return CountTable(a.keys_alt, counts, n_out, a.key_bytes, a.k, a.wide)
 
+    @_on_device
     def sort_uniq(self, a: KeyArray, end_bit: Optional[int] = None) -> KeyArray:
         """sort() + singletons() in one native call (kmg_sort_uniq).  Repeated keys are dropped, so
         their order is irrelevant and 8-byte keys take the hybrid finish with the payload.  Consumes `a`."""
@@ -339,11 +371,11 @@ class Engine:
         )
         a.hist = None
         self._last_sort_ws = ws
-        self._status(ws)
-        n_out = int(self._small[2:3].cpu().numpy().view(np.uint64)[0])
+        n_out = self._sort_result_rows(ws)
         k_, v_ = (a.keys_alt, a.vals_alt) if sel.value else (a.keys, a.vals)
         return KeyArray(k_, None, v_, None, n_out, a.key_bytes, a.val_bytes, a.k, a.wide, is_sorted=True)
 
+    @_on_device
     def singletons(self, a: KeyArray) -> KeyArray:
         """Keys (+payload) that occur exactly once, ascending (written into the alt buffers)."""
         assert a.is_sorted
@@ -361,6 +393,7 @@ class Engine:
         return KeyArray(a.keys_alt, None, a.vals_alt, None, n_out, a.key_bytes, a.val_bytes, a.k, a.wide, is_sorted=True)
 
     # ---- K5 -----------------------------------------------------------------------------------
+    @_on_device
     def range_partition(self, a: KeyArray, n_parts: int) -> Tuple[KeyArray, np.ndarray]:
         """Stable split by the top key bits into n_parts regions (into the alt buffers)."""
         ws_bytes = self.lib.kmg_partition_workspace_bytes(max(a.n, 1), a.key_bytes, a.val_bytes)
@@ -378,6 +411,7 @@ class Engine:
         return a, pc.cpu().numpy().astype(np.int64)
 
     # ---- K6 -----------------------------------------------------------------------------------
+    @_on_device
     def format_counts(self, t: CountTable, rna: int = 0) -> torch.Tensor:
         """Device text "SEQ\\tCOUNT\\n" for one stream (uint8 tensor, exact length)."""
         if t.n == 0:
@@ -394,6 +428,7 @@ class Engine:
         nbytes = int(self._small[4:5].cpu().numpy().view(np.uint64)[0])
         return text[:nbytes]
 
+    @_on_device
     def format_uniq(self, s: KeyArray, d: DeviceInput) -> torch.Tensor:
         """Device text ">NAME:START-END:STRAND\\nSEQ\\n" for one stream."""
         if s.n == 0:
@@ -414,6 +449,7 @@ class Engine:
         nbytes = int(self._small[4:5].cpu().numpy().view(np.uint64)[0])
         return text[:nbytes]
 
+    @_on_device
     def merge_ranks(self, narrow_keys: torch.Tensor, n_narrow: int, wide_keys: torch.Tensor, n_wide: int, k: int,
                     rna: int) -> Tuple[torch.Tensor, torch.Tensor]:
         rn = torch.zeros(max(n_narrow, 1), dtype=torch.int64, device=self.device)
@@ -438,11 +474,60 @@ class Engine:
             out.append(self.sort(self.extract(d, k, rc, wide=True, val_bytes=val_bytes)))
         return out
 
+    def _pipeline_buffers(self, d: DeviceInput, k: int, rc: bool, val_bytes: int, reuse: Optional[str],
+                          win_begin: int, win_end: Optional[int]):
+        if k <= 1:
+            raise AssertionError(f"k must be >= 1, got {k} instead.")  # batcher.py:477-478
+        if k > 64:
+            raise ValueError(f"k={k}: this build supports k <= 64 (no CPU fallback)")
+        n_win_total = max(0, d.n_bases - k + 1)
+        win_end = n_win_total if win_end is None else min(win_end, n_win_total)
+        win_begin = min(win_begin, win_end)
+        kb = 16 if k > 32 else 8
+        cap = max((win_end - win_begin) * (2 if rc else 1), 1)
+        mk = (lambda nm, nb: self._buf(reuse + nm, nb)) if reuse else (lambda nm, nb: self._new(nb))
+        keys, keys_alt = mk("keys", cap * kb), mk("keys_alt", cap * kb)
+        vals = mk("vals", cap * val_bytes) if val_bytes else None
+        vals_alt = mk("vals_alt", cap * val_bytes) if val_bytes else None
+        ws_bytes = self.lib.kmg_pipeline_workspace_bytes(win_end - win_begin, k, int(rc), val_bytes)
+        ws = self._buf("ws_pipeline", ws_bytes)
+        return win_begin, win_end, kb, cap, keys, keys_alt, vals, vals_alt, ws, ws_bytes
+
+    @_on_device
+    def count_narrow(self, d: DeviceInput, k: int, rc: bool = False, reuse: Optional[str] = None, win_begin: int = 0,
+                     win_end: Optional[int] = None) -> Tuple[CountTable, int]:
+        """(k-mer, count) table of the narrow stream in ONE native call (kmg_extract_sort_count: the
+        extraction kernel is the sort's first prefix pass), and the number of windows that belong
+        to the wide stream.  seq.py:284-328 + batch.py:156-168 + join.py:63-130,265-285."""
+        win_begin, win_end, kb, cap, keys, keys_alt, _, _, ws, ws_bytes = self._pipeline_buffers(
+            d, k, rc, 0, reuse, win_begin, win_end)
+        counts = self._buf(reuse + "counts", cap * 4) if reuse else self._new(cap * 4)
+        res = (C.c_uint64 * 4)()
+        _lib.check(self.lib.kmg_extract_sort_count(d.bases.data_ptr(), d.n_bases, win_begin, win_end, k, int(rc),
+                                                   d.lut.data_ptr(), keys.data_ptr(), keys_alt.data_ptr(),
+                                                   counts.data_ptr(), res, ws.data_ptr(), ws_bytes, self._stream()))
+        return CountTable(keys_alt if res[3] else keys, counts, int(res[0]), kb, k, False), int(res[2])
+
+    @_on_device
+    def uniq_narrow(self, d: DeviceInput, k: int, rc: bool = False, reuse: Optional[str] = None, win_begin: int = 0,
+                    win_end: Optional[int] = None, val_bytes: Optional[int] = None) -> Tuple[KeyArray, int]:
+        """Singleton keys with their (position << 1 | strand) payload of the narrow stream in ONE native
+        call (kmg_extract_sort_uniq), and the number of wide-stream windows.  join.py:243-263."""
+        vb = val_bytes or (4 if ((d.pos_offset + d.n_bases) << 1) < (1 << 32) else 8)
+        win_begin, win_end, kb, cap, keys, keys_alt, vals, vals_alt, ws, ws_bytes = self._pipeline_buffers(
+            d, k, rc, vb, reuse, win_begin, win_end)
+        res = (C.c_uint64 * 4)()
+        _lib.check(self.lib.kmg_extract_sort_uniq(d.bases.data_ptr(), d.n_bases, win_begin, win_end, k, int(rc),
+                                                  d.lut.data_ptr(), keys.data_ptr(), keys_alt.data_ptr(), vals.data_ptr(),
+                                                  vals_alt.data_ptr(), vb, d.pos_offset, res, ws.data_ptr(), ws_bytes,
+                                                  self._stream()))
+        k_, v_ = (keys_alt, vals_alt) if res[3] else (keys, vals)
+        return KeyArray(k_, None, v_, None, int(res[0]), kb, vb, k, False, is_sorted=True), int(res[2])
+
     def count(self, d: DeviceInput, k: int, rc: bool = False) -> List[CountTable]:
         """`kmer count` (SEQ_COUNT) on device: one CountTable per stream."""
-        narrow = self.extract(d, k, rc, wide=False, val_bytes=0, want_hist=True)
-        n_other = narrow.n_other
-        out = [self.sort_count(narrow)]
+        tab, n_other = self.count_narrow(d, k, rc)
+        out = [tab]
         if n_other:
             if k > 32:
                 raise ValueError(
@@ -455,9 +540,8 @@ class Engine:
     def uniq(self, d: DeviceInput, k: int, rc: bool = False) -> List[KeyArray]:
         """`kmer uniq` on device: singleton keys with payload, one KeyArray per stream."""
         vb = 4 if ((d.pos_offset + d.n_bases) << 1) < (1 << 32) else 8
-        narrow = self.extract(d, k, rc, wide=False, val_bytes=vb, want_hist=True)
-        n_other = narrow.n_other
-        out = [self.sort_uniq(narrow)]
+        sing, n_other = self.uniq_narrow(d, k, rc, val_bytes=vb)
+        out = [sing]
         if n_other:
             if k > 32:
                 raise ValueError(

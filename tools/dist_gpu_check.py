@@ -1,6 +1,13 @@
 #!/usr/bin/env python
-"""Multi-GPU parity check (run under torchrun on the GPU box): distributed count/uniq of a small
-duplicated genome against the CPU oracle; rank-order concatenation must equal the global table."""
+"""Multi-GPU parity check (run under torchrun on the GPU box, 2..8 ranks): distributed count / uniq
+against the CPU oracle; rank-order concatenation of the per-rank tables must equal the global table.
+
+Inputs are MULTI-RECORD flat buffers WITH their separators (chunk boundaries fall anywhere, also on
+and next to a separator; kmermaid/seq.py:361-383 chunking, batcher.py:387-388 records never share a
+k-mer), with duplicated stretches (counts > 1), N runs + isolated IUPAC symbols (the wide stream
+under the default alphabet) and soft-masked lower case; consecutive calls on ONE counter use inputs
+whose lengths differ (also by one window), so that ranks see different chunk sizes from call to
+call.  Used by tests/test_gpu_dist.py (pytest -m gpu, when the box has >= 2 GPUs) and by hand."""
 import os
 import sys
 
@@ -21,38 +28,85 @@ torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 eng = get_engine(lr)
 dc = DistributedCounter(eng)
-print("p2p path:", dc.p2p, flush=True) if rank == 0 else None
+if rank == 0:
+    print("p2p path:", dc.p2p, "shared cursors:", dc.shared, flush=True)
+
+
+def genome(seed, n, n_rec, with_other):
+    rng = np.random.default_rng(seed)
+    b = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, size=n, dtype=np.uint8)].copy()
+    b[n // 2 : n // 2 + n // 4] = b[: n // 4]  # duplicated stretch: counts > 1, non-singletons
+    if with_other:
+        for _ in range(6):
+            s, ln = int(rng.integers(0, n - 3000)), int(rng.integers(1, 2500))
+            b[s : s + ln] = ord("N")
+        iso = rng.integers(0, n, size=40)
+        b[iso] = np.frombuffer(b"RYKMSW", np.uint8)[rng.integers(0, 6, size=iso.size)]
+        b[n // 3 : n // 3 + n // 9] |= 0x20  # soft-masked
+    cuts = sorted(int(x) for x in rng.integers(1, n - 1, size=n_rec - 1))
+    # one record boundary exactly where a rank's chunk starts (2 ranks: the middle)
+    cuts[0] = n // 2
+    cuts = sorted(set(cuts))
+    recs, prev = [], 0
+    for i, c in enumerate(cuts + [n]):
+        recs.append(("chr%d" % (i + 1), b[prev:c].tobytes().decode()))
+        prev = c
+    return recs
+
+
+def rows(limbs):
+    return limbs[0] if len(limbs) == 1 else np.stack([limbs[1], limbs[0]], axis=1)
+
+
 ok = True
-for k, rc in ((31, False), (21, True), (45, False)):
-    seq = ko.synth_bases(3_000_000, 77).decode()
-    seq = seq[:2_000_000] + seq[:1_000_000]
-    recs = [("chr1", seq)]
+CASES = [
+    # k, rc, n_bases, records, alphabet, non-ACGT symbols
+    (31, False, 3_000_000, 5, "ACGT", False),
+    (31, False, 2_999_999, 5, "ACGT", False),   # one base shorter on the same counter (dist.py cap key)
+    (21, True, 2_500_001, 3, "ACGT", False),
+    (45, False, 2_400_000, 4, "ACGT", False),
+    (25, False, 2_600_000, 4, None, True),      # default IUPAC alphabet: N / R / Y windows are the wide stream
+    (25, True, 1_300_000, 3, None, True),
+    (31, False, 3_400_001, 2, "ACGT", True),    # ACGT-only alphabet: windows with N are skipped
+]
+for k, rc, n, n_rec, alphabet, other in CASES:
+    recs = genome(1000 + k + n % 7, n, n_rec, other)
     flat = fasta.from_records(recs)
-    # single flat record + separator: drop the separator so chunking sees only bases
-    flat = fasta.FlatInput(flat.bases[:-1], flat.rec_starts, flat.names, flat.titles)
-    d = dc.shard(flat, k, alphabet="ACGT")
-    tab = dc.count(d, k, rc)
-    ku, cu = tab.keys_host().copy(), tab.counts_host().copy()
-    s = dc.uniq(d, k, rc)
-    su, sv = s.keys_host().copy(), s.vals_host().copy()
+    d = dc.shard(flat, k, alphabet=alphabet)
+    tabs = dc.count_streams(d, k, rc)
+    got_c = [(t.keys_host().copy(), t.counts_host().copy()) for t in tabs]
+    sing = dc.uniq_streams(d, k, rc)
+    got_u = [(s.keys_host().copy(), s.vals_host().copy()) for s in sing]
     out = [None] * world
-    dist.all_gather_object(out, (ku, cu, su, sv))
+    dist.all_gather_object(out, (got_c, got_u))
     if rank == 0:
-        _, _, det = ko.count_np(recs, k, rc, "ACGT")
-        gk = np.concatenate([o[0] for o in out])
-        gc = np.concatenate([o[1] for o in out])
-        want = det["narrow"]["keys"]
-        wk = want[0] if len(want) == 1 else np.stack([want[1], want[0]], axis=1)
-        good = gk.shape == wk.shape and (gk == wk).all() and (gc == det["narrow"]["counts"]).all()
-        *_, du = ko.uniq_np(recs, k, rc, "ACGT")
-        want = du["narrow"]["keys"]
-        wk = want[0] if len(want) == 1 else np.stack([want[1], want[0]], axis=1)
-        gs = np.concatenate([o[2] for o in out])
-        gv = np.concatenate([o[3] for o in out])
-        wv = (du["narrow"]["pos"].astype(np.uint64) << np.uint64(1)) | du["narrow"]["strand"].astype(np.uint64)
-        good2 = gs.shape == wk.shape and (gs == wk).all() and (gv == wv).all()
-        print(f"k={k} rc={rc} world={world}: count {'OK' if good else 'MISMATCH'} ({gk.shape[0]} distinct), uniq {'OK' if good2 else 'MISMATCH'} ({gs.shape[0]})", flush=True)
-        ok = ok and good and good2
+        ab = alphabet or ko.DEFAULT_ALPHABET
+        _, _, det = ko.count_np(recs, k, rc, ab)
+        *_, du = ko.uniq_np(recs, k, rc, ab)
+        msgs = []
+        for si, name in enumerate(("narrow", "wide")):
+            wk = rows(det[name]["keys"])
+            if name == "wide":
+                if wk.shape[0] == 0:
+                    assert all(len(o[0]) == 1 for o in out), "no wide windows, yet a rank returned a wide table"
+                    continue
+                if wk.ndim == 1:  # the device always uses 128-bit wide keys
+                    wk = np.stack([wk, np.zeros_like(wk)], axis=1)
+            gk = np.concatenate([o[0][si][0].reshape((-1,) + wk.shape[1:]) for o in out])
+            gc = np.concatenate([o[0][si][1] for o in out])
+            good = gk.shape == wk.shape and (gk == wk).all() and (gc == det[name]["counts"]).all()
+            uk = rows(du[name]["keys"])
+            if name == "wide" and uk.ndim == 1:
+                uk = np.stack([uk, np.zeros_like(uk)], axis=1)
+            gs = np.concatenate([o[1][si][0].reshape((-1,) + uk.shape[1:]) for o in out])
+            gv = np.concatenate([o[1][si][1] for o in out])
+            wv = (du[name]["pos"].astype(np.uint64) << np.uint64(1)) | du[name]["strand"].astype(np.uint64)
+            good2 = gs.shape == uk.shape and (gs == uk).all() and (gv.astype(np.uint64) == wv).all()
+            msgs.append(f"{name}: count {'OK' if good else 'MISMATCH'} ({gk.shape[0]} distinct), "
+                        f"uniq {'OK' if good2 else 'MISMATCH'} ({gs.shape[0]})")
+            ok = ok and good and good2
+        print(f"k={k} rc={rc} n={n} records={n_rec} alphabet={ab} world={world}: " + "; ".join(msgs), flush=True)
+dc.close()
 dist.barrier()
 dist.destroy_process_group()
 if rank == 0:

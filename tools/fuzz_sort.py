@@ -88,7 +88,7 @@ def main():
             head = np.ones(n, bool)
             head[1:] = srt[1:] != srt[:-1]
         idx = np.flatnonzero(head)
-        desc = f"trial {trials}: n={n} bits={bits} mode={mode} pb={lib.kmg_get_stat(b'hybrid_backoff')}"
+        desc = f"trial {trials}: n={n} bits={bits} mode={mode} path={lib.kmg_get_stat(b'hybrid_path')}"
         if mode == "sort":
             a = KeyArray(t(raw), z(n * kb), None, None, n, kb, 0, bits // 2, False)
             a = eng.sort(a, 0, bits)

@@ -103,7 +103,7 @@ def main():
         print(f"hybrid {hy}: {nk} k-mers, {tab.n} distinct, {u.n} occur once")
         print(f"   count {t_c:7.3f} ms = {nk/t_c/1e6:6.2f} G k-mers/s  (passes {st_c[0]}, path {st_c[1]}, irregular tiles {st_c[2]})")
         print(f"   uniq  {t_u:7.3f} ms = {nk/t_u/1e6:6.2f} G k-mers/s  (passes {st_u[0]}, path {st_u[1]}, irregular tiles {st_u[2]})")
-        print(f"   back-off now {eng.lib.kmg_get_stat(b'hybrid_backoff')}, runs sorted by the block in the last hybrid sort {eng.lib.kmg_get_stat(b'hybrid_big_runs')}")
+        print(f"   runs sorted by the block in the last hybrid sort {eng.lib.kmg_get_stat(b'hybrid_big_runs')}")
     eng.lib.kmg_set_option(b"hybrid_pb", 0)
     assert res[0] == res[1] == res[2] == res[3], "hybrid and plain sorts disagree"
     print("GENOME_LIKE_OK")
