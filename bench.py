@@ -4,11 +4,17 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg2|cfg3]
   (N>1: launched by torchrun, one rank per GPU; rank 0 prints ONE JSON line)
 
-A "step" is one pass of the hot path over one synthetic input:
+A "step" is one pass of the hot path over one synthetic input (--workload auto):
   N=1 : config 2 of BASELINE.json -- 100 Mbp random-ACGT single record, k=31, count
-  N>1 : weak scaling -- the genome is N x 100 Mbp, every rank holds a 100 Mbp chunk (k-1 base
-        overlap), keys are range-partitioned and exchanged with one all-to-all
-        (--workload cfg3 runs the 3.1 Gbp strong-scaling configuration instead)
+  N>1 : config 3 -- 3.1 Gbp synthetic genome of 24 records (lengths proportional to the human
+        chromosomes), k=31, count, STRONG scaling: every rank holds 1/N of the flat base buffer (k-1
+        base overlap, chunk boundaries fall anywhere, also inside and next to record separators),
+        keys are range-partitioned by their top bits and exchanged over NVLink
+        (--workload cfg2 keeps the round-1 weak-scaling workload: one 100 Mbp chunk per GPU;
+         --workload cfg3 runs config 3 on any N, one GPU included)
+`verify`  : checked outside the timed region on every N: counts sum to the number of windows, distinct
+           keys strictly ascending inside every rank and across rank boundaries, and sum(key * count)
+           == sum of all extracted keys (mod 2^64, all-reduced)
 `value`  : whole-job k-mers/s with the bases already resident in HBM (device-timed, max over ranks)
 `e2e`    : the same metric through the host-buffer C-ABI call kmg_count_host (N=1) or the
            distributed Python API (N>1), pinned host memory, H2D of the bases and D2H of the
@@ -39,6 +45,35 @@ K = 31
 CFG2_BASES = 100_000_000
 CFG3_BASES = 3_100_000_000
 METRIC = "k-mers/sec (extract+sort+count, k=31)"
+CFG3_RECORDS = 24
+HUMAN_MBP = [248, 242, 198, 190, 182, 171, 159, 145, 138, 134, 135, 133, 114, 107, 102, 90, 83, 80, 59, 64, 47, 51, 156, 57]
+
+
+def cfg3_layout(total=CFG3_BASES):
+    """Flat buffer of config 3: `total` bytes, record r followed by one '\n' separator.  Returns
+    (separator positions, number of windows = sum over records of max(0, len - K + 1))."""
+    w = np.array(HUMAN_MBP, np.float64)
+    ends = np.floor(np.cumsum(w) / w.sum() * total).astype(np.int64)
+    ends[-1] = total
+    seps = ends - 1  # last byte of every record's slot is its separator
+    starts = np.concatenate(([0], ends[:-1]))
+    lens = seps - starts
+    return seps, int(np.maximum(0, lens - K + 1).sum())
+
+
+def cfg3_slice(b: int, e: int) -> np.ndarray:
+    """Bytes [b, e) of config 3's flat buffer: block i of 100 Mbp comes from seed 1234+i, so every
+    rank builds only its own slice."""
+    blk = 100_000_000
+    parts = []
+    for i in range(b // blk, (e + blk - 1) // blk):
+        x = synth_bases(blk, 1234 + i)
+        parts.append(x[max(b - i * blk, 0) : min(e - i * blk, blk)])
+    out = np.concatenate(parts)
+    seps, _ = cfg3_layout()
+    inside = seps[(seps >= b) & (seps < e)]
+    out[inside - b] = 10
+    return out
 
 
 def synth_bases(n: int, seed: int) -> np.ndarray:
@@ -122,7 +157,8 @@ class ClockSampler:
 
 # ---- reference arm / cpu baseline -------------------------------------------------------------------
 def cpu_port_rate(sample_bases: int, steps: int, warmup: int):
-    """k-mers/s of the oracle's numpy port (extract -> stable sort -> run-length), 1 host core."""
+    """k-mers/s of the oracle's numpy port of the same stages the GPU arm times (extract -> stable
+    sort -> run-length grouping into the binary (k-mer, count) table), 1 host core."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import kmer_oracle as ko
 
@@ -131,7 +167,7 @@ def cpu_port_rate(sample_bases: int, steps: int, warmup: int):
     ts = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        txt, counts, det = ko.count_np(recs, K, False, "ACGT")
+        keys, counts = ko.count_table_np(recs, K, False, "ACGT")
         dt = time.perf_counter() - t0
         if i >= warmup:
             ts.append(dt)
@@ -144,15 +180,18 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = 10_000_000
-    steps = max(1, min(args.steps, 5))
-    warm = max(0, min(args.warmup, 1))
+    # N=1: the FULL configuration (config 2, 100 Mbp), one pass (about a minute of one host core).
+    # N>1: config 3 is 3.1 Gbp -- the port would need > 100 GB of host memory and most of an hour; its
+    # step is a 100 Mbp sample of the same generator.
+    sample = CFG2_BASES
+    steps, warm = 1, 0
     rate, sec = cpu_port_rate(sample, steps, warm)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "k-mers/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": workload_config(args, sample_note=f"bounded sample: {sample} bases of the same generator"),
+        "config": workload_config(args, sample_note=("the full configuration, one pass" if args.workload == "cfg2" and args.gpus == 1
+                                                      else f"bounded sample: {sample} bases of the same generator, one pass")),
         "cpu_baseline": {"value": rate, "unit": "k-mers/s", "cores": 1, "kind": "port",
                          "sample": f"{sample} bp random ACGT, k={K}, count; oracle numpy port (np.sort is single-threaded)",
                          "host_cores_available": os.cpu_count()},
@@ -167,7 +206,11 @@ def workload_config(args, sample_note=None, p2p=None, shared=None):
     if p2p is None:
         p2p = os.environ.get("KMG_DIST_P2P", "1") != "0"
     if args.workload == "cfg3":
-        wl = f"config 3: {CFG3_BASES} bp synthetic random-ACGT genome, k={K}, count, strong scaling over {n} GPU(s)"
+        wl = (f"config 3: {CFG3_BASES} bp synthetic random-ACGT genome in {CFG3_RECORDS} records (lengths proportional to "
+              f"the human chromosomes), k={K}, count, strong scaling over {n} GPU(s): 1/{n} of the flat base buffer per GPU "
+              "with k-1 overlap, range partition by the top key bits"
+              + ("" if n == 1 else ("; exchange: fused extract+partition kernel storing into the owners' buffers over NVLink "
+                                     "(CUDA IPC peer memory)" if p2p else "; exchange: range partition pass + NCCL all-to-all")))
     elif n == 1:
         wl = f"config 2: {CFG2_BASES} bp synthetic random-ACGT single record (seed 1234), k={K}, count"
     else:
@@ -177,10 +220,46 @@ def workload_config(args, sample_note=None, p2p=None, shared=None):
                   + ("one launch, shared per-destination cursors" if shared else "count-only launch + exact regions"))
                  if p2p else "range partition pass + NCCL all-to-all of the partitioned keys"))
     cfg = {"workload": wl, "k": K, "mode": "count", "alphabet": "ACGT",
-           "l2": "working set per step (keys 2x0.8 GB + table 1.2 GB per GPU) >> 126 MB L2; no explicit flush"}
+           "l2": "working set per step (>= 0.8 GB of keys written and re-read + a 1.2 GB table per 100 M k-mers per GPU) "
+                 ">> 126 MB L2; no explicit flush"}
     if sample_note:
         cfg["reference_sample"] = sample_note
     return cfg
+
+
+def verify_table(eng, d, tab, n_win_global, world, rank):
+    """Outside the timed region: size-independent properties of the result of ONE step, over all ranks.
+    (kmermaid/join.py:95-130: every window lands in exactly one group; batch.py:156-168 + join.py:63-93:
+    groups come out in ascending key order; rank r owns key range r.)"""
+    import torch
+    import torch.distributed as dist
+
+    keys = tab.keys[: tab.n * 8].view(torch.int64)
+    counts = tab.counts[: tab.n * 4].view(torch.int32).to(torch.int64)
+    asc = bool((keys[1:] > keys[:-1]).all()) if tab.n > 1 else True  # 62-bit keys: signed compare is exact
+    a = eng.extract(d, K, False, val_bytes=0)  # this rank's windows, extraction order
+    sum_in = a.keys[: a.n * 8].view(torch.int64).sum() if a.n else torch.zeros((), dtype=torch.int64, device=eng.device)
+    n_in = a.n
+    del a
+    red = torch.stack([counts.sum(), (keys * counts).sum(), sum_in, torch.tensor(n_in, device=eng.device),
+                       torch.tensor(tab.n, device=eng.device), torch.tensor(0 if asc else 1, device=eng.device)])
+    edge = torch.stack([keys[0], keys[-1]]) if tab.n else torch.tensor([-1, -1], dtype=torch.int64, device=eng.device)
+    cross = True
+    if world > 1:
+        dist.all_reduce(red)  # (int64 sums wrap modulo 2^64 on every path alike)
+        edges = torch.empty(2 * world, dtype=torch.int64, device=eng.device)
+        dist.all_gather_into_tensor(edges, edge)
+        prev = -1
+        for r, (first, last) in enumerate(edges.view(world, 2).tolist()):
+            if first < 0:
+                continue
+            cross = cross and first > prev
+            prev = last
+    total, kc, ks, n_keys, rows, bad = (int(x) for x in red.tolist())
+    ok = total == n_win_global and n_keys == n_win_global and kc == ks and bad == 0 and cross
+    return {"ok": bool(ok), "windows": n_win_global, "counts_sum": total, "keys_extracted": n_keys, "distinct": rows,
+            "ascending_within_ranks": bad == 0, "ascending_across_ranks": bool(cross),
+            "sum_key_times_count_eq_sum_keys_mod_2_64": kc == ks}
 
 
 # ---- GPU arm --------------------------------------------------------------------------------------
@@ -195,7 +274,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     if args.workload == "auto":
-        args.workload = "cfg2"
+        # N=1: the configuration the single-GPU path is quoted on; N>1: BASELINE.json's scaling configuration
+        args.workload = "cfg2" if args.gpus == 1 else "cfg3"
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
@@ -223,13 +303,8 @@ def main():
 
         total = CFG3_BASES
         b, e = chunk_bases(total, K, world)[rank]
-        # every rank generates only its slice: seed per 100 Mbp block keeps it reproducible
-        blk = 100_000_000
-        parts = []
-        for i in range(b // blk, (e + blk - 1) // blk):
-            x = synth_bases(blk, 1234 + i)
-            parts.append(x[max(b - i * blk, 0) : min(e - i * blk, blk)])
-        chunk = np.concatenate(parts)
+        chunk = cfg3_slice(b, e)  # every rank generates only its slice
+        n_win_global = cfg3_layout()[1]
     else:
         total = CFG2_BASES * world
         # weak scaling: rank r owns block r (+ k-1 bases of block r+1)
@@ -237,7 +312,7 @@ def main():
         if rank + 1 < world:
             chunk = np.concatenate([chunk, synth_bases(CFG2_BASES, 1234 + rank + 1)[: K - 1]])
         b = rank * CFG2_BASES
-    n_win_global = total - K + 1
+        n_win_global = total - K + 1
     flat = fasta.FlatInput(chunk, np.array([0, chunk.size + 1], np.uint64), ["chr1"], ["chr1"])
     d = eng.upload(flat, alphabet="ACGT", with_names=False)
     d.pos_offset = b
@@ -263,11 +338,8 @@ def main():
 
     for _ in range(args.warmup):
         tab = step()
-    # sanity: the job counted every window exactly once
-    tot = torch.tensor([int(tab.counts[: tab.n * 4].view(torch.int32).sum(dtype=torch.int64))], dtype=torch.int64, device=eng.device)
-    if world > 1:
-        dist.all_reduce(tot)
-    assert int(tot.item()) == n_win_global, (int(tot.item()), n_win_global)
+    verify = verify_table(eng, d, tab, n_win_global, world, rank)
+    assert verify["ok"], verify
 
     lib.kmg_set_option(b"time_passes", 1)
     lib.kmg_get_stat(b"reset_launches")
@@ -423,7 +495,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong" if args.workload == "cfg3" else "weak", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic", "config": workload_config(args, p2p=(dc.p2p if world > 1 else None), shared=(dc.shared if world > 1 else None)), "clocks": clocks,
-            "e2e": e2e,
+            "e2e": e2e, "verify": verify,
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "wall_ms_per_step": t_wall / args.steps * 1e3, "kmers_per_step": n_win_global,
         }

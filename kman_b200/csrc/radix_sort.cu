@@ -420,6 +420,7 @@ __global__ void __launch_bounds__(BLOCK, min_ctas(BLOCK, IPT)) onesweep_kernel(c
 }
 
 #include "local_sort.cuh"
+#include "local_sort2.cuh"
 
 // kmg_set_option("sort_config", i) -> (threads, keys per thread, ranking mix), see dispatch_tile():
 //   0: 256x16 mix2   1: 256x16 mix0   2: 256x16 mix1   3: 256x24 mix2 (default)   4: 512x16 mix2
@@ -562,6 +563,7 @@ int g_hybrid = 1;     // kmg_set_option("hybrid", 0/1)
 int g_unstable_config = 10;  // kmg_set_option("unstable_config", 10 | 11 | 12): tile shape of that pass
 int g_hybrid_unstable = 1;  // kmg_set_option("hybrid_unstable", 0/1): first prefix pass without stable ranking
 int g_local_tile = 7936;  // kmg_set_option("local_tile", positions): target tile width of the local sort
+int g_local_v = 2;     // kmg_set_option("local_v", 1 | 2): generation of the local sort kernel (local_sort2.cuh)
 int g_count_fused = 1;  // kmg_set_option("count_fused", 0/1): let the hybrid finish emit the count table itself
 int g_hybrid_pb = 0;  // kmg_set_option("hybrid_pb", 0 | 16 | 24): force the prefix width (0 = by n and skew)
 constexpr uint64_t HYBRID_MIN_N = 1ull << 20;
@@ -856,8 +858,9 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
         timing_begin(st);
 #define KMG_LS_LAUNCH(K, E, V)                                                                                   \
     do {                                                                                                         \
-        KMG_CUDA(cudaFuncSetAttribute(local_sort_kernel<K, E, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        local_sort_kernel<K, E, V><<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);                                       \
+        auto kern = g_local_v == 1 ? local_sort_kernel<K, E, V> : local_sort2_kernel<K, E, V>;                   \
+        KMG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+        kern<<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);                                                            \
     } while (0)
         if (fused && pairs) {
             if (val_bytes == 4) KMG_LS_LAUNCH(uint64_t, 2, 4);

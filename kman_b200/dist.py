@@ -61,6 +61,47 @@ def sort_bits_after_partition(key_bits: int, world: int) -> int:
     return key_bits
 
 
+
+# ---- collectives ---------------------------------------------------------------------------------
+# The product backend is NCCL (one process per GPU; collectives are stream-ordered, so an all-reduce
+# doubles as a device-side fence).  A gloo group is accepted for the TEST topology "two ranks sharing
+# ONE GPU" (tests/test_gpu_dist.py: NCCL refuses two ranks per device, CUDA IPC does not): the tensor is
+# staged through the host, which also makes every collective a full host-level barrier.
+def _staged(group) -> bool:
+    return dist.get_backend(group) == "gloo"
+
+
+def _all_reduce(t: torch.Tensor, op=None, group=None) -> None:
+    op = dist.ReduceOp.SUM if op is None else op
+    if t.is_cuda and _staged(group):
+        h = t.cpu()
+        dist.all_reduce(h, op=op, group=group)
+        t.copy_(h)
+    else:
+        dist.all_reduce(t, op=op, group=group)
+
+
+def _all_gather_into_tensor(out: torch.Tensor, t: torch.Tensor, group=None) -> None:
+    if t.is_cuda and _staged(group):
+        world = dist.get_world_size(group)
+        parts = [torch.empty(t.shape, dtype=t.dtype) for _ in range(world)]
+        dist.all_gather(parts, t.cpu(), group=group)
+        out.copy_(torch.cat([p.reshape(-1) for p in parts]).reshape(out.shape))
+    else:
+        dist.all_gather_into_tensor(out, t, group=group)
+
+
+def _all_to_all_single(recv: torch.Tensor, send: torch.Tensor, output_split_sizes, input_split_sizes, group=None) -> None:
+    if send.is_cuda and _staged(group):
+        h = torch.empty(recv.shape, dtype=recv.dtype)
+        dist.all_to_all_single(h, send.cpu(), output_split_sizes=output_split_sizes,
+                               input_split_sizes=input_split_sizes, group=group)
+        recv.copy_(h)
+    else:
+        dist.all_to_all_single(recv, send, output_split_sizes=output_split_sizes, input_split_sizes=input_split_sizes,
+                               group=group)
+
+
 # ---- exchange ------------------------------------------------------------------------------------
 def gather_count_matrix(send_counts: np.ndarray, device: torch.device, group=None) -> np.ndarray:
     """All-gather of every rank's per-destination counts -> (world, world) int64 matrix
@@ -68,7 +109,7 @@ def gather_count_matrix(send_counts: np.ndarray, device: torch.device, group=Non
     world = dist.get_world_size(group)
     mine = torch.from_numpy(np.ascontiguousarray(send_counts, dtype=np.int64)).to(device)
     allc = torch.empty(world * world, dtype=torch.int64, device=device)
-    dist.all_gather_into_tensor(allc, mine, group=group)
+    _all_gather_into_tensor(allc, mine, group=group)
     return allc.cpu().numpy().reshape(world, world)
 
 
@@ -81,7 +122,7 @@ def exchange(send: torch.Tensor, send_counts: np.ndarray, elems_per_item: int = 
         matrix = gather_count_matrix(send_counts, send.device, group)
     recv_counts = matrix[:, rank].copy()
     recv = torch.empty(int(recv_counts.sum()) * elems_per_item, dtype=send.dtype, device=send.device)
-    dist.all_to_all_single(
+    _all_to_all_single(
         recv,
         send[: int(np.sum(send_counts)) * elems_per_item],
         output_split_sizes=[int(c) * elems_per_item for c in recv_counts],
@@ -250,7 +291,7 @@ class DistributedCounter:
             setattr(self, which, None)
         cur = PeerBuffers(self.eng, int(nbytes * 1.1) + 4096, self.group)
         flag = torch.tensor([1 if cur.ok else 0], dtype=torch.int64, device=self.eng.device)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        _all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
         if int(flag.item()) == 0:
             err = cur.error or "a peer could not map the receive buffers"
             cur.release_local()  # no collective: ranks that failed early hold nothing to fence
@@ -294,7 +335,7 @@ class DistributedCounter:
         counts = self._dest_counts(d, k, rc, kb)
         self._mark("per-destination counts")
         allc = torch.empty(G * (G + 1), dtype=torch.int64, device=eng.device)
-        dist.all_gather_into_tensor(allc, counts, group=self.group)
+        _all_gather_into_tensor(allc, counts, group=self.group)
         M = allc.view(G, G + 1)
         # my region inside destination dst starts after the regions of the sources before me
         cursors = M[: self.rank, :G].sum(dim=0) if self.rank else torch.zeros(G, dtype=torch.int64, device=eng.device)
@@ -323,7 +364,7 @@ class DistributedCounter:
             self._mark("extract + scatter kernel")
             # device-side fence (no host sync): every rank's peer stores, stream-ordered before its
             # contribution, have landed when the all-reduce completes; it also carries the overflow flag
-            dist.all_reduce(status, op=dist.ReduceOp.MAX, group=self.group)
+            _all_reduce(status, op=dist.ReduceOp.MAX, group=self.group)
             self._info_host[:5].copy_(torch.cat([info, status.to(torch.int64)]), non_blocking=True)
             torch.cuda.current_stream(eng.device).synchronize()
             n_recv, recv_max, n_wide, overflow = (int(self._info_host[i]) for i in (0, 1, 2, 3))
@@ -359,7 +400,7 @@ class DistributedCounter:
         self._mark("(outside)")
         if self._cap_elems == 0:  # first exchange of this counter -- on every rank
             t = torch.tensor([n_mine], dtype=torch.int64, device=eng.device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            _all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
             self._cap_elems = int(int(t.item()) * scale) + 4096
         cap = self._cap_elems
         pk = self._ensure_peer("_peer_keys", cap * kb)
@@ -370,7 +411,7 @@ class DistributedCounter:
         pk.cursor.zero_()
         # device-side barrier (no host sync): every cursor is zero, nobody still reads the last step's keys
         fence = torch.zeros(1, dtype=torch.int32, device=eng.device)
-        dist.all_reduce(fence, group=self.group)
+        _all_reduce(fence, group=self.group)
         self._mark("fence 1")
         _lib.check(lib.kmg_extract_scatter_shared(d.bases.data_ptr(), d.n_bases, 0, n_win, k, int(rc), d.lut.data_ptr(), G,
                                                   pk.data_table.data_ptr(), pv.data_table.data_ptr() if pv else None, kb,
@@ -380,7 +421,7 @@ class DistributedCounter:
         # fence + agreement: every rank's peer stores (stream-ordered before its contribution) have landed
         status[:2] = status32
         status[2] = n_mine
-        dist.all_reduce(status, op=dist.ReduceOp.MAX, group=self.group)
+        _all_reduce(status, op=dist.ReduceOp.MAX, group=self.group)
         self._info_host[:4].copy_(torch.cat([status, pk.cursor]), non_blocking=True)
         torch.cuda.current_stream(eng.device).synchronize()
         overflow, wide_seen, n_max, n_recv = (int(self._info_host[i]) for i in range(4))
@@ -461,7 +502,7 @@ class DistributedCounter:
                 self._fall_back(exc)
         a = self.eng.extract(d, k, rc, wide=False, val_bytes=8 if with_vals else 0)
         n_other = torch.tensor([a.n_other], dtype=torch.int64, device=a.keys.device)
-        dist.all_reduce(n_other, group=self.group)
+        _all_reduce(n_other, group=self.group)
         return self._partition_exchange(a, with_vals), int(n_other.item())
 
     def _wide(self, d, k: int, rc: bool, with_vals: bool):

@@ -437,6 +437,17 @@ def count_np(records, k, rc=False, alphabet=DEFAULT_ALPHABET, natype="DNA"):
     return txt, counts, detail
 
 
+def count_table_np(records, k, rc=False, alphabet=DEFAULT_ALPHABET, natype="DNA"):
+    """The binary (k-mer, count) table of the NARROW stream only -- distinct packed keys ascending
+    (limb list) and their multiplicities -- without decoding to text: the stages bench.py's GPU arm
+    times (seq.py:284-328 -> batch.py:156-168 -> join.py:95-130), used by its cpu_baseline leg."""
+    st = extract_np(records, k, rc, alphabet, natype)["narrow"]
+    order = _lexsort_limbs(st["keys"])
+    srt = [l[order] for l in st["keys"]]
+    heads, lens = _rle(srt)
+    return [l[heads] for l in srt], lens
+
+
 def uniq_np(records, k, rc=False, alphabet=DEFAULT_ALPHABET, natype="DNA"):
     """`kmer uniq` in canonical binary form: singletons ascending by sequence.
 

@@ -6,6 +6,7 @@
     tests/test_batch.py:80-87 in /root/reference), restated here as data.
 """
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -130,3 +131,42 @@ def test_k_must_exceed_one():  # batcher.py:477-478
         ko.count_text_py([("a", "ACGT")], 1)
     with pytest.raises(AssertionError):
         ko.count_text_np([("a", "ACGT")], 1)
+
+
+# ---- large-configuration table hashes (tests/golden/table_hashes.json) -------------------------------
+def test_table_hash_digests_follow_the_text_tier():
+    """The digests oracle/gen_table_hashes.py commits are computed on packed keys; on a small
+    config-4-shaped input (N runs, soft-masked bases, IUPAC symbols, three records) the same
+    keys, decoded, must be exactly the text the literal pure-Python tier writes."""
+    import gen_table_hashes as gth
+    import synth_configs as sc
+
+    recs = sc.cfg4(30_000)
+    for k, rc, ab in ((25, False, "IUPAC"), (25, True, "ACGT"), (45, False, "IUPAC")):
+        ex = ko.extract_np(recs, k, rc, ab)
+        d_count, d_uniq = gth.digests(recs, k, rc, ab, "count"), gth.digests(recs, k, rc, ab, "uniq")
+        txt = ko.count_text_py(recs, k, rc, alphabet=ab)
+        assert txt == ko.count_text_np(recs, k, rc, ab)
+        assert txt.count(b"\n") == d_count["narrow"]["rows"] + d_count["wide"]["rows"]
+        assert d_count["narrow"]["total"] + d_count["wide"]["total"] == len(ex["narrow"]["pos"]) + len(ex["wide"]["pos"])
+        utxt = ko.uniq_text_py(recs, k, rc, alphabet=ab)
+        assert utxt.count(b"\n") == 2 * (d_uniq["narrow"]["rows"] + d_uniq["wide"]["rows"])
+        # the count digest is the hash of exactly the table count_np groups
+        _, _, det = ko.count_np(recs, k, rc, ab)
+        assert d_count["narrow"] == {**sc.count_digest(sc.key_rows(det["narrow"]["keys"]), det["narrow"]["counts"]),
+                                     "keys_in": len(ex["narrow"]["pos"])}
+
+
+def test_committed_table_hashes_reproduce():
+    """One committed case is recomputed here (about 20 s): the file is what the generator writes."""
+    import json
+
+    import gen_table_hashes as gth
+
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "table_hashes.json")))
+    assert set(gold) == set(gth.CASES)
+    name = "cfg3_24mbp_24rec_k31_count"
+    make, k, rc, ab, mode = gth.CASES[name]
+    got = gth.digests(make(), k, rc, ab, mode)
+    for key, val in got.items():
+        assert gold[name][key] == val, key

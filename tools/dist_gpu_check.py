@@ -24,12 +24,21 @@ from kman_b200.dist import DistributedCounter  # noqa: E402
 from kman_b200.engine import get_engine  # noqa: E402
 
 rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+# KMG_TEST_ONE_GPU=1: every rank uses cuda:0 and the plumbing runs over gloo (NCCL refuses two ranks on
+# one device; the peer buffers are CUDA-IPC mappings either way) -- the topology the driver's
+# single-GPU test box can run
+one_gpu = os.environ.get("KMG_TEST_ONE_GPU") == "1"
+if one_gpu:
+    lr = 0
 torch.cuda.set_device(lr)
-dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+if one_gpu:
+    dist.init_process_group("gloo")
+else:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 eng = get_engine(lr)
 dc = DistributedCounter(eng)
 if rank == 0:
-    print("p2p path:", dc.p2p, "shared cursors:", dc.shared, flush=True)
+    print("p2p path:", dc.p2p, "shared cursors:", dc.shared, "backend:", dist.get_backend(), flush=True)
 
 
 def genome(seed, n, n_rec, with_other):
@@ -59,6 +68,7 @@ def rows(limbs):
 
 
 ok = True
+only = os.environ.get("KMG_TEST_CASES")  # e.g. "0,4": a subset (the pytest wrapper keeps its run short)
 CASES = [
     # k, rc, n_bases, records, alphabet, non-ACGT symbols
     (31, False, 3_000_000, 5, "ACGT", False),
@@ -69,6 +79,8 @@ CASES = [
     (25, True, 1_300_000, 3, None, True),
     (31, False, 3_400_001, 2, "ACGT", True),    # ACGT-only alphabet: windows with N are skipped
 ]
+if only:
+    CASES = [CASES[int(i)] for i in only.split(",")]
 for k, rc, n, n_rec, alphabet, other in CASES:
     recs = genome(1000 + k + n % 7, n, n_rec, other)
     flat = fasta.from_records(recs)
