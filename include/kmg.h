@@ -134,8 +134,9 @@ int kmg_sort_count(void* d_keys, void* d_keys_alt, uint64_t n, int key_bytes, in
 /* sort + select_singletons in one call (the uniq path: join.py:63-130 + join_unique :243-263).
  * Leaves the keys that occur exactly once, ascending, with their payload in (d_keys, d_vals)
  * (*h_selector_out = 0) or (d_keys_alt, d_vals_alt) (1); *d_n_out (device) = their number.  Because
- * repeated keys are dropped, their relative order does not matter and 8-byte keys take the
- * hybrid finish with the payload following through a 16-bit index (6144-key tiles); its local
+ * repeated keys are dropped, their relative order does not matter and the keys take the
+ * hybrid finish with the payload following through a 16-bit index (tiles of 6144 8-byte / 4096
+ * 16-byte keys); its local
  * sort emits the singletons itself unless irregular tiles force sort + kmg_select_singletons. */
 size_t kmg_sort_uniq_workspace_bytes(uint64_t n, int key_bytes, int val_bytes, int end_bit);
 int kmg_sort_uniq(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_alt, uint64_t n, int key_bytes,
@@ -148,7 +149,7 @@ int kmg_select_singletons(const void* d_sorted_keys, const void* d_vals, uint64_
 /* ---- K1-K4 in one call: the device path of `kmer count` / `kmer uniq` for the narrow stream -------
  * (FastaBatcher.do batcher.py:454-487 + KJoiner.join join.py:337-391 on one flat base buffer.)
  * Same results as kmg_extract followed by kmg_sort_count / kmg_sort_uniq, but when the hybrid sort
- * applies (>= 2^20 keys, k >= 16; with payload: k <= 32) the extraction kernel itself is the sort's
+ * applies (>= 2^20 keys, k >= 16) the extraction kernel itself is the sort's
  * first prefix pass: a pre-pass over the BASES yields the histograms of the top key bytes (4-mer
  * histogram), then every key is written once, straight into the region of its digit -- the keys are
  * never stored in extraction order.  Two host synchronisations per call (32 + 56 bytes read back).
@@ -278,8 +279,6 @@ int kmg_uniq_host(kmg_ctx* ctx, const uint8_t* h_bases, uint64_t n_bases, int k,
  *   "unstable_config" [10] tile shape of that pass (10: 256x24, 11: 256x16, 12: 384x16)
  *   "count_fused" [1]      kmg_sort_count: the local sort emits the (k-mer, count) table itself
  *   "local_tile" [7936]    target tile width of the local sort (positions)
- *   "local_v" [2]          generation of the local sort kernel (1: per-thread insertion walks, 2: rank by
- *                          reading the cell + ballot emission)
  *   "sort_config" [3]      tile configuration of the onesweep kernel (radix_sort.cu: dispatch_tile)
  *   "lb_group" [32]        tiles per look-back group of the onesweep kernel
  *   "prefetch_tiles" [192] L2 prefetch distance of the onesweep kernel, in tiles (0: off)

@@ -31,6 +31,11 @@ struct LS<uint64_t, true> {
     static constexpr int IPT = 12;
     static constexpr int CPT = 12;
 };
+template <>
+struct LS<u128, true> {  // uniq at k > 32
+    static constexpr int IPT = 8;
+    static constexpr int CPT = 8;
+};
 constexpr int LS_BLOCK = 512;
 template <typename KeyT, bool PAIRS>
 __host__ __device__ constexpr int ls_cap() { return LS_BLOCK * LS<KeyT, PAIRS>::IPT; }  // keys a tile can own
@@ -259,14 +264,9 @@ __global__ void __launch_bounds__(LS_BLOCK, 2) local_sort_kernel(const HybridPar
         cm.inv = range <= (uint64_t)CELLS ? 0u : (uint32_t)((((uint64_t)CELLS) << 32) / range);
     }
     __syncthreads();     // cells are zero
-    uint32_t meta[IPT];  // cell | slot inside the cell << CELL_BITS
 #pragma unroll
     for (int j = 0; j < IPT; ++j) {
-        const uint32_t idx = t + j * LS_BLOCK;
-        if (idx < m) {
-            const uint32_t c = cm(keys[j]);
-            meta[j] = c | (atomicAdd(&s_cell[pc<KeyT, PAIRS>(c)], 1u) << CELL_BITS);
-        }
+        if (t + j * LS_BLOCK < m) atomicAdd(&s_cell[pc<KeyT, PAIRS>(cm(keys[j]))], 1u);
     }
     __syncthreads();
     // exclusive prefix over the cells: CPT consecutive cells per thread, 128 bits at a time
@@ -288,14 +288,16 @@ __global__ void __launch_bounds__(LS_BLOCK, 2) local_sort_kernel(const HybridPar
 #undef KMG_LS_STEP
         cv[i] = q[i];
     }
-    asm volatile("" ::: "memory");
-    if (t == LS_BLOCK - 1) s_cell[pc<KeyT, PAIRS>(CELLS)] = run;  // sentinel: end of the last cell
     __syncthreads();
+    // Placement: a second atomic on the cell's running start hands out the slots (arrival order), so
+    // nothing but the keys lives in registers between the phases -- a per-key (cell, slot) word kept
+    // from the counting pass cost 16 more registers and spilled under the 64-register cap
+    // (profiles/r02_ncu_local_sort_experiments.md).  Afterwards a cell's word is its END.
 #pragma unroll
     for (int j = 0; j < IPT; ++j) {
         const uint32_t idx = t + j * LS_BLOCK;
         if (idx < m) {
-            const uint32_t at = s_cell[pc<KeyT, PAIRS>(meta[j] & ((1u << CELL_BITS) - 1u))] + (meta[j] >> CELL_BITS);
+            const uint32_t at = atomicAdd(&s_cell[pc<KeyT, PAIRS>(cm(keys[j]))], 1u);
             s_stage[at] = keys[j];
             if constexpr (PAIRS) s_idx[at] = (uint16_t)idx;
         }
@@ -304,7 +306,7 @@ __global__ void __launch_bounds__(LS_BLOCK, 2) local_sort_kernel(const HybridPar
     // Order every cell in place.  The cells are already in order among themselves, so a thread
     // simply insertion-sorts the contiguous run of its CPT cells (~11 / ~6 keys): a key moves only
     // inside its own cell, equal keys cost one compare each.
-    const uint32_t lo = s_cell[pc<KeyT, PAIRS>(t * CPT)], hi = s_cell[pc<KeyT, PAIRS>((t + 1) * CPT)];
+    const uint32_t lo = t ? s_cell[pc<KeyT, PAIRS>(t * CPT - 1)] : 0u, hi = s_cell[pc<KeyT, PAIRS>((t + 1) * CPT - 1)];
     // COUNT: equal keys share a cell, hence a thread's run, so the run heads (distinct keys) can be
     // counted while inserting: a key is new unless it lands right after an equal one
     uint32_t hc = 0;

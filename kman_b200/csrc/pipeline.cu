@@ -14,7 +14,7 @@
 //   4. the remaining 1-2 stable prefix passes (onesweep_kernel), tile bounds, local_sort_kernel with
 //      the fused count / singleton emission (radix_sort.cu: sort_impl with `pre`).
 //   5. ONE host read-back (the sort's status words, 56 bytes) carries the result count.
-// Inputs the hybrid finish does not take (fewer than 2^20 keys, k < 16, payload with 16-byte keys)
+// Inputs the hybrid finish does not take (fewer than 2^20 keys, k < 16)
 // run kmg_extract + kmg_sort_count / kmg_sort_uniq inside the same call: same result either way.
 #include <algorithm>
 

@@ -420,7 +420,6 @@ __global__ void __launch_bounds__(BLOCK, min_ctas(BLOCK, IPT)) onesweep_kernel(c
 }
 
 #include "local_sort.cuh"
-#include "local_sort2.cuh"
 
 // kmg_set_option("sort_config", i) -> (threads, keys per thread, ranking mix), see dispatch_tile():
 //   0: 256x16 mix2   1: 256x16 mix0   2: 256x16 mix1   3: 256x24 mix2 (default)   4: 512x16 mix2
@@ -563,7 +562,6 @@ int g_hybrid = 1;     // kmg_set_option("hybrid", 0/1)
 int g_unstable_config = 10;  // kmg_set_option("unstable_config", 10 | 11 | 12): tile shape of that pass
 int g_hybrid_unstable = 1;  // kmg_set_option("hybrid_unstable", 0/1): first prefix pass without stable ranking
 int g_local_tile = 7936;  // kmg_set_option("local_tile", positions): target tile width of the local sort
-int g_local_v = 2;     // kmg_set_option("local_v", 1 | 2): generation of the local sort kernel (local_sort2.cuh)
 int g_count_fused = 1;  // kmg_set_option("count_fused", 0/1): let the hybrid finish emit the count table itself
 int g_hybrid_pb = 0;  // kmg_set_option("hybrid_pb", 0 | 16 | 24): force the prefix width (0 = by n and skew)
 constexpr uint64_t HYBRID_MIN_N = 1ull << 20;
@@ -623,9 +621,9 @@ static SortWs carve_sort_ws(void* ws, uint64_t n, int key_bytes, bool hybrid, in
 }
 
 // Payload sorts take it only when the caller does not need equal keys in input order (`pairs_ok`:
-// kmg_sort_uniq), and only with 8-byte keys.
+// kmg_sort_uniq).
 static bool hybrid_applies(uint64_t n, int key_bytes, int val_bytes, int begin_bit, int end_bit, bool pairs_ok) {
-    if (val_bytes != 0 && !(pairs_ok && key_bytes == 8)) return false;
+    if (val_bytes != 0 && !pairs_ok) return false;
     return g_hybrid && begin_bit == 0 && end_bit >= 32 && n >= HYBRID_MIN_N && n <= HYBRID_MAX_N;
 }
 
@@ -652,7 +650,9 @@ static_assert(sizeof(HybridHeaderView) == 56, "layout of the header words");
 // fullest top byte -- real genomes are skewed enough to need the third pass early
 // (a tile must hold one bucket-wide window plus the straddling bucket: capacity / 2.4)
 static bool hybrid_pb16_ok(unsigned long long max_top_byte_count, int key_bytes, int val_bytes) {
-    return max_top_byte_count / 256 <= (unsigned long long)(key_bytes == 16 ? 1700 : (val_bytes ? 2500 : 3400));
+    // (16-byte keys: tiles of 4096; measured at 100 M keys, k = 63: buckets of 1526 fill a tile to 37 % and
+    // the local sort takes 2.57 ms against 1.56 ms + a 0.84 ms pass with the 24-bit prefix)
+    return max_top_byte_count / 256 <= (unsigned long long)(key_bytes == 16 ? 800 : (val_bytes ? 2500 : 3400));
 }
 int hybrid_choose_pb(uint64_t n, unsigned long long max_top_byte_count, int key_bytes, int val_bytes) {
     if (g_hybrid_pb == 16 || g_hybrid_pb == 24) return g_hybrid_pb;
@@ -800,7 +800,8 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
     // kin now holds the keys ordered by their top pb bits; finish into kout
     const bool wide_key = key_bytes == 16;
     const bool pairs = val_bytes != 0;
-    const int cap = wide_key ? ls_cap<u128, false>() : (pairs ? ls_cap<uint64_t, true>() : ls_cap<uint64_t, false>());
+    const int cap = wide_key ? (pairs ? ls_cap<u128, true>() : ls_cap<u128, false>())
+                             : (pairs ? ls_cap<uint64_t, true>() : ls_cap<uint64_t, false>());
     HybridParams hp;
     memset(&hp, 0, sizeof(hp));
     hp.keys_in = kin;
@@ -831,7 +832,7 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
     hp.tile_state = w.hyb_state;
     hp.ticket = &hv->ls_ticket;
     hp.err = &w.hdr->err;
-    const size_t smem = wide_key ? ls_smem_bytes<u128, false>()
+    const size_t smem = wide_key ? (pairs ? ls_smem_bytes<u128, true>() : ls_smem_bytes<u128, false>())
                                  : (pairs ? ls_smem_bytes<uint64_t, true>() : ls_smem_bytes<uint64_t, false>());
     const int sel_in = kin == (char*)d_keys ? 0 : 1;  // where the prefix-ordered keys are
     const int sel_done = sel_in ^ 1;                   // ... and where the finish puts its result
@@ -858,16 +859,22 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
         timing_begin(st);
 #define KMG_LS_LAUNCH(K, E, V)                                                                                   \
     do {                                                                                                         \
-        auto kern = g_local_v == 1 ? local_sort_kernel<K, E, V> : local_sort2_kernel<K, E, V>;                   \
+        auto kern = local_sort_kernel<K, E, V>;                                                                  \
         KMG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
         kern<<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);                                                            \
     } while (0)
-        if (fused && pairs) {
+        if (fused && pairs && wide_key) {
+            if (val_bytes == 4) KMG_LS_LAUNCH(u128, 2, 4);
+            else KMG_LS_LAUNCH(u128, 2, 8);
+        } else if (fused && pairs) {
             if (val_bytes == 4) KMG_LS_LAUNCH(uint64_t, 2, 4);
             else KMG_LS_LAUNCH(uint64_t, 2, 8);
         } else if (fused) {
             if (wide_key) KMG_LS_LAUNCH(u128, 1, 0);
             else KMG_LS_LAUNCH(uint64_t, 1, 0);
+        } else if (pairs && wide_key) {
+            if (val_bytes == 4) KMG_LS_LAUNCH(u128, 0, 4);
+            else KMG_LS_LAUNCH(u128, 0, 8);
         } else if (pairs) {
             if (val_bytes == 4) KMG_LS_LAUNCH(uint64_t, 0, 4);
             else KMG_LS_LAUNCH(uint64_t, 0, 8);

@@ -355,7 +355,7 @@ class Engine:
     @_on_device
     def sort_uniq(self, a: KeyArray, end_bit: Optional[int] = None) -> KeyArray:
         """sort() + singletons() in one native call (kmg_sort_uniq).  Repeated keys are dropped, so
-        their order is irrelevant and 8-byte keys take the hybrid finish with the payload.  Consumes `a`."""
+        their order is irrelevant and the keys take the hybrid finish with the payload.  Consumes `a`."""
         end_bit = a.key_bits if end_bit is None else end_bit
         assert a.val_bytes in (4, 8)
         if a.n == 0:
