@@ -16,6 +16,7 @@
 //      tiles (32-bit word: 2 flag bits + 30-bit count) -> global base of the digit run
 //   5. keys (then payload) are reordered through shared memory so that every digit run is
 //      written with consecutive threads -> coalesced stores of run-length ~TILE/RADIX keys
+#include <cmath>
 #include <type_traits>
 
 #include "common.cuh"
@@ -646,17 +647,30 @@ struct HybridHeaderView {
 static_assert(sizeof(HybridHeaderView) == 56, "layout of the header words");
 
 // `hybrid` = the workspace was carved for (and the call may take) the hybrid finish
-// a 16-bit prefix is enough (two passes) while its buckets stay well under a tile: judged by the
-// fullest top byte -- real genomes are skewed enough to need the third pass early
-// (a tile must hold one bucket-wide window plus the straddling bucket: capacity / 2.4)
-static bool hybrid_pb16_ok(unsigned long long max_top_byte_count, int key_bytes, int val_bytes) {
+// A 16-bit prefix is enough (two passes instead of three) in two situations, judged by the fullest top
+// byte (real genomes are skewed enough to need the third pass early):
+//  * its buckets stay well under a tile, so that a tile holds a window of a few buckets plus the
+//    straddling one (capacity / 2.4);
+//  * the keys are spread evenly (fullest top byte within 4 % of the mean, e.g. random sequence) and ONE
+//    bucket fits a tile with 6 sigma to spare: every tile then owns exactly one bucket (the windows are
+//    made narrower than the smallest bucket, see tile_width).  This is config 3 on 8 GPUs: 387 M keys
+//    per rank, buckets of 5913 -- one pass fewer (0.5 ms per 100 M keys) for tiles that are 72 % full.
+static int hybrid_tile_cap(int key_bytes, int val_bytes) {
+    return key_bytes == 16 ? (val_bytes ? ls_cap<u128, true>() : ls_cap<u128, false>())
+                           : (val_bytes ? ls_cap<uint64_t, true>() : ls_cap<uint64_t, false>());
+}
+static bool hybrid_pb16_ok(uint64_t n, unsigned long long max_top_byte_count, int key_bytes, int val_bytes) {
     // (16-byte keys: tiles of 4096; measured at 100 M keys, k = 63: buckets of 1526 fill a tile to 37 % and
     // the local sort takes 2.57 ms against 1.56 ms + a 0.84 ms pass with the 24-bit prefix)
-    return max_top_byte_count / 256 <= (unsigned long long)(key_bytes == 16 ? 800 : (val_bytes ? 2500 : 3400));
+    const unsigned long long fullest = max_top_byte_count / 256;  // expected size of the largest 16-bit bucket
+    if (fullest <= (unsigned long long)(key_bytes == 16 ? 800 : (val_bytes ? 2500 : 3400))) return true;
+    if (key_bytes == 16) return false;
+    const double avg = (double)n / 65536.0;
+    return (double)fullest <= 1.04 * avg && avg + 6.0 * std::sqrt(avg) <= (double)hybrid_tile_cap(key_bytes, val_bytes) - 64.0;
 }
 int hybrid_choose_pb(uint64_t n, unsigned long long max_top_byte_count, int key_bytes, int val_bytes) {
     if (g_hybrid_pb == 16 || g_hybrid_pb == 24) return g_hybrid_pb;
-    return n <= (1ull << 27) && hybrid_pb16_ok(max_top_byte_count, key_bytes, val_bytes) ? 16 : 24;
+    return hybrid_pb16_ok(n, max_top_byte_count, key_bytes, val_bytes) ? 16 : 24;
 }
 
 // `pre` (fused pipeline): the keys in d_keys are ALREADY grouped by the lowest prefix byte (the first,
@@ -712,17 +726,15 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
         }
         pb = pre ? pre->pb : (g_hybrid_pb == 16 || g_hybrid_pb == 24 ? g_hybrid_pb : 0);
         if (!pb) {
-            // a 16-bit prefix is enough (two passes) while its buckets stay well under a tile: judge
-            // by the fullest top byte -- real genomes are skewed enough to need the third pass early
+            // 16-bit or 24-bit prefix: see hybrid_pb16_ok (needs the top byte's histogram on the host)
             pb = 24;
-            if (n <= (1ull << 27)) {
+            if (n <= (1ull << 29)) {
                 unsigned long long h_top[SORT_RADIX];
                 KMG_CUDA(cudaMemcpyAsync(h_top, w.hist + 2 * SORT_RADIX, sizeof(h_top), cudaMemcpyDeviceToHost, st));
                 KMG_CUDA(cudaStreamSynchronize(st));
                 unsigned long long mx = 0;
                 for (int i = 0; i < SORT_RADIX; ++i) mx = std::max(mx, h_top[i]);
-                // (a tile must hold one bucket-wide window plus the straddling bucket: capacity / 2.4)
-                if (hybrid_pb16_ok(mx, key_bytes, val_bytes)) pb = 16;
+                if (hybrid_pb16_ok(n, mx, key_bytes, val_bytes)) pb = 16;
             }
         }
         np = pb / 8;
@@ -814,6 +826,8 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
     // gives (for evenly filled buckets) every tile the same k buckets instead of k-1 or k
     const double avg = (double)n / (double)(1ull << pb);  // average prefix bucket
     auto tile_width = [&](double want) {
+        // (one bucket per tile: windows narrower than the smallest bucket, so that none holds two starts)
+        if (avg > cap / 2.4) return (uint32_t)std::max<double>(LS_T_MIN, std::min<double>(cap - 256, avg - 6.0 * std::sqrt(avg) - 8.0));
         double target = std::min<double>(want, cap - std::max(256.0, 1.35 * avg));
         target = std::max<double>(target, LS_T_MIN);
         if (avg < 64) return (uint32_t)target;
