@@ -25,7 +25,7 @@
  *   reference's string order (batch.py:156-168) for equal-length upper-case strings.
  * Key format ("wide" stream, windows that pass the alphabet test but hold >= 1 other
  *   symbol, e.g. N): 4-bit ASCII-rank codes over "ABCDGHKMNRSTUVWY", MSB first,
- *   k <= 16 : uint64, k <= 32 : 128-bit.
+ *   k <= 32 : 128-bit {lo, hi}; k <= 64 : 256-bit, four little-endian 64-bit limbs (key_bytes = 32).
  * Payload ("val") format: (global window start in the flat base buffer << 1) | strand
  *   (0 '+', 1 '-'), as uint32 (val_bytes 4) or uint64 (val_bytes 8).
  */
@@ -256,6 +256,20 @@ int kmg_fasta_flatten(const uint8_t* d_raw, uint64_t n_raw, uint8_t* d_bases_out
 int kmg_merge_ranks(const void* d_narrow_keys, uint64_t n_narrow, int narrow_key_bytes, const void* d_wide_keys,
                     uint64_t n_wide, int wide_key_bytes, int k, int rna, uint64_t* d_rank_of_narrow,
                     uint64_t* d_rank_of_wide, void* stream);
+/* The same for 33 <= k <= 64: 16-byte narrow keys, 32-byte wide keys; d_tmp16 = n_wide 16-byte slots of scratch. */
+int kmg_merge_ranks_wide(const void* d_narrow_keys, uint64_t n_narrow, const void* d_wide_keys, uint64_t n_wide, int k,
+                         int rna, uint64_t* d_rank_of_narrow, uint64_t* d_rank_of_wide, void* d_tmp16, void* stream);
+
+/* ---- the wide stream at 33 <= k <= 64: 256-bit keys (four little-endian 64-bit limbs, 4-bit codes) -----
+ * kmermaid/seq.py:317-318 puts no bound on k for windows that hold N / IUPAC symbols.  kmg_extract
+ * (wide = 1) emits them with key_bytes = 32; kmg_sort256 sorts them stably (batch.py:156-168) on bits
+ * [0, end_bit) into d_keys_out / d_vals_out (two stable 128-bit sorts carrying the element index, then
+ * one gather); kmg_rle_count, kmg_select_singletons, kmg_format_counts and kmg_format_uniq take
+ * key_bytes = 32. */
+size_t kmg_sort256_workspace_bytes(uint64_t n);
+int kmg_sort256(const void* d_keys, void* d_keys_out, const void* d_vals, void* d_vals_out, uint64_t n, int val_bytes,
+                int end_bit, void* d_ws, size_t ws_bytes, void* stream);
+
 
 /* ---- whole-path calls with HOST buffers (what FastaBatcher.do + KJoiner.join do) ------
  * A context owns device scratch on one GPU and a private stream; calls are synchronous.

@@ -40,6 +40,9 @@ SIGNATURES = {
     "kmg_pipeline_workspace_bytes": (sz, [u64, i32, i32, i32]),
     "kmg_extract_sort_count": (i32, [vp, u64, u64, u64, i32, i32, vp, vp, vp, vp, u64p, vp, sz, vp]),
     "kmg_extract_sort_uniq": (i32, [vp, u64, u64, u64, i32, i32, vp, vp, vp, vp, vp, i32, u64, u64p, vp, sz, vp]),
+    "kmg_sort256_workspace_bytes": (sz, [u64]),
+    "kmg_sort256": (i32, [vp, vp, vp, vp, u64, i32, i32, vp, sz, vp]),
+    "kmg_merge_ranks_wide": (i32, [vp, u64, vp, u64, i32, i32, vp, vp, vp, vp]),
     "kmg_select_singletons": (i32, [vp, vp, u64, i32, i32, vp, vp, vp, vp, sz, vp]),
     "kmg_partition_workspace_bytes": (sz, [u64, i32, i32]),
     "kmg_range_partition": (i32, [vp, vp, u64, i32, i32, i32, i32, vp, vp, vp, vp, sz, vp]),

@@ -119,6 +119,16 @@ __host__ __device__ __forceinline__ bool operator<(const u128& a, const u128& b)
     return a.hi < b.hi || (a.hi == b.hi && a.lo < b.lo);
 }
 
+// ---- 256-bit key: the wide (4-bit code) stream at 33 <= k <= 64 ---------------------------------------
+struct __align__(16) u256 {
+    u128 lo, hi;
+};
+__host__ __device__ __forceinline__ bool operator==(const u256& a, const u256& b) { return a.lo == b.lo && a.hi == b.hi; }
+__host__ __device__ __forceinline__ bool operator!=(const u256& a, const u256& b) { return !(a == b); }
+__host__ __device__ __forceinline__ bool operator<(const u256& a, const u256& b) {
+    return a.hi < b.hi || (a.hi == b.hi && a.lo < b.lo);
+}
+
 // digit = (key >> shift) & mask ; shift < 8*sizeof(key), digit width <= 16
 __device__ __forceinline__ uint32_t key_digit(uint64_t k, int shift, uint32_t mask) {
     return (uint32_t)(k >> shift) & mask;
@@ -133,6 +143,10 @@ __device__ __forceinline__ uint32_t key_digit(const u128& k, int shift, uint32_t
         v = (k.lo >> shift) | (k.hi << (64 - shift));
     }
     return (uint32_t)v & mask;
+}
+// (digits of a 256-bit key never straddle its 128-bit halves where this is used: 4-bit symbols)
+__device__ __forceinline__ uint32_t key_digit(const u256& k, int shift, uint32_t mask) {
+    return shift >= 128 ? key_digit(k.hi, shift - 128, mask) : key_digit(k.lo, shift, mask);
 }
 __device__ __forceinline__ uint64_t key_all_ones(uint64_t) { return ~0ull; }
 __device__ __forceinline__ u128 key_all_ones(u128) { return u128{~0ull, ~0ull}; }

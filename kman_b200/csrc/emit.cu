@@ -188,13 +188,23 @@ __global__ void __launch_bounds__(FMT_BLOCK) format_uniq_kernel(const FmtParams 
 // the first non-plain symbol and c the number of plain bases whose letter sorts before it.
 // A narrow key N sorts before W  <=>  N < T(W) with T = ((prefix_j(W) << 2) + c) << 2(k-1-j),
 // and T >= 1 always (no symbol sorts before 'A'), so T' = T-1 fits 64 bits even when T = 2^64.
-__global__ void wide_threshold_kernel(const u128* __restrict__ wide, uint64_t n, int k, int rna,
-                                      uint64_t* __restrict__ tprime) {
+template <typename NarrowT>
+__device__ __forceinline__ NarrowT narrow_from_u128(unsigned __int128 v);
+template <>
+__device__ __forceinline__ uint64_t narrow_from_u128<uint64_t>(unsigned __int128 v) { return (uint64_t)v; }
+template <>
+__device__ __forceinline__ u128 narrow_from_u128<u128>(unsigned __int128 v) { return u128{(uint64_t)v, (uint64_t)(v >> 64)}; }
+
+// WideT / NarrowT: u128 / uint64_t (k <= 32) or u256 / u128 (k <= 64).  T' = T - 1 is assembled without
+// ever holding T (which can be 2^(2k)): T - 1 = ((prefix << 2) + c - 1) << 2 rem | (4^rem - 1), c >= 1.
+template <typename WideT, typename NarrowT>
+__global__ void wide_threshold_kernel(const WideT* __restrict__ wide, uint64_t n, int k, int rna,
+                                      NarrowT* __restrict__ tprime) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const u128 w = wide[i];
+    const WideT w = wide[i];
     const uint32_t r3 = rna ? 12u : 11u;  // rank of T / U
-    unsigned __int128 T = 0;
+    unsigned __int128 A = 0;
     int j = 0;
     for (; j < k; ++j) {
         const uint32_t s = key_digit(w, 4 * (k - 1 - j), 0xFu);
@@ -204,27 +214,29 @@ __global__ void wide_threshold_kernel(const u128* __restrict__ wide, uint64_t n,
         else if (s == 4) code = 2;
         else if (s == r3) code = 3;
         if (code < 4) {
-            T = (T << 2) | code;
+            A = (A << 2) | code;
             continue;
         }
-        const uint32_t c = (s > 0) + (s > 2) + (s > 4) + (s > r3);
-        T = (T << 2) + c;
+        const uint32_t c = (s > 0) + (s > 2) + (s > 4) + (s > r3);  // >= 1: no symbol sorts before 'A'
+        A = (A << 2) + (c - 1);
         break;
     }
-    // j == k cannot happen for a wide key; treat it as "after its own narrow twin"
-    const int rem = j < k ? k - 1 - j : 0;
-    T <<= 2 * rem;
-    if (j == k) T += 1;
-    tprime[i] = (uint64_t)(T - 1);
+    // j == k cannot happen for a wide key; treat it as "right after its own narrow twin" (T' = the twin)
+    if (j < k) {
+        const int rem = k - 1 - j;
+        A = (A << (2 * rem)) | ((((unsigned __int128)1) << (2 * rem)) - 1);
+    }
+    tprime[i] = narrow_from_u128<NarrowT>(A);
 }
 
 // rank_of_narrow[j] = #{i : T'_i < N_j}  (lower bound in the non-decreasing T')
-__global__ void rank_narrow_kernel(const uint64_t* __restrict__ narrow, uint64_t n_narrow,
-                                   const uint64_t* __restrict__ tprime, uint64_t n_wide,
+template <typename NarrowT>
+__global__ void rank_narrow_kernel(const NarrowT* __restrict__ narrow, uint64_t n_narrow,
+                                   const NarrowT* __restrict__ tprime, uint64_t n_wide,
                                    uint64_t* __restrict__ rank_of_narrow) {
     const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_narrow) return;
-    const uint64_t key = narrow[j];
+    const NarrowT key = narrow[j];
     uint64_t lo = 0, hi = n_wide;
     while (lo < hi) {
         const uint64_t mid = (lo + hi) >> 1;
@@ -234,19 +246,20 @@ __global__ void rank_narrow_kernel(const uint64_t* __restrict__ narrow, uint64_t
     rank_of_narrow[j] = lo;
 }
 
-// rank_of_wide[i] = #{j : N_j <= T'_i}  (upper bound); in place over the T' array
-__global__ void rank_wide_kernel(const uint64_t* __restrict__ narrow, uint64_t n_narrow, uint64_t n_wide,
-                                 uint64_t* __restrict__ tprime_inout) {
+// rank_of_wide[i] = #{j : N_j <= T'_i}  (upper bound); tprime may alias rank_of_wide (8-byte narrow keys)
+template <typename NarrowT>
+__global__ void rank_wide_kernel(const NarrowT* __restrict__ narrow, uint64_t n_narrow, uint64_t n_wide,
+                                 const NarrowT* tprime, uint64_t* rank_of_wide) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_wide) return;
-    const uint64_t t = tprime_inout[i];
+    const NarrowT t = tprime[i];
     uint64_t lo = 0, hi = n_narrow;
     while (lo < hi) {
         const uint64_t mid = (lo + hi) >> 1;
-        if (narrow[mid] <= t) lo = mid + 1;
+        if (!(t < narrow[mid])) lo = mid + 1;
         else hi = mid;
     }
-    tprime_inout[i] = lo;
+    rank_of_wide[i] = lo;
 }
 
 }  // namespace kmg
@@ -277,7 +290,7 @@ extern "C" int kmg_format_counts(const void* d_keys, const uint32_t* d_counts, u
                                  size_t ws_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     KMG_REQUIRE(d_bytes_out, KMG_ERR_ARG, "d_bytes_out is null");
-    KMG_REQUIRE(key_bytes == 8 || key_bytes == 16, KMG_ERR_ARG, "key_bytes must be 8 or 16");
+    KMG_REQUIRE(key_bytes == 8 || key_bytes == 16 || key_bytes == 32, KMG_ERR_ARG, "key_bytes must be 8, 16 or 32");
     KMG_REQUIRE(k >= 2 && k * (wide ? 4 : 2) <= key_bytes * 8, KMG_ERR_ARG, "k=%d does not fit the key", k);
     KMG_CUDA(cudaMemsetAsync(d_bytes_out, 0, sizeof(uint64_t), st));
     if (n == 0) return KMG_OK;
@@ -299,9 +312,12 @@ extern "C" int kmg_format_counts(const void* d_keys, const uint32_t* d_counts, u
     if (key_bytes == 8) {
         KMG_CUDA(cudaFuncSetAttribute(format_counts_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         format_counts_kernel<uint64_t><<<tiles, FMT_BLOCK, smem, st>>>(p);
-    } else {
+    } else if (key_bytes == 16) {
         KMG_CUDA(cudaFuncSetAttribute(format_counts_kernel<u128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         format_counts_kernel<u128><<<tiles, FMT_BLOCK, smem, st>>>(p);
+    } else {
+        KMG_CUDA(cudaFuncSetAttribute(format_counts_kernel<u256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        format_counts_kernel<u256><<<tiles, FMT_BLOCK, smem, st>>>(p);
     }
     KMG_LAUNCH_CHECK();
     return KMG_OK;
@@ -341,11 +357,38 @@ extern "C" int kmg_format_uniq(const void* d_keys, const void* d_vals, uint64_t 
     if (key_bytes == 8) {
         if (val_bytes == 4) format_uniq_kernel<uint64_t, 4><<<tiles, FMT_BLOCK, 0, st>>>(p);
         else format_uniq_kernel<uint64_t, 8><<<tiles, FMT_BLOCK, 0, st>>>(p);
-    } else {
+    } else if (key_bytes == 16) {
         if (val_bytes == 4) format_uniq_kernel<u128, 4><<<tiles, FMT_BLOCK, 0, st>>>(p);
         else format_uniq_kernel<u128, 8><<<tiles, FMT_BLOCK, 0, st>>>(p);
+    } else {
+        if (val_bytes == 4) format_uniq_kernel<u256, 4><<<tiles, FMT_BLOCK, 0, st>>>(p);
+        else format_uniq_kernel<u256, 8><<<tiles, FMT_BLOCK, 0, st>>>(p);
     }
     KMG_LAUNCH_CHECK();
+    return KMG_OK;
+}
+
+template <typename WideT, typename NarrowT>
+static int merge_ranks_impl(const void* d_narrow_keys, uint64_t n_narrow, const void* d_wide_keys, uint64_t n_wide, int k,
+                            int rna, uint64_t* d_rank_of_narrow, uint64_t* d_rank_of_wide, NarrowT* d_tprime,
+                            cudaStream_t st) {
+    if (n_wide) {
+        KMG_REQUIRE(d_wide_keys && d_rank_of_wide && d_tprime, KMG_ERR_ARG, "null pointer argument");
+        wide_threshold_kernel<WideT, NarrowT><<<(unsigned)((n_wide + 255) / 256), 256, 0, st>>>((const WideT*)d_wide_keys, n_wide, k,
+                                                                                               rna, d_tprime);
+        KMG_LAUNCH_CHECK();
+    }
+    if (n_narrow) {
+        KMG_REQUIRE(d_narrow_keys && d_rank_of_narrow, KMG_ERR_ARG, "null pointer argument");
+        rank_narrow_kernel<NarrowT><<<(unsigned)((n_narrow + 255) / 256), 256, 0, st>>>((const NarrowT*)d_narrow_keys, n_narrow, d_tprime,
+                                                                                        n_wide, d_rank_of_narrow);
+        KMG_LAUNCH_CHECK();
+    }
+    if (n_wide) {
+        rank_wide_kernel<NarrowT><<<(unsigned)((n_wide + 255) / 256), 256, 0, st>>>((const NarrowT*)d_narrow_keys, n_narrow, n_wide,
+                                                                                    d_tprime, d_rank_of_wide);
+        KMG_LAUNCH_CHECK();
+    }
     return KMG_OK;
 }
 
@@ -353,21 +396,17 @@ extern "C" int kmg_merge_ranks(const void* d_narrow_keys, uint64_t n_narrow, int
                                const void* d_wide_keys, uint64_t n_wide, int wide_key_bytes, int k, int rna,
                                uint64_t* d_rank_of_narrow, uint64_t* d_rank_of_wide, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    KMG_REQUIRE(k >= 2 && k <= 32, KMG_ERR_RANGE, "merge of the wide stream supports k <= 32, got %d", k);
+    KMG_REQUIRE(k >= 2 && k <= 32, KMG_ERR_RANGE, "8-byte narrow / 16-byte wide keys hold k <= 32, got %d (kmg_merge_ranks_wide)", k);
     KMG_REQUIRE(narrow_key_bytes == 8 && wide_key_bytes == 16, KMG_ERR_ARG, "expected 8-byte narrow and 16-byte wide keys");
-    if (n_wide) {
-        KMG_REQUIRE(d_wide_keys && d_rank_of_wide, KMG_ERR_ARG, "null pointer argument");
-        wide_threshold_kernel<<<(unsigned)((n_wide + 255) / 256), 256, 0, st>>>((const u128*)d_wide_keys, n_wide, k, rna, d_rank_of_wide);
-        KMG_LAUNCH_CHECK();
-    }
-    if (n_narrow) {
-        KMG_REQUIRE(d_narrow_keys && d_rank_of_narrow, KMG_ERR_ARG, "null pointer argument");
-        rank_narrow_kernel<<<(unsigned)((n_narrow + 255) / 256), 256, 0, st>>>((const uint64_t*)d_narrow_keys, n_narrow, d_rank_of_wide, n_wide, d_rank_of_narrow);
-        KMG_LAUNCH_CHECK();
-    }
-    if (n_wide) {
-        rank_wide_kernel<<<(unsigned)((n_wide + 255) / 256), 256, 0, st>>>((const uint64_t*)d_narrow_keys, n_narrow, n_wide, d_rank_of_wide);
-        KMG_LAUNCH_CHECK();
-    }
-    return KMG_OK;
+    // (the thresholds live in the wide rank array until the last kernel turns them into ranks)
+    return merge_ranks_impl<u128, uint64_t>(d_narrow_keys, n_narrow, d_wide_keys, n_wide, k, rna, d_rank_of_narrow, d_rank_of_wide,
+                                            d_rank_of_wide, st);
+}
+
+extern "C" int kmg_merge_ranks_wide(const void* d_narrow_keys, uint64_t n_narrow, const void* d_wide_keys, uint64_t n_wide, int k,
+                                    int rna, uint64_t* d_rank_of_narrow, uint64_t* d_rank_of_wide, void* d_tmp16, void* stream) {
+    KMG_REQUIRE(k >= 33 && k <= 64, KMG_ERR_RANGE, "16-byte narrow / 32-byte wide keys are for 33 <= k <= 64, got %d", k);
+    KMG_REQUIRE(((uintptr_t)d_tmp16 & 15) == 0, KMG_ERR_ARG, "d_tmp16 misaligned");
+    return merge_ranks_impl<u256, u128>(d_narrow_keys, n_narrow, d_wide_keys, n_wide, k, rna, d_rank_of_narrow, d_rank_of_wide,
+                                        (u128*)d_tmp16, (cudaStream_t)stream);
 }

@@ -405,11 +405,31 @@ constexpr int EXW_BLOCK = 256;
 constexpr int EXW_PPT = 4;
 constexpr int EXW_TILE = EXW_BLOCK * EXW_PPT;
 
-template <bool RC, int VAL_BYTES>
+// LIMBS: 64-bit limbs of a key, 2 (k <= 32, u128) or 4 (k <= 64, u256); limb 0 is the least significant
+template <int LIMBS>
+struct WideKey {
+    uint64_t w[LIMBS];
+    __device__ __forceinline__ void push(uint32_t code) {  // key = key << 4 | code
+#pragma unroll
+        for (int i = LIMBS - 1; i > 0; --i) w[i] = (w[i] << 4) | (w[i - 1] >> 60);
+        w[0] = (w[0] << 4) | code;
+    }
+    __device__ __forceinline__ uint32_t pop() {  // lowest nibble; key >>= 4
+        const uint32_t c = (uint32_t)w[0] & 0xFu;
+#pragma unroll
+        for (int i = 0; i < LIMBS - 1; ++i) w[i] = (w[i] >> 4) | (w[i + 1] << 60);
+        w[LIMBS - 1] >>= 4;
+        return c;
+    }
+    __device__ __forceinline__ void set_nibble(int q, uint32_t c) { w[q >> 4] |= (uint64_t)c << (4 * (q & 15)); }
+};
+
+template <bool RC, int VAL_BYTES, int LIMBS>
 __global__ void __launch_bounds__(EXW_BLOCK) extract_wide_kernel(const ExtractParams p) {
     using ValT = typename std::conditional<VAL_BYTES == 4, uint32_t, uint64_t>::type;
+    using KeyT = WideKey<LIMBS>;  // same layout as u128 / u256
     constexpr int OUT_PER_WIN = RC ? 2 : 1;
-    __shared__ uint8_t s_e[EXW_TILE + 64];  // LUT entries of the tile bytes (+ halo)
+    __shared__ uint8_t s_e[EXW_TILE + 64];  // LUT entries of the tile bytes (+ halo: k <= 64)
     __shared__ uint8_t s_lut[256];
     __shared__ uint8_t s_comp[16];
     __shared__ uint32_t s_scan[EXW_BLOCK / 32 + 1];
@@ -430,22 +450,23 @@ __global__ void __launch_bounds__(EXW_BLOCK) extract_wide_kernel(const ExtractPa
     __syncthreads();
 
     const int k = p.k;
-    u128 keys[EXW_PPT];
+    KeyT keys[EXW_PPT];
     uint32_t vf = 0;
 #pragma unroll
     for (int j = 0; j < EXW_PPT; ++j) {
         const int o = t * EXW_PPT + j;
         const uint64_t pos = tile_pos + o;
         uint32_t any_inv = 0, any_nonplain = 0;
-        uint64_t lo = 0, hi = 0;
+        KeyT key;
+#pragma unroll
+        for (int i = 0; i < LIMBS; ++i) key.w[i] = 0;
         for (int q = 0; q < k; ++q) {
             const uint32_t e = s_e[o + q];
             any_inv |= e & 0x80u;
             any_nonplain |= e & 0x40u;
-            hi = (hi << 4) | (lo >> 60);
-            lo = (lo << 4) | ((e >> 2) & 0xFu);
+            key.push((e >> 2) & 0xFu);
         }
-        keys[j] = u128{lo, hi};
+        keys[j] = key;
         if (pos >= p.win_begin && pos < p.win_end && !any_inv && any_nonplain) vf |= 1u << j;
     }
     const uint32_t cnt = __popc(vf);
@@ -457,7 +478,7 @@ __global__ void __launch_bounds__(EXW_BLOCK) extract_wide_kernel(const ExtractPa
     }
     __syncthreads();
     const uint64_t base = s_base;
-    u128* keys_out = reinterpret_cast<u128*>(p.keys_out);
+    KeyT* keys_out = reinterpret_cast<KeyT*>(p.keys_out);
     ValT* vals_out = reinterpret_cast<ValT*>(p.vals_out);
     uint64_t r = base + (uint64_t)excl * OUT_PER_WIN;
 #pragma unroll
@@ -468,18 +489,12 @@ __global__ void __launch_bounds__(EXW_BLOCK) extract_wide_kernel(const ExtractPa
         if constexpr (VAL_BYTES != 0) vals_out[r] = make_val<ValT>(pos, 0);
         ++r;
         if constexpr (RC) {
-            // reverse complement: symbol q of the window becomes nibble q (from the LSB)
-            uint64_t lo = 0, hi = 0;
-            u128 f = keys[j];
-            for (int q = k - 1; q >= 0; --q) {  // q-th symbol sits at nibble k-1-q of f
-                const uint32_t c = s_comp[f.lo & 0xFu];
-                f.lo = (f.lo >> 4) | (f.hi << 60);
-                f.hi >>= 4;
-                // symbol index q (just popped, from the end) -> nibble index q
-                if (q < 16) lo |= (uint64_t)c << (4 * q);
-                else hi |= (uint64_t)c << (4 * (q - 16));
-            }
-            keys_out[r] = u128{lo, hi};
+            // reverse complement: symbol q of the window (nibble k-1-q of the key) becomes nibble q
+            KeyT f = keys[j], rcv;
+#pragma unroll
+            for (int i = 0; i < LIMBS; ++i) rcv.w[i] = 0;
+            for (int q = k - 1; q >= 0; --q) rcv.set_nibble(q, s_comp[f.pop()]);
+            keys_out[r] = rcv;
             if constexpr (VAL_BYTES != 0) vals_out[r] = make_val<ValT>(pos, 1);
             ++r;
         }
@@ -652,11 +667,11 @@ __global__ void hist_top_finalize_kernel(const unsigned long long* __restrict__ 
     }
 }
 
-template <bool RC>
+template <bool RC, int LIMBS>
 static int dispatch_wide(const ExtractParams& p, uint32_t n_tiles, int vb, cudaStream_t st) {
-    if (vb == 0) extract_wide_kernel<RC, 0><<<n_tiles, EXW_BLOCK, 0, st>>>(p);
-    else if (vb == 4) extract_wide_kernel<RC, 4><<<n_tiles, EXW_BLOCK, 0, st>>>(p);
-    else extract_wide_kernel<RC, 8><<<n_tiles, EXW_BLOCK, 0, st>>>(p);
+    if (vb == 0) extract_wide_kernel<RC, 0, LIMBS><<<n_tiles, EXW_BLOCK, 0, st>>>(p);
+    else if (vb == 4) extract_wide_kernel<RC, 4, LIMBS><<<n_tiles, EXW_BLOCK, 0, st>>>(p);
+    else extract_wide_kernel<RC, 8, LIMBS><<<n_tiles, EXW_BLOCK, 0, st>>>(p);
     KMG_LAUNCH_CHECK();
     return KMG_OK;
 }
@@ -757,11 +772,10 @@ extern "C" int kmg_extract(const uint8_t* d_bases, uint64_t n_bases, uint64_t wi
     cudaStream_t st = (cudaStream_t)stream;
     KMG_REQUIRE(k >= 2, KMG_ERR_ARG, "k must be >= 2, got %d", k);  // batcher.py:477-478
     KMG_REQUIRE(k <= 64, KMG_ERR_RANGE, "k=%d: this build supports k <= 64 (no CPU fallback)", k);
-    KMG_REQUIRE(!wide || k <= 32, KMG_ERR_RANGE, "wide (non-ACGT) stream supports k <= 32, got %d", k);
     KMG_REQUIRE(win_begin <= win_end, KMG_ERR_ARG, "win_begin > win_end");
     KMG_REQUIRE(val_bytes == 0 || val_bytes == 4 || val_bytes == 8, KMG_ERR_ARG, "val_bytes must be 0, 4 or 8");
     KMG_REQUIRE((val_bytes == 0) == (d_vals_out == nullptr), KMG_ERR_ARG, "d_vals_out / val_bytes mismatch");
-    const int want_kb = wide ? 16 : (k <= 32 ? 8 : 16);
+    const int want_kb = wide ? (k <= 32 ? 16 : 32) : (k <= 32 ? 8 : 16);
     KMG_REQUIRE(key_bytes == want_kb, KMG_ERR_ARG, "key_bytes must be %d for k=%d wide=%d", want_kb, k, wide);
     KMG_REQUIRE(((uintptr_t)d_bases & 15) == 0, KMG_ERR_ARG, "d_bases must be 16-byte aligned");
     KMG_REQUIRE(((uintptr_t)d_keys_out & (key_bytes - 1)) == 0, KMG_ERR_ARG, "d_keys_out misaligned");
@@ -827,8 +841,10 @@ extern "C" int kmg_extract(const uint8_t* d_bases, uint64_t n_bases, uint64_t wi
         }
     }
 
-    if (wide) return rc ? dispatch_wide<true>(p, (uint32_t)n_tiles, val_bytes, st)
-                        : dispatch_wide<false>(p, (uint32_t)n_tiles, val_bytes, st);
+    if (wide && k <= 32) return rc ? dispatch_wide<true, 2>(p, (uint32_t)n_tiles, val_bytes, st)
+                                   : dispatch_wide<false, 2>(p, (uint32_t)n_tiles, val_bytes, st);
+    if (wide) return rc ? dispatch_wide<true, 4>(p, (uint32_t)n_tiles, val_bytes, st)
+                        : dispatch_wide<false, 4>(p, (uint32_t)n_tiles, val_bytes, st);
     int rcode;
     if (key_bytes == 8) rcode = dispatch_narrow<uint64_t, 16>(p, (uint32_t)n_tiles, rc, val_bytes, d_hist_out != nullptr, st);
     else rcode = dispatch_narrow<u128, 8>(p, (uint32_t)n_tiles, rc, val_bytes, d_hist_out != nullptr, st);

@@ -38,6 +38,10 @@ template <>
 __device__ __forceinline__ u128 shfl_key<u128>(const u128& k, int src) {
     return u128{__shfl_sync(0xffffffffu, k.lo, src), __shfl_sync(0xffffffffu, k.hi, src)};
 }
+template <>
+__device__ __forceinline__ u256 shfl_key<u256>(const u256& k, int src) {  // wide stream at k > 32 (wide256.cu)
+    return u256{shfl_key<u128>(k.lo, src), shfl_key<u128>(k.hi, src)};
+}
 
 struct RleParams {
     const void* keys_in;
@@ -376,7 +380,7 @@ extern "C" size_t kmg_rle_workspace_bytes(uint64_t n) {
 }
 
 static int rle_setup(RleParams& p, uint64_t n, int key_bytes, void* d_ws, size_t ws_bytes, cudaStream_t st) {
-    KMG_REQUIRE(key_bytes == 8 || key_bytes == 16, KMG_ERR_ARG, "key_bytes must be 8 or 16");
+    KMG_REQUIRE(key_bytes == 8 || key_bytes == 16 || key_bytes == 32, KMG_ERR_ARG, "key_bytes must be 8, 16 or 32");
     KMG_REQUIRE(d_ws, KMG_ERR_ARG, "null workspace");
     KMG_REQUIRE(ws_bytes >= kmg_rle_workspace_bytes(n), KMG_ERR_WS, "rle workspace too small");
     const uint64_t tile = key_bytes == 8 ? RLE_BLOCK * RLE_IPT8 : RLE_BLOCK * RLE_IPT16;
@@ -403,7 +407,8 @@ static int rle_setup(RleParams& p, uint64_t n, int key_bytes, void* d_ws, size_t
 
 static int rle_prepass(const RleParams& p, int key_bytes, int want_singles, cudaStream_t st) {
     if (key_bytes == 8) rle_tile_aggregates<uint64_t, RLE_IPT8><<<p.n_tiles, RLE_BLOCK, 0, st>>>(p);
-    else rle_tile_aggregates<u128, RLE_IPT16><<<p.n_tiles, RLE_BLOCK, 0, st>>>(p);
+    else if (key_bytes == 16) rle_tile_aggregates<u128, RLE_IPT16><<<p.n_tiles, RLE_BLOCK, 0, st>>>(p);
+    else rle_tile_aggregates<u256, RLE_IPT16><<<p.n_tiles, RLE_BLOCK, 0, st>>>(p);
     KMG_LAUNCH_CHECK();
     const uint32_t tile_keys = key_bytes == 8 ? RLE_BLOCK * RLE_IPT8 : RLE_BLOCK * RLE_IPT16;
     rle_scan_tiles<<<1, SCAN_BLOCK, 0, st>>>(p, tile_keys, want_singles);
@@ -429,7 +434,8 @@ extern "C" int kmg_rle_count(const void* d_sorted_keys, uint64_t n, int key_byte
     rcode = rle_prepass(p, key_bytes, 0, st);
     if (rcode != KMG_OK) return rcode;
     if (key_bytes == 8) rle_count_kernel<uint64_t, RLE_IPT8><<<p.n_tiles, RLE_BLOCK, 0, st>>>(p);
-    else rle_count_kernel<u128, RLE_IPT16><<<p.n_tiles, RLE_BLOCK, 0, st>>>(p);
+    else if (key_bytes == 16) rle_count_kernel<u128, RLE_IPT16><<<p.n_tiles, RLE_BLOCK, 0, st>>>(p);
+    else rle_count_kernel<u256, RLE_IPT16><<<p.n_tiles, RLE_BLOCK, 0, st>>>(p);
     KMG_LAUNCH_CHECK();
     return KMG_OK;
 }
@@ -461,10 +467,14 @@ extern "C" int kmg_select_singletons(const void* d_sorted_keys, const void* d_va
         if (val_bytes == 0) select_singletons_kernel<uint64_t, 0, RLE_IPT8><<<tiles, RLE_BLOCK, 0, st>>>(p);
         else if (val_bytes == 4) select_singletons_kernel<uint64_t, 4, RLE_IPT8><<<tiles, RLE_BLOCK, 0, st>>>(p);
         else select_singletons_kernel<uint64_t, 8, RLE_IPT8><<<tiles, RLE_BLOCK, 0, st>>>(p);
-    } else {
+    } else if (key_bytes == 16) {
         if (val_bytes == 0) select_singletons_kernel<u128, 0, RLE_IPT16><<<tiles, RLE_BLOCK, 0, st>>>(p);
         else if (val_bytes == 4) select_singletons_kernel<u128, 4, RLE_IPT16><<<tiles, RLE_BLOCK, 0, st>>>(p);
         else select_singletons_kernel<u128, 8, RLE_IPT16><<<tiles, RLE_BLOCK, 0, st>>>(p);
+    } else {
+        if (val_bytes == 0) select_singletons_kernel<u256, 0, RLE_IPT16><<<tiles, RLE_BLOCK, 0, st>>>(p);
+        else if (val_bytes == 4) select_singletons_kernel<u256, 4, RLE_IPT16><<<tiles, RLE_BLOCK, 0, st>>>(p);
+        else select_singletons_kernel<u256, 8, RLE_IPT16><<<tiles, RLE_BLOCK, 0, st>>>(p);
     }
     KMG_LAUNCH_CHECK();
     return KMG_OK;

@@ -507,13 +507,46 @@ class DistributedCounter:
 
     def _wide(self, d, k: int, rc: bool, with_vals: bool):
         """The wide (non-ACGT alphabet symbols) stream across ranks: windows are rare, so the plain
-        path does it -- local extraction, range partition on the 4-bit keys, NCCL all-to-all.
+        path does it -- local extraction, range partition on the 4-bit keys, all-to-all.
         Collective: every rank calls it once any rank saw a wide window."""
-        if k > 32:
-            raise ValueError(f"input holds windows with non-ACGT alphabet symbols and k={k} > 32: the wide stream "
-                             "supports k <= 32 in this build (no CPU fallback)")
         a = self.eng.extract(d, k, rc, wide=True, val_bytes=8 if with_vals else 0)
+        if a.key_bytes == 32:
+            return self._wide256_exchange(a, with_vals)
         return self._partition_exchange(a, with_vals)
+
+    def _wide256_exchange(self, a, with_vals: bool):
+        """33 <= k <= 64: 256-bit wide keys.  Sorted locally first, a rank's share of every key range is a
+        contiguous slice; the slices travel with one all-to-all and the receiver sorts its G sorted runs
+        again (kmg_sort256 both times).  Same range rule as the narrow stream: part = (top 16 key bits * G) >> 16."""
+        from kman_b200.engine import KeyArray
+
+        eng, G = self.eng, self.world
+        a = eng.sort(a)
+        dev = a.keys.device
+        limbs = a.keys[: max(a.n, 1) * 32].view(torch.int64).view(-1, 4)[: a.n]
+        sh = a.key_bits - 16  # >= 116: the top 16 bits sit in limb sh // 64 and possibly the next one
+        li, off = sh // 64, sh % 64
+        top = (limbs[:, li] >> off) & ((1 << (64 - off)) - 1 if off else -1)
+        if off > 48:
+            top = top | (limbs[:, li + 1] << (64 - off))
+        part = ((top & 0xFFFF) * G) >> 16
+        pc = torch.bincount(part, minlength=G).cpu().numpy().astype(np.int64) if a.n else np.zeros(G, np.int64)
+        matrix = gather_count_matrix(pc, dev, self.group)
+        send = a.keys[: max(a.n, 1) * 32].view(torch.int64)
+        recv, recv_counts = exchange(send, pc, 4, self.group, matrix)
+        n = int(recv_counts.sum())
+        rvals = None
+        if with_vals:
+            rv, _ = exchange(a.vals[: max(a.n, 1) * 8].view(torch.int64), pc, 1, self.group, matrix)
+            rvals = rv.view(torch.uint8)
+        kbuf = recv.view(torch.uint8)
+        if kbuf.numel() == 0:
+            kbuf = torch.empty(32, dtype=torch.uint8, device=dev)
+        if with_vals and rvals.numel() == 0:
+            rvals = torch.empty(16, dtype=torch.uint8, device=dev)
+        alt = torch.empty(max(kbuf.numel(), 32), dtype=torch.uint8, device=dev)
+        valt = torch.empty(max(rvals.numel(), 16), dtype=torch.uint8, device=dev) if with_vals else None
+        return KeyArray(kbuf, alt, rvals, valt, n, 32, 8 if with_vals else 0, a.k, True)
 
     def count_streams(self, d, k: int, rc: bool = False, reuse: Optional[str] = "p2p_"):
         """This rank's slice (key range `rank`) of the global count table: [narrow] or [narrow, wide]

@@ -88,7 +88,7 @@ class KeyArray:
 
     def keys_host(self) -> np.ndarray:
         raw = self.keys[: self.n * self.key_bytes].cpu().numpy()
-        return raw.view(np.uint64) if self.key_bytes == 8 else raw.view(np.uint64).reshape(-1, 2)
+        return raw.view(np.uint64) if self.key_bytes == 8 else raw.view(np.uint64).reshape(-1, self.key_bytes // 8)
 
     def vals_host(self) -> Optional[np.ndarray]:
         if self.vals is None:
@@ -108,7 +108,7 @@ class CountTable:
 
     def keys_host(self) -> np.ndarray:
         raw = self.keys[: self.n * self.key_bytes].cpu().numpy()
-        return raw.view(np.uint64) if self.key_bytes == 8 else raw.view(np.uint64).reshape(-1, 2)
+        return raw.view(np.uint64) if self.key_bytes == 8 else raw.view(np.uint64).reshape(-1, self.key_bytes // 8)
 
     def counts_host(self) -> np.ndarray:
         return self.counts[: self.n * 4].cpu().numpy().view(np.uint32)
@@ -253,7 +253,8 @@ class Engine:
         win_end = n_win_total if win_end is None else min(win_end, n_win_total)
         win_begin = min(win_begin, win_end)
         n_win = win_end - win_begin
-        kb = 16 if (wide or k > 32) else 8
+        # narrow: 2-bit codes, 8 / 16 bytes; wide: 4-bit codes, 16 bytes up to k = 32, 32 bytes up to k = 64
+        kb = (16 if k <= 32 else 32) if wide else (8 if k <= 32 else 16)
         cap = max(n_win * (2 if rc else 1), 1)
         mk = (lambda nm, nb: self._buf(reuse + nm, nb)) if reuse else (lambda nm, nb: self._new(nb))
         keys = mk("keys", cap * kb)
@@ -282,6 +283,8 @@ class Engine:
     @_on_device
     def sort(self, a: KeyArray, begin_bit: int = 0, end_bit: Optional[int] = None) -> KeyArray:
         end_bit = a.key_bits if end_bit is None else end_bit
+        if a.key_bytes == 32:
+            return self._sort256(a, end_bit)
         if a.n > 1 and end_bit > begin_bit:
             ws_bytes = self.lib.kmg_radix_sort_workspace_bytes(a.n, a.key_bytes, a.val_bytes, begin_bit, end_bit)
             ws = self._buf("ws_sort", ws_bytes)
@@ -301,12 +304,26 @@ class Engine:
         a.is_sorted = True
         return a
 
+    def _sort256(self, a: KeyArray, end_bit: int) -> KeyArray:
+        """256-bit keys (wide stream, 33 <= k <= 64): kmg_sort256 sorts out of place into the alt buffers."""
+        if a.n > 1 and end_bit > 0:
+            ws_bytes = self.lib.kmg_sort256_workspace_bytes(a.n)
+            ws = self._buf("ws_sort256", ws_bytes)
+            _lib.check(self.lib.kmg_sort256(a.keys.data_ptr(), a.keys_alt.data_ptr(), _ptr(a.vals), _ptr(a.vals_alt), a.n,
+                                            a.val_bytes, end_bit, ws.data_ptr(), ws_bytes, self._stream()))
+            a.keys, a.keys_alt = a.keys_alt, a.keys
+            a.vals, a.vals_alt = a.vals_alt, a.vals
+        a.is_sorted = True
+        return a
+
     @_on_device
     def sort_count(self, a: KeyArray, end_bit: Optional[int] = None, reuse: Optional[str] = None) -> CountTable:
         """sort() + rle_count() in one native call (kmg_sort_count): when the hybrid finish applies,
         its local sort emits the (k-mer, count) table directly.  Consumes `a` (both key buffers)."""
         end_bit = a.key_bits if end_bit is None else end_bit
         assert a.val_bytes == 0
+        if a.key_bytes == 32:
+            return self.rle_count(self.sort(a, 0, end_bit), reuse=reuse)
         counts = self._buf(reuse + "counts", a.n * 4) if reuse else self._new(a.n * 4)
         if a.n == 0:
             return CountTable(a.keys_alt, counts, 0, a.key_bytes, a.k, a.wide)
@@ -358,6 +375,8 @@ class Engine:
         their order is irrelevant and the keys take the hybrid finish with the payload.  Consumes `a`."""
         end_bit = a.key_bits if end_bit is None else end_bit
         assert a.val_bytes in (4, 8)
+        if a.key_bytes == 32:
+            return self.singletons(self.sort(a, 0, end_bit))
         if a.n == 0:
             return KeyArray(a.keys_alt, None, a.vals_alt, None, 0, a.key_bytes, a.val_bytes, a.k, a.wide, is_sorted=True)
         ws_bytes = self.lib.kmg_sort_uniq_workspace_bytes(a.n, a.key_bytes, a.val_bytes, end_bit)
@@ -454,10 +473,17 @@ class Engine:
                     rna: int) -> Tuple[torch.Tensor, torch.Tensor]:
         rn = torch.zeros(max(n_narrow, 1), dtype=torch.int64, device=self.device)
         rw = torch.zeros(max(n_wide, 1), dtype=torch.int64, device=self.device)
-        _lib.check(
-            self.lib.kmg_merge_ranks(narrow_keys.data_ptr(), n_narrow, 8, wide_keys.data_ptr(), n_wide, 16, k, rna,
-                                     rn.data_ptr(), rw.data_ptr(), self._stream())
-        )
+        if k <= 32:
+            _lib.check(
+                self.lib.kmg_merge_ranks(narrow_keys.data_ptr(), n_narrow, 8, wide_keys.data_ptr(), n_wide, 16, k, rna,
+                                         rn.data_ptr(), rw.data_ptr(), self._stream())
+            )
+        else:  # 16-byte narrow keys, 32-byte wide keys
+            tmp = self._new(max(n_wide, 1) * 16)
+            _lib.check(
+                self.lib.kmg_merge_ranks_wide(narrow_keys.data_ptr(), n_narrow, wide_keys.data_ptr(), n_wide, k, rna,
+                                              rn.data_ptr(), rw.data_ptr(), tmp.data_ptr(), self._stream())
+            )
         return rn[:n_narrow], rw[:n_wide]
 
     # ---- whole path on one GPU ------------------------------------------------------------------
@@ -466,11 +492,6 @@ class Engine:
         narrow = self.sort(self.extract(d, k, rc, wide=False, val_bytes=val_bytes, want_hist=True))
         out = [narrow]
         if narrow.n_other:
-            if k > 32:
-                raise ValueError(
-                    f"input holds {narrow.n_other} windows with non-ACGT alphabet symbols and k={k} > 32: "
-                    "the wide stream supports k <= 32 in this build (no CPU fallback)"
-                )
             out.append(self.sort(self.extract(d, k, rc, wide=True, val_bytes=val_bytes)))
         return out
 
@@ -529,11 +550,6 @@ class Engine:
         tab, n_other = self.count_narrow(d, k, rc)
         out = [tab]
         if n_other:
-            if k > 32:
-                raise ValueError(
-                    f"input holds {n_other} windows with non-ACGT alphabet symbols and k={k} > 32: "
-                    "the wide stream supports k <= 32 in this build (no CPU fallback)"
-                )
             out.append(self.sort_count(self.extract(d, k, rc, wide=True, val_bytes=0)))
         return out
 
@@ -543,11 +559,6 @@ class Engine:
         sing, n_other = self.uniq_narrow(d, k, rc, val_bytes=vb)
         out = [sing]
         if n_other:
-            if k > 32:
-                raise ValueError(
-                    f"input holds {n_other} windows with non-ACGT alphabet symbols and k={k} > 32: "
-                    "the wide stream supports k <= 32 in this build (no CPU fallback)"
-                )
             out.append(self.sort_uniq(self.extract(d, k, rc, wide=True, val_bytes=vb)))
         return out
 

@@ -169,8 +169,6 @@ class Sequence(_NucleicAcid):
         a = eng.extract(d, k, rc, wide=False, val_bytes=8)
         streams.append(a)
         if a.n_other:
-            if k > 32:
-                raise ValueError("windows with non-ACGT alphabet symbols need k <= 32 in this build")
             streams.append(eng.extract(d, k, rc, wide=True, val_bytes=8))
         vals = np.concatenate([s.vals_host() for s in streams]) if streams else np.zeros(0, np.uint64)
         txt = np.concatenate([decode_keys(s.keys_host(), k, s.wide, t) for s in streams])

@@ -91,17 +91,16 @@ def cfg5(n: int = 10_000_000, n_rec: int = 8, dup: bool = False) -> List[Tuple[s
 
 # ---- canonical binary form ---------------------------------------------------------------------
 def key_rows(limbs) -> np.ndarray:
-    """oracle limb list [hi, lo] / [lo] -> the device layout: u64[n] or (lo, hi) rows u64[n, 2]."""
+    """oracle limb list [hi, ..., lo] -> the device layout: u64[n], or rows of 2 / 4 limbs, least significant first."""
     if len(limbs) == 1:
         return np.ascontiguousarray(limbs[0], dtype=np.uint64)
-    return np.ascontiguousarray(np.stack([limbs[-1], limbs[-2]], axis=1), dtype=np.uint64)
+    return np.ascontiguousarray(np.stack(limbs[::-1], axis=1), dtype=np.uint64)
 
 
 def widen_rows(limbs) -> np.ndarray:
-    """4-bit keys always live in 128-bit device keys."""
-    if len(limbs) == 1:
-        return key_rows([np.zeros_like(limbs[0]), limbs[0]])
-    return key_rows(limbs)
+    """4-bit keys live in 128-bit device keys up to k = 32, in 256-bit ones up to k = 64."""
+    want = 2 if len(limbs) <= 2 else 4
+    return key_rows([np.zeros_like(limbs[0])] * (want - len(limbs)) + list(limbs))
 
 
 def sha(*arrays: np.ndarray) -> str:

@@ -13,16 +13,16 @@ def first_diff(a: np.ndarray, b: np.ndarray) -> str:
 
 
 def limbs_to_rows(limbs) -> np.ndarray:
-    """oracle limb list [hi, lo] / [lo] -> array comparable with Engine host views:
-    8-byte keys -> (n,) uint64 ; 16-byte keys -> (n, 2) uint64 as (lo, hi)."""
+    """oracle limb list [hi, ..., lo] -> array comparable with Engine host views:
+    8-byte keys -> (n,) uint64 ; 16- / 32-byte keys -> (n, 2) / (n, 4) uint64, least significant limb first."""
     if len(limbs) == 1:
         return limbs[0]
-    assert len(limbs) == 2
-    return np.stack([limbs[1], limbs[0]], axis=1)
+    assert len(limbs) in (2, 4)
+    return np.stack(limbs[::-1], axis=1)
 
 
 def widen(limbs):
-    """4-bit oracle keys for k<=16 come as one limb; the device always uses 128-bit wide keys."""
-    if len(limbs) == 1:
-        return [np.zeros_like(limbs[0]), limbs[0]]
-    return limbs
+    """4-bit oracle keys come with as many limbs as they need; the device uses 128-bit wide keys up to
+    k = 32 and 256-bit ones up to k = 64."""
+    want = 2 if len(limbs) <= 2 else 4
+    return [np.zeros_like(limbs[0])] * (want - len(limbs)) + list(limbs)

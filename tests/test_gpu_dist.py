@@ -34,7 +34,7 @@ def _run(world, extra_env, port):
 
 @pytest.mark.parametrize("variant", ["shared", "exact", "alltoall"])
 def test_two_ranks_on_one_gpu(variant):
-    env = {"KMG_TEST_ONE_GPU": "1", "KMG_TEST_CASES": "0,1,2,4,5"}
+    env = {"KMG_TEST_ONE_GPU": "1", "KMG_TEST_CASES": "0,1,2,4,5,7"}
     if variant == "shared":
         env["KMG_DIST_SHARED"] = "1"
     elif variant == "exact":

@@ -49,12 +49,7 @@ def test_every_golden_case_is_tested():
     assert set(GOLD) == set(MAKERS)
 
 
-# (the wide stream, 4-bit codes, holds k <= 32 in 128-bit keys: k = 45 with IUPAC symbols needs 256-bit keys)
-WIDE_K_GT_32 = {"cfg4_10mbp_k45_uniq_iupac"}
-
-
-@pytest.mark.parametrize("name", [pytest.param(n, marks=pytest.mark.xfail(raises=ValueError, strict=True)) if n in WIDE_K_GT_32
-                                  else n for n in sorted(MAKERS)])
+@pytest.mark.parametrize("name", sorted(MAKERS))
 def test_table_hash_matches_oracle(eng, name):
     import torch
 

@@ -66,7 +66,7 @@ def test_extract_narrow_matches_oracle(eng, k, rc):
             assert first_diff(a.vals_host().astype(np.uint64), wv) == "equal"
 
 
-@pytest.mark.parametrize("k", [2, 5, 16, 17, 25, 32])
+@pytest.mark.parametrize("k", [2, 5, 16, 17, 25, 32, 33, 45, 48, 49, 63, 64])
 @pytest.mark.parametrize("rc", [False, True])
 def test_extract_wide_matches_oracle(eng, k, rc):
     rng = np.random.default_rng(200 + k)
@@ -79,6 +79,21 @@ def test_extract_wide_matches_oracle(eng, k, rc):
     assert first_diff(a.keys_host(), want) == "equal"
     wv = (ex["wide"]["pos"].astype(np.uint64) << np.uint64(1)) | ex["wide"]["strand"].astype(np.uint64)
     assert first_diff(a.vals_host(), wv) == "equal"
+
+
+@pytest.mark.parametrize("k", [33, 40, 47, 48, 57, 64])
+@pytest.mark.parametrize("rc", [False, True])
+def test_wide_stream_beyond_k32_count_and_uniq_text(eng, k, rc):
+    """Windows holding N / IUPAC symbols at k > 32 (256-bit 4-bit-code keys, kmermaid/seq.py:317-318 has no
+    bound on k): kmg_sort256 + run-length / singleton stage + text + the narrow/wide interleave, byte for
+    byte against the oracle (duplicated stretches so that counts > 1 and non-singletons exist)."""
+    rng = np.random.default_rng(3300 + k)
+    recs = _rand_records(rng, 3, 7000, p_other=0.004)
+    t, s0 = recs[0]
+    recs[0] = (t, s0 + s0[: len(s0) // 2] + "N" * 150 + s0[-300:])
+    d = eng.upload(_flat(recs))
+    assert eng.count_text(d, k, rc) == ko.count_text_np(recs, k, rc), (k, rc)
+    assert eng.uniq_text(d, k, rc) == ko.uniq_text_np(recs, k, rc), (k, rc)
 
 
 def test_extract_window_ranges_partition_the_input(eng):

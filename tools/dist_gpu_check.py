@@ -64,7 +64,13 @@ def genome(seed, n, n_rec, with_other):
 
 
 def rows(limbs):
-    return limbs[0] if len(limbs) == 1 else np.stack([limbs[1], limbs[0]], axis=1)
+    return limbs[0] if len(limbs) == 1 else np.stack(limbs[::-1], axis=1)
+
+
+def wide_rows(limbs):
+    """the device keeps 4-bit keys in 128 bits up to k = 32 and in 256 bits up to k = 64"""
+    want = 2 if len(limbs) <= 2 else 4
+    return rows([np.zeros_like(limbs[0])] * (want - len(limbs)) + list(limbs))
 
 
 ok = True
@@ -78,6 +84,7 @@ CASES = [
     (25, False, 2_600_000, 4, None, True),      # default IUPAC alphabet: N / R / Y windows are the wide stream
     (25, True, 1_300_000, 3, None, True),
     (31, False, 3_400_001, 2, "ACGT", True),    # ACGT-only alphabet: windows with N are skipped
+    (45, True, 1_200_000, 3, None, True),       # k > 32 with IUPAC symbols: 256-bit wide keys
 ]
 if only:
     CASES = [CASES[int(i)] for i in only.split(",")]
@@ -97,19 +104,15 @@ for k, rc, n, n_rec, alphabet, other in CASES:
         *_, du = ko.uniq_np(recs, k, rc, ab)
         msgs = []
         for si, name in enumerate(("narrow", "wide")):
-            wk = rows(det[name]["keys"])
+            wk = rows(det[name]["keys"]) if name == "narrow" else wide_rows(det[name]["keys"])
             if name == "wide":
                 if wk.shape[0] == 0:
                     assert all(len(o[0]) == 1 for o in out), "no wide windows, yet a rank returned a wide table"
                     continue
-                if wk.ndim == 1:  # the device always uses 128-bit wide keys
-                    wk = np.stack([wk, np.zeros_like(wk)], axis=1)
             gk = np.concatenate([o[0][si][0].reshape((-1,) + wk.shape[1:]) for o in out])
             gc = np.concatenate([o[0][si][1] for o in out])
             good = gk.shape == wk.shape and (gk == wk).all() and (gc == det[name]["counts"]).all()
-            uk = rows(du[name]["keys"])
-            if name == "wide" and uk.ndim == 1:
-                uk = np.stack([uk, np.zeros_like(uk)], axis=1)
+            uk = rows(du[name]["keys"]) if name == "narrow" else wide_rows(du[name]["keys"])
             gs = np.concatenate([o[1][si][0].reshape((-1,) + uk.shape[1:]) for o in out])
             gv = np.concatenate([o[1][si][1] for o in out])
             wv = (du[name]["pos"].astype(np.uint64) << np.uint64(1)) | du[name]["strand"].astype(np.uint64)
