@@ -329,7 +329,7 @@ extern "C" int kmg_format_uniq(const void* d_keys, const void* d_vals, uint64_t 
                                uint64_t* d_bytes_out, void* d_ws, size_t ws_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     KMG_REQUIRE(d_bytes_out, KMG_ERR_ARG, "d_bytes_out is null");
-    KMG_REQUIRE(key_bytes == 8 || key_bytes == 16, KMG_ERR_ARG, "key_bytes must be 8 or 16");
+    KMG_REQUIRE(key_bytes == 8 || key_bytes == 16 || key_bytes == 32, KMG_ERR_ARG, "key_bytes must be 8, 16 or 32");
     KMG_REQUIRE(val_bytes == 4 || val_bytes == 8, KMG_ERR_ARG, "val_bytes must be 4 or 8");
     KMG_REQUIRE(k >= 2 && k * (wide ? 4 : 2) <= key_bytes * 8, KMG_ERR_ARG, "k=%d does not fit the key", k);
     KMG_CUDA(cudaMemsetAsync(d_bytes_out, 0, sizeof(uint64_t), st));
