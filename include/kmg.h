@@ -249,6 +249,18 @@ int kmg_fasta_flatten(const uint8_t* d_raw, uint64_t n_raw, uint8_t* d_bases_out
                       uint64_t* d_hdr_begin, uint64_t max_rec, uint64_t* d_totals, void* d_ws, size_t ws_bytes,
                       void* stream);
 
+/* ---- abundance vectors: `kmer count -m VEC_COUNT / VEC_COUNT_MASKED` (join.py:287-335, abundance.py:104-146)
+ * Input: one stream's keys STABLY sorted with their payload (kmg_radix_sort / kmg_sort256 with vals), so that
+ * equal keys are adjacent and their payloads ascend.  Every element writes, at out[strand][position - pos_base],
+ * the size of its group of equal keys (masked = 0) or the number of group members that start in OTHER records
+ * (masked = 1; elements of groups confined to one record write nothing).  The vectors are uint32 per flat
+ * position, zeroed by the caller; positions nobody writes stay 0 like the reference's np.zeros.
+ * d_rec_starts[n_rec + 1]: flat start of every record (the entry past the last one: one past the end).
+ * *d_err (zeroed by the caller) becomes 2 if a count does not fit uint32. */
+int kmg_abundance_scatter(const void* d_sorted_keys, const void* d_vals, uint64_t n, int key_bytes, int val_bytes,
+                          const uint64_t* d_rec_starts, uint32_t n_rec, int masked, uint64_t pos_base,
+                          uint32_t* d_out_plus, uint32_t* d_out_minus, uint32_t* d_err, void* stream);
+
 /* ---- merge ranks between the narrow and the wide stream -------------------------------
  * For two sorted, disjoint key lists, rank_of_wide[i] = number of narrow keys that sort
  * before wide key i in the reference's ASCII order (and vice versa), so that the merged

@@ -317,11 +317,18 @@ class DeviceBatch:
         return list(self._records(do_sort=True))
 
     def write(self, doSort: bool = False, force: bool = False) -> None:
-        """Export as a reference-format batch file: FASTA, one k-mer per record."""
+        """Export as a reference-format batch file: FASTA, one k-mer per record (batch.py:281-296).
+        Sorted export (what `kmer batch` asks for) is formatted on the GPU; the unsorted record order
+        is only produced for callers that insist on it."""
         if not self._written or force:
-            with open(self.tmp, "w+") as th:
-                for r in self._records(do_sort=bool(doSort)):
-                    th.write(r.as_fasta())
+            if doSort:
+                with open(self.tmp, "wb") as th:
+                    for chunk in self._eng.batch_text_chunks(self.device_input, self.k, self.reverse):
+                        th.write(chunk)
+            else:
+                with open(self.tmp, "w+") as th:
+                    for r in self._records(do_sort=False):
+                        th.write(r.as_fasta())
             self._written = True
 
     def unwrite(self) -> None:
@@ -332,3 +339,92 @@ class DeviceBatch:
     def reset(self) -> None:
         self.unwrite()
         self._n = None
+
+
+class LoadedKmerBatch(DeviceBatch):
+    """Reference-format batch files (`kmer batch` output, kmermaid/batch.py:281-296: ">ref:start-end:strand\nSEQ\n"
+    records) re-imported as device keys -- the `-B` reload of `kmer count` / `kmer uniq`
+    (kmermaid/batcher.py:616-636, batch.py:298-344).
+
+    Every stored k-mer becomes one record of k bases in a flat base buffer ("SEQ\n" is exactly the
+    record + separator layout of the device path), so the extraction kernel at window length k packs
+    one key per stored k-mer and its payload (window start) / (k + 1) is the index of the k-mer's
+    header.  Reverse complements were materialised when the batches were made, so nothing is
+    complemented again."""
+
+    def __init__(self, engine, paths: List[str], natype: NATYPES, tmp_dir: str, alphabet: Optional[str] = None):
+        import gzip
+
+        from kman_b200 import fasta
+
+        raw = []
+        for path in paths:
+            opener = gzip.open if path.endswith(".gz") else open
+            with opener(path, "rb") as fh:
+                b = fh.read()
+            if b and not b.endswith(b"\n"):
+                b += b"\n"
+            raw.append(b)
+        buf = np.frombuffer(b"".join(raw), np.uint8)
+        nl = np.flatnonzero(buf == 10)
+        if nl.size % 2 or nl.size == 0:
+            raise AssertionError("batch files must hold two-line records (>header / sequence)")
+        starts = np.concatenate(([0], nl[:-1] + 1))
+        h_b, h_e = starts[0::2], nl[0::2]  # header lines (with '>')
+        s_b, s_e = starts[1::2], nl[1::2]  # sequence lines
+        if not (buf[h_b] == ord(">")).all():
+            raise AssertionError("batch files must hold two-line records (>header / sequence)")
+        lens = s_e - s_b
+        k = int(lens[0])
+        if k < 2 or not (lens == k).all():
+            raise AssertionError("batch files must hold k-mers of one length")
+        n = int(lens.size)
+        # flat base buffer: "SEQ\n" per stored k-mer
+        idx = (s_b[:, None] + np.arange(k + 1)[None, :]).reshape(-1)
+        bases = buf[idx]
+        self._hdr_buf = buf
+        self._hdr_b, self._hdr_e = h_b + 1, h_e  # without '>'
+        flat = fasta.FlatInput(bases, np.array([0, bases.size], np.uint64), ["batch"], ["batch"])
+        d = engine.upload(flat, alphabet, natype, with_names=False)
+        super().__init__(engine, d, k, False, natype, tmp_dir, size=max(2, n))
+        self._n = n
+        self.paths = list(paths)
+
+    def count_text(self) -> bytes:
+        return self._eng.count_text(self.device_input, self.k, False)
+
+    def uniq_text(self) -> bytes:
+        """">HEADER\nSEQ\n" of the k-mers that occur once, ascending by sequence (join.py:243-263), with the
+        headers the batch files stored."""
+        eng, d, k = self._eng, self.device_input, self.k
+        streams = eng.uniq(d, k, False)
+        keys = [s.keys_host() for s in streams]
+        rec = [(s.vals_host().astype(np.int64) >> 1) // (k + 1) for s in streams]
+        txt = [decode_keys(kk, k, s.wide, self.natype) for kk, s in zip(keys, streams)]
+        if len(streams) == 2 and streams[1].n and streams[0].n:
+            rn, rw = eng.merge_ranks(streams[0].keys, streams[0].n, streams[1].keys, streams[1].n, k, d.rna)
+            pos = [np.arange(streams[0].n) + rn.cpu().numpy(), np.arange(streams[1].n) + rw.cpu().numpy()]
+            total = streams[0].n + streams[1].n
+            order_rec, order_txt = np.empty(total, np.int64), np.empty((total, k), np.uint8)
+            for p_, r_, t_ in zip(pos, rec, txt):
+                order_rec[p_], order_txt[p_] = r_, t_
+        else:
+            i = 1 if (len(streams) == 2 and streams[1].n) else 0
+            order_rec, order_txt = rec[i], txt[i]
+        m = order_rec.shape[0]
+        if m == 0:
+            return b""
+        hb, hl = self._hdr_b[order_rec], (self._hdr_e - self._hdr_b)[order_rec]
+        line = hl + k + 3  # '>' header '\n' seq '\n'
+        off = np.concatenate(([0], np.cumsum(line)))
+        out = np.empty(int(off[-1]), np.uint8)
+        out[off[:-1]] = ord(">")
+        # ragged copy of the headers: for every output byte of a header, its source index
+        tot_h = int(hl.sum())
+        within = np.arange(tot_h) - np.repeat(np.cumsum(hl) - hl, hl)
+        out[np.repeat(off[:-1] + 1, hl) + within] = self._hdr_buf[np.repeat(hb, hl) + within]
+        out[off[:-1] + 1 + hl] = 10
+        seq_at = off[:-1] + 2 + hl
+        out[(seq_at[:, None] + np.arange(k)[None, :]).reshape(-1)] = order_txt.reshape(-1)
+        out[seq_at + k] = 10
+        return out.tobytes()

@@ -224,9 +224,23 @@ class FastaRecordBatcher(BatcherThreading):
         return b
 
 
-def load_batches(previous_batches: str, threads: int = 1, re_sort: bool = False) -> List[Batch]:
-    """Same guard as the reference (batcher.py:631), which -- as shipped -- rejects every
-    non-empty folder; kept so `-B` behaves identically."""
-    if not os.path.isdir(previous_batches) or len(os.listdir(previous_batches)) > 0:
+def load_batches(previous_batches: str, threads: int = 1, re_sort: bool = False, natype: NATYPES = NATYPES.DNA,
+                 alphabet: Optional[str] = None) -> List:
+    """Previously generated batch files (`kmer batch` output, plain or .gz) re-imported as device keys
+    (kmermaid/batcher.py:616-636).
+
+    DELIBERATE FIX: the reference's guard is inverted -- `len(os.listdir(dir)) > 0` raises, so as shipped it
+    rejects every folder that holds batches (batcher.py:631) and `-B` can never
+    work.  Here the folder must exist and hold at least one file, as the reference's own docstring says
+    ("input folder must exist and be non-empty").  `re_sort` is accepted and irrelevant: the device path
+    always sorts."""
+    if not os.path.isdir(previous_batches) or len(os.listdir(previous_batches)) == 0:
         raise AssertionError(f"folder with previous batches empty or not found: {previous_batches}")
-    return BatcherThreading.from_files(previous_batches, threads, reSort=re_sort)
+    from kman_b200.batch import LoadedKmerBatch
+    from kman_b200.engine import get_engine
+
+    paths = [os.path.join(previous_batches, f) for f in sorted(os.listdir(previous_batches))]
+    paths = [p for p in paths if os.path.isfile(p)]
+    if not paths:
+        raise AssertionError(f"folder with previous batches empty or not found: {previous_batches}")
+    return [LoadedKmerBatch(get_engine(), paths, natype, tempfile.gettempdir(), alphabet)]

@@ -605,6 +605,47 @@ class Engine:
             out[offs[prev] :] = tn[sn[idx_n] :]
         return out.tobytes()
 
+    @_on_device
+    def abundance(self, d: DeviceInput, k: int, rc: bool = False, masked: bool = False) -> Tuple[np.ndarray, np.ndarray]:
+        """VEC_COUNT / VEC_COUNT_MASKED (join.py:287-335): per flat position the number of occurrences of the
+        k-mer that starts there ('+' vector) / of its reverse complement ('-' vector); masked: occurrences
+        in other records only.  Both streams are sorted stably with their payload, then every element
+        scatters its group's size (kmg_abundance_scatter).  Returns host uint32 arrays over the flat buffer."""
+        vb = 4 if ((d.pos_offset + d.n_bases) << 1) < (1 << 32) else 8
+        if d.rec_starts is None:
+            self._upload_names(d)
+        out = torch.zeros(2 * (d.n_bases + 1), dtype=torch.int32, device=self.device)
+        plus, minus = out[: d.n_bases + 1], out[d.n_bases + 1:]
+        err = torch.zeros(1, dtype=torch.int32, device=self.device)
+        for s in self.sorted_streams(d, k, rc, vb):
+            if s.n == 0:
+                continue
+            _lib.check(self.lib.kmg_abundance_scatter(s.keys.data_ptr(), s.vals.data_ptr(), s.n, s.key_bytes, s.val_bytes,
+                                                      d.rec_starts.data_ptr(), d.flat.n_rec, int(masked), d.pos_offset,
+                                                      plus.data_ptr(), minus.data_ptr(), err.data_ptr(), self._stream()))
+        if int(err.item()):
+            raise ValueError("a k-mer occurs more than 2^32-1 times: count does not fit uint32")
+        host = out.cpu().numpy().view(np.uint32)
+        return host[: d.n_bases + 1], host[d.n_bases + 1:]
+
+    def batch_text_chunks(self, d: DeviceInput, k: int, rc: bool = False, chunk: int = 8_000_000):
+        """Text of the reference's batch files (batch.py:281-296: every k-mer as ">ref:start-end:strand\nSEQ\n",
+        stably sorted by sequence, batch.py:156-168), formatted on the GPU and yielded as bytes in chunks of
+        `chunk` records.  How the records are split over files is not a contract of the reference
+        (SURVEY.md f-3); concatenating the chunks gives one sorted batch."""
+        vb = 4 if ((d.pos_offset + d.n_bases) << 1) < (1 << 32) else 8
+        streams = self.sorted_streams(d, k, rc, vb)  # stable payload sorts: equal sequences keep emission order
+        if len(streams) == 2 and streams[1].n:
+            texts = [self.format_uniq(s, d) for s in streams]
+            yield self._interleave(texts, [s.keys for s in streams], [s.n for s in streams], k, d.rna, [])
+            return
+        s = streams[0]
+        for lo in range(0, s.n, chunk):
+            m = min(chunk, s.n - lo)
+            part = KeyArray(s.keys[lo * s.key_bytes:], None, s.vals[lo * s.val_bytes:], None, m, s.key_bytes, s.val_bytes,
+                            k, False, is_sorted=True)
+            yield self.format_uniq(part, d).cpu().numpy().tobytes()
+
     def count_text(self, d: DeviceInput, k: int, rc: bool = False) -> bytes:
         """Bytes of the reference's `kmer count` output file (join.py:284)."""
         tabs = self.count(d, k, rc)

@@ -18,6 +18,7 @@ import numpy as np
 
 from kman_b200 import fasta
 from kman_b200.batch import Batch, BatchAppendable, DeviceBatch
+from kman_b200.seq import SequenceCoords
 
 
 class Crawler:
@@ -124,13 +125,20 @@ class KJoiner:
         return (seq, len(headers))
 
     @staticmethod
-    def join_vector_count(headers, seq, OH, vector=None, **kwargs) -> None:
-        # the reference raises here as shipped (abundance.py:123 -> :60)
-        raise NotImplementedError("VEC_COUNT has no working reference implementation to match")
+    def join_vector_count(headers: List[str], seq: str, OH, vector=None, **kwargs) -> None:
+        """join.py:287-308: every member of the group stores the group's size at its start position."""
+        hcount = len(headers)
+        for header in headers:
+            c = SequenceCoords.from_str(header)
+            vector.add_count(c.ref, c.strand.label, int(c.start), hcount, len(seq))
 
     @staticmethod
-    def join_vector_count_masked(headers, seq, OH, vector=None, **kwargs) -> None:
-        raise NotImplementedError("VEC_COUNT_MASKED has no working reference implementation to match")
+    def join_vector_count_masked(headers: List[str], seq: str, OH, vector=None, **kwargs) -> None:
+        """join.py:310-335: only groups spread over several records count, and only the other records' members."""
+        coords = [SequenceCoords.from_str(h) for h in headers]
+        if len(coords) != 1 and len({c.ref for c in coords}) != 1:
+            for c in coords:
+                vector.add_count(c.ref, c.strand.label, int(c.start), sum(1 for o in coords if o.ref != c.ref), len(seq))
 
     # ---- GPU join ------------------------------------------------------------------------------
     @staticmethod
@@ -156,9 +164,27 @@ class KJoiner:
         return b0._eng.upload(flat, b0.device_input.alphabet, b0.natype)
 
     def _join_device(self, batches: List[DeviceBatch], outpath: str) -> None:
-        if self.mode.name.startswith("VEC_"):
-            raise NotImplementedError(f"{self.mode.name} has no working reference implementation to match")
         b0 = batches[0]
+        if self.mode.name.startswith("VEC_"):
+            from kman_b200 import abundance
+            from kman_b200.batch import LoadedKmerBatch
+
+            if any(isinstance(b, LoadedKmerBatch) for b in batches):
+                raise AssertionError("abundance vectors need the FASTA input, not re-imported batch files")
+            d = self._merged_device_input(batches)
+            vecs = abundance.device_vectors(b0._eng, d, b0.k, b0.reverse, self.mode == self.MODE.VEC_COUNT_MASKED)
+            abundance.write_vectors(vecs, b0.k, outpath)  # join.py:370-372 -> abundance.py:148-172
+            return
+        from kman_b200.batch import LoadedKmerBatch
+
+        if any(isinstance(b, LoadedKmerBatch) for b in batches):
+            # `-B`: re-imported batch files carry their own headers (one LoadedKmerBatch covers a folder)
+            if len(batches) != 1:
+                raise AssertionError("re-imported batch files cannot be joined together with other batches")
+            text = b0.count_text() if self.mode == self.MODE.SEQ_COUNT else b0.uniq_text()
+            with open(outpath, "wb") as oh:
+                oh.write(text)
+            return
         d = self._merged_device_input(batches)
         if self.mode == self.MODE.SEQ_COUNT:
             text = b0._eng.count_text(d, b0.k, b0.reverse)
@@ -175,9 +201,15 @@ class KJoiner:
         if any(isinstance(b, DeviceBatch) for b in live):
             raise AssertionError("cannot join device batches together with host batches")
         # host batches only (records built by callers through the Batch API): reference protocol
-        if self.mode.name.startswith("VEC_"):
-            raise NotImplementedError(f"{self.mode.name} has no working reference implementation to match")
         print("Joining...")
+        if self.mode.name.startswith("VEC_"):  # join.py:337-372
+            from kman_b200.abundance import AbundanceVector
+
+            vector = AbundanceVector()
+            for headers, seq in Crawler().do_batch(live):
+                self.join_function(headers, seq, OH=outpath, vector=vector)
+            vector.write_to(outpath)
+            return
         with open(outpath, "w+") as oh:
             for headers, seq in Crawler().do_batch(live):
                 self.join_function(headers, seq, OH=oh)

@@ -558,6 +558,83 @@ def uniq_text_np(records, k, rc=False, alphabet=DEFAULT_ALPHABET, natype="DNA") 
     return buf.tobytes()
 
 
+# ---- abundance vectors: `kmer count -m VEC_COUNT / VEC_COUNT_MASKED` ---------------------------------
+# kmermaid/join.py:287-335 (what a group contributes) + abundance.py:92-172 (the per record-and-strand
+# vectors and their files).  The reference crashes in these modes as shipped: AbundanceVector.add_count
+# calls super().add_count, and the abstract base raises NotImplementedError (abundance.py:123 -> :60,
+# SURVEY.md Appendix A4).  Everything else in the two files works; oracle/gen_golden_vec.py runs the
+# reference with that one abstract method neutralised at run time and the goldens pin both tiers below.
+def vec_count_py(records, k, rc=False, masked=False, alphabet=DEFAULT_ALPHABET, natype="DNA") -> Dict[str, bytes]:
+    """Literal tier.  Returns {file name "REF___STRAND.gz": decompressed file content}."""
+    data: Dict[str, Dict[str, List[int]]] = {}
+
+    def add_count(ref, strand, pos, count):  # abundance.py:104-146
+        vec = data.setdefault(ref, {}).setdefault(strand, [])
+        if len(vec) < pos + 1:
+            vec.extend([0] * (pos + 1 - len(vec)))
+        if vec[pos] != 0:
+            raise AssertionError("can't update non-zero count w/o replace")
+        vec[pos] = count
+
+    for headers, seq in crawl_groups_py(batches_py(records, k, rc, 1_000_000, alphabet, natype)):
+        coords = []
+        for h in headers:  # "ref:start-end:strand", greedy ref (seq.py:44-48)
+            left, strand = h.rsplit(":", 1)
+            ref, span = left.rsplit(":", 1)
+            coords.append((ref, strand, int(span.split("-")[0])))
+        if not masked:  # join.py:303-308
+            for ref, strand, start in coords:
+                add_count(ref, strand, start, len(headers))
+        elif len(coords) != 1 and len({c[0] for c in coords}) != 1:  # join.py:326-335
+            for ref, strand, start in coords:
+                add_count(ref, strand, start, sum(1 for c in coords if c[0] != ref))
+    out = {}
+    for ref, per in data.items():  # abundance.py:162-172
+        for strand, vec in per.items():
+            out["%s___%s.gz" % (ref, strand)] = b"# k=%d\n" % k + b"".join(b"%d\n" % c for c in vec)
+    return out
+
+
+def vec_count_np(records, k, rc=False, masked=False, alphabet=DEFAULT_ALPHABET, natype="DNA") -> Dict[str, bytes]:
+    """numpy tier of vec_count_py: run lengths scattered back through the window positions."""
+    ex = extract_np(records, k, rc, alphabet, natype)
+    starts = ex["rec_starts"]
+    n_flat = int(ex["bases"].shape[0])
+    vec = np.zeros((2, n_flat + 1), np.int64)
+    names = ex["names"]
+    if len(set(names)) != len(names):
+        raise AssertionError("can't update non-zero count w/o replace")  # two records write the same vector
+    for name in ("narrow", "wide"):
+        st = ex[name]
+        if st["pos"].size == 0:
+            continue
+        order = _lexsort_limbs(st["keys"])
+        srt = [l[order] for l in st["keys"]]
+        pos, strand = st["pos"][order], st["strand"][order].astype(np.int64)
+        heads, lens = _rle(srt)
+        group = np.repeat(np.arange(heads.size), lens)
+        cnt = lens[group]
+        if masked:
+            rec = np.searchsorted(starts, pos, side="right") - 1
+            # members of my group in my own record: pairs (group, record) are contiguous after the stable sort
+            gr = group.astype(np.int64) * (len(names) + 1) + rec
+            _, inv, same = np.unique(gr, return_inverse=True, return_counts=True)
+            cnt = cnt - same[inv]
+            keep = cnt > 0
+            pos, strand, cnt = pos[keep], strand[keep], cnt[keep]
+        vec[strand, pos] = cnt
+    out = {}
+    for r, nm in enumerate(names):
+        b, e = int(starts[r]), int(starts[r + 1]) - 1
+        for s_i, label in ((0, "+"), (1, "-")):
+            v = vec[s_i, b:e]
+            nz = np.flatnonzero(v)
+            if nz.size:
+                v = v[: int(nz[-1]) + 1]
+                out["%s___%s.gz" % (nm, label)] = b"# k=%d\n" % k + b"".join(b"%d\n" % c for c in v.tolist())
+    return out
+
+
 # ---- deterministic synthetic inputs (SURVEY.md §8d / Appendix B) -------------------------
 def synth_bases(n: int, seed: int) -> bytes:
     rng = np.random.default_rng(seed)

@@ -127,10 +127,11 @@ def test_batcher_and_joiner_argument_validation(tmp_path):
         KJoiner(mode="UNIQUE")
     j.threads = 10**6
     assert 1 <= j.threads <= os.cpu_count()
-    # -B: the reference's guard rejects every non-empty folder
-    (tmp_path / "x.fa").write_text(">c:0-4:+\nACGT\n")
+    # -B: the folder must exist and be non-empty (the reference's docstring; its shipped guard is inverted,
+    # batcher.py:631, SURVEY Appendix A5 -- fixed here on purpose).  A non-empty folder needs the GPU.
+    (tmp_path / "empty").mkdir()
     with pytest.raises(AssertionError):
-        load_batches(str(tmp_path))
+        load_batches(str(tmp_path / "empty"))
     with pytest.raises(AssertionError):
         load_batches(str(tmp_path / "missing"))
 
@@ -151,5 +152,35 @@ def test_host_batches_join_like_the_reference(tmp_path):
     out = tmp_path / "uniq.fa"
     KJoinerThreading().join([a, b], str(out))
     assert out.read_text() == ">c:1-5:+\nCGTA\n>c:2-6:+\nGTAC\n>d:1-5:+\nTTTT\n"
-    with pytest.raises(NotImplementedError):
-        KJoinerThreading(KJoiner.MODE.VEC_COUNT).join([a, b], str(out))
+
+
+def test_host_batches_join_abundance_vectors(tmp_path):
+    """VEC_COUNT / VEC_COUNT_MASKED over host Batch objects (join.py:287-372, abundance.py:92-172): the
+    reference's record-by-record protocol, with its crashing abstract call removed."""
+    import gzip
+
+    from kman_b200.abundance import AbundanceVector, vector_text
+
+    a, b = Batch(KMer, str(tmp_path), 4), Batch(KMer, str(tmp_path), 4)
+    a.add_all([KMer("c", 0, 4, "ACGT"), KMer("c", 1, 5, "CGTA"), KMer("c", 3, 7, "ACGT")])
+    b.add_all([KMer("d", 0, 4, "ACGT"), KMer("d", 2, 6, "TTTT")])
+    a.write(doSort=True)
+    b.write(doSort=True)
+    out = tmp_path / "vec.txt"
+    KJoinerThreading(KJoiner.MODE.VEC_COUNT).join([a, b], str(out))
+    read = lambda f: gzip.open(tmp_path / "vec" / f, "rb").read()  # noqa: E731
+    assert read("c___+.gz") == b"# k=4\n3\n1\n0\n3\n"
+    assert read("d___+.gz") == b"# k=4\n3\n0\n1\n"
+    out2 = tmp_path / "masked.txt"
+    KJoinerThreading(KJoiner.MODE.VEC_COUNT_MASKED).join([a, b], str(out2))
+    read2 = lambda f: gzip.open(tmp_path / "masked" / f, "rb").read()  # noqa: E731
+    assert read2("c___+.gz") == b"# k=4\n1\n0\n0\n1\n"  # ACGT: one occurrence in the other record
+    assert read2("d___+.gz") == b"# k=4\n2\n"
+    v = AbundanceVector()
+    v.add_count("r", "+", 2, 5, 4)
+    with pytest.raises(AssertionError):
+        v.add_count("r", "+", 2, 1, 4)  # abundance.py:128-131
+    with pytest.raises(AssertionError):
+        v.add_count("r", "+", 3, 1, 5)  # abundance.py:37-39: one k per join
+    assert vector_text([0, 7, 10, 123456, 99], 21) == b"# k=21\n0\n7\n10\n123456\n99\n"
+    assert vector_text([], 3) == b"# k=3\n"

@@ -90,6 +90,49 @@ def test_cli_batch_files_merge_to_reference_multiset(golden, tmp_path, monkeypat
         _run_cli(["batch", str(fa), str(outdir), "4"])
 
 
+@pytest.mark.parametrize("rc", [False, True])
+@pytest.mark.parametrize("k", [7, 25, 40])
+def test_batch_files_reload_gives_the_direct_result(tmp_path, monkeypatch, k, rc):
+    """`kmer batch` -> `kmer count/uniq -B` (kmermaid/batcher.py:616-636, with its inverted guard fixed)
+    must equal the direct run and the oracle: the batch files are formatted on the GPU, re-imported as
+    device keys, and the uniq output keeps the headers the files stored.  Also through a gzipped copy."""
+    import gzip
+
+    import kmer_oracle as ko
+    import numpy as np
+
+    monkeypatch.setenv("KMG_ALPHABET", "IUPAC")
+    rng = np.random.default_rng(500 + k)
+    s1 = "".join(rng.choice(list("ACGT"), size=5000))
+    s2 = "".join(rng.choice(list("ACGT"), size=3000))
+    recs = [("chrA first", s1 + s1[:800].lower() + "NNNNNNNNNNRY" + s1[100:400]), ("chrB", s2 + "N" + s2[:500] + "ACGTN")]
+    fa = tmp_path / "in.fa"
+    fa.write_bytes(ko.synth_fasta_bytes([(t, s.encode()) for t, s in recs]))
+    extra = ["-r"] if rc else []
+    outdir = tmp_path / "batches"
+    _run_cli(["batch", *extra, str(fa), str(outdir), str(k)])
+    files = sorted(os.listdir(outdir))
+    assert files
+    # the files hold every k-mer record, sorted by sequence, in the reference's record format
+    lines = b"".join((outdir / f).read_bytes() for f in files).split(b"\n")[:-1]
+    assert len(lines) % 2 == 0 and all(h.startswith(b">") for h in lines[0::2])
+    seqs = lines[1::2]
+    assert seqs == sorted(seqs) and all(len(x) == k for x in seqs)
+    # one batch (fewer records than the batch size): byte for byte the reference's stably sorted batch file
+    (one,) = ko.batches_py(recs, k, rc)
+    assert list(zip(lines[0::2], seqs)) == [(b">" + h.encode(), q.encode()) for h, q in one]
+    gz = tmp_path / "batches_gz"
+    gz.mkdir()
+    for f in files:
+        with gzip.open(gz / (f + ".gz"), "wb") as oh:
+            oh.write((outdir / f).read_bytes())
+    for cmd, want in (("count", ko.count_text_np(recs, k, rc)), ("uniq", ko.uniq_text_np(recs, k, rc))):
+        for src in (outdir, gz):
+            out = tmp_path / f"{cmd}_{src.name}.txt"
+            _run_cli([cmd, "-B", str(src), str(fa), str(out), str(k)])
+            assert out.read_bytes() == want, (cmd, src.name)
+
+
 def test_two_fastas_appended_join_as_one(tmp_path):
     """FEED_MODE.APPEND of two inputs: the joiner sees both batches (join.py:93 merges them)."""
     import kmer_oracle as ko
@@ -158,3 +201,50 @@ def test_gpu_fasta_loader_matches_host_loader(golden, tmp_path):
     (tmp_path / "nohdr.fa").write_text("no header here\nACGT\n")
     with pytest.raises(AssertionError):
         eng.load_fasta(str(tmp_path / "nohdr.fa"))
+
+
+def test_abundance_vectors_match_reference_goldens(tmp_path, monkeypatch):
+    """`kmer count -m VEC_COUNT / VEC_COUNT_MASKED` through the command line: every REF___STRAND.gz file
+    of every golden case (reference outputs, tests/golden/golden_vec.json)."""
+    import gzip
+    import json
+
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden_vec.json")))
+    n = 0
+    for c in gold["cases"]:
+        monkeypatch.setenv("KMG_ALPHABET", c["alphabet"])
+        fa = tmp_path / f"in_{n}.fa"
+        fa.write_bytes(c["fasta_text"].encode("latin-1"))
+        out = tmp_path / f"vec_{n}.txt"
+        _run_cli(["count", "-m", c["mode"], *(["-r"] if c["rc"] else []), str(fa), str(out), str(c["k"])])
+        d = tmp_path / f"vec_{n}"
+        got = {f: gzip.open(d / f, "rb").read().decode("latin-1") for f in sorted(os.listdir(d))} if d.is_dir() else {}
+        assert got == c["files"], (c["name"], c["k"], c["alphabet"], c["rc"], c["mode"])
+        n += 1
+    assert n >= 130
+
+
+@pytest.mark.parametrize("k,rc", [(31, False), (21, True), (45, False)])
+def test_abundance_vectors_large_input_vs_oracle(k, rc):
+    """> 2^20 k-mers with duplicated stretches shared between records, N runs (groups of 10^4 equal wide
+    k-mers), soft-masked bases: device vectors against the oracle's numpy tier, both modes."""
+    import kmer_oracle as ko
+    import numpy as np
+
+    from kman_b200 import abundance, fasta
+    from kman_b200.engine import get_engine
+
+    rng = np.random.default_rng(77 + k)
+    b = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, size=1_300_000, dtype=np.uint8)].copy()
+    b[600_000:700_000] = b[100_000:200_000]      # shared between records 1 and 2
+    b[900_000:950_000] = b[880_000:930_000]      # repeated inside record 3
+    b[300_000:312_000] = ord("N")
+    b[1_000_000:1_020_000] |= 0x20
+    recs = [("r1 a", b[:500_000].tobytes().decode()), ("r2", b[500_000:800_000].tobytes().decode()),
+            ("r3", b[800_000:].tobytes().decode())]
+    eng = get_engine()
+    d = eng.upload(fasta.from_records(recs))
+    for masked in (False, True):
+        vecs = abundance.device_vectors(eng, d, k, rc, masked)
+        got = {"%s___%s.gz" % (r, s): abundance.vector_text(v, k) for r, per in vecs.items() for s, v in per.items()}
+        assert got == ko.vec_count_np(recs, k, rc, masked), (k, rc, masked)
