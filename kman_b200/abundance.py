@@ -6,7 +6,7 @@ with a "# k=K" first line.
 DELIBERATE FIX: the reference's AbundanceVector.add_count first calls the abstract base method, which raises
 NotImplementedError (abundance.py:123 -> :60), so both modes crash as shipped.
 The call is dropped here; everything else follows the reference, and the goldens were produced by the
-reference with that one abstract method neutralised (oracle/gen_golden_vec.py).
+reference with that one abstract method neutralised (tests/golden/golden_vec.json).
 
 Two producers fill the same files: the host classes below (records fed one by one through
 KJoiner.join_vector_count*, the reference's protocol for host batches) and the device path
