@@ -18,6 +18,7 @@ extern int g_lb_group;
 extern int g_hybrid;
 extern int g_hybrid_pb;
 extern int g_count_fused;
+extern int g_local_v;
 extern int g_hybrid_unstable;
 extern int g_unstable_config;
 extern int g_local_tile;
@@ -67,6 +68,11 @@ extern "C" int kmg_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "local_tile")) {
         KMG_REQUIRE(value >= 2048 && value <= 7936, KMG_ERR_ARG, "local_tile must be in [2048,7936]");
         g_local_tile = (int)value;
+        return KMG_OK;
+    }
+    if (!strcmp(name, "local_v")) {
+        KMG_REQUIRE(value == 1 || value == 2, KMG_ERR_ARG, "local_v must be 1 or 2");
+        g_local_v = (int)value;
         return KMG_OK;
     }
     if (!strcmp(name, "unstable_config")) {

@@ -421,6 +421,7 @@ __global__ void __launch_bounds__(BLOCK, min_ctas(BLOCK, IPT)) onesweep_kernel(c
 }
 
 #include "local_sort.cuh"
+#include "local_sort_fine.cuh"
 
 // kmg_set_option("sort_config", i) -> (threads, keys per thread, ranking mix), see dispatch_tile():
 //   0: 256x16 mix2   1: 256x16 mix0   2: 256x16 mix1   3: 256x24 mix2 (default)   4: 512x16 mix2
@@ -563,6 +564,7 @@ int g_hybrid = 1;     // kmg_set_option("hybrid", 0/1)
 int g_unstable_config = 10;  // kmg_set_option("unstable_config", 10 | 11 | 12): tile shape of that pass
 int g_hybrid_unstable = 1;  // kmg_set_option("hybrid_unstable", 0/1): first prefix pass without stable ranking
 int g_local_tile = 7936;  // kmg_set_option("local_tile", positions): target tile width of the local sort
+int g_local_v = 1;     // kmg_set_option("local_v", 1 | 2): 2 = the fine-cell local sort (local_sort_fine.cuh)
 int g_count_fused = 1;  // kmg_set_option("count_fused", 0/1): let the hybrid finish emit the count table itself
 int g_hybrid_pb = 0;  // kmg_set_option("hybrid_pb", 0 | 16 | 24): force the prefix width (0 = by n and skew)
 constexpr uint64_t HYBRID_MIN_N = 1ull << 20;
@@ -846,8 +848,11 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
     hp.tile_state = w.hyb_state;
     hp.ticket = &hv->ls_ticket;
     hp.err = &w.hdr->err;
-    const size_t smem = wide_key ? (pairs ? ls_smem_bytes<u128, true>() : ls_smem_bytes<u128, false>())
-                                 : (pairs ? ls_smem_bytes<uint64_t, true>() : ls_smem_bytes<uint64_t, false>());
+    const bool fine = g_local_v == 2;
+    const size_t smem = fine ? (wide_key ? (pairs ? lsf_smem_bytes<u128, true>() : lsf_smem_bytes<u128, false>())
+                                         : (pairs ? lsf_smem_bytes<uint64_t, true>() : lsf_smem_bytes<uint64_t, false>()))
+                             : (wide_key ? (pairs ? ls_smem_bytes<u128, true>() : ls_smem_bytes<u128, false>())
+                                         : (pairs ? ls_smem_bytes<uint64_t, true>() : ls_smem_bytes<uint64_t, false>()));
     const int sel_in = kin == (char*)d_keys ? 0 : 1;  // where the prefix-ordered keys are
     const int sel_done = sel_in ^ 1;                   // ... and where the finish puts its result
     const bool want_fused = co != nullptr && g_count_fused;
@@ -873,7 +878,7 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
         timing_begin(st);
 #define KMG_LS_LAUNCH(K, E, V)                                                                                   \
     do {                                                                                                         \
-        auto kern = local_sort_kernel<K, E, V>;                                                                  \
+        auto kern = fine ? local_sort_fine_kernel<K, E, V> : local_sort_kernel<K, E, V>;                         \
         KMG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
         kern<<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);                                                            \
     } while (0)
