@@ -305,7 +305,7 @@ int kmg_uniq_host(kmg_ctx* ctx, const uint8_t* h_bases, uint64_t n_bases, int k,
  *   "unstable_config" [10] tile shape of that pass (10: 256x24, 11: 256x16, 12: 384x16)
  *   "count_fused" [1]      kmg_sort_count: the local sort emits the (k-mer, count) table itself
  *   "local_tile" [7936]    target tile width of the local sort (positions)
- *   "local_v" [1]          local sort kernel: 1 = one cell per key + per-thread walks, 2 = fine cells
+ *   "local_v" [2]          local sort kernel: 1 = one cell per key + per-thread walks, 2 = fine cells
  *                          (only colliding keys are ever compared; local_sort_fine.cuh)
  *   "sort_config" [3]      tile configuration of the onesweep kernel (radix_sort.cu: dispatch_tile)
  *   "lb_group" [32]        tiles per look-back group of the onesweep kernel

@@ -564,7 +564,7 @@ int g_hybrid = 1;     // kmg_set_option("hybrid", 0/1)
 int g_unstable_config = 10;  // kmg_set_option("unstable_config", 10 | 11 | 12): tile shape of that pass
 int g_hybrid_unstable = 1;  // kmg_set_option("hybrid_unstable", 0/1): first prefix pass without stable ranking
 int g_local_tile = 7936;  // kmg_set_option("local_tile", positions): target tile width of the local sort
-int g_local_v = 1;     // kmg_set_option("local_v", 1 | 2): 2 = the fine-cell local sort (local_sort_fine.cuh)
+int g_local_v = 2;     // kmg_set_option("local_v", 1 | 2): 2 = the fine-cell local sort (local_sort_fine.cuh)
 int g_count_fused = 1;  // kmg_set_option("count_fused", 0/1): let the hybrid finish emit the count table itself
 int g_hybrid_pb = 0;  // kmg_set_option("hybrid_pb", 0 | 16 | 24): force the prefix width (0 = by n and skew)
 constexpr uint64_t HYBRID_MIN_N = 1ull << 20;
@@ -880,7 +880,8 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
     do {                                                                                                         \
         auto kern = fine ? local_sort_fine_kernel<K, E, V> : local_sort_kernel<K, E, V>;                         \
         KMG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
-        kern<<<hp.n_tiles, LS_BLOCK, smem, st>>>(hp);                                                            \
+        /* (the fine-cell kernel is persistent: two CTAs per SM take tiles from a ticket) */                     \
+        kern<<<fine ? std::min<uint32_t>(hp.n_tiles, 2u * (uint32_t)sms) : hp.n_tiles, LS_BLOCK, smem, st>>>(hp); \
     } while (0)
         if (fused && pairs && wide_key) {
             if (val_bytes == 4) KMG_LS_LAUNCH(u128, 2, 4);
