@@ -405,7 +405,7 @@ def main():
             n_distinct = int(tab.n)
             ls_bytes = W * n_keys + (W + 4) * n_distinct
             ls_ach = ls_bytes / (avg_local_ms / 1e3) / 1e9
-            local = {"bound": "hbm", "kernel": "kmg::local_sort_kernel<uint64_t, EMIT=count, VB=0> (hybrid finish + run-length count: reads every "
+            local = {"bound": "hbm", "kernel": "kmg::local_sort_fine_kernel<uint64_t, EMIT=count, VB=0> (hybrid finish + run-length count: reads every "
                      "key, writes the (k-mer, count) table)",
                      "achieved": ls_ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ls_ach / peak,
                      "traffic": None, "algorithmic_bytes_per_launch": ls_bytes, "avg_launch_ms": avg_local_ms,
