@@ -18,6 +18,7 @@ extern int g_lb_group;
 extern int g_hybrid;
 extern int g_hybrid_pb;
 extern int g_count_fused;
+extern int g_dx_align;
 extern int g_local_v;
 extern int g_hybrid_unstable;
 extern int g_unstable_config;
@@ -70,8 +71,12 @@ extern "C" int kmg_set_option(const char* name, int64_t value) {
         g_local_tile = (int)value;
         return KMG_OK;
     }
+    if (!strcmp(name, "dx_align")) {
+        g_dx_align = value != 0;
+        return KMG_OK;
+    }
     if (!strcmp(name, "local_v")) {
-        KMG_REQUIRE(value == 1 || value == 2, KMG_ERR_ARG, "local_v must be 1 or 2");
+        KMG_REQUIRE(value >= 1 && value <= 3, KMG_ERR_ARG, "local_v must be 1, 2 or 3");
         g_local_v = (int)value;
         return KMG_OK;
     }

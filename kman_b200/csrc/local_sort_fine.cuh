@@ -34,6 +34,7 @@
 #pragma once
 
 constexpr int LSF_THREAD_MAX = 12;   // keys of a cell its list thread insertion-sorts
+constexpr int LSF_PEND = 8;          // tiles without output a CTA may skip over while it holds a tile
 // counter words (one per key slot, two cells each) + the list of crowded cells (u16, at most one per two keys)
 template <typename KeyT, bool PAIRS>
 __host__ __device__ constexpr int lsf_cell_words() { return ls_cap<KeyT, PAIRS>() + ls_cap<KeyT, PAIRS>() / 4; }
@@ -76,6 +77,7 @@ __global__ void __launch_bounds__(LS_BLOCK, 2) local_sort_fine_kernel(const Hybr
     // what thread 0 learns about a ticket: kind 0 = no tile left, 1 = a tile to sort, 2 = a tile without
     // output (no bucket starts in it, or it owns more keys than the scheme holds: flagged)
     __shared__ uint32_t s_t_kind, s_t_tile, s_t_m;
+    __shared__ uint32_t s_pend[LSF_PEND];
     __shared__ uint64_t s_t_s;
     const int t = threadIdx.x;
     const uint32_t lane = t & 31u, warp = t >> 5;
@@ -125,16 +127,20 @@ __global__ void __launch_bounds__(LS_BLOCK, 2) local_sort_fine_kernel(const Hybr
             if (t == 0) tile_prefix_publish(p.tile_state, tile, 0);
         }
     };
+    // ... but only its side effects matter: as the last tile of a group (super-group) its resolve publishes
+    // the group's sum (the chained prefix), as the last tile of all the total.  Any other tile without output
+    // is done once it has published its zero -- no waiting for the earlier tiles.
+    auto needs_resolve = [&](uint32_t tile) { return tile % SC_GROUP == SC_GROUP - 1 || tile == p.n_tiles - 1; };
     auto resolve_nothing = [&](uint32_t tile) {
         if constexpr (FUSED) {
-            if (t < 32) {
+            if (t < 32 && needs_resolve(tile)) {
                 const uint64_t base = tile_prefix_resolve_warp(p.tile_state, p.n_tiles, tile, 0, p.err);
                 if (t == 0 && tile == p.n_tiles - 1) *p.n_out = *p.n_out_copy = base;
             }
         }
     };
     // next tile to SORT; tiles without output met on the way are dealt with on the spot (only legal while
-    // this CTA holds no unpublished tile: their resolve waits for every earlier tile)
+    // this CTA holds no unresolved tile: see the pipeline loop)
     auto fetch_sortable = [&]() -> Tile {
         for (;;) {
             const Tile x = fetch();
@@ -430,17 +436,29 @@ __global__ void __launch_bounds__(LS_BLOCK, 2) local_sort_fine_kernel(const Hybr
     for (;;) {
         // A sits in s_stage in cell order; its list has s_nfix[0] entries.  Take the next ticket and get its
         // keys on their way before A's crowded cells are sorted.
+        // Tiles without output met on the way are published on the spot, but RESOLVED only after A: a resolve
+        // also publishes its group's (and super-group's) sum, and the one of A's group may be A's own job --
+        // every CTA has to meet its obligations (publish, resolve) in ascending tile order, or a tile without
+        // output in the group after A waits for a group sum that this very CTA has not written yet.
         Tile N = fetch();
+        uint32_t n_pend = 0;  // (block-uniform)
+        while (N.kind == 2 && n_pend < (uint32_t)LSF_PEND) {
+            publish_nothing(N.tile);
+            if (needs_resolve(N.tile)) {
+                if (t == 0) s_pend[n_pend] = N.tile;
+                ++n_pend;
+            }
+            N = fetch();
+        }
         if (N.kind == 1 && t == 0) {  // (TMA prefetch into L2: no registers held while A is being finished)
             const uintptr_t a0 = reinterpret_cast<uintptr_t>(reinterpret_cast<const KeyT*>(p.keys_in) + N.s);
             const uintptr_t a1 = a0 + (uintptr_t)N.m * sizeof(KeyT);
             tma_prefetch_l2(reinterpret_cast<const void*>(a0 & ~(uintptr_t)15), (uint32_t)(((a1 + 15) & ~(uintptr_t)15) - (a0 & ~(uintptr_t)15)));
         }
-        if (N.kind == 2) publish_nothing(N.tile);  // (its resolve has to wait until A is published)
+        if (N.kind == 2) publish_nothing(N.tile);  // (more of them in a row than the list holds)
         const bool ok = fixup(A, s_nfix[0]);
         const uint32_t ndup = s_ndup;
         // A's aggregate: distinct keys (count), singletons (uniq; known here only without duplicates)
-        bool published = false;
         if (!ok && t == 0) {
             atomicAdd(p.irregular, 1ull);
             p.flag[A.tile] = 1;
@@ -448,18 +466,11 @@ __global__ void __launch_bounds__(LS_BLOCK, 2) local_sort_fine_kernel(const Hybr
         if constexpr (FUSED) {
             if (!ok) {
                 publish_nothing(A.tile);
-                published = true;
             } else if (COUNT || ndup == 0) {
                 if (t == 0) tile_prefix_publish(p.tile_state, A.tile, A.m - ndup);
-                published = true;
             }
         }
-        // the next tile's front, between A's publish and A's resolve (a tile without output can only be
-        // resolved, and a replacement be looked for, once A is published)
-        if (N.kind == 2 && published) {
-            resolve_nothing(N.tile);
-            N = fetch_sortable();
-        }
+        // the next tile's front, between A's publish and A's resolve
         uint32_t meta_n[IPT];
         if (N.kind == 1) {
             KeyT keys[IPT];
@@ -572,10 +583,11 @@ __global__ void __launch_bounds__(LS_BLOCK, 2) local_sort_fine_kernel(const Hybr
                     }
                 }
             }
-            // a tile without output whose resolve had to wait for A (uniq with duplicates: A is published only now)
-            if (N.kind == 2) {
+            // the tiles without output taken since A, in ascending order
+            if (n_pend != 0 || N.kind == 2) {
                 __syncthreads();
-                resolve_nothing(N.tile);
+                for (uint32_t i = 0; i < n_pend; ++i) resolve_nothing(s_pend[i]);
+                if (N.kind == 2) resolve_nothing(N.tile);
             }
         }
         __syncthreads();  // everyone is done with s_stage, the bitmask and the per-tile flags

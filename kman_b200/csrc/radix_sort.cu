@@ -564,7 +564,7 @@ int g_hybrid = 1;     // kmg_set_option("hybrid", 0/1)
 int g_unstable_config = 10;  // kmg_set_option("unstable_config", 10 | 11 | 12): tile shape of that pass
 int g_hybrid_unstable = 1;  // kmg_set_option("hybrid_unstable", 0/1): first prefix pass without stable ranking
 int g_local_tile = 7936;  // kmg_set_option("local_tile", positions): target tile width of the local sort
-int g_local_v = 2;     // kmg_set_option("local_v", 1 | 2): 2 = the fine-cell local sort (local_sort_fine.cuh)
+int g_local_v = 2;     // kmg_set_option("local_v", 1 | 2 | 3): 2 = the fine-cell local sort (local_sort_fine.cuh) where it wins, 3 = always
 int g_count_fused = 1;  // kmg_set_option("count_fused", 0/1): let the hybrid finish emit the count table itself
 int g_hybrid_pb = 0;  // kmg_set_option("hybrid_pb", 0 | 16 | 24): force the prefix width (0 = by n and skew)
 constexpr uint64_t HYBRID_MIN_N = 1ull << 20;
@@ -848,7 +848,12 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
     hp.tile_state = w.hyb_state;
     hp.ticket = &hv->ls_ticket;
     hp.err = &w.hdr->err;
-    const bool fine = g_local_v == 2;
+    // The persistent fine-cell kernel wins wherever a tile holds several prefix buckets; with ONE bucket per
+    // tile (a 16-bit prefix under >= 224 M evenly spread keys: config 3 on 8 GPUs) it measured 28 ms against
+    // the first kernel's 4.3 ms per 387.5 M keys (gpurun_out/r2_rank_sim2*.log), so that regime keeps the
+    // first kernel (local_v 3 forces the fine cells there too)
+    const bool one_bucket_tiles = (double)n / (double)(1ull << pb) > cap / 2.4;
+    const bool fine = g_local_v == 3 || (g_local_v == 2 && !one_bucket_tiles);
     const size_t smem = fine ? (wide_key ? (pairs ? lsf_smem_bytes<u128, true>() : lsf_smem_bytes<u128, false>())
                                          : (pairs ? lsf_smem_bytes<uint64_t, true>() : lsf_smem_bytes<uint64_t, false>()))
                              : (wide_key ? (pairs ? ls_smem_bytes<u128, true>() : ls_smem_bytes<u128, false>())

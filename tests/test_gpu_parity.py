@@ -983,3 +983,66 @@ def test_hybrid_sort_family_fuzz(eng, seed, monkeypatch, capsys):
     runpy.run_path(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "fuzz_sort.py"),
                    run_name="__main__")
     assert "FUZZ_OK 12 trials" in capsys.readouterr().out
+
+
+# ---- tiles without output (no prefix bucket starts in them) in the persistent local sort -----------------
+def _sparse_prefix_keys(rng, n, n_prefixes, bits, dup):
+    """n keys of `bits` bits whose top 24 bits take only `n_prefixes` values: prefix buckets of
+    n / n_prefixes keys, several narrow tiles wide."""
+    pref = rng.choice(1 << 24, size=n_prefixes, replace=False).astype(np.uint64)
+    pool_n = max(1, n // dup)
+    pool = (pref[rng.integers(0, n_prefixes, size=pool_n)] << np.uint64(bits - 24)) | \
+        rng.integers(0, 1 << (bits - 24), size=pool_n, dtype=np.uint64)
+    return pool if dup == 1 else pool[rng.integers(0, pool_n, size=n)]
+
+
+@pytest.mark.parametrize("mode", ["count", "count_dup3", "uniq", "uniq_dup2", "sort"])
+def test_hybrid_tiles_without_output_keep_the_tile_prefix_moving(eng, mode):
+    """Buckets of ~5000 keys under 2048-wide tiles: three tiles in five own no bucket start and emit nothing.
+    Such a tile's resolve also publishes its group's sum, so a CTA of the persistent kernel has to resolve
+    it AFTER the tile it still holds (config 3 on 8 GPUs -- one 16-bit bucket per tile, 8 % of the tiles
+    empty -- ran into the look-back spin limit when it did not)."""
+    n, bits = 4_000_037, 62
+    rng = np.random.default_rng(len(mode))
+    dup = 3 if mode == "count_dup3" else 2 if mode == "uniq_dup2" else 1
+    raw = _sparse_prefix_keys(rng, n, 800, bits, dup)
+    eng.lib.kmg_set_option(b"hybrid_pb", 24)
+    eng.lib.kmg_set_option(b"local_tile", 2048)
+    try:
+        if mode.startswith("count"):
+            keys, counts = _sort_count(eng, raw, bits)
+            wk, wc = np.unique(raw, return_counts=True)
+            assert first_diff(keys, wk) == "equal"
+            assert first_diff(counts.astype(np.uint64), wc.astype(np.uint64)) == "equal"
+        elif mode.startswith("uniq"):
+            vals = np.arange(n, dtype=np.uint32)
+            keys, got_v = _sort_uniq(eng, raw, vals, bits)
+            wk, wv = _want_singletons(raw, vals)
+            assert first_diff(keys, wk) == "equal"
+            assert first_diff(got_v.astype(np.uint64), wv.astype(np.uint64)) == "equal"
+        else:
+            a = _keyonly_sort(eng, raw, bits)
+            assert first_diff(a.keys_host(), np.sort(raw)) == "equal"
+    finally:
+        eng.lib.kmg_set_option(b"hybrid_pb", 0)
+        eng.lib.kmg_set_option(b"local_tile", 7936)
+    assert eng.lib.kmg_get_stat(b"hybrid_path") == 1
+    assert eng.lib.kmg_get_stat(b"hybrid_irregular") == 0
+
+
+def test_hybrid_tiles_without_output_u128(eng):
+    n, bits = 3_000_017, 126
+    rng = np.random.default_rng(77)
+    raw = _u128_keys(rng, n, bits)
+    pref = rng.choice(1 << 24, size=1500, replace=False).astype(np.uint64)
+    raw[:, 1] = (raw[:, 1] & np.uint64((1 << 38) - 1)) | (pref[rng.integers(0, 1500, size=n)] << np.uint64(38))
+    eng.lib.kmg_set_option(b"hybrid_pb", 24)
+    eng.lib.kmg_set_option(b"local_tile", 2048)
+    try:
+        keys, counts = _sort_count(eng, raw, bits)
+    finally:
+        eng.lib.kmg_set_option(b"hybrid_pb", 0)
+        eng.lib.kmg_set_option(b"local_tile", 7936)
+    assert first_diff(keys, _u128_sorted(raw)) == "equal"
+    assert int(counts.astype(np.uint64).sum()) == n
+    assert eng.lib.kmg_get_stat(b"hybrid_path") in (1, 2)  # (two bucket starts in one window can overflow a tile)
