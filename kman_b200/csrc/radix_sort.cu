@@ -848,12 +848,16 @@ static int sort_impl(void* d_keys, void* d_keys_alt, void* d_vals, void* d_vals_
     hp.tile_state = w.hyb_state;
     hp.ticket = &hv->ls_ticket;
     hp.err = &w.hdr->err;
-    // The persistent fine-cell kernel wins wherever a tile holds several prefix buckets; with ONE bucket per
-    // tile (a 16-bit prefix under >= 224 M evenly spread keys: config 3 on 8 GPUs) it measured 28 ms against
-    // the first kernel's 4.3 ms per 387.5 M keys (gpurun_out/r2_rank_sim2*.log), so that regime keeps the
-    // first kernel (local_v 3 forces the fine cells there too)
-    const bool one_bucket_tiles = (double)n / (double)(1ull << pb) > cap / 2.4;
-    const bool fine = g_local_v == 3 || (g_local_v == 2 && !one_bucket_tiles);
+    // The persistent fine-cell kernel wins wherever a tile holds several prefix buckets.  With about ONE bucket
+    // per tile (a 16-bit prefix under more than ~160 M evenly spread keys: config 3 on 8 GPUs, 387.5 M keys per
+    // rank) its tile prefix jams -- 70 % of the warp samples sit behind warp 0's look-back polls, 28 ms against
+    // the first kernel's 4.3 ms (profiles/r02_local_sort_one_bucket_tiles.md) -- so tiles narrower than two
+    // average buckets keep the first kernel (local_v 3 forces the fine cells there too).
+    const double avg_bucket = (double)n / (double)(1ull << pb);
+    const bool few_bucket_tiles =
+        avg_bucket > cap / 2.4 ||
+        (avg_bucket >= 64 && std::min<double>(g_local_tile, cap - std::max(256.0, 1.35 * avg_bucket)) < 2.0 * avg_bucket);
+    const bool fine = g_local_v == 3 || (g_local_v == 2 && !few_bucket_tiles);
     const size_t smem = fine ? (wide_key ? (pairs ? lsf_smem_bytes<u128, true>() : lsf_smem_bytes<u128, false>())
                                          : (pairs ? lsf_smem_bytes<uint64_t, true>() : lsf_smem_bytes<uint64_t, false>()))
                              : (wide_key ? (pairs ? ls_smem_bytes<u128, true>() : ls_smem_bytes<u128, false>())
