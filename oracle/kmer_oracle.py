@@ -20,7 +20,8 @@ Two tiers, cross-checked against each other in the CPU test-suite:
   * tier A (`*_py`): literal pure-Python restatement, string k-mers, Python
     `sorted`, `heapq.merge`, grouping loop.  Small inputs only.
   * tier B (`*_np`): numpy restatement on packed integer keys.  Used for
-    Mbp-scale inputs and as the `cpu_baseline` of bench.py.
+    Mbp-scale inputs and as the `cpu_baseline` of bench.py (count_table_np_threads: the
+    same stages on all host threads, chunked and merged the way `kmer batch --threads N` is).
 
 Reference citations are relative to /root/reference/.
 """
@@ -446,6 +447,57 @@ def count_table_np(records, k, rc=False, alphabet=DEFAULT_ALPHABET, natype="DNA"
     srt = [l[order] for l in st["keys"]]
     heads, lens = _rle(srt)
     return [l[heads] for l in srt], lens
+
+
+def count_table_np_threads(records, k, rc=False, alphabet=DEFAULT_ALPHABET, natype="DNA", threads: int = 0,
+                           batch_size: Optional[int] = None):
+    """count_table_np on `threads` host threads -- the shape of the reference's own parallel run
+    (`kmer batch --threads N`: batcher.py:454-487 hands Sequence.batcher's chunks, seq.py:361-383, k-1
+    overlap, to joblib workers that each extract and sort one batch, batch.py:156-168; the join then
+    merges the sorted batches, join.py:63-130).  Here every worker extracts and sorts the keys of its
+    chunks (numpy releases the GIL inside its kernels), and the merge is split by KEY RANGE so that it
+    runs in parallel too: worker r takes the r-th key range of every sorted batch (two binary searches
+    per batch), merges them with a stable sort (timsort on pre-sorted runs = an n-way merge) and
+    run-length groups its range; the ranges concatenate in key order.  Same table as count_table_np."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+
+    T = threads if threads > 0 else len(os.sched_getaffinity(0))
+    total = sum(len(s) for _, s in records)
+    bs = batch_size if batch_size else max(k, -(-total // (4 * T)) + k - 1)  # ~4 batches per worker
+    pieces: List[Record] = []
+    for title, seq in records:
+        for chunk, _start in batcher_py(seq, k, bs):
+            pieces.append((title, chunk))
+    n_limbs = 1 if k <= 32 else 2
+
+    def sort_batch(piece: Record):
+        st = extract_np([piece], k, rc, alphabet, natype)["narrow"]
+        order = _lexsort_limbs(st["keys"])
+        return [l[order] for l in st["keys"]]
+
+    with ThreadPoolExecutor(T) as pool:
+        batches = list(pool.map(sort_batch, pieces))
+        # key ranges by the top limb: T equal slices of the key space actually in use
+        top_bits = 2 * k - 64 * (n_limbs - 1)
+        edges = [(r << top_bits) // T for r in range(1, T)]
+
+        def cuts(b):
+            return np.concatenate(([0], np.searchsorted(b[0], np.array(edges, np.uint64), side="left"), [b[0].shape[0]]))
+
+        cut = [cuts(b) for b in batches]
+
+        def merge_range(r: int):
+            limbs = [np.concatenate([b[j][c[r]:c[r + 1]] for b, c in zip(batches, cut)]) if batches else np.zeros(0, np.uint64)
+                     for j in range(n_limbs)]
+            order = _lexsort_limbs(limbs)
+            srt = [l[order] for l in limbs]
+            heads, lens = _rle(srt)
+            return [l[heads] for l in srt], lens
+
+        parts = list(pool.map(merge_range, range(T)))
+    keys = [np.concatenate([p[0][j] for p in parts]) for j in range(n_limbs)]
+    return keys, np.concatenate([p[1] for p in parts])
 
 
 def uniq_np(records, k, rc=False, alphabet=DEFAULT_ALPHABET, natype="DNA"):

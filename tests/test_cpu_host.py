@@ -183,8 +183,11 @@ def test_bench_reference_arm_contract():
     sys.path.insert(0, ROOT)
     import bench
 
-    rate, sec = bench.cpu_port_rate(200_000, 1, 0)
-    assert rate > 0 and sec > 0
+    rate, sec, threads, steps = bench.cpu_port_rate(200_000, 2, 0)
+    assert rate > 0 and sec > 0 and steps == 2
+    assert threads == len(os.sched_getaffinity(0))  # every host thread the process may use
+    # the time budget cuts a long run short and says so
+    assert bench.cpu_port_rate(200_000, 5, 0, budget_s=0.0)[3] == 1
 
 
 def test_every_option_and_stat_is_documented_in_the_header():

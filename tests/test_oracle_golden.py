@@ -126,6 +126,25 @@ def test_np_extract_matches_py_random():
                     assert ko.uniq_text_np(recs, k, rc, ab) == ko.uniq_text_py(recs, k, rc, alphabet=ab), (trial, k, rc, ab)
 
 
+def test_threaded_count_table_equals_the_single_threaded_tier():
+    """count_table_np_threads (bench.py's reference arm: chunks with k-1 overlap sorted by a thread each,
+    merge + grouping split by key range) gives count_table_np's table for any chunk size and thread count."""
+    rng = np.random.default_rng(11)
+    for trial in range(6):
+        recs = []
+        for r in range(int(rng.integers(1, 5))):
+            n = int(rng.integers(0, 3000))
+            recs.append(("r%d" % r, "".join(rng.choice(list("ACGTacgtN"), p=[.23, .23, .23, .23, .02, .02, .02, .01, .01], size=n))))
+        for k in (2, 9, 31, 32, 33, 63):
+            for rc in (False, True):
+                want = ko.count_table_np(recs, k, rc, "ACGT")
+                for threads, bs in ((1, None), (3, None), (4, 64 + k), (7, 1000)):
+                    got = ko.count_table_np_threads(recs, k, rc, "ACGT", threads=threads, batch_size=bs)
+                    assert len(got[0]) == len(want[0])
+                    assert all(np.array_equal(a, b) for a, b in zip(got[0], want[0])), (trial, k, rc, threads, bs)
+                    assert np.array_equal(got[1], want[1]), (trial, k, rc, threads, bs)
+
+
 def test_k_must_exceed_one():  # batcher.py:477-478
     with pytest.raises(AssertionError):
         ko.count_text_py([("a", "ACGT")], 1)
