@@ -261,12 +261,8 @@ class DeviceBatch:
     def current_size(self) -> int:
         """Number of k-mer records (valid windows, x2 with reverse complement)."""
         if self._n is None:
-            d = self.device_input
-            a = self._eng.extract(d, self.k, self.reverse, wide=False, val_bytes=0)
-            n = a.n
-            if a.n_other:
-                n += a.n_other * (2 if self.reverse else 1)
-            self._n = n
+            n, n_other = self._eng.count_windows(self.device_input, self.k, self.reverse)
+            self._n = n + n_other * (2 if self.reverse else 1)
         return self._n
 
     @property

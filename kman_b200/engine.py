@@ -192,7 +192,11 @@ class Engine:
             raise AssertionError("premature end of file or empty file")
         n_raw = len(raw)
         d_raw = torch.empty(((n_raw + 15) // 16 + 1) * 16, dtype=torch.uint8, device=self.device)
-        d_raw[:n_raw].copy_(torch.frombuffer(bytearray(raw), dtype=torch.uint8))
+        import warnings
+
+        with warnings.catch_warnings():  # (a read-only view of the bytes object: no second host copy)
+            warnings.simplefilter("ignore", UserWarning)
+            d_raw[:n_raw].copy_(torch.from_numpy(np.frombuffer(raw, np.uint8)))
         bases = torch.empty(((n_raw + 15) // 16 + 2) * 16, dtype=torch.uint8, device=self.device)
         max_rec = 1 << 16
         while True:
@@ -235,6 +239,25 @@ class Engine:
         offs[1:] = np.cumsum([len(b) for b in nb])
         d.name_offs = torch.from_numpy(offs).to(self.device)
         d.names_buf = torch.from_numpy(np.frombuffer(b"".join(nb) + b"\0", np.uint8).copy()).to(self.device)
+
+    @_on_device
+    def count_windows(self, d: DeviceInput, k: int, rc: bool = False) -> Tuple[int, int]:
+        """(narrow keys, wide-stream windows) of an input WITHOUT building a key: for k >= 12 the 4-mer
+        histogram pre-pass of the bases knows both (kmg_extract_dest_counts with one destination);
+        smaller k runs the extraction."""
+        n_win = max(0, d.n_bases - k + 1)
+        if n_win == 0:
+            return 0, 0
+        if k < 12:
+            a = self.extract(d, k, rc, wide=False, val_bytes=0)
+            return a.n, a.n_other
+        counts = torch.zeros(2, dtype=torch.int64, device=self.device)
+        ws_bytes = self.lib.kmg_dest_counts_workspace_bytes()
+        ws = self._buf("ws_dest_counts", ws_bytes)
+        _lib.check(self.lib.kmg_extract_dest_counts(d.bases.data_ptr(), d.n_bases, 0, n_win, k, int(rc), d.lut.data_ptr(), 1,
+                                                    counts.data_ptr(), ws.data_ptr(), ws_bytes, self._stream()))
+        n, n_other = (int(x) for x in counts.cpu())
+        return n, n_other
 
     # ---- K1+K2 ------------------------------------------------------------------------------
     @_on_device

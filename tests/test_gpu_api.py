@@ -248,3 +248,26 @@ def test_abundance_vectors_large_input_vs_oracle(k, rc):
         vecs = abundance.device_vectors(eng, d, k, rc, masked)
         got = {"%s___%s.gz" % (r, s): abundance.vector_text(v, k) for r, per in vecs.items() for s, v in per.items()}
         assert got == ko.vec_count_np(recs, k, rc, masked), (k, rc, masked)
+
+
+@pytest.mark.parametrize("k", [5, 12, 31, 33, 64])
+@pytest.mark.parametrize("rc", [False, True])
+def test_count_windows_equals_the_extraction_counts(k, rc):
+    """Engine.count_windows (DeviceBatch.current_size: the 4-mer-histogram pre-pass for k >= 12) against
+    the counts a full extraction reports, on records with N runs, IUPAC symbols, foreign bytes and
+    records shorter than k."""
+    import numpy as np
+
+    from kman_b200 import fasta
+    from kman_b200.engine import get_engine
+
+    eng = get_engine(0)
+    rng = np.random.default_rng(k * 2 + rc)
+    recs = []
+    for r, n in enumerate((50_000, 3, 0, 70, 20_000)):
+        s = "".join(rng.choice(list("ACGTacgtNRX"), p=[.24, .24, .24, .24, .01, .01, .005, .005, .004, .003, .003], size=n))
+        recs.append(("r%d" % r, s))
+    for alphabet in ("IUPAC", "ACGT"):
+        d = eng.upload(fasta.from_records(recs), alphabet=alphabet)
+        a = eng.extract(d, k, rc, wide=False, val_bytes=0)
+        assert eng.count_windows(d, k, rc) == (a.n, a.n_other), (alphabet, k, rc)
