@@ -497,7 +497,7 @@ def main():
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        # (a bounded sample: half of config 2, one pass after a short warm-up; ~5 s on 16 threads)
+        # (a bounded sample: half of config 2, one pass; ~5 s on 8-16 threads)
         rate, sec, threads, _ = cpu_port_rate(50_000_000, 1, 0)
         cpu_baseline = {"value": rate, "unit": "k-mers/s", "cores": threads, "kind": "port",
                         "sample": f"50000000 bp of the same generator, k={K}, count; oracle numpy port on {threads} threads, "
