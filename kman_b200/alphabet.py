@@ -9,7 +9,6 @@ the default.  Environment override: KMG_ALPHABET=ACGT|IUPAC.
 """
 from __future__ import annotations
 
-import ctypes as C
 import os
 from enum import Enum
 from functools import lru_cache

@@ -12,7 +12,7 @@ from __future__ import annotations
 import logging
 import multiprocessing as mp
 from enum import Enum
-from typing import IO, Any, Dict, Iterator, List, Optional, Tuple
+from typing import IO, Any, Iterator, List, Optional, Tuple
 
 import numpy as np
 
