@@ -195,14 +195,14 @@ def run_reference(args):
     # > 100 GB of host memory; its step is a 100 Mbp sample of the same generator.  Either way a step is
     # one pass over 100 Mbp (~10 s on 16 threads); --steps / --warmup are honoured as far as a 4-minute
     # budget allows (one warm-up pass at most), and `steps` reports the passes actually timed.
-    sample = CFG2_BASES
+    sample = int(os.environ.get("KMG_BENCH_REF_BASES", CFG2_BASES))  # (the CPU test-suite shrinks it)
     warm = min(args.warmup, 1)
     rate, sec, threads, steps = cpu_port_rate(sample, max(1, args.steps), warm)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "k-mers/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": workload_config(args, sample_note=("the full configuration" if args.workload == "cfg2" and args.gpus == 1
+        "config": workload_config(args, sample_note=("the full configuration" if args.workload == "cfg2" and args.gpus == 1 and sample == CFG2_BASES
                                                       else f"bounded sample: {sample} bases of the same generator per step")),
         "cpu_baseline": {"value": rate, "unit": "k-mers/s", "cores": threads, "kind": "port",
                          "sample": f"{sample} bp random ACGT, k={K}, count; oracle numpy port on {threads} threads "

@@ -190,6 +190,33 @@ def test_bench_reference_arm_contract():
     assert bench.cpu_port_rate(200_000, 5, 0, budget_s=0.0)[3] == 1
 
 
+@pytest.mark.parametrize("gpus", [1, 4])
+def test_bench_reference_arm_prints_the_contract_line(gpus):
+    """`bench.py --impl reference` (the driver's reference arm): one JSON line on stdout with the arm's own
+    metric / unit / config, `impl`, `cpu_baseline` (kind, cores, sample) and an `e2e` that repeats the value."""
+    import json
+    import subprocess
+
+    env = dict(os.environ, KMG_BENCH_REF_BASES="300000", RANK="0", WORLD_SIZE=str(gpus))
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", str(gpus), "--steps", "2",
+                        "--warmup", "1"], capture_output=True, text=True, timeout=300, env=env)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, p.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "k-mers/s" and d["higher_is_better"] is True
+    assert d["metric"].startswith("k-mers/sec") and d["n_gpus"] == gpus and d["steps"] == 2 and d["warmup"] == 1
+    assert d["value"] > 0 and d["e2e"] == {"value": d["value"], "unit": "k-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] == len(os.sched_getaffinity(0)) and cb["value"] == d["value"] and cb["sample"]
+    assert ("config 2" if gpus == 1 else "config 3") in d["config"]["workload"]
+    # the other ranks of a torchrun launch exit 0 without work
+    env["RANK"] = "1"
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", str(gpus)],
+                       capture_output=True, text=True, timeout=300, env=env)
+    assert p.returncode == 0 and p.stdout.strip() == ""
+
+
 def test_every_option_and_stat_is_documented_in_the_header():
     """kmg_set_option / kmg_get_stat names handled in api.cu must appear in include/kmg.h's
     tuning section (and nothing documented may be unknown to the library)."""
